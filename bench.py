@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- GCUPS of the affine-gap DP hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic pairs resident in HBM.
+Workload (BASELINE.json configs[1], "C2"): P = 10^7 pairs per GPU, target 500 x query 150,
+AffineGapLocal semantics (free end gaps), HumanChimpTwo matrix, O=-600, E=-150, score only.
+The same line also carries configs[2] ("C3": the same pairs with full traceback + CIGAR) under
+"traceback".  GCUPS counts each DP cell once: sum(n*m) / seconds / 1e9.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_LEN, M_LEN = 500, 150
+GAP_OPEN, GAP_EXTEND = -600, -150
+SEED = 20260102
+# algorithmic bytes: inputs 2-bit packed + 16 B offsets + 8 B score per pair;
+# traceback adds 0.75 B per cell (three 2-bit source-plane codes)
+BYTES_PER_PAIR_SCORE = (N_LEN + 3) // 4 + (M_LEN + 3) // 4 + 16 + 8
+BYTES_PER_CELL_TRACE = 0.75
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_gcups(n_pairs: int, want_cigar: bool, threads: int):
+    """The oracle (C restatement of the Go path) on the host cores: the reported CPU baseline."""
+    import oracle as orc
+    from gonomics_b200.synth import synth_pairs
+    a, ao, b, bo = synth_pairs(SEED, n_pairs, N_LEN, M_LEN)
+    t0 = time.perf_counter()
+    orc.batch(a, ao, b, bo, orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, GAP_OPEN, GAP_EXTEND, 1, want_cigar, threads)
+    dt = time.perf_counter() - t0
+    return n_pairs * N_LEN * M_LEN / dt / 1e9, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The Go toolchain is not in
+    this image, so this is the C restatement (oracle/), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = max(2000, 1500 * threads)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        g, dt = cpu_reference_gcups(sample, False, threads)
+        if i >= args.warmup:
+            vals.append((g, dt))
+    gcups = sample * N_LEN * M_LEN * len(vals) / sum(d for _, d in vals) / 1e9
+    line = {
+        "impl": "reference", "metric": "GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(d for _, d in vals) / len(vals),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": "C2: target 500 x query 150 semi-global affine (AffineGapLocal), score only",
+                   "matrix": "HumanChimpTwo", "gap_open": GAP_OPEN, "gap_extend": GAP_EXTEND},
+        "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": threads, "kind": "port",
+                         "sample": f"{sample} pairs of the C2 batch per step (C restatement of the Go path; "
+                                   "Go toolchain absent)"},
+        "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=10_000_000, help="pairs per GPU per step")
+    ap.add_argument("--impl", default="gnx", choices=["gnx", "reference"])
+    ap.add_argument("--no-traceback", action="store_true", help="skip the C3 (traceback) block")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from gonomics_b200 import align
+    from gonomics_b200._lib import CIGAR_DTYPE, load
+    from gonomics_b200.synth import synth_pairs
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    P = args.pairs
+    S = align.HumanChimpTwoScoreMatrix
+    L = load()
+    ctx = align.Context(local)
+    cells = P * N_LEN * M_LEN
+
+    # ---- synthetic inputs: this rank's shard of the global batch, in pinned host memory ----------
+    na, nb = P * N_LEN, P * M_LEN
+    import ctypes as C
+    pa, pb_ = L.gnx_host_alloc(na), L.gnx_host_alloc(nb)
+    h_alpha = np.ctypeslib.as_array(C.cast(pa, C.POINTER(C.c_uint8)), shape=(na,))
+    h_beta = np.ctypeslib.as_array(C.cast(pb_, C.POINTER(C.c_uint8)), shape=(nb,))
+    t0 = time.perf_counter()
+    _, ao, _, bo = synth_pairs(SEED, P, N_LEN, M_LEN, first_pair=rank * P, alpha_out=h_alpha, beta_out=h_beta)
+    ao -= ao[0]
+    bo -= bo[0]
+    gen_s = time.perf_counter() - t0
+    d_alpha = torch.from_numpy(h_alpha).to(dev)
+    d_beta = torch.from_numpy(h_beta).to(dev)
+    d_ao, d_bo = torch.from_numpy(ao).to(dev), torch.from_numpy(bo).to(dev)
+    d_score = torch.zeros(P, dtype=torch.int64, device=dev)
+    d_status = torch.zeros(1, dtype=torch.int32, device=dev)
+    cig_cap = P * 12
+    d_cig = torch.zeros(cig_cap * 16, dtype=torch.uint8, device=dev)
+    d_off = torch.zeros(P + 1, dtype=torch.int64, device=dev)
+    gathered = torch.zeros(world * P, dtype=torch.int64, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(want_cigar: bool):
+        ctx.batch_device(1, d_alpha.data_ptr(), d_ao.data_ptr(), d_beta.data_ptr(), d_bo.data_ptr(), ao, bo, P, S,
+                         GAP_OPEN, GAP_EXTEND, want_cigar, d_score.data_ptr(), d_cig.data_ptr() if want_cigar else 0,
+                         d_off.data_ptr() if want_cigar else 0, cig_cap, d_status.data_ptr(), stream)
+        if world > 1:  # the path's only exchange: gather the per-shard scores (north_star)
+            dist.all_gather_into_tensor(gathered, d_score)
+
+    def timed_device(want_cigar: bool):
+        for _ in range(args.warmup):
+            device_step(want_cigar)
+        barrier()
+        launches0 = ctx.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fill_ms = 0.0
+        fill_launches = 0
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0.record()
+        for _ in range(args.steps):
+            device_step(want_cigar)
+        e1.record()
+        barrier()
+        clocks = sampler.stop()
+        ms = e0.elapsed_time(e1)
+        # fill-kernel device time of the LAST step (CUDA events recorded by the library on this stream)
+        f_ms, f_n, _ = ctx.last_fill_stats()
+        fill_ms, fill_launches = f_ms, f_n
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        assert int(d_status.item()) == 0, "device status != 0"
+        return ms, ctx.launch_count - launches0, fill_ms, fill_launches, clocks
+
+    peak, peak_src = hbm_peak()
+
+    # ---- C2: score only (headline value) ---------------------------------------------------------
+    ms, launches, fill_ms, fill_n, clocks = timed_device(False)
+    gcups = world * cells * args.steps / (ms * 1e-3) / 1e9
+    alg_bytes = P * BYTES_PER_PAIR_SCORE  # per step, all fill launches of the step together
+    achieved = alg_bytes / (fill_ms * 1e-3) / 1e9 if fill_ms > 0 else None
+    line = {
+        "metric": "GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "C2 (BASELINE.json configs[1]): %d pairs/GPU, target 500 x query 150, semi-global "
+                               "affine gap (AffineGapLocal), score only" % P,
+                   "matrix": "HumanChimpTwo", "gap_open": GAP_OPEN, "gap_extend": GAP_EXTEND,
+                   "pairs_per_gpu": P, "cells_per_step_per_gpu": cells,
+                   "l2": "inputs (%.1f GB/GPU) exceed the 126 MB L2; no flush needed" % ((na + nb) / 1e9),
+                   "sharding": "independent pair shards per rank; all_gather of scores only (N>1)",
+                   "synth_seconds": round(gen_s, 1)},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "peak_source": peak_src, "kernel": "affine_fill_kernel<C=5,TRACE=0,FREE=1>",
+                     "fill_ms_per_step": fill_ms, "fill_launches_per_step": fill_n,
+                     "algorithmic_bytes_per_step": alg_bytes,
+                     "note": "score-only fill moves 187 B per 75,000-cell pair: HBM cannot bind it; the binding "
+                             "roof is integer issue (see issue_roofline and DESIGN.md)"},
+    }
+    if fill_ms > 0 and clocks.get("sm_mhz"):
+        sm = torch.cuda.get_device_properties(local).multi_processor_count
+        slots = sm * 4 * clocks["sm_mhz"] * 1e6  # warp-instruction issue slots per second
+        line["issue_roofline"] = {"cells_per_s_fill": cells / (fill_ms * 1e-3),
+                                  "issue_slots_per_s": slots,
+                                  "issue_slots_per_warp_cell": slots / (cells / 32 / (fill_ms * 1e-3))}
+
+    # ---- C3: traceback + CIGAR on the same pairs -------------------------------------------------
+    if not args.no_traceback:
+        ms3, launches3, fill3, filln3, clocks3 = timed_device(True)
+        g3 = world * cells * args.steps / (ms3 * 1e-3) / 1e9
+        alg3 = cells * BYTES_PER_CELL_TRACE + P * BYTES_PER_PAIR_SCORE
+        ach3 = alg3 / (fill3 * 1e-3) / 1e9 if fill3 > 0 else None
+        line["traceback"] = {
+            "workload": "C3 (configs[2]): same pairs, full traceback + CIGAR", "value": g3, "unit": "GCUPS",
+            "ms_per_step": ms3 / args.steps, "gpu_launches": launches3, "clocks": clocks3,
+            "roofline": {"bound": "hbm", "achieved": ach3, "peak": peak, "unit": "GB/s",
+                         "frac": (ach3 / peak) if ach3 else None, "traffic": None, "peak_source": peak_src,
+                         "kernel": "affine_fill_kernel<C=5,TRACE=1,FREE=1>", "fill_ms_per_step": fill3,
+                         "fill_launches_per_step": filln3, "algorithmic_bytes_per_step": alg3}}
+
+    # ---- e2e: the public host-buffer API, pinned host inputs, H2D + D2H inside the timed region --
+    if not args.no_e2e:
+        def e2e(want_cigar: bool):
+            out_score = np.zeros(P, dtype=np.int64)
+            out_off = np.zeros(P + 1, dtype=np.int64) if want_cigar else None
+            out_cig = np.zeros(cig_cap, dtype=CIGAR_DTYPE) if want_cigar else None
+            out = (out_score, out_off, out_cig)
+            for _ in range(2):
+                ctx.affine_gap_batch(h_alpha, ao, h_beta, bo, S, GAP_OPEN, GAP_EXTEND, True, want_cigar, out=out)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                ctx.affine_gap_batch(h_alpha, ao, h_beta, bo, S, GAP_OPEN, GAP_EXTEND, True, want_cigar, out=out)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            h2d = na + nb + 2 * (P + 1) * 8
+            d2h = P * 8 + ((P + 1) * 8 + int(out_off[-1]) * 16 if want_cigar else 0)
+            return world * cells * args.steps / dt / 1e9, h2d, d2h, out_score
+        v, h2d, d2h, sc_host = e2e(False)
+        line["e2e"] = {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "api": "gnx_affine_batch (host buffers, pinned), score only"}
+        assert np.array_equal(sc_host, d_score.cpu().numpy()), "host-API scores differ from device-API scores"
+        if not args.no_traceback:
+            v3, h2d3, d2h3, _ = e2e(True)
+            line["traceback"]["e2e"] = {"value": v3, "unit": "GCUPS", "h2d_bytes_per_step": h2d3,
+                                        "d2h_bytes_per_step": d2h3}
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores ----------------------
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        sample = max(2000, 1500 * threads)
+        g, dt = cpu_reference_gcups(sample, True, threads)
+        line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": threads, "kind": "port",
+                                "sample": f"first {sample} pairs of the batch, traceback + cigar, {dt:.1f} s "
+                                          "(C restatement of the Go path; Go toolchain absent)"}
+        # spot-check: the GPU scores of that prefix equal the oracle's
+        import oracle as orc
+        k = min(sample, 20000)
+        osc, _, _ = orc.batch(h_alpha[:k * N_LEN], ao[:k + 1], h_beta[:k * M_LEN], bo[:k + 1],
+                              orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, GAP_OPEN, GAP_EXTEND, 1, False, threads)
+        line["parity_spot_check"] = bool(np.array_equal(osc, d_score[:k].cpu().numpy()))
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    L.gnx_host_free(pa)
+    L.gnx_host_free(pb_)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

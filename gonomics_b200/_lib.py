@@ -1,0 +1,85 @@
+"""ctypes loader for libgnxalign.so (the C ABI declared in include/gnxalign.h).
+
+The product path never falls back to a CPU implementation: if the library is missing or there
+is no CUDA device, loading / context creation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgnxalign.so")
+
+GNX_OK, GNX_EBASE, GNX_ECAP, GNX_ECHUNK, GNX_EEMPTY, GNX_ECUDA, GNX_EARG, GNX_ERANGE = range(8)
+GNX_GLOBAL, GNX_FREE_END = 0, 1
+
+# every symbol include/gnxalign.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "gnx_device_count", "gnx_create", "gnx_destroy", "gnx_last_error", "gnx_version", "gnx_host_alloc",
+    "gnx_host_free", "gnx_affine_batch", "gnx_const_batch", "gnx_affine_chunk_batch", "gnx_copy_last_cigars",
+    "gnx_batch_device", "gnx_launch_count", "gnx_last_fill_stats", "gnx_set_option",
+]
+
+
+class GnxCigar(C.Structure):
+    """align.Cigar{RunLength int64; Op ColType} (align/align.go:21-24)."""
+    _fields_ = [("run_length", C.c_int64), ("op", C.c_uint8)]
+
+
+CIGAR_DTYPE = np.dtype({"names": ["run_length", "op"], "formats": ["<i8", "u1"], "offsets": [0, 8], "itemsize": 16})
+
+_lib = None
+
+
+class GnxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"gnxalign error {code}: {msg}")
+        self.code = code
+
+
+def load() -> C.CDLL:
+    """dlopen libgnxalign.so; raise if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m gonomics_b200.build` (nvcc, sm_100a). "
+            "gonomics_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    u8p, i64p, cgp, vp = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p  # raw addresses (host or device)
+    i64, ci = C.c_int64, C.c_int
+    L.gnx_device_count.restype = ci
+    L.gnx_create.argtypes = [ci, C.c_size_t]
+    L.gnx_create.restype = vp
+    L.gnx_destroy.argtypes = [vp]
+    L.gnx_destroy.restype = None
+    L.gnx_last_error.argtypes = [vp]
+    L.gnx_last_error.restype = C.c_char_p
+    L.gnx_version.restype = C.c_char_p
+    L.gnx_host_alloc.argtypes = [C.c_size_t]
+    L.gnx_host_alloc.restype = vp
+    L.gnx_host_free.argtypes = [vp]
+    L.gnx_host_free.restype = None
+    L.gnx_affine_batch.argtypes = [vp, u8p, i64p, u8p, i64p, i64, i64p, ci, i64, i64, ci, ci, i64p, cgp, i64p, i64]
+    L.gnx_affine_batch.restype = ci
+    L.gnx_const_batch.argtypes = [vp, u8p, i64p, u8p, i64p, i64, i64p, ci, i64, ci, i64p, cgp, i64p, i64]
+    L.gnx_const_batch.restype = ci
+    L.gnx_affine_chunk_batch.argtypes = [vp, u8p, i64p, u8p, i64p, i64, i64p, ci, i64, i64, i64, i64p, cgp, i64p, i64]
+    L.gnx_affine_chunk_batch.restype = ci
+    L.gnx_copy_last_cigars.argtypes = [vp, cgp, i64]
+    L.gnx_copy_last_cigars.restype = ci
+    L.gnx_batch_device.argtypes = [vp, ci, u8p, i64p, u8p, i64p, i64p, i64p, i64, i64p, ci, i64, i64, ci, i64p, cgp,
+                                   i64p, i64, vp, vp]
+    L.gnx_batch_device.restype = ci
+    L.gnx_launch_count.argtypes = [vp]
+    L.gnx_launch_count.restype = i64
+    L.gnx_last_fill_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64)]
+    L.gnx_last_fill_stats.restype = ci
+    L.gnx_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.gnx_set_option.restype = ci
+    _lib = L
+    return L

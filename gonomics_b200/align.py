@@ -1,0 +1,339 @@
+"""Host-side mirror of gonomics' `align` package API over the libgnxalign C ABI.
+
+Names, argument order and meaning follow the Go functions (reference paths relative to the
+gonomics tree):
+
+    AffineGap, AffineGap_customizeCheckersize      align/affineGap.go:59,73
+    AffineGap_highMem, AffineGapLocal              align/affineGap_highMem.go:99,105
+    GoAffineGapLocalEngine, TargetQueryPair        align/affineGap_highMem.go:110-125
+    ConstGap, ConstGap_customizeCheckersize        align/constGap.go:13,73
+    ConstGap_highMem                               align/constGap_highMem.go:11
+    AffineGapChunk                                 align/affineGap_highMem.go:227
+
+Every call goes through the CUDA library; there is no CPU path here.  Single-pair functions are
+thin wrappers over the batched entry points (`affine_gap_batch`, `const_gap_batch`), which are the
+performant boundary: one call per 10^4..10^7 pairs.
+
+Sequences are `dna.Base` byte arrays (A,C,G,T,N = 0..4); cigars are returned as lists of
+`Cigar(RunLength, Op)` with Op in {ColM=0, ColI=1, ColD=2} (align/align.go:12-24).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import queue
+import threading
+from dataclasses import dataclass, field
+from typing import List, NamedTuple, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import CIGAR_DTYPE, GNX_ECAP, GNX_FREE_END, GNX_GLOBAL, GNX_OK, GnxError
+
+ColM, ColI, ColD = 0, 1, 2
+
+
+class Cigar(NamedTuple):
+    RunLength: int
+    Op: int
+
+
+# align/align.go:28-64
+DefaultScoreMatrix = np.array(
+    [[91, -114, -31, -123, -44], [-114, 100, -125, -31, -43], [-31, -125, 100, -114, -43],
+     [-123, -31, -114, 91, -44], [-44, -43, -43, -44, -43]], dtype=np.int64)
+HoxD55ScoreMatrix = np.array(
+    [[91, -114, -31, -123, 0], [-114, 100, -125, -31, 0], [-31, -125, 100, -114, 0],
+     [-123, -31, -114, 91, 0], [0, 0, 0, 0, 0]], dtype=np.int64)
+MouseRatScoreMatrix = HoxD55ScoreMatrix.copy()
+HumanChimpTwoScoreMatrix = np.array(
+    [[90, -330, -236, -356, -208], [-330, 100, -318, -236, -196], [-236, -318, 100, -330, -196],
+     [-356, -236, -330, 90, -208], [-208, -196, -196, -208, -202]], dtype=np.int64)
+
+
+def _addr(a: Optional[np.ndarray]) -> Optional[int]:
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One gnx_ctx: a CUDA device, its streams and scratch.  Not thread-safe (one per thread)."""
+
+    def __init__(self, device: int = 0, workspace_bytes: int = 0):
+        self._L = _lib.load()
+        self._h = self._L.gnx_create(int(device), int(workspace_bytes))
+        if not self._h:
+            raise GnxError(_lib.GNX_ECUDA, self._L.gnx_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gnx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- helpers ------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != GNX_OK:
+            raise GnxError(rc, self._L.gnx_last_error(self._h).decode())
+
+    def set_option(self, name: str, value: int):
+        self._check(self._L.gnx_set_option(self._h, name.encode(), int(value)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.gnx_launch_count(self._h))
+
+    def last_fill_stats(self) -> Tuple[float, int, int]:
+        ms, n, cells = C.c_double(0), C.c_int64(0), C.c_int64(0)
+        self._check(self._L.gnx_last_fill_stats(self._h, C.byref(ms), C.byref(n), C.byref(cells)))
+        return ms.value, n.value, cells.value
+
+    # ---- batched entry points (host buffers) ------------------------------------------
+    def _batch(self, kind, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_open, gap_extend, want_cigar,
+               cigar_cap=None, out=None):
+        alpha_cat = np.ascontiguousarray(alpha_cat, dtype=np.uint8)
+        beta_cat = np.ascontiguousarray(beta_cat, dtype=np.uint8)
+        alpha_off = np.ascontiguousarray(alpha_off, dtype=np.int64)
+        beta_off = np.ascontiguousarray(beta_off, dtype=np.int64)
+        scores = np.ascontiguousarray(scores, dtype=np.int64)
+        dim = int(scores.shape[0])
+        n_pairs = len(alpha_off) - 1
+        assert len(beta_off) == n_pairs + 1 and scores.shape == (dim, dim)
+        if out is not None:
+            out_score, out_off, out_cig = out
+        else:
+            out_score = np.zeros(n_pairs, dtype=np.int64)
+            out_off = np.zeros(n_pairs + 1, dtype=np.int64) if want_cigar else None
+            if want_cigar:
+                if cigar_cap is None:
+                    cigar_cap = 16 * n_pairs + 64
+                out_cig = np.zeros(max(int(cigar_cap), 1), dtype=CIGAR_DTYPE)
+            else:
+                out_cig = None
+        cap = 0 if out_cig is None else len(out_cig)
+        if kind == 2:
+            rc = self._L.gnx_const_batch(self._h, _addr(alpha_cat), _addr(alpha_off), _addr(beta_cat), _addr(beta_off),
+                                         n_pairs, _addr(scores), dim, int(gap_open), int(bool(want_cigar)),
+                                         _addr(out_score), _addr(out_cig), _addr(out_off), cap)
+        else:
+            rc = self._L.gnx_affine_batch(self._h, _addr(alpha_cat), _addr(alpha_off), _addr(beta_cat),
+                                          _addr(beta_off), n_pairs, _addr(scores), dim, int(gap_open),
+                                          int(gap_extend), GNX_FREE_END if kind == 1 else GNX_GLOBAL,
+                                          int(bool(want_cigar)), _addr(out_score), _addr(out_cig), _addr(out_off), cap)
+        if rc == GNX_ECAP and out is None:
+            total = int(out_off[-1])
+            out_cig = np.zeros(max(total, 1), dtype=CIGAR_DTYPE)
+            self._check(self._L.gnx_copy_last_cigars(self._h, _addr(out_cig), len(out_cig)))
+            rc = GNX_OK
+        self._check(rc)
+        if want_cigar:
+            return out_score, out_off, out_cig[:int(out_off[-1])] if out is None else out_cig
+        return out_score, None, None
+
+    def affine_gap_batch(self, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_open, gap_extend,
+                         free_end_gaps=False, want_cigar=True, cigar_cap=None, out=None):
+        """Batched AffineGap_highMem (free_end_gaps=False) / AffineGapLocal (True).
+
+        Returns (scores int64[n], cigar_off int64[n+1] | None, cigars CIGAR_DTYPE[] | None)."""
+        return self._batch(1 if free_end_gaps else 0, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_open,
+                           gap_extend, want_cigar, cigar_cap, out)
+
+    def const_gap_batch(self, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_pen, want_cigar=True,
+                        cigar_cap=None, out=None):
+        """Batched ConstGap_highMem."""
+        return self._batch(2, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_pen, 0, want_cigar, cigar_cap, out)
+
+    # ---- device-resident entry point (raw device addresses, e.g. torch tensor .data_ptr()) ----
+    def batch_device(self, kind, d_alpha_cat, d_alpha_off, d_beta_cat, d_beta_off, alpha_off_host, beta_off_host,
+                     n_pairs, scores, gap_open, gap_extend, want_cigar, d_out_score, d_out_cigar=0, d_out_cigar_off=0,
+                     cigar_cap=0, d_status=0, stream=0):
+        scores = np.ascontiguousarray(scores, dtype=np.int64)
+        aoh = None if alpha_off_host is None else np.ascontiguousarray(alpha_off_host, dtype=np.int64)
+        boh = None if beta_off_host is None else np.ascontiguousarray(beta_off_host, dtype=np.int64)
+        rc = self._L.gnx_batch_device(self._h, int(kind), d_alpha_cat, d_alpha_off, d_beta_cat, d_beta_off,
+                                      _addr(aoh), _addr(boh), int(n_pairs), _addr(scores), int(scores.shape[0]),
+                                      int(gap_open), int(gap_extend), int(bool(want_cigar)), d_out_score,
+                                      d_out_cigar or None, d_out_cigar_off or None, int(cigar_cap), d_status or None,
+                                      stream or None)
+        self._check(rc)
+
+
+_default_ctx: Optional[Context] = None
+_default_lock = threading.Lock()
+
+
+def default_context() -> Context:
+    global _default_ctx
+    with _default_lock:
+        if _default_ctx is None:
+            _default_ctx = Context(0)
+        return _default_ctx
+
+
+def _concat(seqs: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    if len(seqs):
+        np.cumsum([len(s) for s in seqs], out=off[1:])
+    cat = np.concatenate([np.asarray(s, dtype=np.uint8) for s in seqs]) if len(seqs) and off[-1] > 0 \
+        else np.zeros(0, dtype=np.uint8)
+    return cat, off
+
+
+def _split(off: np.ndarray, cig: np.ndarray) -> List[List[Cigar]]:
+    rl, op = cig["run_length"], cig["op"]
+    return [[Cigar(int(rl[k]), int(op[k])) for k in range(int(off[p]), int(off[p + 1]))] for p in range(len(off) - 1)]
+
+
+def affine_gap_pairs(alphas, betas, scores, gapOpen, gapExtend, free_end_gaps=False, ctx: Optional[Context] = None):
+    """List-of-arrays convenience form: returns [(score, [Cigar...])...]."""
+    ctx = ctx or default_context()
+    ac, ao = _concat(alphas)
+    bc, bo = _concat(betas)
+    sc, off, cig = ctx.affine_gap_batch(ac, ao, bc, bo, scores, gapOpen, gapExtend, free_end_gaps)
+    return list(zip((int(x) for x in sc), _split(off, cig)))
+
+
+def const_gap_pairs(alphas, betas, scores, gapPen, ctx: Optional[Context] = None):
+    ctx = ctx or default_context()
+    ac, ao = _concat(alphas)
+    bc, bo = _concat(betas)
+    sc, off, cig = ctx.const_gap_batch(ac, ao, bc, bo, scores, gapPen)
+    return list(zip((int(x) for x in sc), _split(off, cig)))
+
+
+# ---- the reference's single-pair API -------------------------------------------------------
+def AffineGap_highMem(alpha, beta, scores, gapOpen, gapExtend, ctx=None):
+    """align.AffineGap_highMem (align/affineGap_highMem.go:99)."""
+    return affine_gap_pairs([alpha], [beta], scores, gapOpen, gapExtend, False, ctx)[0]
+
+
+def AffineGapLocal(target, query, scores, gapOpen, gapExtend, ctx=None):
+    """align.AffineGapLocal (align/affineGap_highMem.go:105): free target overhangs."""
+    return affine_gap_pairs([target], [query], scores, gapOpen, gapExtend, True, ctx)[0]
+
+
+def _require_nonempty(alpha, beta, what):
+    if len(alpha) == 0 or len(beta) == 0:
+        # the reference's low-mem drivers index out of range / never terminate on an empty input
+        raise GnxError(_lib.GNX_EEMPTY, f"{what}: empty sequence (undefined in the reference)")
+
+
+def AffineGap_customizeCheckersize(alpha, beta, scores, gapOpen, gapExtend, checkersize_i, checkersize_j, ctx=None):
+    """align.AffineGap_customizeCheckersize (align/affineGap.go:73).
+
+    The checkerboard is the reference's memory-saving device, not part of the result for inputs that
+    fit one board; for longer inputs this returns the AffineGap_highMem alignment (DESIGN.md,
+    "multi-board divergence")."""
+    _require_nonempty(alpha, beta, "AffineGap_customizeCheckersize")
+    return affine_gap_pairs([alpha], [beta], scores, gapOpen, gapExtend, False, ctx)[0]
+
+
+def AffineGap(alpha, beta, scores, gapOpen, gapExtend, ctx=None):
+    """align.AffineGap (align/affineGap.go:59): checker size 10000 x 10000."""
+    return AffineGap_customizeCheckersize(alpha, beta, scores, gapOpen, gapExtend, 10000, 10000, ctx)
+
+
+def ConstGap_highMem(alpha, beta, scores, gapPen, ctx=None):
+    """align.ConstGap_highMem (align/constGap_highMem.go:11)."""
+    return const_gap_pairs([alpha], [beta], scores, gapPen, ctx)[0]
+
+
+def ConstGap_customizeCheckersize(alpha, beta, scores, gapPen, checkersize_i, checkersize_j, ctx=None):
+    """align.ConstGap_customizeCheckersize (align/constGap.go:73)."""
+    _require_nonempty(alpha, beta, "ConstGap_customizeCheckersize")
+    return const_gap_pairs([alpha], [beta], scores, gapPen, ctx)[0]
+
+
+def ConstGap(alpha, beta, scores, gapPen, ctx=None):
+    """align.ConstGap (align/constGap.go:13)."""
+    return ConstGap_customizeCheckersize(alpha, beta, scores, gapPen, 10000, 10000, ctx)
+
+
+# ---- pretty printers (align/view.go) -------------------------------------------------------
+def PrintCigar(operations) -> str:
+    """align.PrintCigar (align/view.go:25-33)."""
+    return "".join(f"{c[0]}{'MID'[c[1]]}" for c in operations)
+
+
+_RUNES = "ACGTNacgtn-.*"
+
+
+def View(alpha, beta, operations) -> str:
+    """align.View (align/view.go:37-63)."""
+    one, two, i, j = [], [], 0, 0
+    for run, op in operations:
+        for _ in range(run):
+            if op == ColM:
+                one.append(_RUNES[int(alpha[i])]); two.append(_RUNES[int(beta[j])]); i += 1; j += 1
+            elif op == ColI:
+                one.append("-"); two.append(_RUNES[int(beta[j])]); j += 1
+            else:
+                one.append(_RUNES[int(alpha[i])]); two.append("-"); i += 1
+    return "".join(one) + "\n" + "".join(two) + "\n"
+
+
+# ---- streaming engine ------------------------------------------------------------------------
+@dataclass
+class TargetQueryPair:
+    """align.TargetQueryPair (align/affineGap_highMem.go:110-115)."""
+    Target: np.ndarray
+    Query: np.ndarray
+    Score: int = 0
+    Cigar: List[Cigar] = field(default_factory=list)
+
+
+_CLOSE = object()
+
+
+def GoAffineGapLocalEngine(scores, gapOpen, gapExtend, max_batch: int = 1 << 16, device: int = 0):
+    """align.GoAffineGapLocalEngine (align/affineGap_highMem.go:120-179).
+
+    Returns (inputs, outputs) queues (the Go channels, capacity 1000).  A worker thread drains
+    whatever is queued (up to max_batch pairs), aligns it as ONE GPU batch with AffineGapLocal
+    semantics and emits results in input order (FIFO, as the single reference goroutine does).
+    Put `engine_close` (or call inputs.close()) to end the stream; outputs then yields None."""
+    inputs: "queue.Queue" = queue.Queue(maxsize=1000)
+    outputs: "queue.Queue" = queue.Queue(maxsize=1000)
+
+    def worker():
+        ctx = Context(device)
+        try:
+            done = False
+            while not done:
+                item = inputs.get()
+                batch = []
+                while True:
+                    if item is _CLOSE:
+                        done = True
+                        break
+                    batch.append(item)
+                    if len(batch) >= max_batch:
+                        break
+                    try:
+                        item = inputs.get_nowait()
+                    except queue.Empty:
+                        break
+                if batch:
+                    res = affine_gap_pairs([p.Target for p in batch], [p.Query for p in batch], scores, gapOpen,
+                                           gapExtend, True, ctx)
+                    for p, (s, c) in zip(batch, res):
+                        p.Score, p.Cigar = s, c
+                        outputs.put(p)
+            outputs.put(None)  # close(outputs)
+        finally:
+            ctx.close()
+
+    threading.Thread(target=worker, daemon=True).start()
+    inputs.close = lambda: inputs.put(_CLOSE)  # type: ignore[attr-defined]
+    return inputs, outputs

@@ -1,0 +1,1039 @@
+// gnx_api.cu -- libgnxalign.so: context, chunk pipeline and the exported C ABI (include/gnxalign.h).
+//
+// Host pipeline for the host-buffer entry points (DESIGN.md "Pipeline"): the batch is cut into
+// chunks whose traceback matrices fit the per-slot share of the workspace; kSlots chunks are in
+// flight on kSlots streams, each going  H2D -> classify -> fill -> traceback -> scan -> [total to
+// host] -> expand -> D2H, so copies of one chunk overlap the DP fill of another.
+#include "../../include/gnxalign.h"
+#include "gnx_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+using namespace gnx;
+
+constexpr int kSlots = 3;
+constexpr int kSlotCap = 24; // cigar elements kept per pair before the overflow pass
+
+static_assert(sizeof(gnx_cigar) == 16, "gnx_cigar must match Go's align.Cigar layout");
+static_assert(sizeof(CigarOut) == 16, "device cigar record must match gnx_cigar");
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap)
+            return cudaSuccess;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess)
+            cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap)
+            return cudaSuccess;
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess)
+            cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_total = nullptr, ev_done = nullptr;
+    DevBuf alpha, beta, aoff, boff, cls, trace, trace_off, slots, counts, score, cig_off, cigars, edge, misc;
+    PinBuf h_stage_a, h_stage_b, h_total, h_trace_off, h_score, h_off, h_cig;
+    // chunk in flight
+    int64_t begin = 0, end = 0;
+    bool busy = false;
+};
+
+struct FillEvent {
+    cudaEvent_t a, b;
+};
+
+} // namespace
+
+struct gnx_ctx {
+    int device = 0;
+    std::string err;
+    size_t workspace = 0;
+    Slot slot[kSlots];
+    DevBuf status;       // int32 device status word
+    DevBuf dr_misc;      // device-resident path scratch (running total, counters)
+    int64_t launches = 0;
+    // options
+    int opt_cols = 0;          // 0 = auto
+    int64_t opt_chunk_pairs = 1 << 18;
+    int opt_blocks_per_sm = 8;
+    int sm_count = 148;
+    // stats of the last batch call
+    std::vector<FillEvent> fill_events;
+    size_t fill_events_used = 0;
+    double last_fill_ms = 0;
+    int64_t last_fill_launches = 0, last_cells = 0;
+    // cigars retained after GNX_ECAP
+    std::vector<gnx_cigar> retained;
+    bool have_retained = false;
+};
+
+namespace {
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            char buf_[512];                                                                            \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                     __LINE__);                                                                        \
+            ctx->err = buf_;                                                                           \
+            return GNX_ECUDA;                                                                          \
+        }                                                                                              \
+    } while (0)
+
+int fail(gnx_ctx *ctx, int code, const char *msg)
+{
+    ctx->err = msg;
+    return code;
+}
+
+struct Problem {
+    int kind; // 0 affine global, 1 affine free-end, 2 const gap
+    int want_cigar;
+    int dim;
+    int64_t scores[64];
+    int64_t gap_open, gap_extend;
+    int h00, h00_plane;
+    bool prmt_ok;  // 16-bit PRMT tables usable for ACGT-only pairs
+};
+
+// Exact-arithmetic range analysis for the scaled int32 kernels (DESIGN.md "Arithmetic width").
+// Every finite plane value v obeys |v| <= bound.  With values carried as scale*v and -inf = -2^30,
+// 2*bound*scale < 2^30 guarantees that nothing wraps and that every "-inf + addend" stays strictly
+// below every finite candidate, so the int32 kernels make exactly the comparisons the int64
+// reference makes.
+int analyse(gnx_ctx *ctx, Problem &pb, int64_t max_n, int64_t max_m)
+{
+    int64_t smin = 0, smax = 0;
+    for (int i = 0; i < pb.dim * pb.dim; ++i) {
+        smin = std::min(smin, pb.scores[i]);
+        smax = std::max(smax, pb.scores[i]);
+    }
+    const int64_t O = pb.gap_open, E = pb.gap_extend;
+    const int64_t absO = O < 0 ? -O : O, absE = E < 0 ? -E : E;
+    const int64_t sabs = std::max(-smin, smax);
+    const int64_t len = max_n + max_m + 2;
+    int64_t core;
+    if (O <= 0 && E <= 0) {
+        // H(i,j) >= 2O + (i+j)E (all-insert-then-all-delete path); H <= min(n,m) * max score
+        core = std::max(2 * absO + len * absE, std::min(max_n, max_m) * std::max<int64_t>(smax, 0));
+    } else {
+        core = 2 * absO + len * std::max<int64_t>({absE, sabs, absO, 1});
+    }
+    const int64_t bound = core + 2 * (absO + absE) + sabs + 64;
+    const int64_t scale = pb.want_cigar ? (pb.kind == 2 ? 4 : kScale) : 1;
+    if (2 * bound * scale >= (int64_t(1) << 30) || max_n >= (1 << 24) || max_m >= (1 << 24))
+        return fail(ctx, GNX_ERANGE, "scores/penalties x lengths exceed the exact int32 range of the DP kernels");
+    pb.prmt_ok = sabs * scale + 4 <= 32767;
+    // H(0,0) = tripleMaxTrace(0, O, D(0,0))  (affineGap_highMem.go:185-192 + affineTrace :62)
+    const int64_t d00 = pb.kind == 1 ? 0 : O;
+    if (0 >= O && 0 >= d00) {
+        pb.h00 = 0;
+        pb.h00_plane = 0;
+    } else if (O >= d00) {
+        pb.h00 = (int)O;
+        pb.h00_plane = 1;
+    } else {
+        pb.h00 = (int)d00;
+        pb.h00_plane = 2;
+    }
+    return GNX_OK;
+}
+
+int pick_cols(const gnx_ctx *ctx, int64_t max_m)
+{
+    if (ctx->opt_cols == 5 || ctx->opt_cols == 10)
+        return ctx->opt_cols;
+    return (max_m <= 160) ? 5 : 10;
+}
+
+inline int64_t pair_trace_words(const Problem &pb, int64_t n, int64_t m, int C)
+{
+    return pb.kind == 2 ? const_trace_words(n, m, C) : trace_words(n, m, C);
+}
+
+FillEvent &next_fill_event(gnx_ctx *ctx)
+{
+    if (ctx->fill_events_used == ctx->fill_events.size()) {
+        FillEvent fe;
+        cudaEventCreate(&fe.a);
+        cudaEventCreate(&fe.b);
+        ctx->fill_events.push_back(fe);
+    }
+    return ctx->fill_events[ctx->fill_events_used++];
+}
+
+template <int C, bool TRACE, bool FREE, int LOOKUP>
+void launch_affine(const FillParams &fp, int grid, cudaStream_t st)
+{
+    affine_fill_kernel<C, TRACE, FREE, LOOKUP><<<grid, 128, 0, st>>>(fp);
+}
+template <int C, bool TRACE, int LOOKUP> void launch_const(const FillParams &fp, int grid, cudaStream_t st)
+{
+    const_fill_kernel<C, TRACE, LOOKUP><<<grid, 128, 0, st>>>(fp);
+}
+
+template <int C, int LOOKUP>
+void dispatch_fill_cl(const Problem &pb, const FillParams &fp, int grid, cudaStream_t st)
+{
+    if (pb.kind == 2) {
+        if (pb.want_cigar)
+            launch_const<C, true, LOOKUP>(fp, grid, st);
+        else
+            launch_const<C, false, LOOKUP>(fp, grid, st);
+    } else if (pb.kind == 1) {
+        if (pb.want_cigar)
+            launch_affine<C, true, true, LOOKUP>(fp, grid, st);
+        else
+            launch_affine<C, false, true, LOOKUP>(fp, grid, st);
+    } else {
+        if (pb.want_cigar)
+            launch_affine<C, true, false, LOOKUP>(fp, grid, st);
+        else
+            launch_affine<C, false, false, LOOKUP>(fp, grid, st);
+    }
+}
+
+void dispatch_fill(const Problem &pb, const FillParams &fp, int C, int lookup, int grid, cudaStream_t st)
+{
+    if (C == 5) {
+        if (lookup == 0)
+            dispatch_fill_cl<5, 0>(pb, fp, grid, st);
+        else
+            dispatch_fill_cl<5, 1>(pb, fp, grid, st);
+    } else {
+        if (lookup == 0)
+            dispatch_fill_cl<10, 0>(pb, fp, grid, st);
+        else
+            dispatch_fill_cl<10, 1>(pb, fp, grid, st);
+    }
+}
+
+// Device buffers of one chunk, all addressed with GLOBAL pair indices (pointers are pre-biased).
+struct ChunkDev {
+    const uint8_t *alpha, *beta;      // biased so that absolute offsets index them
+    const int64_t *aoff, *boff;       // biased: aoff[pair] valid for pair in [begin, end]
+    uint8_t *cls;                     // biased by -begin
+    uint32_t *trace;
+    const int64_t *trace_off;         // chunk-local index
+    int2 *edge;
+    int64_t edge_stride;
+    uint32_t *slots;
+    int *counts;                      // chunk-local
+    int64_t *score;                   // biased by -begin (global pair index)
+};
+
+// classify + fill (+ traceback pass 0) for chunk [begin, end) on stream st.
+int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, int64_t begin, int64_t end, int C,
+                          bool any_long, cudaStream_t st)
+{
+    const int64_t np = end - begin;
+    if (np <= 0)
+        return GNX_OK;
+    int *status = ctx->status.as<int>();
+    const int warps_per_block = 4;
+    const int max_grid = ctx->sm_count * ctx->opt_blocks_per_sm;
+    const int grid = (int)std::min<int64_t>((np + warps_per_block - 1) / warps_per_block, max_grid);
+    classify_kernel<<<grid, 128, 0, st>>>(cd.alpha, cd.aoff, cd.beta, cd.boff, begin, end, pb.dim, cd.cls, status);
+    ctx->launches++;
+
+    FillParams fp;
+    memset(&fp, 0, sizeof fp);
+    fp.alpha = cd.alpha;
+    fp.alpha_off = cd.aoff;
+    fp.beta = cd.beta;
+    fp.beta_off = cd.boff;
+    fp.pair_begin = begin;
+    fp.pair_end = end;
+    fp.pair_class = cd.cls;
+    fp.gap_open = (int)pb.gap_open;
+    fp.gap_extend = (int)pb.gap_extend;
+    fp.h00 = pb.h00;
+    fp.dim = pb.dim;
+    for (int i = 0; i < pb.dim * pb.dim; ++i)
+        fp.scores[i] = (int)pb.scores[i];
+    fp.trace = cd.trace;
+    fp.trace_off = cd.trace_off;
+    fp.edge = any_long ? cd.edge : nullptr;
+    fp.edge_stride = cd.edge_stride;
+    fp.out_score = cd.score;
+
+    // class 0 (ACGT only) with the PRMT tables when the matrix fits 16 bits, else the smem lookup
+    FillEvent &fe = next_fill_event(ctx);
+    cudaEventRecord(fe.a, st);
+    fp.want_class = 0;
+    dispatch_fill(pb, fp, C, pb.prmt_ok ? 0 : 1, grid, st);
+    ctx->launches++;
+    ctx->last_fill_launches++;
+    // class 1 (contains N or other bases < dim): generic lookup.  Warps skip pairs of the other class.
+    fp.want_class = 1;
+    dispatch_fill(pb, fp, C, 1, grid, st);
+    ctx->launches++;
+    ctx->last_fill_launches++;
+    cudaEventRecord(fe.b, st);
+
+    if (pb.want_cigar) {
+        TraceParams tp;
+        memset(&tp, 0, sizeof tp);
+        tp.alpha_off = cd.aoff;
+        tp.beta_off = cd.boff;
+        tp.pair_begin = begin;
+        tp.pair_end = end;
+        tp.trace = cd.trace;
+        tp.trace_off = cd.trace_off;
+        tp.C = C;
+        tp.kind = pb.kind == 2 ? 2 : 0;
+        tp.h00_plane = pb.h00_plane;
+        tp.slots = cd.slots;
+        tp.slot_cap = kSlotCap;
+        tp.counts = cd.counts;
+        tp.pass = 0;
+        traceback_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
+        ctx->launches++;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        ctx->err = std::string("kernel launch failed: ") + cudaGetErrorString(e);
+        return GNX_ECUDA;
+    }
+    return GNX_OK;
+}
+
+// expand slots (+ overflow traceback pass) into cigars[] at cig_off (chunk-local offsets) .
+int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, int64_t begin, int64_t end, int C,
+                         const int64_t *cig_off, gnx_cigar *cigars, int64_t cap, cudaStream_t st)
+{
+    const int64_t np = end - begin;
+    if (np <= 0)
+        return GNX_OK;
+    int *status = ctx->status.as<int>();
+    expand_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(cd.slots, kSlotCap, cd.counts, cig_off, np,
+                                                          (CigarOut *)cigars, cap, status);
+    ctx->launches++;
+    TraceParams tp;
+    memset(&tp, 0, sizeof tp);
+    tp.alpha_off = cd.aoff;
+    tp.beta_off = cd.boff;
+    tp.pair_begin = begin;
+    tp.pair_end = end;
+    tp.trace = cd.trace;
+    tp.trace_off = cd.trace_off;
+    tp.C = C;
+    tp.kind = pb.kind == 2 ? 2 : 0;
+    tp.h00_plane = pb.h00_plane;
+    tp.slots = cd.slots;
+    tp.slot_cap = kSlotCap;
+    tp.counts = cd.counts;
+    tp.cigar_off = const_cast<int64_t *>(cig_off);
+    tp.out_cigar = cigars;
+    tp.out_cap = cap;
+    tp.pass = 1;
+    traceback_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        ctx->err = std::string("kernel launch failed: ") + cudaGetErrorString(e);
+        return GNX_ECUDA;
+    }
+    return GNX_OK;
+}
+
+// Greedy chunk planning: consecutive pairs until the traceback matrices fill `budget_words`
+// or the chunk reaches opt_chunk_pairs.
+struct Plan {
+    std::vector<int64_t> bounds;      // chunk boundaries (pair indices), size = chunks+1
+    int64_t max_n = 0, max_m = 0, cells = 0;
+    bool any_long = false;            // some pair needs more than one strip
+};
+
+int make_plan(gnx_ctx *ctx, const Problem &pb, const int64_t *aoff, const int64_t *boff, int64_t n_pairs,
+              int64_t budget_words, int &C, Plan &plan)
+{
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        const int64_t n = aoff[p + 1] - aoff[p], m = boff[p + 1] - boff[p];
+        if (n < 0 || m < 0)
+            return fail(ctx, GNX_EARG, "offset arrays must be non-decreasing");
+        plan.max_n = std::max(plan.max_n, n);
+        plan.max_m = std::max(plan.max_m, m);
+        plan.cells += n * m;
+    }
+    C = pick_cols(ctx, plan.max_m);
+    plan.any_long = plan.max_m > 32 * C;
+    plan.bounds.push_back(0);
+    int64_t words = 0, count = 0;
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        const int64_t w =
+            pb.want_cigar ? pair_trace_words(pb, aoff[p + 1] - aoff[p], boff[p + 1] - boff[p], C) : 0;
+        if (w > budget_words)
+            return fail(ctx, GNX_ERANGE, "one pair's traceback matrix exceeds the context workspace");
+        if (count > 0 && (words + w > budget_words || count >= ctx->opt_chunk_pairs)) {
+            plan.bounds.push_back(p);
+            words = 0;
+            count = 0;
+        }
+        words += w;
+        ++count;
+    }
+    plan.bounds.push_back(n_pairs);
+    return GNX_OK;
+}
+
+int collect_fill_stats(gnx_ctx *ctx)
+{
+    double ms = 0;
+    for (size_t i = 0; i < ctx->fill_events_used; ++i) {
+        float f = 0;
+        if (cudaEventElapsedTime(&f, ctx->fill_events[i].a, ctx->fill_events[i].b) == cudaSuccess)
+            ms += f;
+    }
+    ctx->last_fill_ms = ms;
+    return GNX_OK;
+}
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer batch: the pipelined path behind gnx_affine_batch / gnx_const_batch.
+// ---------------------------------------------------------------------------------------------
+int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const int64_t *aoff, const uint8_t *beta_cat,
+                   const int64_t *boff, int64_t n_pairs, int64_t *out_score, gnx_cigar *out_cigar,
+                   int64_t *out_cigar_off, int64_t cigar_cap)
+{
+    CU(cudaSetDevice(ctx->device));
+    ctx->fill_events_used = 0;
+    ctx->last_fill_launches = 0;
+    ctx->last_fill_ms = 0;
+    ctx->last_cells = 0;
+    ctx->have_retained = false;
+    ctx->retained.clear();
+    if (n_pairs == 0) {
+        if (out_cigar_off)
+            out_cigar_off[0] = 0;
+        return GNX_OK;
+    }
+    Plan plan;
+    int C = 5;
+    const int64_t budget_words = (int64_t)(ctx->workspace / kSlots / 4);
+    int rc = make_plan(ctx, pb, aoff, boff, n_pairs, budget_words, C, plan);
+    if (rc != GNX_OK)
+        return rc;
+    rc = analyse(ctx, pb, plan.max_n, plan.max_m);
+    if (rc != GNX_OK)
+        return rc;
+    ctx->last_cells = plan.cells;
+    CU(cudaMemsetAsync(ctx->status.p, 0, sizeof(int), ctx->slot[0].stream));
+    CU(cudaStreamSynchronize(ctx->slot[0].stream));
+
+    const bool pin_a = is_pinned(alpha_cat), pin_b = is_pinned(beta_cat);
+    const bool pin_ao = is_pinned(aoff), pin_bo = is_pinned(boff);
+    const bool pin_score = is_pinned(out_score);
+    const bool pin_off = out_cigar_off && is_pinned(out_cigar_off);
+    const bool pin_cig = out_cigar && is_pinned(out_cigar);
+    const int nwarps_total = ctx->sm_count * ctx->opt_blocks_per_sm * 4;
+    const int64_t edge_stride = plan.max_n + 2;
+
+    const int64_t n_chunks = (int64_t)plan.bounds.size() - 1;
+    int64_t cig_total = 0;   // cigar elements produced by finished chunks
+    bool overflow = false;   // user's cigar buffer too small -> retain in ctx
+
+    struct Pending {
+        int slot;
+        int64_t begin, end;
+        ChunkDev cd;
+    };
+    std::vector<Pending> pending;
+
+    auto finish = [&](const Pending &pd) -> int {
+        Slot &s = ctx->slot[pd.slot];
+        const int64_t np = pd.end - pd.begin;
+        int64_t total = 0;
+        if (pb.want_cigar) {
+            CU(cudaEventSynchronize(s.ev_total));
+            total = *s.h_total.as<int64_t>();
+            CU(s.cigars.ensure((size_t)std::max<int64_t>(total, 1) * sizeof(gnx_cigar)));
+            rc = enqueue_chunk_expand(ctx, pb, pd.cd, pd.begin, pd.end, C, s.cig_off.as<int64_t>(),
+                                      s.cigars.as<gnx_cigar>(), total, s.stream);
+            if (rc != GNX_OK)
+                return rc;
+        }
+        // scores
+        if (pin_score) {
+            CU(cudaMemcpyAsync(out_score + pd.begin, s.score.p, (size_t)np * 8, cudaMemcpyDeviceToHost, s.stream));
+        } else {
+            CU(s.h_score.ensure((size_t)np * 8));
+            CU(cudaMemcpyAsync(s.h_score.p, s.score.p, (size_t)np * 8, cudaMemcpyDeviceToHost, s.stream));
+        }
+        if (pb.want_cigar) {
+            CU(s.h_off.ensure((size_t)(np + 1) * 8));
+            CU(cudaMemcpyAsync(s.h_off.p, s.cig_off.p, (size_t)(np + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
+            const bool fits = !overflow && out_cigar && cig_total + total <= cigar_cap;
+            if (!fits && !overflow) { // first overflow: keep what the user already holds in the retained copy
+                overflow = true;
+                ctx->retained.resize((size_t)cig_total);
+                if (out_cigar && cig_total > 0) // earlier chunks were synchronised when they finished
+                    memcpy(ctx->retained.data(), out_cigar, (size_t)cig_total * sizeof(gnx_cigar));
+            }
+            const bool direct = fits && pin_cig;
+            if (total > 0) {
+                if (direct) {
+                    CU(cudaMemcpyAsync(out_cigar + cig_total, s.cigars.p, (size_t)total * sizeof(gnx_cigar),
+                                       cudaMemcpyDeviceToHost, s.stream));
+                } else {
+                    CU(s.h_cig.ensure((size_t)total * sizeof(gnx_cigar)));
+                    CU(cudaMemcpyAsync(s.h_cig.p, s.cigars.p, (size_t)total * sizeof(gnx_cigar),
+                                       cudaMemcpyDeviceToHost, s.stream));
+                }
+            }
+            CU(cudaStreamSynchronize(s.stream));
+            if (total > 0 && !direct) {
+                if (fits) {
+                    memcpy(out_cigar + cig_total, s.h_cig.p, (size_t)total * sizeof(gnx_cigar));
+                } else {
+                    ctx->retained.resize((size_t)(cig_total + total));
+                    memcpy(ctx->retained.data() + cig_total, s.h_cig.p, (size_t)total * sizeof(gnx_cigar));
+                }
+            }
+            const int64_t *ho = s.h_off.as<int64_t>();
+            for (int64_t k = 0; k < np; ++k)
+                out_cigar_off[pd.begin + k] = cig_total + ho[k];
+            cig_total += total;
+            out_cigar_off[pd.end] = cig_total;
+        } else {
+            CU(cudaStreamSynchronize(s.stream));
+        }
+        if (!pin_score)
+            memcpy(out_score + pd.begin, s.h_score.p, (size_t)np * 8);
+        s.busy = false;
+        return GNX_OK;
+    };
+
+    for (int64_t ci = 0; ci < n_chunks; ++ci) {
+        const int si = (int)(ci % kSlots);
+        Slot &s = ctx->slot[si];
+        // the slot's previous chunk must be fully retired before its buffers are reused
+        if (s.busy) {
+            auto it = std::find_if(pending.begin(), pending.end(), [&](const Pending &q) { return q.slot == si; });
+            if (it != pending.end()) {
+                Pending pd = *it;
+                pending.erase(it);
+                rc = finish(pd);
+                if (rc != GNX_OK)
+                    return rc;
+            }
+        }
+        const int64_t begin = plan.bounds[ci], end = plan.bounds[ci + 1], np = end - begin;
+        const int64_t a_lo = aoff[begin], a_hi = aoff[end], b_lo = boff[begin], b_hi = boff[end];
+        CU(s.alpha.ensure((size_t)std::max<int64_t>(a_hi - a_lo, 1)));
+        CU(s.beta.ensure((size_t)std::max<int64_t>(b_hi - b_lo, 1)));
+        CU(s.aoff.ensure((size_t)(np + 1) * 8));
+        CU(s.boff.ensure((size_t)(np + 1) * 8));
+        CU(s.cls.ensure((size_t)np));
+        CU(s.score.ensure((size_t)np * 8));
+        // H2D (pinned user memory is DMA'd directly, pageable memory goes through a pinned stage)
+        auto h2d = [&](void *dst, const void *src, size_t bytes, bool pinned, PinBuf &stage) -> int {
+            if (bytes == 0)
+                return GNX_OK;
+            if (pinned) {
+                CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s.stream));
+            } else {
+                CU(stage.ensure(bytes));
+                memcpy(stage.p, src, bytes);
+                CU(cudaMemcpyAsync(dst, stage.p, bytes, cudaMemcpyHostToDevice, s.stream));
+            }
+            return GNX_OK;
+        };
+        if ((rc = h2d(s.alpha.p, alpha_cat + a_lo, (size_t)(a_hi - a_lo), pin_a, s.h_stage_a)) != GNX_OK)
+            return rc;
+        if ((rc = h2d(s.beta.p, beta_cat + b_lo, (size_t)(b_hi - b_lo), pin_b, s.h_stage_b)) != GNX_OK)
+            return rc;
+        // offsets are small; always DMA from the caller's arrays when pinned, else pageable memcpy
+        CU(cudaMemcpyAsync(s.aoff.p, aoff + begin, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(s.boff.p, boff + begin, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+        (void)pin_ao;
+        (void)pin_bo;
+        (void)pin_off;
+
+        ChunkDev cd;
+        memset(&cd, 0, sizeof cd);
+        cd.alpha = s.alpha.as<uint8_t>() - a_lo;
+        cd.beta = s.beta.as<uint8_t>() - b_lo;
+        cd.aoff = s.aoff.as<int64_t>() - begin;
+        cd.boff = s.boff.as<int64_t>() - begin;
+        cd.cls = s.cls.as<uint8_t>() - begin;
+        cd.score = s.score.as<int64_t>() - begin;
+        if (pb.want_cigar) {
+            CU(s.h_trace_off.ensure((size_t)(np + 1) * 8));
+            int64_t *to = s.h_trace_off.as<int64_t>();
+            int64_t acc = 0;
+            for (int64_t k = 0; k < np; ++k) {
+                to[k] = acc;
+                acc += pair_trace_words(pb, aoff[begin + k + 1] - aoff[begin + k],
+                                        boff[begin + k + 1] - boff[begin + k], C);
+            }
+            to[np] = acc;
+            CU(s.trace.ensure((size_t)std::max<int64_t>(acc, 1) * 4));
+            CU(s.trace_off.ensure((size_t)(np + 1) * 8));
+            CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+            CU(s.slots.ensure((size_t)np * kSlotCap * 4));
+            CU(s.counts.ensure((size_t)np * 4));
+            CU(s.cig_off.ensure((size_t)(np + 1) * 8));
+            cd.trace = s.trace.as<uint32_t>();
+            cd.trace_off = s.trace_off.as<int64_t>();
+            cd.slots = s.slots.as<uint32_t>();
+            cd.counts = s.counts.as<int>();
+        }
+        if (plan.any_long) {
+            CU(s.edge.ensure((size_t)nwarps_total * 2 * edge_stride * sizeof(int2)));
+            cd.edge = s.edge.as<int2>();
+            cd.edge_stride = edge_stride;
+        }
+        rc = enqueue_chunk_compute(ctx, pb, cd, begin, end, C, plan.any_long, s.stream);
+        if (rc != GNX_OK)
+            return rc;
+        if (pb.want_cigar) {
+            CU(s.misc.ensure(64));
+            CU(cudaMemsetAsync(s.misc.p, 0, 8, s.stream));
+            scan_counts_kernel<<<1, 1024, 0, s.stream>>>(cd.counts, np, s.cig_off.as<int64_t>(), s.misc.as<int64_t>());
+            ctx->launches++;
+            CU(s.h_total.ensure(8));
+            CU(cudaMemcpyAsync(s.h_total.p, s.cig_off.as<int64_t>() + np, 8, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaEventRecord(s.ev_total, s.stream));
+        }
+        s.busy = true;
+        s.begin = begin;
+        s.end = end;
+        pending.push_back(Pending{si, begin, end, cd});
+        // retire the oldest chunk once the pipeline is full so that its D2H overlaps this fill
+        if ((int)pending.size() >= kSlots) {
+            Pending pd = pending.front();
+            pending.erase(pending.begin());
+            rc = finish(pd);
+            if (rc != GNX_OK)
+                return rc;
+        }
+    }
+    while (!pending.empty()) {
+        Pending pd = pending.front();
+        pending.erase(pending.begin());
+        rc = finish(pd);
+        if (rc != GNX_OK)
+            return rc;
+    }
+    for (int k = 0; k < kSlots; ++k)
+        CU(cudaStreamSynchronize(ctx->slot[k].stream));
+    collect_fill_stats(ctx);
+    int st = 0;
+    CU(cudaMemcpy(&st, ctx->status.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st == kEBase)
+        return fail(ctx, GNX_EBASE, "a sequence holds a base >= dim (Go: index out of range in scores[a][b])");
+    if (overflow) {
+        ctx->have_retained = true;
+        return fail(ctx, GNX_ECAP, "cigar_cap too small; call gnx_copy_last_cigars with a larger buffer");
+    }
+    return GNX_OK;
+}
+
+int fill_problem(gnx_ctx *ctx, Problem &pb, int kind, int want_cigar, const int64_t *scores, int dim, int64_t gap_open,
+                 int64_t gap_extend)
+{
+    if (!scores || dim < 4 || dim > 8)
+        return fail(ctx, GNX_EARG, "scores must be a dim x dim matrix with 4 <= dim <= 8");
+    pb.kind = kind;
+    pb.want_cigar = want_cigar ? 1 : 0;
+    pb.dim = dim;
+    memset(pb.scores, 0, sizeof pb.scores);
+    for (int i = 0; i < dim * dim; ++i) {
+        if (scores[i] > (1 << 20) || scores[i] < -(1 << 20))
+            return fail(ctx, GNX_ERANGE, "score matrix entry out of range");
+        pb.scores[i] = scores[i];
+    }
+    if (gap_open > (1 << 24) || gap_open < -(1 << 24) || gap_extend > (1 << 24) || gap_extend < -(1 << 24))
+        return fail(ctx, GNX_ERANGE, "gap penalty out of range");
+    pb.gap_open = gap_open;
+    pb.gap_extend = gap_extend;
+    pb.prmt_ok = false;
+    pb.h00 = 0;
+    pb.h00_plane = 0;
+    return GNX_OK;
+}
+
+} // namespace
+
+// =================================================================================================
+// exported C ABI
+// =================================================================================================
+extern "C" {
+
+int gnx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char *gnx_version(void) { return "gnxalign 0.1 (sm_100a)"; }
+
+gnx_ctx *gnx_create(int device, size_t workspace_bytes)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (device < 0 || device >= n) {
+        g_create_error = "device index out of range";
+        return nullptr;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return nullptr;
+    }
+    gnx_ctx *ctx = new gnx_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess)
+        ctx->sm_count = prop.multiProcessorCount;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (workspace_bytes == 0)
+        workspace_bytes = std::min<size_t>(free_b / 4, (size_t)32 << 30);
+    ctx->workspace = workspace_bytes;
+    for (int k = 0; k < kSlots; ++k) {
+        cudaStreamCreateWithFlags(&ctx->slot[k].stream, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&ctx->slot[k].ev_total, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->slot[k].ev_done, cudaEventDisableTiming);
+    }
+    if (ctx->status.ensure(64) != cudaSuccess || ctx->dr_misc.ensure(256) != cudaSuccess) {
+        g_create_error = "cudaMalloc failed at context creation";
+        delete ctx;
+        return nullptr;
+    }
+    cudaMemset(ctx->status.p, 0, 64);
+    return ctx;
+}
+
+void gnx_destroy(gnx_ctx *ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int k = 0; k < kSlots; ++k) {
+        Slot &s = ctx->slot[k];
+        DevBuf *d[] = {&s.alpha, &s.beta, &s.aoff, &s.boff, &s.cls, &s.trace, &s.trace_off, &s.slots,
+                       &s.counts, &s.score, &s.cig_off, &s.cigars, &s.edge, &s.misc};
+        for (DevBuf *b : d)
+            b->release();
+        PinBuf *h[] = {&s.h_stage_a, &s.h_stage_b, &s.h_total, &s.h_trace_off, &s.h_score, &s.h_off, &s.h_cig};
+        for (PinBuf *b : h)
+            b->release();
+        if (s.stream)
+            cudaStreamDestroy(s.stream);
+        if (s.ev_total)
+            cudaEventDestroy(s.ev_total);
+        if (s.ev_done)
+            cudaEventDestroy(s.ev_done);
+    }
+    for (auto &fe : ctx->fill_events) {
+        cudaEventDestroy(fe.a);
+        cudaEventDestroy(fe.b);
+    }
+    ctx->status.release();
+    ctx->dr_misc.release();
+    delete ctx;
+}
+
+const char *gnx_last_error(gnx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void *gnx_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void gnx_host_free(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
+}
+
+int gnx_affine_batch(gnx_ctx *ctx, const uint8_t *alpha_cat, const int64_t *alpha_off, const uint8_t *beta_cat,
+                     const int64_t *beta_off, int64_t n_pairs, const int64_t *scores, int dim, int64_t gap_open,
+                     int64_t gap_extend, int mode, int want_cigar, int64_t *out_score, gnx_cigar *out_cigar,
+                     int64_t *out_cigar_off, int64_t cigar_cap)
+{
+    if (!ctx)
+        return GNX_EARG;
+    if (n_pairs < 0 || !alpha_off || !beta_off || !out_score || (mode != GNX_GLOBAL && mode != GNX_FREE_END))
+        return fail(ctx, GNX_EARG, "bad argument to gnx_affine_batch");
+    if (want_cigar && !out_cigar_off)
+        return fail(ctx, GNX_EARG, "out_cigar_off is required when want_cigar != 0");
+    Problem pb;
+    int rc = fill_problem(ctx, pb, mode == GNX_FREE_END ? 1 : 0, want_cigar, scores, dim, gap_open, gap_extend);
+    if (rc != GNX_OK)
+        return rc;
+    return run_host_batch(ctx, pb, alpha_cat, alpha_off, beta_cat, beta_off, n_pairs, out_score, out_cigar,
+                          out_cigar_off, out_cigar ? cigar_cap : 0);
+}
+
+int gnx_const_batch(gnx_ctx *ctx, const uint8_t *alpha_cat, const int64_t *alpha_off, const uint8_t *beta_cat,
+                    const int64_t *beta_off, int64_t n_pairs, const int64_t *scores, int dim, int64_t gap_pen,
+                    int want_cigar, int64_t *out_score, gnx_cigar *out_cigar, int64_t *out_cigar_off,
+                    int64_t cigar_cap)
+{
+    if (!ctx)
+        return GNX_EARG;
+    if (n_pairs < 0 || !alpha_off || !beta_off || !out_score)
+        return fail(ctx, GNX_EARG, "bad argument to gnx_const_batch");
+    if (want_cigar && !out_cigar_off)
+        return fail(ctx, GNX_EARG, "out_cigar_off is required when want_cigar != 0");
+    Problem pb;
+    int rc = fill_problem(ctx, pb, 2, want_cigar, scores, dim, gap_pen, 0);
+    if (rc != GNX_OK)
+        return rc;
+    return run_host_batch(ctx, pb, alpha_cat, alpha_off, beta_cat, beta_off, n_pairs, out_score, out_cigar,
+                          out_cigar_off, out_cigar ? cigar_cap : 0);
+}
+
+int gnx_affine_chunk_batch(gnx_ctx *ctx, const uint8_t *, const int64_t *, const uint8_t *, const int64_t *, int64_t,
+                           const int64_t *, int, int64_t, int64_t, int64_t, int64_t *, gnx_cigar *, int64_t *, int64_t)
+{
+    if (!ctx)
+        return GNX_EARG;
+    return fail(ctx, GNX_EARG, "gnx_affine_chunk_batch: not built yet");
+}
+
+int gnx_copy_last_cigars(gnx_ctx *ctx, gnx_cigar *out_cigar, int64_t cigar_cap)
+{
+    if (!ctx)
+        return GNX_EARG;
+    if (!ctx->have_retained)
+        return fail(ctx, GNX_EARG, "no retained cigars (the last batch call did not return GNX_ECAP)");
+    if (!out_cigar || cigar_cap < (int64_t)ctx->retained.size())
+        return fail(ctx, GNX_ECAP, "cigar_cap still too small");
+    memcpy(out_cigar, ctx->retained.data(), ctx->retained.size() * sizeof(gnx_cigar));
+    return GNX_OK;
+}
+
+int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const int64_t *d_alpha_off,
+                     const uint8_t *d_beta_cat, const int64_t *d_beta_off, const int64_t *alpha_off_host,
+                     const int64_t *beta_off_host, int64_t n_pairs, const int64_t *scores, int dim, int64_t gap_open,
+                     int64_t gap_extend, int want_cigar, int64_t *d_out_score, gnx_cigar *d_out_cigar,
+                     int64_t *d_out_cigar_off, int64_t cigar_cap, int32_t *d_status, void *cuda_stream)
+{
+    if (!ctx)
+        return GNX_EARG;
+    if (n_pairs < 0 || kind < 0 || kind > 2 || !d_alpha_off || !d_beta_off || !d_out_score)
+        return fail(ctx, GNX_EARG, "bad argument to gnx_batch_device");
+    if (want_cigar && (!d_out_cigar_off || !d_out_cigar))
+        return fail(ctx, GNX_EARG, "d_out_cigar and d_out_cigar_off are required when want_cigar != 0");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Problem pb;
+    int rc = fill_problem(ctx, pb, kind, want_cigar, scores, dim, gap_open, kind == 2 ? 0 : gap_extend);
+    if (rc != GNX_OK)
+        return rc;
+    ctx->fill_events_used = 0;
+    ctx->last_fill_launches = 0;
+    ctx->last_fill_ms = 0;
+    ctx->last_cells = 0;
+    if (n_pairs == 0)
+        return GNX_OK;
+    std::vector<int64_t> ha, hb;
+    if (!alpha_off_host) {
+        ha.resize((size_t)n_pairs + 1);
+        CU(cudaMemcpyAsync(ha.data(), d_alpha_off, (size_t)(n_pairs + 1) * 8, cudaMemcpyDeviceToHost, st));
+        alpha_off_host = ha.data();
+    }
+    if (!beta_off_host) {
+        hb.resize((size_t)n_pairs + 1);
+        CU(cudaMemcpyAsync(hb.data(), d_beta_off, (size_t)(n_pairs + 1) * 8, cudaMemcpyDeviceToHost, st));
+        beta_off_host = hb.data();
+    }
+    if (!ha.empty() || !hb.empty())
+        CU(cudaStreamSynchronize(st));
+    Plan plan;
+    int C = 5;
+    const int64_t budget_words = (int64_t)(ctx->workspace / 4); // single slot: chunks run back to back
+    rc = make_plan(ctx, pb, alpha_off_host, beta_off_host, n_pairs, budget_words, C, plan);
+    if (rc != GNX_OK)
+        return rc;
+    rc = analyse(ctx, pb, plan.max_n, plan.max_m);
+    if (rc != GNX_OK)
+        return rc;
+    ctx->last_cells = plan.cells;
+    Slot &s = ctx->slot[0];
+    const int nwarps_total = ctx->sm_count * ctx->opt_blocks_per_sm * 4;
+    const int64_t edge_stride = plan.max_n + 2;
+    CU(cudaMemsetAsync(ctx->status.p, 0, sizeof(int), st));
+    CU(cudaMemsetAsync(ctx->dr_misc.p, 0, 8, st)); // running cigar total
+    const int64_t n_chunks = (int64_t)plan.bounds.size() - 1;
+    CU(s.cls.ensure((size_t)n_pairs));
+    for (int64_t ci = 0; ci < n_chunks; ++ci) {
+        const int64_t begin = plan.bounds[ci], end = plan.bounds[ci + 1], np = end - begin;
+        ChunkDev cd;
+        memset(&cd, 0, sizeof cd);
+        cd.alpha = d_alpha_cat;
+        cd.beta = d_beta_cat;
+        cd.aoff = d_alpha_off;
+        cd.boff = d_beta_off;
+        cd.cls = s.cls.as<uint8_t>();
+        cd.score = d_out_score;
+        if (pb.want_cigar) {
+            // pinned staging is reused by the next chunk's host writes: fence on the previous upload
+            if (ci > 0)
+                CU(cudaEventSynchronize(s.ev_done));
+            CU(s.h_trace_off.ensure((size_t)(np + 1) * 8));
+            int64_t *to = s.h_trace_off.as<int64_t>();
+            int64_t acc = 0;
+            for (int64_t k = 0; k < np; ++k) {
+                to[k] = acc;
+                acc += pair_trace_words(pb, alpha_off_host[begin + k + 1] - alpha_off_host[begin + k],
+                                        beta_off_host[begin + k + 1] - beta_off_host[begin + k], C);
+            }
+            to[np] = acc;
+            CU(s.trace.ensure((size_t)std::max<int64_t>(acc, 1) * 4));
+            CU(s.trace_off.ensure((size_t)(np + 1) * 8));
+            CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, st));
+            CU(cudaEventRecord(s.ev_done, st));
+            CU(s.slots.ensure((size_t)np * kSlotCap * 4));
+            CU(s.counts.ensure((size_t)np * 4));
+            cd.trace = s.trace.as<uint32_t>();
+            cd.trace_off = s.trace_off.as<int64_t>();
+            cd.slots = s.slots.as<uint32_t>();
+            cd.counts = s.counts.as<int>();
+        }
+        if (plan.any_long) {
+            CU(s.edge.ensure((size_t)nwarps_total * 2 * edge_stride * sizeof(int2)));
+            cd.edge = s.edge.as<int2>();
+            cd.edge_stride = edge_stride;
+        }
+        rc = enqueue_chunk_compute(ctx, pb, cd, begin, end, C, plan.any_long, st);
+        if (rc != GNX_OK)
+            return rc;
+        if (pb.want_cigar) {
+            scan_counts_kernel<<<1, 1024, 0, st>>>(cd.counts, np, d_out_cigar_off + begin, ctx->dr_misc.as<int64_t>());
+            ctx->launches++;
+            rc = enqueue_chunk_expand(ctx, pb, cd, begin, end, C, d_out_cigar_off + begin, d_out_cigar, cigar_cap, st);
+            if (rc != GNX_OK)
+                return rc;
+        }
+    }
+    if (d_status)
+        CU(cudaMemcpyAsync(d_status, ctx->status.p, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return GNX_OK;
+}
+
+int64_t gnx_launch_count(gnx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int gnx_last_fill_stats(gnx_ctx *ctx, double *fill_ms, int64_t *fill_launches, int64_t *cells)
+{
+    if (!ctx)
+        return GNX_EARG;
+    cudaSetDevice(ctx->device);
+    collect_fill_stats(ctx);
+    if (fill_ms)
+        *fill_ms = ctx->last_fill_ms;
+    if (fill_launches)
+        *fill_launches = ctx->last_fill_launches;
+    if (cells)
+        *cells = ctx->last_cells;
+    return GNX_OK;
+}
+
+int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
+{
+    if (!ctx || !name)
+        return GNX_EARG;
+    std::string k(name);
+    if (k == "cols_per_lane") {
+        if (value != 0 && value != 5 && value != 10)
+            return fail(ctx, GNX_EARG, "cols_per_lane must be 0 (auto), 5 or 10");
+        ctx->opt_cols = (int)value;
+    } else if (k == "chunk_pairs") {
+        if (value < 1)
+            return fail(ctx, GNX_EARG, "chunk_pairs must be >= 1");
+        ctx->opt_chunk_pairs = value;
+    } else if (k == "blocks_per_sm") {
+        if (value < 1 || value > 32)
+            return fail(ctx, GNX_EARG, "blocks_per_sm must be in 1..32");
+        ctx->opt_blocks_per_sm = (int)value;
+    } else if (k == "workspace_bytes") {
+        if (value < (1 << 20))
+            return fail(ctx, GNX_EARG, "workspace_bytes must be >= 1 MiB");
+        ctx->workspace = (size_t)value;
+    } else {
+        return fail(ctx, GNX_EARG, "unknown option");
+    }
+    return GNX_OK;
+}
+
+} // extern "C"

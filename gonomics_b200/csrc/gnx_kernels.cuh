@@ -1,0 +1,675 @@
+// gnx_kernels.cuh -- sm_100a kernels for the gonomics `align` DP hot path.
+//
+// Mapping (DESIGN.md "Kernels"): one (alpha, beta) pair per warp.  The beta (query) axis is cut
+// into strips of 32*C columns; lane l owns C consecutive columns of the strip and sweeps the alpha
+// (target) rows with a one-row skew per lane (lane l is on row t-l at step t), so every cell's
+// three neighbours are either in the lane's own registers or arrive from lane l-1 through two
+// __shfl_up_sync per step.  Integer max-plus only: VIMNMX3 / VIADDMNMX (DPX) -- no tensor cores.
+//
+// Bit-exactness (align/align.go:76-84 tripleMaxTrace, ties M >= I >= D) is obtained by carrying
+// every plane value as 64*v and adding a 2-bit tag (M=2, I=1, D=0) to the three candidates of a
+// max in a field private to that max (I-plane: bits 1:0, D-plane: bits 3:2, H=max(M,I,D): bits
+// 5:4).  One 3-way integer max then yields value and winning plane with the reference's
+// tie order; the three tags of a cell sum into its 6-bit traceback code.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gnx {
+
+constexpr int kTagBits = 6;
+constexpr int kScale = 1 << kTagBits; // 64
+constexpr int kFI = 1;                // tag field of the I-plane max  (code bits 1:0)
+constexpr int kFD = 4;                // tag field of the D-plane max  (code bits 3:2)
+constexpr int kFH = 16;               // tag field of H = max(M,I,D)   (code bits 5:4)
+constexpr int kNeg32 = -(1 << 30);    // "-inf" for scaled int32 planes (real -2^24)
+
+// status codes mirrored from gnxalign.h (device side)
+constexpr int kOk = 0, kEBase = 1, kECap = 2;
+
+struct FillParams {
+    const uint8_t *alpha;
+    const int64_t *alpha_off; // absolute offsets into alpha, indexed by global pair id
+    const uint8_t *beta;
+    const int64_t *beta_off;
+    int64_t pair_begin, pair_end; // chunk = [pair_begin, pair_end)
+    const uint8_t *pair_class;    // per global pair: 0 = ACGT only, 1 = has base in [4,dim), 2 = invalid
+    int want_class;               // warps skip pairs whose class differs
+    int gap_open, gap_extend;     // unscaled
+    int h00;                      // H(0,0) = T(0, O, D(0,0)) unscaled
+    int dim;
+    int scores[64];               // unscaled, [a*dim + b]
+    uint32_t *trace;              // chunk trace buffer (TRACE kernels)
+    const int64_t *trace_off;     // per pair in chunk (index pair - pair_begin): offset in 32-bit words
+    int2 *edge;                   // per-warp strip hand-off buffers: 2 * edge_stride int2 per warp
+    int64_t edge_stride;
+    int64_t *out_score;           // indexed by global pair id
+};
+
+__device__ __forceinline__ int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); } // max(a+b, c)
+__device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
+
+// Number of 32-bit trace words per lane per step: 5 six-bit codes per word.
+__host__ __device__ constexpr int trace_wpl(int C) { return (C + 4) / 5; }
+// Trace words for one pair: strips * (n + 31) steps * wpl * 32 lanes.
+__host__ __device__ inline int64_t trace_words(int64_t n, int64_t m, int C)
+{
+    if (n <= 0 || m <= 0)
+        return 0;
+    const int64_t strips = (m + 32 * C - 1) / (32 * C);
+    return strips * (n + 31) * trace_wpl(C) * 32;
+}
+
+// ------------------------------------------------------------------------------------------------
+// classify: per pair, the largest base value decides the kernel class (and the GNX_EBASE error).
+// One warp per pair, 16-byte vector loads where alignment allows.
+// ------------------------------------------------------------------------------------------------
+__global__ void classify_kernel(const uint8_t *alpha, const int64_t *alpha_off, const uint8_t *beta,
+                                const int64_t *beta_off, int64_t pair_begin, int64_t pair_end, int dim,
+                                uint8_t *pair_class, int *status)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t p = pair_begin + warp; p < pair_end; p += nwarps) {
+        unsigned mx = 0;
+        const int64_t a0 = alpha_off[p], a1 = alpha_off[p + 1], b0 = beta_off[p], b1 = beta_off[p + 1];
+        for (int64_t i = a0 + lane; i < a1; i += 32)
+            mx = max(mx, (unsigned)alpha[i]);
+        for (int64_t i = b0 + lane; i < b1; i += 32)
+            mx = max(mx, (unsigned)beta[i]);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0) {
+            uint8_t cls = mx < 4 ? 0 : (mx < (unsigned)dim ? 1 : 2);
+            if (a1 == a0 || b1 == b0)
+                cls = cls == 2 ? 1 : cls; // Go never indexes the matrix when a side is empty: no panic
+            pair_class[p] = cls;
+            if (cls == 2)
+                atomicMax(status, kEBase);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Affine-gap fill.  Reference recurrence: align/affineGap_highMem.go:181-220 (global and
+// freeEndGaps), identical arithmetic in align/affineGap.go:159-191.
+//   C      columns per lane (strip width 32*C)
+//   TRACE  write the 6-bit/cell traceback codes (values scaled by 64 + tags) or score only
+//   FREE   freeEndGaps (AffineGapLocal): D(i,0) = 0 and an un-penalised D in the last column
+//   LOOKUP 0: ACGT-only pairs, substitution scores from per-column 16-bit tables via PRMT
+//          1: any base < dim, scores from a shared-memory copy of the matrix
+// ------------------------------------------------------------------------------------------------
+template <int C, bool TRACE, bool FREE, int LOOKUP>
+__global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
+{
+    constexpr int SC = TRACE ? kScale : 1;
+    constexpr int FI = TRACE ? kFI : 0, FD = TRACE ? kFD : 0, FH = TRACE ? kFH : 0;
+    constexpr int WPL = trace_wpl(C);
+    constexpr int NEG = kNeg32;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    __shared__ int s_scores[64];
+    if (LOOKUP == 1) {
+        if (threadIdx.x < 64)
+            s_scores[threadIdx.x] = P.scores[threadIdx.x] * SC;
+        __syncthreads();
+    }
+
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+
+    const int O = P.gap_open, E = P.gap_extend;
+    const int oe_s = (O + E) * SC, e_s = E * SC;
+    // addends of the I-plane max (candidates M, I, D of the cell to the left)
+    const int iM = oe_s + 2 * FI, iI = e_s + FI, iD = oe_s;
+    // addends of the D-plane max (candidates M, I, D of the cell above), regular columns
+    const int dM = oe_s + 2 * FD, dI = oe_s + FD, dD = e_s;
+
+    int2 *edge_a = P.edge ? P.edge + (size_t)warp * 2 * P.edge_stride : nullptr;
+    int2 *edge_b = P.edge ? edge_a + P.edge_stride : nullptr;
+
+    for (int64_t pair = P.pair_begin + warp; pair < P.pair_end; pair += nwarps) {
+        if (P.pair_class && P.pair_class[pair] != P.want_class)
+            continue;
+        const int64_t a0 = P.alpha_off[pair], b0 = P.beta_off[pair];
+        const int n = (int)(P.alpha_off[pair + 1] - a0);
+        const int m = (int)(P.beta_off[pair + 1] - b0);
+        const uint8_t *__restrict__ alpha = P.alpha + a0;
+        const uint8_t *__restrict__ beta = P.beta + b0;
+
+        if (n == 0 || m == 0) { // closed forms of the boundary rows (affineGap_highMem.go:185-206)
+            if (lane == 0) {
+                int64_t sc;
+                if (n == 0 && m == 0)
+                    sc = P.h00;
+                else if (n == 0)
+                    sc = (int64_t)O + (int64_t)m * E; // I(0,m); M and D are -inf
+                else
+                    sc = FREE ? 0 : (int64_t)O + (int64_t)n * E; // D(n,0)
+                P.out_score[pair] = sc;
+            }
+            continue;
+        }
+
+        const int T = n + 31; // steps per strip
+        const int strips = (m + 32 * C - 1) / (32 * C);
+        uint32_t *tbase = nullptr;
+        if (TRACE)
+            tbase = P.trace + P.trace_off[pair - P.pair_begin];
+
+        for (int p = 0; p < strips; ++p) {
+            const int jbase = p * 32 * C + lane * C; // columns before mine; my columns are jbase+1..jbase+C
+            // ---- per-column constants -----------------------------------------------------------
+            int q[C];
+            int t01[C], t23[C];       // LOOKUP 0: packed int16 score tables for target base 0,1 | 2,3
+            int aM[C], aI[C], aD[C];  // D-plane addends (FREE: zero in the last column)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int j = jbase + c + 1;
+                q[c] = (j <= m) ? (int)beta[j - 1] : 0;
+                if (LOOKUP == 0) {
+                    const int s0 = P.scores[0 * P.dim + q[c]] * SC, s1 = P.scores[1 * P.dim + q[c]] * SC;
+                    const int s2 = P.scores[2 * P.dim + q[c]] * SC, s3 = P.scores[3 * P.dim + q[c]] * SC;
+                    t01[c] = (s0 & 0xffff) | (s1 << 16);
+                    t23[c] = (s2 & 0xffff) | (s3 << 16);
+                }
+                const bool last = FREE && (j == m);
+                aM[c] = last ? 2 * FD : dM;
+                aI[c] = last ? FD : dI;
+                aD[c] = last ? 0 : dD;
+            }
+            // ---- row 0 state (affineGap_highMem.go:193-197): M=-inf, I=O+jE, D=-inf --------------
+            int Dt[C];   // D(r, col) for the row about to be processed (tagged when TRACE)
+            int Hc[C];   // clean H(r-1, col) of the previous row
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int j = jbase + c + 1;
+                const int i0 = (O + j * E) * SC;
+                Hc[c] = i0; // T(-inf, I, -inf) = I
+                Dt[c] = addmax(NEG, aM[c], addmax(i0, aI[c], NEG + aD[c]));
+            }
+            int hpL = (jbase == 0) ? P.h00 * SC : (O + jbase * E) * SC; // H(0, jbase)
+            int edgeI = 0, edgeH = 0;                                   // what lane+1 consumes
+            const int2 *ein = (p & 1) ? edge_b : edge_a;                // written by strip p-1
+            int2 *eout = (p & 1) ? edge_a : edge_b;
+            uint32_t *tp = TRACE ? tbase + ((size_t)p * T * WPL) * 32 + lane : nullptr;
+
+            // lane 0 boundary stream for its next row (column jbase): I'(r, jbase+1) and H(r, jbase)
+            int bI = 0, bH = 0;
+            auto boundary = [&](int r) {
+                if (p == 0) {
+                    const int d0 = FREE ? 0 : (O + r * E) * SC; // D(r,0); M(r,0)=I(r,0)=-inf
+                    bI = d0 + iD;                               // T(-inf, -inf, D+oe): tag D (0)
+                    bH = d0;
+                } else {
+                    const int2 v = ein[r];
+                    bI = v.x;
+                    bH = v.y;
+                }
+            };
+            if (lane == 0)
+                boundary(1);
+            int a_next = 0;
+            if (lane == 0)
+                a_next = alpha[0];
+
+            for (int t = 0; t < T; ++t) {
+                const int r = t - lane + 1; // my row this step
+                int inI = __shfl_up_sync(FULL, edgeI, 1);
+                int inH = __shfl_up_sync(FULL, edgeH, 1);
+                if (lane == 0) {
+                    inI = bI;
+                    inH = bH;
+                }
+                const bool active = (r >= 1) && (r <= n);
+                const int a = a_next;
+                if (r + 1 >= 1 && r + 1 <= n)
+                    a_next = alpha[r]; // prefetch the next row's base
+                if (active) {
+                    if (lane == 0 && r < n)
+                        boundary(r + 1);
+                    int sel = 0, rowoff = 0;
+                    if (LOOKUP == 0)
+                        sel = a * 0x2222 + 0x9910; // PRMT selector: sign-extended 16-bit entry a
+                    else
+                        rowoff = a * P.dim;
+                    int It = inI;
+                    int hp = hpL;
+                    uint32_t w[WPL];
+#pragma unroll
+                    for (int k = 0; k < WPL; ++k)
+                        w[k] = 0;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        int s;
+                        if (LOOKUP == 0)
+                            s = (int)__byte_perm((unsigned)t01[c], (unsigned)t23[c], (unsigned)sel);
+                        else
+                            s = s_scores[rowoff + q[c]];
+                        const int Mc = hp + s; // M(r,j) = s + H(r-1,j-1)
+                        int cI, cD, Ht, cH;
+                        if (TRACE) {
+                            cI = It & ~(kScale - 1);
+                            cD = Dt[c] & ~(kScale - 1);
+                            Ht = max3(Mc + 2 * FH, cI + FH, cD);
+                            cH = Ht & ~(kScale - 1);
+                            const unsigned code = (unsigned)(It + Dt[c] + Ht) & (kScale - 1);
+                            w[c / 5] = (w[c / 5] << kTagBits) | code;
+                        } else {
+                            cI = It;
+                            cD = Dt[c];
+                            Ht = max3(Mc, cI, cD);
+                            cH = Ht;
+                        }
+                        // I(r, j+1) = T(M+O+E, I+E, D+O+E)   (affineGap_highMem.go:213)
+                        It = addmax(Mc, iM, addmax(cD, iD, cI + iI));
+                        // D(r+1, j) = T(M+O+E, I+O+E, D+E)   (:214; FREE last column :209 has no penalty)
+                        Dt[c] = addmax(Mc, aM[c], addmax(cI, aI[c], cD + aD[c]));
+                        hp = Hc[c];
+                        Hc[c] = cH;
+                    }
+                    edgeI = It;
+                    edgeH = Hc[C - 1];
+                    hpL = inH;
+                    if (TRACE) {
+#pragma unroll
+                        for (int k = 0; k < WPL; ++k)
+                            tp[(size_t)k * 32] = w[k];
+                    }
+                    if (lane == 31 && p + 1 < strips)
+                        eout[r] = make_int2(edgeI, edgeH);
+                }
+                if (TRACE)
+                    tp += WPL * 32;
+            }
+            // ---- score: H(n, m) sits in Hc[] of the lane that owns column m ----------------------
+            const int pm = (m - 1) / (32 * C), lm = ((m - 1) % (32 * C)) / C, cm = (m - 1) % C;
+            if (p == pm && lane == lm) {
+                int h = Hc[0];
+#pragma unroll
+                for (int c = 1; c < C; ++c)
+                    if (c == cm)
+                        h = Hc[c];
+                P.out_score[pair] = (int64_t)(h / SC); // clean values are exact multiples of SC
+            }
+            __syncwarp(); // order the strip's edge writes before the next strip's reads
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Constant-gap (Needleman-Wunsch) fill.  Reference: align/constGap_highMem.go:23-40.
+//   m(i,j), tr = T(m(i-1,j-1)+s, m(i,j-1)+g, m(i-1,j)+g); values carried as 4*v + tag.
+// Trace: 2 bits per cell, 16 codes per 32-bit word.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int const_wpl(int C) { return (C + 15) / 16; }
+__host__ __device__ inline int64_t const_trace_words(int64_t n, int64_t m, int C)
+{
+    if (n <= 0 || m <= 0)
+        return 0;
+    const int64_t strips = (m + 32 * C - 1) / (32 * C);
+    return strips * (n + 31) * const_wpl(C) * 32;
+}
+
+template <int C, bool TRACE, int LOOKUP>
+__global__ void __launch_bounds__(128) const_fill_kernel(const FillParams P)
+{
+    constexpr int SC = TRACE ? 4 : 1;
+    constexpr int WPL = const_wpl(C);
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ int s_scores[64];
+    if (LOOKUP == 1) {
+        if (threadIdx.x < 64)
+            s_scores[threadIdx.x] = P.scores[threadIdx.x] * SC;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int g = P.gap_open; // the single gap penalty
+    const int g_left = g * SC + (TRACE ? 1 : 0), g_up = g * SC;
+    int2 *edge_a = P.edge ? P.edge + (size_t)warp * 2 * P.edge_stride : nullptr;
+    int2 *edge_b = P.edge ? edge_a + P.edge_stride : nullptr;
+
+    for (int64_t pair = P.pair_begin + warp; pair < P.pair_end; pair += nwarps) {
+        if (P.pair_class && P.pair_class[pair] != P.want_class)
+            continue;
+        const int64_t a0 = P.alpha_off[pair], b0 = P.beta_off[pair];
+        const int n = (int)(P.alpha_off[pair + 1] - a0);
+        const int m = (int)(P.beta_off[pair + 1] - b0);
+        const uint8_t *__restrict__ alpha = P.alpha + a0;
+        const uint8_t *__restrict__ beta = P.beta + b0;
+        if (n == 0 || m == 0) {
+            if (lane == 0)
+                P.out_score[pair] = (int64_t)g * (n + m); // boundary row/column (constGap_highMem.go:27-32)
+            continue;
+        }
+        const int T = n + 31;
+        const int strips = (m + 32 * C - 1) / (32 * C);
+        uint32_t *tbase = TRACE ? P.trace + P.trace_off[pair - P.pair_begin] : nullptr;
+        for (int p = 0; p < strips; ++p) {
+            const int jbase = p * 32 * C + lane * C;
+            int q[C], t01[C], t23[C], Hc[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int j = jbase + c + 1;
+                q[c] = (j <= m) ? (int)beta[j - 1] : 0;
+                if (LOOKUP == 0) {
+                    const int s0 = P.scores[0 * P.dim + q[c]] * SC + (TRACE ? 2 : 0);
+                    const int s1 = P.scores[1 * P.dim + q[c]] * SC + (TRACE ? 2 : 0);
+                    const int s2 = P.scores[2 * P.dim + q[c]] * SC + (TRACE ? 2 : 0);
+                    const int s3 = P.scores[3 * P.dim + q[c]] * SC + (TRACE ? 2 : 0);
+                    t01[c] = (s0 & 0xffff) | (s1 << 16);
+                    t23[c] = (s2 & 0xffff) | (s3 << 16);
+                }
+                Hc[c] = j * g * SC; // row 0
+            }
+            int hpL = jbase * g * SC;
+            int edgeH = 0;
+            const int2 *ein = (p & 1) ? edge_b : edge_a;
+            int2 *eout = (p & 1) ? edge_a : edge_b;
+            uint32_t *tp = TRACE ? tbase + ((size_t)p * T * WPL) * 32 + lane : nullptr;
+            int bH = 0;
+            auto boundary = [&](int r) { bH = (p == 0) ? r * g * SC : ein[r].x; };
+            if (lane == 0)
+                boundary(1);
+            int a_next = (lane == 0) ? (int)alpha[0] : 0;
+            for (int t = 0; t < T; ++t) {
+                const int r = t - lane + 1;
+                int inH = __shfl_up_sync(FULL, edgeH, 1);
+                if (lane == 0)
+                    inH = bH;
+                const bool active = (r >= 1) && (r <= n);
+                const int a = a_next;
+                if (r + 1 >= 1 && r + 1 <= n)
+                    a_next = alpha[r];
+                if (active) {
+                    if (lane == 0 && r < n)
+                        boundary(r + 1);
+                    int sel = 0, rowoff = 0;
+                    if (LOOKUP == 0)
+                        sel = a * 0x2222 + 0x9910;
+                    else
+                        rowoff = a * P.dim;
+                    int left = inH; // clean m(r, j-1)
+                    int hp = hpL;   // clean m(r-1, j-1)
+                    uint32_t w[WPL];
+#pragma unroll
+                    for (int k = 0; k < WPL; ++k)
+                        w[k] = 0;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        int s;
+                        if (LOOKUP == 0)
+                            s = (int)__byte_perm((unsigned)t01[c], (unsigned)t23[c], (unsigned)sel);
+                        else
+                            s = s_scores[rowoff + q[c]] + (TRACE ? 2 : 0);
+                        // candidates: diag+s (tag 2 = ColM), left+g (tag 1 = ColI), up+g (tag 0 = ColD)
+                        const int ht = max3(hp + s, left + g_left, Hc[c] + g_up);
+                        int cH = ht;
+                        if (TRACE) {
+                            cH = ht & ~3;
+                            w[c / 16] = (w[c / 16] << 2) | ((unsigned)ht & 3u);
+                        }
+                        hp = Hc[c];
+                        Hc[c] = cH;
+                        left = cH;
+                    }
+                    edgeH = left;
+                    hpL = inH;
+                    if (TRACE) {
+#pragma unroll
+                        for (int k = 0; k < WPL; ++k)
+                            tp[(size_t)k * 32] = w[k];
+                    }
+                    if (lane == 31 && p + 1 < strips)
+                        eout[r] = make_int2(edgeH, 0);
+                }
+                if (TRACE)
+                    tp += WPL * 32;
+            }
+            const int pm = (m - 1) / (32 * C), lm = ((m - 1) % (32 * C)) / C, cm = (m - 1) % C;
+            if (p == pm && lane == lm) {
+                int h = Hc[0];
+#pragma unroll
+                for (int c = 1; c < C; ++c)
+                    if (c == cm)
+                        h = Hc[c];
+                P.out_score[pair] = (int64_t)(h / SC);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Traceback + run-length encoding, one thread per pair.
+// Reference: affineTrace (align/affineGap_highMem.go:57-89) and the cigar loop of
+// ConstGap_highMem (align/constGap_highMem.go:43-65).
+// Ops are produced end-to-start; they are kept in a small per-pair slot (reversed on expansion).
+// ------------------------------------------------------------------------------------------------
+struct TraceParams {
+    const int64_t *alpha_off, *beta_off;
+    int64_t pair_begin, pair_end;
+    const uint32_t *trace;
+    const int64_t *trace_off;
+    int C;          // columns per lane the fill kernel used
+    int kind;       // 0 affine, 2 const gap
+    int h00_plane;  // plane of T(0, O, D(0,0)) (affine)
+    uint32_t *slots; // per pair in chunk: slot_cap entries, run<<2 | op, traceback order
+    int slot_cap;
+    int *counts;    // per pair in chunk: number of cigar elements
+    // second pass (overflowing pairs only): write final gnx_cigar entries directly
+    int64_t *cigar_off;  // per pair in chunk (+1): exclusive scan of counts, relative to chunk base
+    void *out_cigar;     // gnx_cigar* base that cigar_off indexes
+    int64_t out_cap;     // entries available behind out_cigar
+    int pass;            // 0: fill slots + counts, 1: rewrite pairs whose count > slot_cap
+};
+
+struct CigarOut {
+    long long run_length;
+    unsigned char op;
+};
+
+__device__ __forceinline__ unsigned affine_code(const uint32_t *tr, int T, int C, int i, int j)
+{
+    const int wpl = trace_wpl(C);
+    const int jj = j - 1;
+    const int strip = jj / (32 * C);
+    const int within = jj - strip * 32 * C;
+    const int lane = within / C, c = within - lane * C;
+    const int t = (i - 1) + lane;
+    const int nin = (c / 5 == wpl - 1) ? (C - 5 * (wpl - 1)) : 5; // codes held by this word
+    const uint32_t w = tr[(((size_t)strip * T + t) * wpl + c / 5) * 32 + lane];
+    return (w >> (kTagBits * (nin - 1 - (c % 5)))) & (kScale - 1);
+}
+
+__device__ __forceinline__ unsigned const_code(const uint32_t *tr, int T, int C, int i, int j)
+{
+    const int wpl = const_wpl(C);
+    const int jj = j - 1;
+    const int strip = jj / (32 * C);
+    const int within = jj - strip * 32 * C;
+    const int lane = within / C, c = within - lane * C;
+    const int t = (i - 1) + lane;
+    const int nin = (c / 16 == wpl - 1) ? (C - 16 * (wpl - 1)) : 16;
+    const uint32_t w = tr[(((size_t)strip * T + t) * wpl + c / 16) * 32 + lane];
+    return (w >> (2 * (nin - 1 - (c % 16)))) & 3u;
+}
+
+__global__ void traceback_kernel(const TraceParams P)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t pair = P.pair_begin + idx;
+    if (pair >= P.pair_end)
+        return;
+    const int n = (int)(P.alpha_off[pair + 1] - P.alpha_off[pair]);
+    const int m = (int)(P.beta_off[pair + 1] - P.beta_off[pair]);
+    if (P.pass == 1 && P.counts[idx] <= P.slot_cap)
+        return;
+    uint32_t *slot = P.slots + (size_t)idx * P.slot_cap;
+    CigarOut *dst = nullptr;
+    int total = 0;
+    if (P.pass == 1) {
+        total = P.counts[idx];
+        if (P.cigar_off[idx] + total > P.out_cap)
+            return; // expand_kernel has already flagged GNX_ECAP
+        dst = (CigarOut *)P.out_cigar + P.cigar_off[idx];
+    }
+    int cnt = 0;
+    auto emit = [&](int op, int run) {
+        if (P.pass == 0) {
+            if (cnt < P.slot_cap)
+                slot[cnt] = ((uint32_t)run << 2) | (uint32_t)op;
+        } else { // final order is reversed traceback order
+            CigarOut o;
+            o.run_length = run;
+            o.op = (unsigned char)op;
+            dst[total - 1 - cnt] = o;
+        }
+        ++cnt;
+    };
+    if (n == 0 && m == 0) { // route := make([]Cigar, 1): one zero element (affineGap_highMem.go:58)
+        emit(0, 0);
+        if (P.pass == 0)
+            P.counts[idx] = cnt;
+        return;
+    }
+    const uint32_t *tr = P.trace + P.trace_off[idx];
+    const int T = n + 31, C = P.C;
+    int i = n, j = m, cur = -1, run = 0;
+    if (P.kind == 0) {
+        // start plane: T(M,I,D)(n,m) = the H tag of cell (n,m); boundaries are closed-form
+        int k;
+        if (n == 0)
+            k = 1;
+        else if (m == 0)
+            k = 2;
+        else
+            k = 2 - (int)((affine_code(tr, T, C, n, m) >> 4) & 3u);
+        while (i > 0 || j > 0) {
+            if (k == cur) {
+                ++run;
+            } else {
+                if (cur >= 0)
+                    emit(cur, run);
+                cur = k;
+                run = 1;
+            }
+            if (i == 0) { // row 0: trace[1][0][j] = ColI (:196)
+                --j;
+                k = 1;
+            } else if (j == 0) { // column 0: trace[2][i][0] = ColD (:205)
+                --i;
+                k = 2;
+            } else if (k == 0) { // M: the source plane is argmax(M,I,D) of the diagonal neighbour
+                --i;
+                --j;
+                if (i == 0 && j == 0)
+                    k = P.h00_plane;
+                else if (i == 0)
+                    k = 1;
+                else if (j == 0)
+                    k = 2;
+                else
+                    k = 2 - (int)((affine_code(tr, T, C, i, j) >> 4) & 3u);
+            } else if (k == 1) {
+                k = 2 - (int)(affine_code(tr, T, C, i, j) & 3u);
+                --j;
+            } else {
+                k = 2 - (int)((affine_code(tr, T, C, i, j) >> 2) & 3u);
+                --i;
+            }
+        }
+    } else {
+        while (i > 0 || j > 0) {
+            int k;
+            if (i == 0)
+                k = 1; // trace[0][j] = 1 (constGap_highMem.go:28)
+            else if (j == 0)
+                k = 2; // trace[i][0] = 2 (:31)
+            else
+                k = 2 - (int)const_code(tr, T, C, i, j);
+            if (k == cur) {
+                ++run;
+            } else {
+                if (cur >= 0)
+                    emit(cur, run);
+                cur = k;
+                run = 1;
+            }
+            if (k == 0) {
+                --i;
+                --j;
+            } else if (k == 1) {
+                --j;
+            } else {
+                --i;
+            }
+        }
+    }
+    if (cur >= 0)
+        emit(cur, run);
+    if (P.pass == 0)
+        P.counts[idx] = cnt;
+}
+
+// Expand the per-pair slots into gnx_cigar records at the scanned offsets (reversing to start->end
+// order, align/align.go:86-90 reverseCigar).  One thread per pair; cigars are short.
+__global__ void expand_kernel(const uint32_t *slots, int slot_cap, const int *counts, const int64_t *cigar_off,
+                              int64_t n_pairs, CigarOut *out, int64_t out_cap_remaining, int *status)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_pairs)
+        return;
+    const int cnt = counts[idx];
+    const int64_t off = cigar_off[idx];
+    if (off + cnt > out_cap_remaining) {
+        atomicMax(status, kECap);
+        return;
+    }
+    if (cnt > slot_cap)
+        return; // rewritten by traceback pass 1
+    const uint32_t *slot = slots + (size_t)idx * slot_cap;
+    for (int k = 0; k < cnt; ++k) {
+        const uint32_t v = slot[k];
+        CigarOut o;
+        o.run_length = (long long)(v >> 2);
+        o.op = (unsigned char)(v & 3u);
+        out[off + cnt - 1 - k] = o;
+    }
+}
+
+// Exclusive scan of int counts into int64 offsets (n+1 entries), single block, chunk-sized inputs.
+// Chunks are at most a few hundred thousand pairs, so one 1024-thread block striding is enough.
+__global__ void scan_counts_kernel(const int *counts, int64_t n, int64_t *off, int64_t *running_total)
+{
+    __shared__ int64_t s_part[1024];
+    const int tid = threadIdx.x;
+    const int64_t per = (n + blockDim.x - 1) / blockDim.x;
+    const int64_t lo = min(n, (int64_t)tid * per), hi = min(n, lo + per);
+    int64_t sum = 0;
+    for (int64_t i = lo; i < hi; ++i)
+        sum += counts[i];
+    s_part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        int64_t run = *running_total; // offsets continue from the chunks scanned before
+        for (int k = 0; k < (int)blockDim.x; ++k) {
+            const int64_t v = s_part[k];
+            s_part[k] = run;
+            run += v;
+        }
+        off[n] = run;
+        *running_total = run;
+    }
+    __syncthreads();
+    int64_t run = s_part[tid];
+    for (int64_t i = lo; i < hi; ++i) {
+        off[i] = run;
+        run += counts[i];
+    }
+}
+
+} // namespace gnx

@@ -1,0 +1,142 @@
+/*
+ * gnxalign.h -- C ABI of libgnxalign.so: B200 (sm_100a) implementation of the gonomics
+ * `align` package's pairwise DP hot path (score-matrix fill, traceback, Cigar).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.  It is what a
+ * cgo shim in the reference's `align` package binds (see INTEGRATION.md for the Go side) and
+ * what tests load through ctypes.  Every entry point cites the Go function it replaces
+ * (paths relative to the gonomics tree @ bd66b49b).
+ *
+ * Conventions
+ *   - Sequences are `[]dna.Base` byte arrays (dna/dna.go:5-21: A,C,G,T,N = 0..4); a batch is the
+ *     concatenation of all alphas (resp. betas) plus an (n_pairs+1)-entry int64 offset array.
+ *   - `scores` is the reference's `[][]int64` matrix flattened row-major [alpha][beta], dim x dim
+ *     (align/align.go:28-64; dim = 5 for the stock matrices).
+ *   - gnx_cigar is layout-identical to Go's align.Cigar{RunLength int64; Op ColType} (align/align.go:21-24),
+ *     16 bytes, so results can be written straight into a Go-allocated []align.Cigar.
+ *   - Inputs are borrowed and never modified or retained; outputs are caller-owned.
+ *   - All functions return 0 (GNX_OK) or a GNX_E* code; gnx_last_error() gives the text.  The
+ *     reference never returns an error on this path -- it panics (base >= dim indexes past the
+ *     matrix) or log.Fatalf's (chunk misuse); the Go shim maps codes back to those behaviours.
+ *   - A context is bound to one CUDA device and is NOT thread-safe: use one context per calling
+ *     goroutine/thread (contexts are cheap after the first), exactly like the reference's
+ *     per-worker scratch matrices in cmd/gsw.
+ */
+#ifndef GNXALIGN_H
+#define GNXALIGN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gnx_ctx gnx_ctx;
+
+/* align.Cigar (align/align.go:21-24); op: 0 = ColM, 1 = ColI, 2 = ColD (align/align.go:12-18) */
+typedef struct {
+    int64_t run_length;
+    uint8_t op;
+} gnx_cigar;
+
+enum {
+    GNX_OK = 0,
+    GNX_EBASE = 1,  /* a base >= dim in a pair with n>0 and m>0: Go panics (index out of range)      */
+    GNX_ECAP = 2,   /* cigar_cap too small; out_cigar_off is still filled, see gnx_copy_last_cigars  */
+    GNX_ECHUNK = 3, /* AffineGapChunk: a length is not a multiple of chunk (Go: log.Fatalf)          */
+    GNX_EEMPTY = 4, /* low-mem entry point called with an empty sequence (reference undefined)       */
+    GNX_ECUDA = 5,  /* CUDA runtime failure, text in gnx_last_error                                  */
+    GNX_EARG = 6,   /* bad argument (NULL pointer, dim out of range, ...)                            */
+    GNX_ERANGE = 7  /* scores/penalties/lengths exceed the exact-arithmetic range of every kernel    */
+};
+
+/* mode for gnx_affine_batch */
+enum {
+    GNX_GLOBAL = 0,  /* AffineGap_highMem / AffineGap (align/affineGap_highMem.go:99, affineGap.go:59) */
+    GNX_FREE_END = 1 /* AffineGapLocal(target=alpha, query=beta) (align/affineGap_highMem.go:105)      */
+};
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int gnx_device_count(void);
+/* workspace_bytes: device memory the context may use for traceback matrices of the chunks in
+ * flight (0 = default, 1/4 of the device's free memory at creation, capped at 32 GiB). */
+gnx_ctx *gnx_create(int device, size_t workspace_bytes);
+void gnx_destroy(gnx_ctx *ctx);
+const char *gnx_last_error(gnx_ctx *ctx); /* ctx may be NULL: error of the last failed gnx_create */
+const char *gnx_version(void);
+
+/* Page-locked host buffers: inputs/outputs placed here are DMA'd without a staging copy. */
+void *gnx_host_alloc(size_t bytes);
+void gnx_host_free(void *p);
+
+/* ---- affine gap ---------------------------------------------------------------------------- *
+ * Replaces, per pair p (alpha_p, beta_p):
+ *   mode GNX_GLOBAL  : align.AffineGap_highMem(alpha, beta, scores, gapOpen, gapExtend)
+ *                      (align/affineGap_highMem.go:99-101,181-223 + affineTrace :57-89), which for
+ *                      1 <= len <= 10000 is also align.AffineGap / AffineGap_customizeCheckersize
+ *                      (align/affineGap.go:59-144; single checkerboard).
+ *   mode GNX_FREE_END: align.AffineGapLocal(target, query, ...) (align/affineGap_highMem.go:105-107)
+ *                      and each element of the GoAffineGapLocalEngine stream (:120-179).
+ * want_cigar = 0: scores only (out_cigar/out_cigar_off may be NULL).
+ * out_cigar_off has n_pairs+1 entries; pair p's cigar is out_cigar[off[p] .. off[p+1]).  If the
+ * total exceeds cigar_cap the call returns GNX_ECAP with scores and offsets filled; fetch the
+ * cigars with gnx_copy_last_cigars after growing the buffer. */
+int gnx_affine_batch(gnx_ctx *ctx, const uint8_t *alpha_cat, const int64_t *alpha_off,
+                     const uint8_t *beta_cat, const int64_t *beta_off, int64_t n_pairs,
+                     const int64_t *scores, int dim, int64_t gap_open, int64_t gap_extend, int mode,
+                     int want_cigar, int64_t *out_score, gnx_cigar *out_cigar, int64_t *out_cigar_off,
+                     int64_t cigar_cap);
+
+/* ---- constant gap ---------------------------------------------------------------------------- *
+ * Replaces align.ConstGap_highMem (align/constGap_highMem.go:11-67) and, for 1 <= len <= 10000,
+ * align.ConstGap / ConstGap_customizeCheckersize (align/constGap.go:13-124). */
+int gnx_const_batch(gnx_ctx *ctx, const uint8_t *alpha_cat, const int64_t *alpha_off,
+                    const uint8_t *beta_cat, const int64_t *beta_off, int64_t n_pairs,
+                    const int64_t *scores, int dim, int64_t gap_pen, int want_cigar,
+                    int64_t *out_score, gnx_cigar *out_cigar, int64_t *out_cigar_off, int64_t cigar_cap);
+
+/* ---- chunked affine gap ---------------------------------------------------------------------- *
+ * Replaces align.AffineGapChunk (align/affineGap_highMem.go:227-272): DP over chunk-sized blocks,
+ * match = ungappedRegionScore (align/ungapped.go:7-13), gap step = gapExtend*chunk, run lengths
+ * multiplied by chunk (expandCigarRunLength :91-95). */
+int gnx_affine_chunk_batch(gnx_ctx *ctx, const uint8_t *alpha_cat, const int64_t *alpha_off,
+                           const uint8_t *beta_cat, const int64_t *beta_off, int64_t n_pairs,
+                           const int64_t *scores, int dim, int64_t gap_open, int64_t gap_extend,
+                           int64_t chunk, int64_t *out_score, gnx_cigar *out_cigar,
+                           int64_t *out_cigar_off, int64_t cigar_cap);
+
+/* After a GNX_ECAP return: copy the retained cigars of the last batch call (total = the last
+ * entry of that call's out_cigar_off). */
+int gnx_copy_last_cigars(gnx_ctx *ctx, gnx_cigar *out_cigar, int64_t cigar_cap);
+
+/* ---- device-resident form ------------------------------------------------------------------- *
+ * Same computation with every array already in this context's device memory (pointers are device
+ * pointers; *_off_host are optional host copies of the offset arrays used for planning -- pass
+ * NULL to let the library read them back).  Work is enqueued on `cuda_stream` (a cudaStream_t;
+ * NULL = the legacy default stream) and the call returns without synchronising unless it has to
+ * read offsets back.  kind: 0 affine global, 1 affine free-end, 2 const gap (gap_open = penalty).
+ * d_out_cigar_off (n_pairs+1) and d_out_cigar (cigar_cap entries) may be NULL when want_cigar=0.
+ * d_status (one int32, may be NULL) receives a GNX_E* code discovered on the device
+ * (GNX_EBASE, GNX_ECAP). */
+int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const int64_t *d_alpha_off,
+                     const uint8_t *d_beta_cat, const int64_t *d_beta_off,
+                     const int64_t *alpha_off_host, const int64_t *beta_off_host, int64_t n_pairs,
+                     const int64_t *scores, int dim, int64_t gap_open, int64_t gap_extend,
+                     int want_cigar, int64_t *d_out_score, gnx_cigar *d_out_cigar,
+                     int64_t *d_out_cigar_off, int64_t cigar_cap, int32_t *d_status, void *cuda_stream);
+
+/* ---- introspection (used by bench.py / tests) ------------------------------------------------ */
+/* Kernel launches issued by this context since creation (every launch of a libgnxalign kernel). */
+int64_t gnx_launch_count(gnx_ctx *ctx);
+/* Device time (ms, CUDA events on the launching stream) and launches of the DP fill kernels of
+ * the last batch call; used for the roofline line of bench.py. */
+int gnx_last_fill_stats(gnx_ctx *ctx, double *fill_ms, int64_t *fill_launches, int64_t *cells);
+/* Tuning knobs (name/value), e.g. "cols_per_lane", "block_threads", "chunk_pairs". Returns GNX_EARG
+ * for an unknown name. */
+int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNXALIGN_H */

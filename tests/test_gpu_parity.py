@@ -1,0 +1,345 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference's golden
+vectors.  Bit-exact: identical int64 score and identical (RunLength, Op) sequence."""
+import numpy as np
+import pytest
+
+import oracle as orc
+from golden_util import MATRICES, bases, cigar_to_beds, load, random_pair
+from gonomics_b200 import _lib, align
+from gonomics_b200.synth import synth_pairs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = align.Context(0)
+    yield c
+    c.close()
+
+
+def concat(seqs):
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in seqs], out=off[1:])
+    cat = np.concatenate([np.asarray(s, dtype=np.uint8) for s in seqs] + [np.zeros(0, dtype=np.uint8)])
+    return cat, off
+
+
+def check_batch(ctx, alphas, betas, S, O, E, mode, want_cigar=True, threads=8):
+    """mode 0 global affine, 1 free-end affine, 2 const gap (O = penalty)."""
+    ac, ao = concat(alphas)
+    bc, bo = concat(betas)
+    if mode == 2:
+        sc, off, cig = ctx.const_gap_batch(ac, ao, bc, bo, S, O, want_cigar)
+    else:
+        sc, off, cig = ctx.affine_gap_batch(ac, ao, bc, bo, S, O, E, mode == 1, want_cigar)
+    osc, ooff, ocig = orc.batch(ac, ao, bc, bo, S, O, E, mode, want_cigar, threads)
+    bad = np.nonzero(sc != osc)[0]
+    assert len(bad) == 0, f"score mismatch at pairs {bad[:5]}: gpu {sc[bad[:5]]} oracle {osc[bad[:5]]} " \
+                          f"lens {[(len(alphas[i]), len(betas[i])) for i in bad[:5]]}"
+    if want_cigar:
+        if not (np.array_equal(off, ooff) and np.array_equal(cig["run_length"], ocig["run_length"])
+                and np.array_equal(cig["op"], ocig["op"])):
+            for p in range(len(alphas)):
+                g = [(int(r), int(o)) for r, o in cig[off[p]:off[p + 1]]]
+                w = [(int(r), int(o)) for r, o in ocig[ooff[p]:ooff[p + 1]]]
+                assert g == w, f"cigar mismatch pair {p} (n={len(alphas[p])}, m={len(betas[p])}): " \
+                               f"gpu {orc.print_cigar(g)} oracle {orc.print_cigar(w)}"
+    return sc
+
+
+# ---- the reference's golden vectors through the CUDA path ------------------------------------
+def test_golden_affine_global(ctx):
+    g = load("affine_global")
+    S = MATRICES[g["matrix"]]
+    for c in g["cases"]:
+        a, b = bases(c["alpha"]), bases(c["beta"])
+        _, cig = align.AffineGap_highMem(a, b, S, g["gap_open"], g["gap_extend"], ctx)
+        assert align.View(a, b, cig) == c["view"]
+        _, cig2 = align.AffineGap(a, b, S, g["gap_open"], g["gap_extend"], ctx)
+        _, cig3 = align.AffineGap_customizeCheckersize(a, b, S, g["gap_open"], g["gap_extend"], 3, 3, ctx)
+        assert cig2 == cig and cig3 == cig
+
+
+def test_golden_affine_local(ctx):
+    for c in load("affine_local")["cases"]:
+        score, cig = align.AffineGapLocal(bases(c["target"]), bases(c["query"]), MATRICES[c["matrix"]],
+                                          c["gap_open"], c["gap_extend"], ctx)
+        assert (score, align.PrintCigar(cig)) == (c["score"], c["cigar"])
+
+
+def test_golden_const_gap(ctx):
+    g = load("const_gap")
+    S = MATRICES[g["matrix"]]
+    for c in g["cases"]:
+        a, b = bases(c["alpha"]), bases(c["beta"])
+        _, cig = align.ConstGap(a, b, S, g["gap_pen"], ctx)
+        assert align.View(a, b, cig) == c["view"]
+    g = load("global_alignment")
+    a, b = bases(g["alpha"]), bases(g["beta"])
+    score, cig = align.ConstGap(a, b, MATRICES[g["matrix"]], g["gap_pen"], ctx)
+    assert (score, align.PrintCigar(cig), align.View(a, b, cig)) == (-730, "3M3D3M", g["view"])
+
+
+def test_golden_anchor(ctx):
+    g = load("anchor")
+    S = MATRICES[g["matrix"]]
+    for c in g["cases"]:
+        a, b = bases(c["alpha"], upper=True), bases(c["beta"], upper=True)
+        score, cig = align.AffineGap_customizeCheckersize(a, b, S, g["gap_open"], g["gap_extend"], 10000, 10000, ctx)
+        assert score == c["score"] and [list(x) for x in cig] == c["cigar"], c["region1"]
+
+
+def test_golden_cigar_to_bed_10kb(ctx):
+    g = load("cigar_to_bed")
+    S = MATRICES[g["matrix"]]
+    for c in g["cases"]:
+        a, b = bases(c["alpha"], upper=True), bases(c["beta"], upper=True)
+        score, cig = align.AffineGap(a, b, S, g["gap_open"], g["gap_extend"], ctx)
+        ins, dele = cigar_to_beds(cig, c["first_pos_ins"], c["first_pos_del"], c["chrom"])
+        assert ins == c["ins_bed"] and dele == c["del_bed"], c["files"]
+        if len(a) > 9000:
+            assert score == 790738 and len(cig) == 19
+        assert (score, [tuple(x) for x in cig]) == orc.affine_gap_highmem(a, b, S, g["gap_open"], g["gap_extend"])
+
+
+def test_engine_fifo(ctx):
+    cases = load("affine_local")["cases"][:4]
+    inputs, outputs = align.GoAffineGapLocalEngine(MATRICES["Default"], -600, -150)
+    for c in cases:  # align/affineGap_test.go:157-192: put one, get one
+        inputs.put(align.TargetQueryPair(bases(c["target"]), bases(c["query"])))
+        r = outputs.get(timeout=120)
+        assert (r.Score, align.PrintCigar(r.Cigar)) == (c["score"], c["cigar"])
+    for c in cases * 50:  # queued: results must come back in input order
+        inputs.put(align.TargetQueryPair(bases(c["target"]), bases(c["query"])))
+    for c in cases * 50:
+        r = outputs.get(timeout=120)
+        assert (r.Score, align.PrintCigar(r.Cigar)) == (c["score"], c["cigar"])
+    inputs.close()
+    assert outputs.get(timeout=120) is None
+
+
+# ---- randomised differential tests -----------------------------------------------------------
+PENALTIES = [(-400, -30), (-600, -150), (-300, -40), (-200, -50)]
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_random_short_ragged(ctx, mode):
+    rng = np.random.default_rng(100 + mode)
+    for mi, (name, S) in enumerate(MATRICES.items()):
+        O, E = PENALTIES[mi % 4]
+        al, be = [], []
+        for _ in range(600):
+            n, m = int(rng.integers(0, 90)), int(rng.integers(0, 90))
+            a, b = random_pair(rng, n, m, identity=float(rng.uniform(0.5, 1.0)))
+            al.append(a)
+            be.append(b)
+        check_batch(ctx, al, be, S, O if mode != 2 else -430, E, mode)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_random_medium_lengths(ctx, mode):
+    rng = np.random.default_rng(200 + mode)
+    S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX
+    al, be = [], []
+    for _ in range(300):
+        n, m = int(rng.integers(1, 600)), int(rng.integers(1, 600))
+        a, b = random_pair(rng, n, m, identity=float(rng.uniform(0.6, 1.0)))
+        al.append(a)
+        be.append(b)
+    for n, m in [(1, 1), (1, 400), (400, 1), (160, 160), (161, 161), (500, 150), (150, 500), (320, 320), (321, 321),
+                 (31, 5), (5, 31), (1000, 150), (33, 640), (640, 33)]:
+        a, b = random_pair(rng, n, m, identity=0.9)
+        al.append(a)
+        be.append(b)
+    check_batch(ctx, al, be, S, -600 if mode != 2 else -430, -150, mode)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_tie_heavy_inputs(ctx, mode):
+    """Homopolymers and short tandem repeats: many equal-score paths, so any deviation from the
+    M >= I >= D tie-break shows up in the cigar."""
+    rng = np.random.default_rng(300 + mode)
+    al, be = [], []
+    for _ in range(400):
+        unit = rng.integers(0, 4, int(rng.integers(1, 4)), dtype=np.uint8)
+        n, m = int(rng.integers(1, 200)), int(rng.integers(1, 200))
+        a = np.resize(unit, n).copy()
+        b = np.resize(unit, m).copy()
+        for arr in (a, b):  # a few point changes
+            k = int(rng.integers(0, 4))
+            if len(arr) and k:
+                arr[rng.integers(0, len(arr), k)] = rng.integers(0, 4, k)
+        al.append(a)
+        be.append(b)
+    for name, S in MATRICES.items():
+        for O, E in ((-400, -30), (-100, -100), (0, -50), (-91, -91)):
+            check_batch(ctx, al, be, S, O if mode != 2 else E, E, mode)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_pairs_with_N(ctx, mode):
+    rng = np.random.default_rng(400 + mode)
+    al, be = [], []
+    for k in range(300):
+        n, m = int(rng.integers(1, 300)), int(rng.integers(1, 300))
+        a, b = random_pair(rng, n, m, identity=0.85)
+        if k % 3:
+            a[rng.integers(0, n, max(1, n // 20))] = 4
+        if k % 2:
+            b[rng.integers(0, m, max(1, m // 20))] = 4
+        al.append(a)
+        be.append(b)
+    for name in ("Default", "HumanChimpTwo", "HoxD55"):
+        check_batch(ctx, al, be, MATRICES[name], -600 if mode != 2 else -430, -150, mode)
+
+
+def test_score_only_matches(ctx):
+    rng = np.random.default_rng(500)
+    al, be = [], []
+    for _ in range(500):
+        n, m = int(rng.integers(0, 400)), int(rng.integers(0, 400))
+        a, b = random_pair(rng, n, m, identity=0.9)
+        al.append(a)
+        be.append(b)
+    for mode in (0, 1, 2):
+        check_batch(ctx, al, be, orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, -600 if mode != 2 else -430, -150, mode,
+                    want_cigar=False)
+
+
+def test_long_pairs_multi_strip(ctx):
+    rng = np.random.default_rng(600)
+    al, be = [], []
+    for n, m in [(3000, 2500), (2500, 3000), (1200, 5000), (5000, 700)]:
+        a, b = random_pair(rng, n, m, identity=0.92)
+        al.append(a)
+        be.append(b)
+    for mode in (0, 1, 2):
+        check_batch(ctx, al, be, orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, -600 if mode != 2 else -430, -150, mode)
+
+
+def test_chunking_and_small_workspace():
+    """Force many chunks (tiny workspace / chunk_pairs) so chunk boundaries and slot reuse are exercised."""
+    c = align.Context(0, workspace_bytes=8 << 20)
+    try:
+        c.set_option("chunk_pairs", 37)
+        a, ao, b, bo = synth_pairs(11, 1000, 200, 80)
+        al = [a[ao[p]:ao[p + 1]] for p in range(1000)]
+        be = [b[bo[p]:bo[p + 1]] for p in range(1000)]
+        check_batch(c, al, be, orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, -600, -150, 1)
+        check_batch(c, al, be, orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, -600, -150, 0, want_cigar=False)
+    finally:
+        c.close()
+
+
+def test_cigar_cap_overflow_and_fetch(ctx):
+    a, ao, b, bo = synth_pairs(12, 500, 120, 100)
+    S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX
+    want = ctx.affine_gap_batch(a, ao, b, bo, S, -600, -150, True)
+    out_score = np.zeros(500, dtype=np.int64)
+    out_off = np.zeros(501, dtype=np.int64)
+    small = np.zeros(7, dtype=_lib.CIGAR_DTYPE)
+    with pytest.raises(_lib.GnxError) as ei:
+        ctx.affine_gap_batch(a, ao, b, bo, S, -600, -150, True, out=(out_score, out_off, small))
+    assert ei.value.code == _lib.GNX_ECAP
+    assert np.array_equal(out_score, want[0]) and np.array_equal(out_off, want[1])
+    big = np.zeros(int(out_off[-1]), dtype=_lib.CIGAR_DTYPE)
+    assert ctx._L.gnx_copy_last_cigars(ctx._h, big.ctypes.data, len(big)) == 0
+    assert np.array_equal(big["run_length"], want[2]["run_length"]) and np.array_equal(big["op"], want[2]["op"])
+
+
+def test_many_ops_overflow_slot(ctx):
+    """Cigars longer than the per-pair slot take the second traceback pass."""
+    rng = np.random.default_rng(700)
+    al, be = [], []
+    for _ in range(50):  # unrelated pairs with cheap gaps -> dozens of ops
+        al.append(rng.integers(0, 4, 300, dtype=np.uint8))
+        be.append(rng.integers(0, 4, 280, dtype=np.uint8))
+    S = orc.DEFAULT_SCORE_MATRIX
+    check_batch(ctx, al, be, S, -20, -5, 0)
+    check_batch(ctx, al, be, S, -30, 0, 2)
+
+
+def test_invalid_base_is_an_error(ctx):
+    a = np.array([0, 1, 7, 3], dtype=np.uint8)  # LowerG: Go panics with index out of range
+    b = np.array([0, 1, 2, 3], dtype=np.uint8)
+    with pytest.raises(_lib.GnxError) as ei:
+        align.AffineGap_highMem(a, b, orc.DEFAULT_SCORE_MATRIX, -400, -30, ctx)
+    assert ei.value.code == _lib.GNX_EBASE
+    # ... but not when the other side is empty (the matrix is never indexed)
+    s, c = align.AffineGap_highMem(a, np.zeros(0, dtype=np.uint8), orc.DEFAULT_SCORE_MATRIX, -400, -30, ctx)
+    assert (s, c) == (-400 - 4 * 30, [(4, 2)])
+
+
+def test_empty_inputs(ctx):
+    S = orc.DEFAULT_SCORE_MATRIX
+    e = np.zeros(0, dtype=np.uint8)
+    acg = bases("ACG")
+    assert align.AffineGap_highMem(e, e, S, -400, -30, ctx) == (0, [(0, 0)])
+    assert align.AffineGap_highMem(e, acg, S, -400, -30, ctx) == (-490, [(3, 1)])
+    assert align.AffineGap_highMem(acg, e, S, -400, -30, ctx) == (-490, [(3, 2)])
+    assert align.AffineGapLocal(acg, e, S, -400, -30, ctx) == (0, [(3, 2)])
+    assert align.ConstGap_highMem(e, e, S, -430, ctx) == (0, [(0, 0)])
+    assert align.ConstGap_highMem(e, acg, S, -430, ctx) == (-1290, [(3, 1)])
+    with pytest.raises(_lib.GnxError):
+        align.AffineGap(e, acg, S, -400, -30, ctx)
+    sc, off, cig = ctx.affine_gap_batch(e, np.zeros(1, dtype=np.int64), e, np.zeros(1, dtype=np.int64), S, -400, -30)
+    assert len(sc) == 0 and list(off) == [0]
+
+
+def test_device_resident_entry_point(ctx):
+    import torch
+    a, ao, b, bo = synth_pairs(13, 4000, 500, 150)
+    S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX
+    dev = torch.device("cuda:0")
+    ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    tao, tbo = torch.from_numpy(ao).to(dev), torch.from_numpy(bo).to(dev)
+    for kind, want_cigar in ((1, True), (1, False), (0, True), (2, True)):
+        score = torch.zeros(4000, dtype=torch.int64, device=dev)
+        off = torch.zeros(4001, dtype=torch.int64, device=dev)
+        cig = torch.zeros(4000 * 32 * 16, dtype=torch.uint8, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        ctx.batch_device(kind, ta.data_ptr(), tao.data_ptr(), tb.data_ptr(), tbo.data_ptr(), ao, bo, 4000, S, -600,
+                         -150, want_cigar, score.data_ptr(), cig.data_ptr(), off.data_ptr(), 4000 * 32,
+                         status.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert int(status.item()) == 0
+        osc, ooff, ocig = orc.batch(a, ao, b, bo, S, -600, -150, kind, want_cigar, 8)
+        assert np.array_equal(score.cpu().numpy(), osc)
+        if want_cigar:
+            assert np.array_equal(off.cpu().numpy(), ooff)
+            got = cig.cpu().numpy()[:int(ooff[-1]) * 16].view(_lib.CIGAR_DTYPE)
+            assert np.array_equal(got["run_length"], ocig["run_length"]) and np.array_equal(got["op"], ocig["op"])
+
+
+# ---- BASELINE-shaped workloads -----------------------------------------------------------------
+def test_config_c2_c3_prefix_and_properties(ctx):
+    """C2/C3 shape (target 500 x query 150, free end gaps): the first 10^4 pairs are diffed against the
+    oracle; the whole 2*10^5-pair batch is checked through size-independent properties: every cigar
+    consumes exactly n target and m query bases, score-only equals the traceback run's scores."""
+    N = 200_000
+    a, ao, b, bo = synth_pairs(20260103, N, 500, 150)
+    S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX
+    sc, off, cig = ctx.affine_gap_batch(a, ao, b, bo, S, -600, -150, True)
+    sc2, _, _ = ctx.affine_gap_batch(a, ao, b, bo, S, -600, -150, True, want_cigar=False)
+    assert np.array_equal(sc, sc2)
+    K = 10_000
+    osc, ooff, ocig = orc.batch(a[:K * 500], ao[:K + 1], b[:K * 150], bo[:K + 1], S, -600, -150, 1, True, 8)
+    assert np.array_equal(sc[:K], osc)
+    assert np.array_equal(off[:K + 1], ooff)
+    assert np.array_equal(cig["run_length"][:ooff[-1]], ocig["run_length"])
+    assert np.array_equal(cig["op"][:ooff[-1]], ocig["op"])
+    pair_of = np.repeat(np.arange(N), np.diff(off))
+    rl, op = cig["run_length"], cig["op"]
+    assert np.array_equal(np.bincount(pair_of, weights=rl * (op != 1), minlength=N).astype(np.int64), np.full(N, 500))
+    assert np.array_equal(np.bincount(pair_of, weights=rl * (op != 2), minlength=N).astype(np.int64), np.full(N, 150))
+    assert np.all(rl > 0) and np.all(op <= 2)
+    assert np.all((op[1:] != op[:-1]) | (pair_of[1:] != pair_of[:-1]))  # runs are maximal
+
+
+def test_config_c1_global_1kb(ctx):
+    a, ao, b, bo = synth_pairs(20260101, 1000, 1000, 150)
+    al = [a[ao[p]:ao[p + 1]] for p in range(1000)]
+    be = [b[bo[p]:bo[p + 1]] for p in range(1000)]
+    check_batch(ctx, al, be, orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, -600, -150, 0)
