@@ -138,11 +138,15 @@ def main():
     ap.add_argument("--no-traceback", action="store_true", help="skip the C3 (traceback) block")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: no e2e/cpu legs, warm-up not clamped")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
         return
-    args.warmup = max(args.warmup, 3)
+    if args.quick:
+        args.no_e2e = args.no_cpu = True
+    else:
+        args.warmup = max(args.warmup, 3)
 
     import torch
     import torch.distributed as dist

@@ -48,6 +48,14 @@ struct FillParams {
 
 __device__ __forceinline__ int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); } // max(a+b, c)
 __device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
+// PRMT in its default mode: selector nibble bit 3 replicates the sign of the selected byte.
+// (__byte_perm masks that bit off, so the sign-extending 16-bit table lookup needs the PTX form.)
+__device__ __forceinline__ int prmt(int a, int b, int sel)
+{
+    int d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
 
 // Number of 32-bit trace words per lane per step: 5 six-bit codes per word.
 __host__ __device__ constexpr int trace_wpl(int C) { return (C + 4) / 5; }
@@ -244,7 +252,7 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
                     for (int c = 0; c < C; ++c) {
                         int s;
                         if (LOOKUP == 0)
-                            s = (int)__byte_perm((unsigned)t01[c], (unsigned)t23[c], (unsigned)sel);
+                            s = prmt(t01[c], t23[c], sel);
                         else
                             s = s_scores[rowoff + q[c]];
                         const int Mc = hp + s; // M(r,j) = s + H(r-1,j-1)
@@ -402,7 +410,7 @@ __global__ void __launch_bounds__(128) const_fill_kernel(const FillParams P)
                     for (int c = 0; c < C; ++c) {
                         int s;
                         if (LOOKUP == 0)
-                            s = (int)__byte_perm((unsigned)t01[c], (unsigned)t23[c], (unsigned)sel);
+                            s = prmt(t01[c], t23[c], sel);
                         else
                             s = s_scores[rowoff + q[c]] + (TRACE ? 2 : 0);
                         // candidates: diag+s (tag 2 = ColM), left+g (tag 1 = ColI), up+g (tag 0 = ColD)

@@ -297,11 +297,12 @@ def test_device_resident_entry_point(ctx):
     for kind, want_cigar in ((1, True), (1, False), (0, True), (2, True)):
         score = torch.zeros(4000, dtype=torch.int64, device=dev)
         off = torch.zeros(4001, dtype=torch.int64, device=dev)
-        cig = torch.zeros(4000 * 32 * 16, dtype=torch.uint8, device=dev)
+        cap = 4000 * 700  # linear-gap global alignments of 500 vs 150 scatter their 350 deletions
+        cig = torch.zeros(cap * 16, dtype=torch.uint8, device=dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         stream = torch.cuda.current_stream().cuda_stream
         ctx.batch_device(kind, ta.data_ptr(), tao.data_ptr(), tb.data_ptr(), tbo.data_ptr(), ao, bo, 4000, S, -600,
-                         -150, want_cigar, score.data_ptr(), cig.data_ptr(), off.data_ptr(), 4000 * 32,
+                         -150, want_cigar, score.data_ptr(), cig.data_ptr(), off.data_ptr(), cap,
                          status.data_ptr(), stream)
         torch.cuda.synchronize()
         assert int(status.item()) == 0
