@@ -6,6 +6,7 @@
 // host] -> expand -> D2H, so copies of one chunk overlap the DP fill of another.
 #include "../../include/gnxalign.h"
 #include "gnx_kernels.cuh"
+#include "gnx_fill2.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -107,6 +108,9 @@ struct gnx_ctx {
     int opt_cols = 0;          // 0 = auto
     int64_t opt_chunk_pairs = 1 << 18;
     int opt_blocks_per_sm = 8;
+    int opt_fill_impl = 2;     // 1: affine_fill_kernel (v1, 4 warps/CTA), 2: affine_fill2_kernel (1 warp/CTA)
+    int opt_ctas_per_sm = 20;  // fill2 grid = SMs * this
+    int opt_force_lookup = -1; // -1 auto; 0/1 force the PRMT / shared-memory score lookup for ACGT pairs
     int sm_count = 148;
     // stats of the last batch call
     std::vector<FillEvent> fill_events;
@@ -146,6 +150,7 @@ struct Problem {
     int64_t gap_open, gap_extend;
     int h00, h00_plane;
     bool prmt_ok;  // 16-bit PRMT tables usable for ACGT-only pairs
+    bool tagged;   // run the tagged (scaled) arithmetic: traceback wanted, or score only with O > 0
 };
 
 // Exact-arithmetic range analysis for the scaled int32 kernels (DESIGN.md "Arithmetic width").
@@ -172,7 +177,8 @@ int analyse(gnx_ctx *ctx, Problem &pb, int64_t max_n, int64_t max_m)
         core = 2 * absO + len * std::max<int64_t>({absE, sabs, absO, 1});
     }
     const int64_t bound = core + 2 * (absO + absE) + sabs + 64;
-    const int64_t scale = pb.want_cigar ? (pb.kind == 2 ? 4 : kScale) : 1;
+    pb.tagged = pb.want_cigar || (pb.kind != 2 && O > 0);
+    const int64_t scale = pb.tagged ? (pb.kind == 2 ? 4 : kScale) : 1;
     if (2 * bound * scale >= (int64_t(1) << 30) || max_n >= (1 << 24) || max_m >= (1 << 24))
         return fail(ctx, GNX_ERANGE, "scores/penalties x lengths exceed the exact int32 range of the DP kernels");
     pb.prmt_ok = sabs * scale + 4 <= 32767;
@@ -233,15 +239,65 @@ void dispatch_fill_cl(const Problem &pb, const FillParams &fp, int grid, cudaStr
         else
             launch_const<C, false, LOOKUP>(fp, grid, st);
     } else if (pb.kind == 1) {
-        if (pb.want_cigar)
+        if (pb.tagged)
             launch_affine<C, true, true, LOOKUP>(fp, grid, st);
         else
             launch_affine<C, false, true, LOOKUP>(fp, grid, st);
     } else {
-        if (pb.want_cigar)
+        if (pb.tagged)
             launch_affine<C, true, false, LOOKUP>(fp, grid, st);
         else
             launch_affine<C, false, false, LOOKUP>(fp, grid, st);
+    }
+}
+
+template <int C, int LOOKUP, bool MULTI>
+void dispatch_fill2_clm(const Problem &pb, const FillParams &fp, int grid, cudaStream_t st)
+{
+    const bool store = pb.want_cigar;
+    if (pb.kind == 1) {
+        if (!pb.tagged)
+            affine_fill2_kernel<C, false, false, true, LOOKUP, MULTI><<<grid, 32, 0, st>>>(fp);
+        else if (store)
+            affine_fill2_kernel<C, true, true, true, LOOKUP, MULTI><<<grid, 32, 0, st>>>(fp);
+        else
+            affine_fill2_kernel<C, true, false, true, LOOKUP, MULTI><<<grid, 32, 0, st>>>(fp);
+    } else {
+        if (!pb.tagged)
+            affine_fill2_kernel<C, false, false, false, LOOKUP, MULTI><<<grid, 32, 0, st>>>(fp);
+        else if (store)
+            affine_fill2_kernel<C, true, true, false, LOOKUP, MULTI><<<grid, 32, 0, st>>>(fp);
+        else
+            affine_fill2_kernel<C, true, false, false, LOOKUP, MULTI><<<grid, 32, 0, st>>>(fp);
+    }
+}
+
+void dispatch_fill2(const Problem &pb, const FillParams &fp, int C, int lookup, bool multi, int grid, cudaStream_t st)
+{
+    if (C == 5) {
+        if (multi) {
+            if (lookup == 0)
+                dispatch_fill2_clm<5, 0, true>(pb, fp, grid, st);
+            else
+                dispatch_fill2_clm<5, 1, true>(pb, fp, grid, st);
+        } else {
+            if (lookup == 0)
+                dispatch_fill2_clm<5, 0, false>(pb, fp, grid, st);
+            else
+                dispatch_fill2_clm<5, 1, false>(pb, fp, grid, st);
+        }
+    } else {
+        if (multi) {
+            if (lookup == 0)
+                dispatch_fill2_clm<10, 0, true>(pb, fp, grid, st);
+            else
+                dispatch_fill2_clm<10, 1, true>(pb, fp, grid, st);
+        } else {
+            if (lookup == 0)
+                dispatch_fill2_clm<10, 0, false>(pb, fp, grid, st);
+            else
+                dispatch_fill2_clm<10, 1, false>(pb, fp, grid, st);
+        }
     }
 }
 
@@ -303,22 +359,32 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     fp.dim = pb.dim;
     for (int i = 0; i < pb.dim * pb.dim; ++i)
         fp.scores[i] = (int)pb.scores[i];
-    fp.trace = cd.trace;
+    fp.trace = pb.want_cigar ? cd.trace : nullptr; // tagged score-only runs keep the arithmetic, skip the stores
     fp.trace_off = cd.trace_off;
     fp.edge = any_long ? cd.edge : nullptr;
     fp.edge_stride = cd.edge_stride;
     fp.out_score = cd.score;
+    fp.one = 1;
 
     // class 0 (ACGT only) with the PRMT tables when the matrix fits 16 bits, else the smem lookup
     FillEvent &fe = next_fill_event(ctx);
     cudaEventRecord(fe.a, st);
+    const bool v2 = ctx->opt_fill_impl == 2 && pb.kind != 2;
+    const int lookup0 = (ctx->opt_force_lookup == 1 || !pb.prmt_ok) ? 1 : 0;
+    const int grid2 = (int)std::min<int64_t>(np, (int64_t)ctx->sm_count * ctx->opt_ctas_per_sm);
     fp.want_class = 0;
-    dispatch_fill(pb, fp, C, pb.prmt_ok ? 0 : 1, grid, st);
+    if (v2)
+        dispatch_fill2(pb, fp, C, lookup0, any_long, grid2, st);
+    else
+        dispatch_fill(pb, fp, C, lookup0, grid, st);
     ctx->launches++;
     ctx->last_fill_launches++;
     // class 1 (contains N or other bases < dim): generic lookup.  Warps skip pairs of the other class.
     fp.want_class = 1;
-    dispatch_fill(pb, fp, C, 1, grid, st);
+    if (v2)
+        dispatch_fill2(pb, fp, C, 1, any_long, grid2, st);
+    else
+        dispatch_fill(pb, fp, C, 1, grid, st);
     ctx->launches++;
     ctx->last_fill_launches++;
     cudaEventRecord(fe.b, st);
@@ -333,6 +399,7 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         tp.trace = cd.trace;
         tp.trace_off = cd.trace_off;
         tp.C = C;
+        tp.layout = (ctx->opt_fill_impl == 2 && pb.kind != 2) ? 2 : 1;
         tp.kind = pb.kind == 2 ? 2 : 0;
         tp.h00_plane = pb.h00_plane;
         tp.slots = cd.slots;
@@ -370,6 +437,7 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
     tp.trace = cd.trace;
     tp.trace_off = cd.trace_off;
     tp.C = C;
+    tp.layout = (ctx->opt_fill_impl == 2 && pb.kind != 2) ? 2 : 1;
     tp.kind = pb.kind == 2 ? 2 : 0;
     tp.h00_plane = pb.h00_plane;
     tp.slots = cd.slots;
@@ -488,7 +556,7 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
     const bool pin_score = is_pinned(out_score);
     const bool pin_off = out_cigar_off && is_pinned(out_cigar_off);
     const bool pin_cig = out_cigar && is_pinned(out_cigar);
-    const int nwarps_total = ctx->sm_count * ctx->opt_blocks_per_sm * 4;
+    const int nwarps_total = ctx->sm_count * std::max(ctx->opt_blocks_per_sm * 4, ctx->opt_ctas_per_sm);
     const int64_t edge_stride = plan.max_n + 2;
 
     const int64_t n_chunks = (int64_t)plan.bounds.size() - 1;
@@ -931,7 +999,7 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
         return rc;
     ctx->last_cells = plan.cells;
     Slot &s = ctx->slot[0];
-    const int nwarps_total = ctx->sm_count * ctx->opt_blocks_per_sm * 4;
+    const int nwarps_total = ctx->sm_count * std::max(ctx->opt_blocks_per_sm * 4, ctx->opt_ctas_per_sm);
     const int64_t edge_stride = plan.max_n + 2;
     CU(cudaMemsetAsync(ctx->status.p, 0, sizeof(int), st));
     CU(cudaMemsetAsync(ctx->dr_misc.p, 0, 8, st)); // running cigar total
@@ -1026,6 +1094,16 @@ int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
         if (value < 1 || value > 32)
             return fail(ctx, GNX_EARG, "blocks_per_sm must be in 1..32");
         ctx->opt_blocks_per_sm = (int)value;
+    } else if (k == "fill_impl") {
+        if (value != 1 && value != 2)
+            return fail(ctx, GNX_EARG, "fill_impl must be 1 or 2");
+        ctx->opt_fill_impl = (int)value;
+    } else if (k == "force_lookup") {
+        ctx->opt_force_lookup = (int)value;
+    } else if (k == "ctas_per_sm") {
+        if (value < 1 || value > 32)
+            return fail(ctx, GNX_EARG, "ctas_per_sm must be in 1..32");
+        ctx->opt_ctas_per_sm = (int)value;
     } else if (k == "workspace_bytes") {
         if (value < (1 << 20))
             return fail(ctx, GNX_EARG, "workspace_bytes must be >= 1 MiB");

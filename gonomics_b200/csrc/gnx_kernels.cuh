@@ -44,6 +44,7 @@ struct FillParams {
     int2 *edge;                   // per-warp strip hand-off buffers: 2 * edge_stride int2 per warp
     int64_t edge_stride;
     int64_t *out_score;           // indexed by global pair id
+    int one;                      // always 1: an opaque multiplier that keeps adds on the FMA pipe (IMAD)
 };
 
 __device__ __forceinline__ int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); } // max(a+b, c)
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
         const int T = n + 31; // steps per strip
         const int strips = (m + 32 * C - 1) / (32 * C);
         uint32_t *tbase = nullptr;
-        if (TRACE)
+        if (TRACE && P.trace)
             tbase = P.trace + P.trace_off[pair - P.pair_begin];
 
         for (int p = 0; p < strips; ++p) {
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
             int edgeI = 0, edgeH = 0;                                   // what lane+1 consumes
             const int2 *ein = (p & 1) ? edge_b : edge_a;                // written by strip p-1
             int2 *eout = (p & 1) ? edge_a : edge_b;
-            uint32_t *tp = TRACE ? tbase + ((size_t)p * T * WPL) * 32 + lane : nullptr;
+            uint32_t *tp = (TRACE && tbase) ? tbase + ((size_t)p * T * WPL) * 32 + lane : nullptr;
 
             // lane 0 boundary stream for its next row (column jbase): I'(r, jbase+1) and H(r, jbase)
             int bI = 0, bH = 0;
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
                     edgeI = It;
                     edgeH = Hc[C - 1];
                     hpL = inH;
-                    if (TRACE) {
+                    if (TRACE && tp) {
 #pragma unroll
                         for (int k = 0; k < WPL; ++k)
                             tp[(size_t)k * 32] = w[k];
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
                     if (lane == 31 && p + 1 < strips)
                         eout[r] = make_int2(edgeI, edgeH);
                 }
-                if (TRACE)
+                if (TRACE && tp)
                     tp += WPL * 32;
             }
             // ---- score: H(n, m) sits in Hc[] of the lane that owns column m ----------------------
@@ -463,6 +464,7 @@ struct TraceParams {
     const uint32_t *trace;
     const int64_t *trace_off;
     int C;          // columns per lane the fill kernel used
+    int layout;     // 1: affine_fill_kernel word layout, 2: affine_fill2_kernel (gnx_fill2.cuh)
     int kind;       // 0 affine, 2 const gap
     int h00_plane;  // plane of T(0, O, D(0,0)) (affine)
     uint32_t *slots; // per pair in chunk: slot_cap entries, run<<2 | op, traceback order
@@ -480,7 +482,7 @@ struct CigarOut {
     unsigned char op;
 };
 
-__device__ __forceinline__ unsigned affine_code(const uint32_t *tr, int T, int C, int i, int j)
+__device__ __forceinline__ unsigned affine_code(const uint32_t *tr, int T, int C, int i, int j, int layout = 1)
 {
     const int wpl = trace_wpl(C);
     const int jj = j - 1;
@@ -490,6 +492,8 @@ __device__ __forceinline__ unsigned affine_code(const uint32_t *tr, int T, int C
     const int t = (i - 1) + lane;
     const int nin = (c / 5 == wpl - 1) ? (C - 5 * (wpl - 1)) : 5; // codes held by this word
     const uint32_t w = tr[(((size_t)strip * T + t) * wpl + c / 5) * 32 + lane];
+    if (layout == 2) // codes funnel-shifted in from the top (gnx_fill2.cuh)
+        return (w >> (32 - kTagBits * (nin - (c % 5)))) & (kScale - 1);
     return (w >> (kTagBits * (nin - 1 - (c % 5)))) & (kScale - 1);
 }
 
@@ -555,7 +559,7 @@ __global__ void traceback_kernel(const TraceParams P)
         else if (m == 0)
             k = 2;
         else
-            k = 2 - (int)((affine_code(tr, T, C, n, m) >> 4) & 3u);
+            k = 2 - (int)((affine_code(tr, T, C, n, m, P.layout) >> 4) & 3u);
         while (i > 0 || j > 0) {
             if (k == cur) {
                 ++run;
@@ -581,12 +585,12 @@ __global__ void traceback_kernel(const TraceParams P)
                 else if (j == 0)
                     k = 2;
                 else
-                    k = 2 - (int)((affine_code(tr, T, C, i, j) >> 4) & 3u);
+                    k = 2 - (int)((affine_code(tr, T, C, i, j, P.layout) >> 4) & 3u);
             } else if (k == 1) {
-                k = 2 - (int)(affine_code(tr, T, C, i, j) & 3u);
+                k = 2 - (int)(affine_code(tr, T, C, i, j, P.layout) & 3u);
                 --j;
             } else {
-                k = 2 - (int)((affine_code(tr, T, C, i, j) >> 2) & 3u);
+                k = 2 - (int)((affine_code(tr, T, C, i, j, P.layout) >> 2) & 3u);
                 --i;
             }
         }
