@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgnxalign.so")
 SOURCES = ["gnx_api.cu"]
-DEPS = ["gnx_api.cu", "gnx_kernels.cuh", os.path.join("..", "..", "include", "gnxalign.h")]
+DEPS = ["gnx_api.cu", "gnx_kernels.cuh", "gnx_fill2.cuh", "gnx_fill3.cuh", os.path.join("..", "..", "include", "gnxalign.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math", "-Xcompiler", "-fPIC,-O2,-Wall", "-shared", "-cudart", "shared"]
 
@@ -31,7 +31,8 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
-    cmd = [nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+    extra = os.environ.get("GNX_NVCC_EXTRA", "").split()
+    cmd = [nvcc(), *NVCC_FLAGS, *extra, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

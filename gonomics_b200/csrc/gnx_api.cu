@@ -7,6 +7,7 @@
 #include "../../include/gnxalign.h"
 #include "gnx_kernels.cuh"
 #include "gnx_fill2.cuh"
+#include "gnx_fill3.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -108,8 +109,10 @@ struct gnx_ctx {
     int opt_cols = 0;          // 0 = auto
     int64_t opt_chunk_pairs = 1 << 18;
     int opt_blocks_per_sm = 8;
-    int opt_fill_impl = 2;     // 1: affine_fill_kernel (v1, 4 warps/CTA), 2: affine_fill2_kernel (1 warp/CTA)
-    int opt_ctas_per_sm = 20;  // fill2 grid = SMs * this
+    int opt_fill_impl = 3;     // 1: affine_fill_kernel (v1, 4 warps/CTA), 2: affine_fill2_kernel, 3: affine_fill3_kernel
+    int opt_lpp = 0;           // fill3 lanes per pair: 0 auto, 16 or 32
+    int opt_skew = 1;          // fill3 row skew between lanes (1 or 2; 2 measured no faster, kept as an option)
+    int opt_ctas_per_sm = 32;  // fill2/3 persistent grid = SMs * min(this, occupancy)
     int opt_force_lookup = -1; // -1 auto; 0/1 force the PRMT / shared-memory score lookup for ACGT pairs
     int sm_count = 148;
     // stats of the last batch call
@@ -142,7 +145,16 @@ int fail(gnx_ctx *ctx, int code, const char *msg)
     return code;
 }
 
+struct FillCfg {
+    int impl = 1; // 1 affine_fill_kernel / const_fill_kernel, 2 affine_fill2_kernel, 3 affine_fill3_kernel
+    int C = 5;    // columns per lane
+    int lpp = 32; // lanes per pair
+    int skew = 1; // rows between neighbouring lanes (fill3: 2)
+    bool multi = false; // some pair needs more than one strip
+};
+
 struct Problem {
+    FillCfg cfg;
     int kind; // 0 affine global, 1 affine free-end, 2 const gap
     int want_cigar;
     int dim;
@@ -197,16 +209,78 @@ int analyse(gnx_ctx *ctx, Problem &pb, int64_t max_n, int64_t max_m)
     return GNX_OK;
 }
 
-int pick_cols(const gnx_ctx *ctx, int64_t max_m)
+void pick_cfg(const gnx_ctx *ctx, Problem &pb, int64_t max_m, int64_t max_n)
 {
-    if (ctx->opt_cols == 5 || ctx->opt_cols == 10)
-        return ctx->opt_cols;
-    return (max_m <= 160) ? 5 : 10;
+    FillCfg &c = pb.cfg;
+    c.impl = pb.kind == 2 ? 1 : ctx->opt_fill_impl;
+    if (c.impl == 3 && pb.dim > kDimP)
+        c.impl = 2;
+    c.lpp = 32;
+    c.skew = c.impl == 3 ? ctx->opt_skew : 1;
+    if (c.impl == 3) {
+        c.C = ctx->opt_cols == 5 ? 5 : 10;
+        if (c.C == 10 && ctx->opt_lpp != 32 && max_m <= 16 * c.C)
+            c.lpp = 16;
+        if (c.C == 5 && max_m > 32 * c.C)
+            c.C = 10;
+    } else {
+        c.C = (ctx->opt_cols == 5 || ctx->opt_cols == 10) ? ctx->opt_cols : (max_m <= 160 ? 5 : 10);
+    }
+    c.multi = max_m > (int64_t)c.lpp * c.C;
+    if (c.impl == 3 && max_n > kRing) { // single-strip fill3 kernels stage the target in shared memory
+        c.multi = true;
+        c.lpp = 32;
+        c.C = 10;
+    }
 }
 
-inline int64_t pair_trace_words(const Problem &pb, int64_t n, int64_t m, int C)
+
+// Trace words of one group of pairs that share 128-byte trace rows (1 pair, or 2 with lpp == 16);
+// n_eff is the largest row count among the group's non-empty pairs.
+inline int64_t group_trace_words(const Problem &pb, int64_t n_eff, int64_t m)
 {
-    return pb.kind == 2 ? const_trace_words(n, m, C) : trace_words(n, m, C);
+    if (n_eff <= 0 || m <= 0)
+        return 0;
+    const FillCfg &c = pb.cfg;
+    if (pb.kind == 2)
+        return const_trace_words(n_eff, m, c.C);
+    const int64_t strips = (m + (int64_t)c.lpp * c.C - 1) / ((int64_t)c.lpp * c.C);
+    return strips * (n_eff + c.skew * (c.lpp - 1)) * trace_wpl(c.C) * 32;
+}
+
+// Per-pair trace offsets (32-bit words) of chunk [begin, begin+np); returns the chunk's total words.
+int64_t compute_trace_offsets(const Problem &pb, const int64_t *aoff, const int64_t *boff, int64_t begin, int64_t np,
+                              int64_t *to)
+{
+    int64_t acc = 0;
+    auto len = [&](int64_t k, int64_t &n, int64_t &m) {
+        n = aoff[begin + k + 1] - aoff[begin + k];
+        m = boff[begin + k + 1] - boff[begin + k];
+        if (n == 0 || m == 0)
+            n = 0;
+    };
+    if (pb.cfg.lpp == 16) {
+        for (int64_t k = 0; k < np; k += 2) {
+            int64_t n0, m0, n1 = 0, m1 = 0;
+            len(k, n0, m0);
+            if (k + 1 < np)
+                len(k + 1, n1, m1);
+            to[k] = acc;
+            if (k + 1 < np)
+                to[k + 1] = acc + 16;
+            acc += group_trace_words(pb, std::max(n0, n1), std::max(m0, m1));
+        }
+    } else {
+        for (int64_t k = 0; k < np; ++k) {
+            int64_t n, m;
+            len(k, n, m);
+            to[k] = acc;
+            acc += group_trace_words(pb, n, m);
+        }
+    }
+    if (to)
+        to[np] = acc;
+    return acc;
 }
 
 FillEvent &next_fill_event(gnx_ctx *ctx)
@@ -301,6 +375,66 @@ void dispatch_fill2(const Problem &pb, const FillParams &fp, int C, int lookup, 
     }
 }
 
+// Persistent grid: every CTA must be resident at once (pairs are statically strided over CTAs), so the grid
+// is SMs x min(requested CTAs/SM, what the kernel's registers/shared memory allow).
+template <int C, int LPP, int MODE, bool FREE, bool MULTI, int SK>
+void launch_fill3_sk(const FillParams &fp, int64_t groups, int sm_count, int ctas_per_sm, cudaStream_t st)
+{
+    static int occ = 0; // per instantiation
+    if (occ == 0) {
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_fill3_kernel<C, LPP, MODE, FREE, MULTI, SK>, 32,
+                                                          0) != cudaSuccess || o < 1)
+            o = 8;
+        occ = o;
+    }
+    const int grid = (int)std::min<int64_t>(groups, (int64_t)sm_count * std::min(occ, ctas_per_sm));
+    affine_fill3_kernel<C, LPP, MODE, FREE, MULTI, SK><<<grid, 32, 0, st>>>(fp);
+}
+
+template <int C, int LPP, int MODE, bool FREE, bool MULTI>
+void launch_fill3(const FillParams &fp, int64_t groups, int sm_count, int ctas_per_sm, cudaStream_t st, int skew)
+{
+    if (skew == 2)
+        launch_fill3_sk<C, LPP, MODE, FREE, MULTI, 2>(fp, groups, sm_count, ctas_per_sm, st);
+    else
+        launch_fill3_sk<C, LPP, MODE, FREE, MULTI, 1>(fp, groups, sm_count, ctas_per_sm, st);
+}
+
+template <int C, int LPP, bool MULTI>
+void dispatch_fill3_t(const Problem &pb, const FillParams &fp, int64_t groups, int sms, int cps, cudaStream_t st)
+{
+    const int mode = !pb.tagged ? 0 : (pb.want_cigar ? 2 : 1);
+    if (pb.kind == 1) {
+        if (mode == 0)
+            launch_fill3<C, LPP, 0, true, MULTI>(fp, groups, sms, cps, st, pb.cfg.skew);
+        else if (mode == 1)
+            launch_fill3<C, LPP, 1, true, MULTI>(fp, groups, sms, cps, st, pb.cfg.skew);
+        else
+            launch_fill3<C, LPP, 2, true, MULTI>(fp, groups, sms, cps, st, pb.cfg.skew);
+    } else {
+        if (mode == 0)
+            launch_fill3<C, LPP, 0, false, MULTI>(fp, groups, sms, cps, st, pb.cfg.skew);
+        else if (mode == 1)
+            launch_fill3<C, LPP, 1, false, MULTI>(fp, groups, sms, cps, st, pb.cfg.skew);
+        else
+            launch_fill3<C, LPP, 2, false, MULTI>(fp, groups, sms, cps, st, pb.cfg.skew);
+    }
+}
+
+void dispatch_fill3(const Problem &pb, const FillParams &fp, int64_t groups, int sms, int cps, cudaStream_t st)
+{
+    const FillCfg &c = pb.cfg;
+    if (c.C == 5)
+        dispatch_fill3_t<5, 32, false>(pb, fp, groups, sms, cps, st);
+    else if (c.lpp == 16)
+        dispatch_fill3_t<10, 16, false>(pb, fp, groups, sms, cps, st);
+    else if (c.multi)
+        dispatch_fill3_t<10, 32, true>(pb, fp, groups, sms, cps, st);
+    else
+        dispatch_fill3_t<10, 32, false>(pb, fp, groups, sms, cps, st);
+}
+
 void dispatch_fill(const Problem &pb, const FillParams &fp, int C, int lookup, int grid, cudaStream_t st)
 {
     if (C == 5) {
@@ -331,9 +465,11 @@ struct ChunkDev {
 };
 
 // classify + fill (+ traceback pass 0) for chunk [begin, end) on stream st.
-int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, int64_t begin, int64_t end, int C,
-                          bool any_long, cudaStream_t st)
+int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, int64_t begin, int64_t end,
+                          cudaStream_t st)
 {
+    const int C = pb.cfg.C;
+    const bool any_long = pb.cfg.multi;
     const int64_t np = end - begin;
     if (np <= 0)
         return GNX_OK;
@@ -369,24 +505,32 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     // class 0 (ACGT only) with the PRMT tables when the matrix fits 16 bits, else the smem lookup
     FillEvent &fe = next_fill_event(ctx);
     cudaEventRecord(fe.a, st);
-    const bool v2 = ctx->opt_fill_impl == 2 && pb.kind != 2;
     const int lookup0 = (ctx->opt_force_lookup == 1 || !pb.prmt_ok) ? 1 : 0;
-    const int grid2 = (int)std::min<int64_t>(np, (int64_t)ctx->sm_count * ctx->opt_ctas_per_sm);
-    fp.want_class = 0;
-    if (v2)
-        dispatch_fill2(pb, fp, C, lookup0, any_long, grid2, st);
-    else
-        dispatch_fill(pb, fp, C, lookup0, grid, st);
-    ctx->launches++;
-    ctx->last_fill_launches++;
-    // class 1 (contains N or other bases < dim): generic lookup.  Warps skip pairs of the other class.
-    fp.want_class = 1;
-    if (v2)
-        dispatch_fill2(pb, fp, C, 1, any_long, grid2, st);
-    else
-        dispatch_fill(pb, fp, C, 1, grid, st);
-    ctx->launches++;
-    ctx->last_fill_launches++;
+    const int grid2 = (int)std::min<int64_t>(np, (int64_t)ctx->sm_count * std::min(ctx->opt_ctas_per_sm, 20));
+    if (pb.cfg.impl == 3) {
+        // one launch: the per-lane score tables cover every base < dim, so there is no class split
+        const int64_t groups = (np + (32 / pb.cfg.lpp) - 1) / (32 / pb.cfg.lpp);
+        dispatch_fill3(pb, fp, groups, ctx->sm_count, ctx->opt_ctas_per_sm, st);
+        ctx->launches++;
+        ctx->last_fill_launches++;
+    } else {
+        const bool v2 = pb.cfg.impl == 2;
+        fp.want_class = 0;
+        if (v2)
+            dispatch_fill2(pb, fp, C, lookup0, any_long, grid2, st);
+        else
+            dispatch_fill(pb, fp, C, lookup0, grid, st);
+        ctx->launches++;
+        ctx->last_fill_launches++;
+        // class 1 (contains N or other bases < dim): generic lookup.  Warps skip pairs of the other class.
+        fp.want_class = 1;
+        if (v2)
+            dispatch_fill2(pb, fp, C, 1, any_long, grid2, st);
+        else
+            dispatch_fill(pb, fp, C, 1, grid, st);
+        ctx->launches++;
+        ctx->last_fill_launches++;
+    }
     cudaEventRecord(fe.b, st);
 
     if (pb.want_cigar) {
@@ -399,7 +543,9 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         tp.trace = cd.trace;
         tp.trace_off = cd.trace_off;
         tp.C = C;
-        tp.layout = (ctx->opt_fill_impl == 2 && pb.kind != 2) ? 2 : 1;
+        tp.layout = pb.cfg.impl >= 2 ? 2 : 1;
+        tp.lpp = pb.cfg.lpp;
+        tp.skew = pb.cfg.skew;
         tp.kind = pb.kind == 2 ? 2 : 0;
         tp.h00_plane = pb.h00_plane;
         tp.slots = cd.slots;
@@ -418,9 +564,10 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
 }
 
 // expand slots (+ overflow traceback pass) into cigars[] at cig_off (chunk-local offsets) .
-int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, int64_t begin, int64_t end, int C,
+int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, int64_t begin, int64_t end,
                          const int64_t *cig_off, gnx_cigar *cigars, int64_t cap, cudaStream_t st)
 {
+    const int C = pb.cfg.C;
     const int64_t np = end - begin;
     if (np <= 0)
         return GNX_OK;
@@ -437,7 +584,9 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
     tp.trace = cd.trace;
     tp.trace_off = cd.trace_off;
     tp.C = C;
-    tp.layout = (ctx->opt_fill_impl == 2 && pb.kind != 2) ? 2 : 1;
+    tp.layout = pb.cfg.impl >= 2 ? 2 : 1;
+    tp.lpp = pb.cfg.lpp;
+    tp.skew = pb.cfg.skew;
     tp.kind = pb.kind == 2 ? 2 : 0;
     tp.h00_plane = pb.h00_plane;
     tp.slots = cd.slots;
@@ -465,8 +614,8 @@ struct Plan {
     bool any_long = false;            // some pair needs more than one strip
 };
 
-int make_plan(gnx_ctx *ctx, const Problem &pb, const int64_t *aoff, const int64_t *boff, int64_t n_pairs,
-              int64_t budget_words, int &C, Plan &plan)
+int make_plan(gnx_ctx *ctx, Problem &pb, const int64_t *aoff, const int64_t *boff, int64_t n_pairs,
+              int64_t budget_words, Plan &plan)
 {
     for (int64_t p = 0; p < n_pairs; ++p) {
         const int64_t n = aoff[p + 1] - aoff[p], m = boff[p + 1] - boff[p];
@@ -476,22 +625,35 @@ int make_plan(gnx_ctx *ctx, const Problem &pb, const int64_t *aoff, const int64_
         plan.max_m = std::max(plan.max_m, m);
         plan.cells += n * m;
     }
-    C = pick_cols(ctx, plan.max_m);
-    plan.any_long = plan.max_m > 32 * C;
+    pick_cfg(ctx, pb, plan.max_m, plan.max_n);
+    plan.any_long = pb.cfg.multi;
     plan.bounds.push_back(0);
-    int64_t words = 0, count = 0;
+    // exact accounting of the trace words of the chunk being grown (groups of 32/lpp pairs share rows)
+    int64_t words = 0, count = 0, prev_n = 0, prev_m = 0;
     for (int64_t p = 0; p < n_pairs; ++p) {
-        const int64_t w =
-            pb.want_cigar ? pair_trace_words(pb, aoff[p + 1] - aoff[p], boff[p + 1] - boff[p], C) : 0;
+        int64_t n = aoff[p + 1] - aoff[p], m = boff[p + 1] - boff[p];
+        if (n == 0 || m == 0)
+            n = 0;
+        int64_t w = 0;
+        if (pb.want_cigar) {
+            if (pb.cfg.lpp == 16 && (count & 1)) // second pair of a group: the group grows to the larger one
+                w = group_trace_words(pb, std::max(n, prev_n), std::max(m, prev_m)) -
+                    group_trace_words(pb, prev_n, prev_m);
+            else
+                w = group_trace_words(pb, n, m);
+        }
         if (w > budget_words)
             return fail(ctx, GNX_ERANGE, "one pair's traceback matrix exceeds the context workspace");
         if (count > 0 && (words + w > budget_words || count >= ctx->opt_chunk_pairs)) {
             plan.bounds.push_back(p);
             words = 0;
             count = 0;
+            w = pb.want_cigar ? group_trace_words(pb, n, m) : 0;
         }
         words += w;
         ++count;
+        prev_n = n;
+        prev_m = m;
     }
     plan.bounds.push_back(n_pairs);
     return GNX_OK;
@@ -539,9 +701,8 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
         return GNX_OK;
     }
     Plan plan;
-    int C = 5;
     const int64_t budget_words = (int64_t)(ctx->workspace / kSlots / 4);
-    int rc = make_plan(ctx, pb, aoff, boff, n_pairs, budget_words, C, plan);
+    int rc = make_plan(ctx, pb, aoff, boff, n_pairs, budget_words, plan);
     if (rc != GNX_OK)
         return rc;
     rc = analyse(ctx, pb, plan.max_n, plan.max_m);
@@ -578,7 +739,7 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
             CU(cudaEventSynchronize(s.ev_total));
             total = *s.h_total.as<int64_t>();
             CU(s.cigars.ensure((size_t)std::max<int64_t>(total, 1) * sizeof(gnx_cigar)));
-            rc = enqueue_chunk_expand(ctx, pb, pd.cd, pd.begin, pd.end, C, s.cig_off.as<int64_t>(),
+            rc = enqueue_chunk_expand(ctx, pb, pd.cd, pd.begin, pd.end, s.cig_off.as<int64_t>(),
                                       s.cigars.as<gnx_cigar>(), total, s.stream);
             if (rc != GNX_OK)
                 return rc;
@@ -691,13 +852,7 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
         if (pb.want_cigar) {
             CU(s.h_trace_off.ensure((size_t)(np + 1) * 8));
             int64_t *to = s.h_trace_off.as<int64_t>();
-            int64_t acc = 0;
-            for (int64_t k = 0; k < np; ++k) {
-                to[k] = acc;
-                acc += pair_trace_words(pb, aoff[begin + k + 1] - aoff[begin + k],
-                                        boff[begin + k + 1] - boff[begin + k], C);
-            }
-            to[np] = acc;
+            const int64_t acc = compute_trace_offsets(pb, aoff, boff, begin, np, to);
             CU(s.trace.ensure((size_t)std::max<int64_t>(acc, 1) * 4));
             CU(s.trace_off.ensure((size_t)(np + 1) * 8));
             CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
@@ -714,7 +869,7 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
             cd.edge = s.edge.as<int2>();
             cd.edge_stride = edge_stride;
         }
-        rc = enqueue_chunk_compute(ctx, pb, cd, begin, end, C, plan.any_long, s.stream);
+        rc = enqueue_chunk_compute(ctx, pb, cd, begin, end, s.stream);
         if (rc != GNX_OK)
             return rc;
         if (pb.want_cigar) {
@@ -989,9 +1144,8 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
     if (!ha.empty() || !hb.empty())
         CU(cudaStreamSynchronize(st));
     Plan plan;
-    int C = 5;
     const int64_t budget_words = (int64_t)(ctx->workspace / 4); // single slot: chunks run back to back
-    rc = make_plan(ctx, pb, alpha_off_host, beta_off_host, n_pairs, budget_words, C, plan);
+    rc = make_plan(ctx, pb, alpha_off_host, beta_off_host, n_pairs, budget_words, plan);
     if (rc != GNX_OK)
         return rc;
     rc = analyse(ctx, pb, plan.max_n, plan.max_m);
@@ -1021,13 +1175,7 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
                 CU(cudaEventSynchronize(s.ev_done));
             CU(s.h_trace_off.ensure((size_t)(np + 1) * 8));
             int64_t *to = s.h_trace_off.as<int64_t>();
-            int64_t acc = 0;
-            for (int64_t k = 0; k < np; ++k) {
-                to[k] = acc;
-                acc += pair_trace_words(pb, alpha_off_host[begin + k + 1] - alpha_off_host[begin + k],
-                                        beta_off_host[begin + k + 1] - beta_off_host[begin + k], C);
-            }
-            to[np] = acc;
+            const int64_t acc = compute_trace_offsets(pb, alpha_off_host, beta_off_host, begin, np, to);
             CU(s.trace.ensure((size_t)std::max<int64_t>(acc, 1) * 4));
             CU(s.trace_off.ensure((size_t)(np + 1) * 8));
             CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -1044,13 +1192,13 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
             cd.edge = s.edge.as<int2>();
             cd.edge_stride = edge_stride;
         }
-        rc = enqueue_chunk_compute(ctx, pb, cd, begin, end, C, plan.any_long, st);
+        rc = enqueue_chunk_compute(ctx, pb, cd, begin, end, st);
         if (rc != GNX_OK)
             return rc;
         if (pb.want_cigar) {
             scan_counts_kernel<<<1, 1024, 0, st>>>(cd.counts, np, d_out_cigar_off + begin, ctx->dr_misc.as<int64_t>());
             ctx->launches++;
-            rc = enqueue_chunk_expand(ctx, pb, cd, begin, end, C, d_out_cigar_off + begin, d_out_cigar, cigar_cap, st);
+            rc = enqueue_chunk_expand(ctx, pb, cd, begin, end, d_out_cigar_off + begin, d_out_cigar, cigar_cap, st);
             if (rc != GNX_OK)
                 return rc;
         }
@@ -1095,9 +1243,17 @@ int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
             return fail(ctx, GNX_EARG, "blocks_per_sm must be in 1..32");
         ctx->opt_blocks_per_sm = (int)value;
     } else if (k == "fill_impl") {
-        if (value != 1 && value != 2)
-            return fail(ctx, GNX_EARG, "fill_impl must be 1 or 2");
+        if (value < 1 || value > 3)
+            return fail(ctx, GNX_EARG, "fill_impl must be 1, 2 or 3");
         ctx->opt_fill_impl = (int)value;
+    } else if (k == "lanes_per_pair") {
+        if (value != 0 && value != 16 && value != 32)
+            return fail(ctx, GNX_EARG, "lanes_per_pair must be 0 (auto), 16 or 32");
+        ctx->opt_lpp = (int)value;
+    } else if (k == "skew") {
+        if (value != 1 && value != 2)
+            return fail(ctx, GNX_EARG, "skew must be 1 or 2");
+        ctx->opt_skew = (int)value;
     } else if (k == "force_lookup") {
         ctx->opt_force_lookup = (int)value;
     } else if (k == "ctas_per_sm") {

@@ -1,0 +1,288 @@
+// gnx_fill3.cuh -- third-generation affine fill kernel.  Same recurrence, tie-break and 6-bit trace
+// codes as fill2 (gnx_fill2.cuh); what is new:
+//   * LPP lanes per pair (32 or 16).  With LPP = 16 a warp carries two pairs side by side (lanes 0-15 and
+//     16-31), each lane owning C = 10 columns: a 150-column read fills 15 of 16 lanes, the row skew is
+//     15 steps instead of 31, and the per-step overhead (shuffles, base fetch, loop control, stores) is
+//     paid once per 10 cells instead of once per 5.
+//   * substitution scores come from a per-lane shared-memory table laid out [column][base][thread], read
+//     with one LDS per cell at an immediate offset from a per-step base register (bank = thread, so
+//     conflict-free).  The lookup therefore costs no ALU- or FMA-pipe slot (the PRMT of fill2 was an
+//     ALU op) and handles N (dim 5) in the same kernel -- no ACGT/N class split.
+#pragma once
+#include "gnx_fill2.cuh"
+
+namespace gnx {
+
+#ifndef GNX_FILL3_MINB
+#define GNX_FILL3_MINB 12
+#endif
+#ifndef GNX_F3_STAGE
+#define GNX_F3_STAGE 1
+#endif
+#ifndef GNX_F3_UNROLL_TRACE
+#define GNX_F3_UNROLL_TRACE 1
+#endif
+#ifndef GNX_F3_UNROLL_SCORE
+#define GNX_F3_UNROLL_SCORE 4
+#endif
+
+template <int C, int LPP>
+__host__ __device__ inline int64_t trace_words3(int64_t n_max_of_group, int64_t m)
+{
+    if (n_max_of_group <= 0 || m <= 0)
+        return 0;
+    const int64_t strips = (m + LPP * C - 1) / (LPP * C);
+    return strips * (n_max_of_group + LPP - 1) * trace_wpl(C) * 32;
+}
+
+constexpr int kDimP = 5; // rows of the per-lane score table (bases 0..4); matrices with dim > 5 use fill2
+constexpr int kUnrollTrace = GNX_F3_UNROLL_TRACE, kUnrollScore = GNX_F3_UNROLL_SCORE;
+constexpr int kRing = 1024; // single-strip kernels stage the whole target (alpha) in shared memory: n <= kRing
+// MODE 0: score only (untagged, needs O <= 0)   1: tagged arithmetic, no stores   2: tagged + trace stores
+// SK   row skew between neighbouring lanes.  With SK = 2 lane l is two rows behind lane l-1, so the edge
+//      values a step consumes were produced two steps earlier: the shuffles of consecutive steps no
+//      longer serialise them and the (unrolled-by-2) steady loop overlaps the I-plane dependency chains
+//      of two rows (ncu: the SK = 1 kernels sat in fixed-latency `wait` stalls with 1.3 eligible warps).
+template <int C, int LPP, int MODE, bool FREE, bool MULTI, int SK>
+__global__ void __launch_bounds__(32, (C == 5 ? 20 : GNX_FILL3_MINB)) affine_fill3_kernel(const FillParams P)
+{
+    constexpr bool TRACE = MODE >= 1, STORE = MODE == 2;
+    constexpr int G = 32 / LPP;
+    constexpr int SC = TRACE ? kScale : 1;
+    constexpr int FI = TRACE ? kFI : 0, FD = TRACE ? kFD : 0, FH = TRACE ? kFH : 0;
+    constexpr int WPL = trace_wpl(C);
+    constexpr int NEG = kNeg32;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int CLR = ~(kScale - 1);
+    static_assert(!(MULTI && LPP != 32), "multi-strip pairs use one pair per warp");
+
+    __shared__ int s_tab[C * kDimP * 32]; // [c][a][thread]
+    // !MULTI: the pair's target bases, staged once per pair (one coalesced pass) so that the per-step base
+    // fetch is an LDS that never waits on L2/HBM; MULTI (long sequences) streams them with LDG instead.
+    constexpr bool STAGE = !MULTI && GNX_F3_STAGE;
+    constexpr int kTgtPitch = kRing + 64; // +64 B: the two pairs' rows land in different banks
+    __shared__ uint8_t s_tgt[STAGE ? G * kTgtPitch : 4];
+    const int tid = threadIdx.x;
+    const int lane = tid % LPP, half = tid / LPP;
+    const int one = P.one;
+    const int O = P.gap_open, E = P.gap_extend;
+    const int oe_s = (O + E) * SC, e_s = E * SC;
+    const int kI = oe_s + 2 * FI - 2 * FH;
+    const int iI = e_s + FI, iD = oe_s;
+    const int dMn = oe_s + 2 * FD - 2 * FH, dIn = oe_s + FD - FH, dDn = e_s;
+    const int dMl = 2 * FD - 2 * FH, dIl = FD - FH, dDl = 0;
+    const int fh_reg = FH * one;
+
+    int2 *edge_a = MULTI ? P.edge + (size_t)blockIdx.x * 2 * P.edge_stride : nullptr;
+    int2 *edge_b = MULTI ? edge_a + P.edge_stride : nullptr;
+    const int64_t n_groups = (P.pair_end - P.pair_begin + G - 1) / G;
+
+    for (int64_t group = blockIdx.x; group < n_groups; group += gridDim.x) {
+        const int64_t pair = P.pair_begin + group * G + half;
+        int n = 0, m = 0;
+        const uint8_t *__restrict__ alpha = P.alpha;
+        const uint8_t *__restrict__ beta = P.beta;
+        bool mine = pair < P.pair_end && (!P.pair_class || P.pair_class[pair] <= 1);
+        if (mine) {
+            const int64_t a0 = P.alpha_off[pair], b0 = P.beta_off[pair];
+            n = (int)(P.alpha_off[pair + 1] - a0);
+            m = (int)(P.beta_off[pair + 1] - b0);
+            alpha += a0;
+            beta += b0;
+            if (n == 0 || m == 0) { // closed forms of the boundary row / column
+                if (lane == 0) {
+                    int64_t sc;
+                    if (n == 0 && m == 0)
+                        sc = P.h00;
+                    else if (n == 0)
+                        sc = (int64_t)O + (int64_t)m * E;
+                    else
+                        sc = FREE ? 0 : (int64_t)O + (int64_t)n * E;
+                    P.out_score[pair] = sc;
+                }
+                mine = false;
+                n = 0;
+            }
+        }
+        if (!mine)
+            n = 0, m = 0;
+        int nmax = n, nmin = n, mmax = m;
+        if (G > 1) {
+            nmax = max(n, __shfl_xor_sync(FULL, n, 16));
+            nmin = min(n, __shfl_xor_sync(FULL, n, 16));
+            mmax = max(m, __shfl_xor_sync(FULL, m, 16));
+        }
+        if (nmax == 0)
+            continue;
+        const int T = nmax + SK * (LPP - 1); // steps per strip for the whole warp
+        const int Tp = n + SK * (LPP - 1);   // strip pitch of MY pair's trace (MULTI only, G == 1)
+        const int strips = MULTI ? (mmax + LPP * C - 1) / (LPP * C) : 1;
+        uint32_t *tbase = (STORE && mine) ? P.trace + P.trace_off[pair - P.pair_begin] : nullptr;
+
+        for (int p = 0; p < strips; ++p) {
+            const int jbase = p * LPP * C + lane * C;
+            int aM[C], aI[C], aD[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int j = jbase + c + 1;
+                const int q = (mine && j <= m) ? (int)beta[j - 1] : 0;
+#pragma unroll
+                for (int a = 0; a < kDimP; ++a) {
+                    int v = 0;
+                    if (a < P.dim && q < P.dim)
+                        v = P.scores[a * P.dim + q] * SC + 2 * FH;
+                    s_tab[(c * kDimP + a) * 32 + tid] = v;
+                }
+                const bool last = FREE && (j == m);
+                aM[c] = last ? dMl : dMn;
+                aI[c] = last ? dIl : dIn;
+                aD[c] = last ? dDl : dDn;
+            }
+            int Dt[C], Hc[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int j = jbase + c + 1;
+                const int i0 = (O + j * E) * SC;
+                Hc[c] = i0;
+                Dt[c] = max3(NEG + 2 * FH + aM[c], i0 + FH + aI[c], NEG + aD[c]);
+            }
+            int hpL = (jbase == 0) ? P.h00 * SC : (O + jbase * E) * SC;
+            int edgeI = 0, edgeH = 0;   // what lane+1 consumes SK steps after it was produced
+            int edgeI1 = 0, edgeH1 = 0; // SK == 2: the values produced one step ago
+            const int2 *ein = (p & 1) ? edge_b : edge_a;
+            int2 *eout = (p & 1) ? edge_a : edge_b;
+            uint32_t *tp = STORE ? tbase + ((size_t)p * Tp * WPL) * 32 + lane : nullptr;
+            const bool store_edge = MULTI && (lane == LPP - 1) && (p + 1 < strips);
+
+            int bI = 0, bH = 0;
+            auto boundary = [&](int r) {
+                if (!MULTI || p == 0) {
+                    const int d0 = FREE ? 0 : (O + r * E) * SC;
+                    bI = d0 + iD;
+                    bH = d0;
+                } else {
+                    const int2 v = ein[r];
+                    bI = v.x;
+                    bH = v.y;
+                }
+            };
+            if (lane == 0)
+                boundary(1);
+            const uint8_t *tg = alpha; // where this lane reads its row's base
+            if (STAGE) {
+                for (int i = lane; i < n; i += LPP)
+                    s_tgt[half * kTgtPitch + i] = alpha[i];
+                tg = s_tgt + half * kTgtPitch;
+            }
+            __syncwarp();
+            int a_next = (lane == 0 && mine) ? (int)tg[0] : 0;
+
+            auto step = [&](int t, auto check_tag) {
+                constexpr bool CHECK = decltype(check_tag)::value;
+                const int r = t - SK * lane + 1;
+                int inI = __shfl_up_sync(FULL, edgeI, 1, LPP);
+                int inH = __shfl_up_sync(FULL, edgeH, 1, LPP);
+                if (SK == 2) { // age the pipeline: the one-step-old edge becomes visible to lane+1 next step
+                    edgeI = edgeI1;
+                    edgeH = edgeH1;
+                }
+                if (lane == 0) {
+                    inI = bI;
+                    inH = bH;
+                }
+                const int a = a_next;
+                bool active = true;
+                if (CHECK) {
+                    active = (unsigned)(r - 1) < (unsigned)n;
+                    if ((unsigned)r < (unsigned)n)
+                        a_next = tg[r];
+                } else {
+                    a_next = tg[r];
+                }
+                if (active) {
+                    if (lane == 0 && r < n)
+                        boundary(r + 1);
+                    const int *row = s_tab + a * 32 + tid; // &s_tab[(0*kDimP + a)*32 + tid]
+                    int It = inI, hp = hpL;
+                    unsigned w[WPL];
+#pragma unroll
+                    for (int k = 0; k < WPL; ++k)
+                        w[k] = 0;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int s = row[c * kDimP * 32]; // LDS at an immediate offset, bank = thread
+                        const int MH = madd(hp, one, s);
+                        if (TRACE) {
+                            int cIh;
+                            asm("lop3.b32 %0, %1, %2, %3, 0xea;" : "=r"(cIh) : "r"(It), "r"(CLR), "r"(fh_reg));
+                            const int cD = Dt[c] & CLR;
+                            const int Ht = max3(MH, cIh, cD);
+                            if (STORE)
+                                w[c / 5] = shf_r_wrap(w[c / 5], (unsigned)xor3(It, Dt[c], Ht), kTagBits);
+                            It = max3(madd(MH, one, kI), madd(cIh, one, iI - FH), madd(cD, one, iD));
+                            Dt[c] = max3(madd(MH, one, aM[c]), madd(cIh, one, aI[c]), madd(cD, one, aD[c]));
+                            hp = Hc[c];
+                            Hc[c] = Ht & CLR;
+                        } else {
+                            const int H = max3(MH, It, Dt[c]);
+                            const int Ho = madd(H, one, oe_s);
+                            It = addmax(It, e_s, Ho);
+                            Dt[c] = FREE ? addmax(Dt[c], aD[c], madd(H, one, aI[c])) : addmax(Dt[c], e_s, Ho);
+                            hp = Hc[c];
+                            Hc[c] = H;
+                        }
+                    }
+                    if (SK == 2) {
+                        edgeI1 = It;
+                        edgeH1 = Hc[C - 1];
+                    } else {
+                        edgeI = It;
+                        edgeH = Hc[C - 1];
+                    }
+                    hpL = inH;
+                    if (STORE) {
+#pragma unroll
+                        for (int k = 0; k < WPL; ++k)
+                            tp[(size_t)k * 32] = w[k];
+                    }
+                    if (store_edge)
+                        eout[r] = make_int2(It, Hc[C - 1]);
+                }
+                if (STORE)
+                    tp += WPL * 32;
+            };
+
+            int t = 0;
+#pragma unroll 1
+            for (; t < SK * (LPP - 1); ++t)
+                step(t, std::true_type{});
+            if (TRACE) {
+#pragma unroll kUnrollTrace
+                for (; t < nmin - 1; ++t) // steady: every lane of every pair in the warp is on a valid row < n
+                    step(t, std::false_type{});
+            } else {
+#pragma unroll kUnrollScore
+                for (; t < nmin - 1; ++t)
+                    step(t, std::false_type{});
+            }
+#pragma unroll 1
+            for (; t < T; ++t)
+                step(t, std::true_type{});
+
+            if (mine) {
+                const int pm = (m - 1) / (LPP * C), lm = ((m - 1) % (LPP * C)) / C, cm = (m - 1) % C;
+                if (p == pm && lane == lm) {
+                    int h = Hc[0];
+#pragma unroll
+                    for (int c = 1; c < C; ++c)
+                        if (c == cm)
+                            h = Hc[c];
+                    P.out_score[pair] = (int64_t)(h / SC);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+} // namespace gnx

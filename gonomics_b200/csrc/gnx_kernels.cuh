@@ -464,7 +464,9 @@ struct TraceParams {
     const uint32_t *trace;
     const int64_t *trace_off;
     int C;          // columns per lane the fill kernel used
-    int layout;     // 1: affine_fill_kernel word layout, 2: affine_fill2_kernel (gnx_fill2.cuh)
+    int layout;     // 1: affine_fill_kernel word layout, 2: affine_fill2/3_kernel (codes shifted in from the top)
+    int lpp;        // lanes per pair of the fill kernel (32, or 16 for fill3's two-pairs-per-warp form)
+    int skew;       // rows between neighbouring lanes (1, or 2 for fill3's pipelined form)
     int kind;       // 0 affine, 2 const gap
     int h00_plane;  // plane of T(0, O, D(0,0)) (affine)
     uint32_t *slots; // per pair in chunk: slot_cap entries, run<<2 | op, traceback order
@@ -482,14 +484,15 @@ struct CigarOut {
     unsigned char op;
 };
 
-__device__ __forceinline__ unsigned affine_code(const uint32_t *tr, int T, int C, int i, int j, int layout = 1)
+__device__ __forceinline__ unsigned affine_code(const uint32_t *tr, int T, int C, int i, int j, int layout = 1,
+                                                int lpp = 32, int skew = 1)
 {
     const int wpl = trace_wpl(C);
     const int jj = j - 1;
-    const int strip = jj / (32 * C);
-    const int within = jj - strip * 32 * C;
+    const int strip = jj / (lpp * C);
+    const int within = jj - strip * lpp * C;
     const int lane = within / C, c = within - lane * C;
-    const int t = (i - 1) + lane;
+    const int t = (i - 1) + skew * lane;
     const int nin = (c / 5 == wpl - 1) ? (C - 5 * (wpl - 1)) : 5; // codes held by this word
     const uint32_t w = tr[(((size_t)strip * T + t) * wpl + c / 5) * 32 + lane];
     if (layout == 2) // codes funnel-shifted in from the top (gnx_fill2.cuh)
@@ -549,7 +552,7 @@ __global__ void traceback_kernel(const TraceParams P)
         return;
     }
     const uint32_t *tr = P.trace + P.trace_off[idx];
-    const int T = n + 31, C = P.C;
+    const int T = n + (P.kind == 0 ? P.skew * (P.lpp - 1) : 31), C = P.C;
     int i = n, j = m, cur = -1, run = 0;
     if (P.kind == 0) {
         // start plane: T(M,I,D)(n,m) = the H tag of cell (n,m); boundaries are closed-form
@@ -559,7 +562,7 @@ __global__ void traceback_kernel(const TraceParams P)
         else if (m == 0)
             k = 2;
         else
-            k = 2 - (int)((affine_code(tr, T, C, n, m, P.layout) >> 4) & 3u);
+            k = 2 - (int)((affine_code(tr, T, C, n, m, P.layout, P.lpp, P.skew) >> 4) & 3u);
         while (i > 0 || j > 0) {
             if (k == cur) {
                 ++run;
@@ -585,12 +588,12 @@ __global__ void traceback_kernel(const TraceParams P)
                 else if (j == 0)
                     k = 2;
                 else
-                    k = 2 - (int)((affine_code(tr, T, C, i, j, P.layout) >> 4) & 3u);
+                    k = 2 - (int)((affine_code(tr, T, C, i, j, P.layout, P.lpp, P.skew) >> 4) & 3u);
             } else if (k == 1) {
-                k = 2 - (int)(affine_code(tr, T, C, i, j, P.layout) & 3u);
+                k = 2 - (int)(affine_code(tr, T, C, i, j, P.layout, P.lpp, P.skew) & 3u);
                 --j;
             } else {
-                k = 2 - (int)((affine_code(tr, T, C, i, j, P.layout) >> 2) & 3u);
+                k = 2 - (int)((affine_code(tr, T, C, i, j, P.layout, P.lpp, P.skew) >> 2) & 3u);
                 --i;
             }
         }
