@@ -241,7 +241,7 @@ def main():
     line = {
         "metric": "GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u16x2", "data": "synthetic",
         "config": {"workload": "C2 (BASELINE.json configs[1]): %d pairs/GPU, target 500 x query 150, semi-global "
                                "affine gap (AffineGapLocal), score only" % P,
                    "matrix": "HumanChimpTwo", "gap_open": GAP_OPEN, "gap_extend": GAP_EXTEND,
@@ -253,7 +253,7 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": None,
-                     "peak_source": peak_src, "kernel": "affine_fill_kernel<C=5,TRACE=0,FREE=1>",
+                     "peak_source": peak_src, "kernel": "affine_fill16_kernel<FREE=1> (packed 16-bit, 4 pairs/warp)",
                      "fill_ms_per_step": fill_ms, "fill_launches_per_step": fill_n,
                      "algorithmic_bytes_per_step": alg_bytes,
                      "note": "score-only fill moves 187 B per 75,000-cell pair: HBM cannot bind it; the binding "
@@ -262,9 +262,12 @@ def main():
     if fill_ms > 0 and clocks.get("sm_mhz"):
         sm = torch.cuda.get_device_properties(local).multi_processor_count
         slots = sm * 4 * clocks["sm_mhz"] * 1e6  # warp-instruction issue slots per second
+        # 32 lanes x 2 packed pairs = 64 cells per warp-instruction slot in the packed kernel
         line["issue_roofline"] = {"cells_per_s_fill": cells / (fill_ms * 1e-3),
                                   "issue_slots_per_s": slots,
-                                  "issue_slots_per_warp_cell": slots / (cells / 32 / (fill_ms * 1e-3))}
+                                  "issue_slots_per_64_cells": slots / (cells / 64 / (fill_ms * 1e-3)),
+                                  "note": "warp-instruction issue slots spent per 64 DP cells (one packed "
+                                          "warp-cell); the SASS of the steady loop needs ~10.7, see DESIGN.md"}
 
     # ---- C3: traceback + CIGAR on the same pairs -------------------------------------------------
     if not args.no_traceback:
@@ -277,7 +280,7 @@ def main():
             "ms_per_step": ms3 / args.steps, "gpu_launches": launches3, "clocks": clocks3,
             "roofline": {"bound": "hbm", "achieved": ach3, "peak": peak, "unit": "GB/s",
                          "frac": (ach3 / peak) if ach3 else None, "traffic": None, "peak_source": peak_src,
-                         "kernel": "affine_fill_kernel<C=5,TRACE=1,FREE=1>", "fill_ms_per_step": fill3,
+                         "kernel": "affine_fill3_kernel<C=10,LPP=16,MODE=2,FREE=1>", "fill_ms_per_step": fill3,
                          "fill_launches_per_step": filln3, "algorithmic_bytes_per_step": alg3}}
 
     # ---- e2e: the public host-buffer API, pinned host inputs, H2D + D2H inside the timed region --

@@ -8,6 +8,7 @@
 #include "gnx_kernels.cuh"
 #include "gnx_fill2.cuh"
 #include "gnx_fill3.cuh"
+#include "gnx_fill16.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -105,12 +106,14 @@ struct gnx_ctx {
     DevBuf status;       // int32 device status word
     DevBuf dr_misc;      // device-resident path scratch (running total, counters)
     int64_t launches = 0;
+    int gate_rr = 0;     // round-robin slot of the per-chunk max-base gate words (status[1..8])
     // options
     int opt_cols = 0;          // 0 = auto
     int64_t opt_chunk_pairs = 1 << 18;
     int opt_blocks_per_sm = 8;
     int opt_fill_impl = 3;     // 1: affine_fill_kernel (v1, 4 warps/CTA), 2: affine_fill2_kernel, 3: affine_fill3_kernel
     int opt_lpp = 0;           // fill3 lanes per pair: 0 auto, 16 or 32
+    int opt_fill16 = 1;        // allow the packed 16-bit score-only kernel when its range proof holds
     int opt_skew = 1;          // fill3 row skew between lanes (1 or 2; 2 measured no faster, kept as an option)
     int opt_ctas_per_sm = 32;  // fill2/3 persistent grid = SMs * min(this, occupancy)
     int opt_force_lookup = -1; // -1 auto; 0/1 force the PRMT / shared-memory score lookup for ACGT pairs
@@ -146,7 +149,8 @@ int fail(gnx_ctx *ctx, int code, const char *msg)
 }
 
 struct FillCfg {
-    int impl = 1; // 1 affine_fill_kernel / const_fill_kernel, 2 affine_fill2_kernel, 3 affine_fill3_kernel
+    int impl = 1; // 1 affine_fill_kernel / const_fill_kernel, 2 affine_fill2_kernel, 3 affine_fill3_kernel,
+                  // 16 affine_fill16_kernel (packed 16-bit, score only, uniform batch)
     int C = 5;    // columns per lane
     int lpp = 32; // lanes per pair
     int skew = 1; // rows between neighbouring lanes (fill3: 2)
@@ -234,6 +238,29 @@ void pick_cfg(const gnx_ctx *ctx, Problem &pb, int64_t max_m, int64_t max_n)
     }
 }
 
+
+// Range proof for the packed 16-bit score-only kernel (gnx_fill16.cuh): every state it ever holds,
+// including the padding columns up to 160, lies in [LB, UB]; with the +32768 bias both must fit 16 bits.
+bool fill16_ok(const gnx_ctx *ctx, const Problem &pb, int64_t min_n, int64_t max_n, int64_t min_m, int64_t max_m)
+{
+    if (!ctx->opt_fill16 || ctx->opt_fill_impl != 3 || pb.kind == 2 || pb.want_cigar || pb.dim > kDimP)
+        return false;
+    if (min_n != max_n || min_m != max_m || max_n < 1 || max_m < 1 || max_m > 160) // uniform batch only
+        return false;
+    const int64_t O = pb.gap_open, E = pb.gap_extend;
+    if (O > 0 || E > 0)
+        return false;
+    int64_t smin = 0, smax = 0;
+    for (int i = 0; i < pb.dim * pb.dim; ++i) {
+        smin = std::min(smin, pb.scores[i]);
+        smax = std::max(smax, pb.scores[i]);
+    }
+    // free end gaps: H(i,j) >= O + jE (enter from D(i,0)=0);  global: H(i,j) >= 2O + (i+j)E
+    const int64_t hlow = pb.kind == 1 ? O + 161 * E : 2 * O + (max_n + 161) * E;
+    const int64_t lb = hlow + (O + E) + smin - 64;
+    const int64_t ub = smax * std::min(max_n, max_m) + smax + 64;
+    return lb >= -32768 && ub <= 32767 && -smin <= 32000 && smax <= 32000;
+}
 
 // Trace words of one group of pairs that share 128-byte trace rows (1 pair, or 2 with lpp == 16);
 // n_eff is the largest row count among the group's non-empty pairs.
@@ -462,6 +489,7 @@ struct ChunkDev {
     uint32_t *slots;
     int *counts;                      // chunk-local
     int64_t *score;                   // biased by -begin (global pair index)
+    int64_t a_lo, a_hi, b_lo, b_hi;   // absolute byte ranges of the chunk inside alpha / beta
 };
 
 // classify + fill (+ traceback pass 0) for chunk [begin, end) on stream st.
@@ -477,8 +505,24 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     const int warps_per_block = 4;
     const int max_grid = ctx->sm_count * ctx->opt_blocks_per_sm;
     const int grid = (int)std::min<int64_t>((np + warps_per_block - 1) / warps_per_block, max_grid);
-    classify_kernel<<<grid, 128, 0, st>>>(cd.alpha, cd.aoff, cd.beta, cd.boff, begin, end, pb.dim, cd.cls, status);
-    ctx->launches++;
+    if (pb.cfg.impl == 3 || pb.cfg.impl == 16) {
+        // these kernels take any base < dim, so the per-pair pass is only needed to find WHICH pair is
+        // invalid; gate it on the chunk's largest base (vectorised, HBM-bound)
+        int *gate = status + 1 + ctx->gate_rr;
+        ctx->gate_rr = (ctx->gate_rr + 1) % 8;
+        cudaMemsetAsync(gate, 0, sizeof(int), st);
+        cudaMemsetAsync(cd.cls + begin, 0, (size_t)np, st);
+        const int mb_grid = ctx->sm_count * 4;
+        maxbase_kernel<<<mb_grid, 256, 0, st>>>(cd.alpha, cd.a_lo, cd.a_hi, gate);
+        maxbase_kernel<<<mb_grid, 256, 0, st>>>(cd.beta, cd.b_lo, cd.b_hi, gate);
+        classify_kernel<<<grid, 128, 0, st>>>(cd.alpha, cd.aoff, cd.beta, cd.boff, begin, end, pb.dim, cd.cls, status,
+                                              gate);
+        ctx->launches += 3;
+    } else {
+        classify_kernel<<<grid, 128, 0, st>>>(cd.alpha, cd.aoff, cd.beta, cd.boff, begin, end, pb.dim, cd.cls, status,
+                                              nullptr);
+        ctx->launches++;
+    }
 
     FillParams fp;
     memset(&fp, 0, sizeof fp);
@@ -507,7 +551,24 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     cudaEventRecord(fe.a, st);
     const int lookup0 = (ctx->opt_force_lookup == 1 || !pb.prmt_ok) ? 1 : 0;
     const int grid2 = (int)std::min<int64_t>(np, (int64_t)ctx->sm_count * std::min(ctx->opt_ctas_per_sm, 20));
-    if (pb.cfg.impl == 3) {
+    if (pb.cfg.impl == 16) {
+        static int occ16[2] = {0, 0};
+        const int fi = pb.kind == 1 ? 1 : 0;
+        if (occ16[fi] == 0) {
+            int o = 0;
+            cudaError_t e = fi ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_fill16_kernel<true>, 32, 0)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_fill16_kernel<false>, 32, 0);
+            occ16[fi] = (e == cudaSuccess && o > 0) ? o : 8;
+        }
+        const int64_t quads = (np + 3) / 4;
+        const int g16 = (int)std::min<int64_t>(quads, (int64_t)ctx->sm_count * std::min(occ16[fi], ctx->opt_ctas_per_sm));
+        if (fi)
+            affine_fill16_kernel<true><<<g16, 32, 0, st>>>(fp);
+        else
+            affine_fill16_kernel<false><<<g16, 32, 0, st>>>(fp);
+        ctx->launches++;
+        ctx->last_fill_launches++;
+    } else if (pb.cfg.impl == 3) {
         // one launch: the per-lane score tables cover every base < dim, so there is no class split
         const int64_t groups = (np + (32 / pb.cfg.lpp) - 1) / (32 / pb.cfg.lpp);
         dispatch_fill3(pb, fp, groups, ctx->sm_count, ctx->opt_ctas_per_sm, st);
@@ -610,7 +671,7 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
 // or the chunk reaches opt_chunk_pairs.
 struct Plan {
     std::vector<int64_t> bounds;      // chunk boundaries (pair indices), size = chunks+1
-    int64_t max_n = 0, max_m = 0, cells = 0;
+    int64_t max_n = 0, max_m = 0, min_n = INT64_MAX, min_m = INT64_MAX, cells = 0;
     bool any_long = false;            // some pair needs more than one strip
 };
 
@@ -623,9 +684,18 @@ int make_plan(gnx_ctx *ctx, Problem &pb, const int64_t *aoff, const int64_t *bof
             return fail(ctx, GNX_EARG, "offset arrays must be non-decreasing");
         plan.max_n = std::max(plan.max_n, n);
         plan.max_m = std::max(plan.max_m, m);
+        plan.min_n = std::min(plan.min_n, n);
+        plan.min_m = std::min(plan.min_m, m);
         plan.cells += n * m;
     }
     pick_cfg(ctx, pb, plan.max_m, plan.max_n);
+    if (fill16_ok(ctx, pb, plan.min_n, plan.max_n, plan.min_m, plan.max_m)) {
+        pb.cfg.impl = 16;
+        pb.cfg.C = 10;
+        pb.cfg.lpp = 16;
+        pb.cfg.skew = 1;
+        pb.cfg.multi = false;
+    }
     plan.any_long = pb.cfg.multi;
     plan.bounds.push_back(0);
     // exact accounting of the trace words of the chunk being grown (groups of 32/lpp pairs share rows)
@@ -849,6 +919,10 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
         cd.boff = s.boff.as<int64_t>() - begin;
         cd.cls = s.cls.as<uint8_t>() - begin;
         cd.score = s.score.as<int64_t>() - begin;
+        cd.a_lo = a_lo;
+        cd.a_hi = a_hi;
+        cd.b_lo = b_lo;
+        cd.b_hi = b_hi;
         if (pb.want_cigar) {
             CU(s.h_trace_off.ensure((size_t)(np + 1) * 8));
             int64_t *to = s.h_trace_off.as<int64_t>();
@@ -1169,6 +1243,10 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
         cd.boff = d_beta_off;
         cd.cls = s.cls.as<uint8_t>();
         cd.score = d_out_score;
+        cd.a_lo = alpha_off_host[begin];
+        cd.a_hi = alpha_off_host[end];
+        cd.b_lo = beta_off_host[begin];
+        cd.b_hi = beta_off_host[end];
         if (pb.want_cigar) {
             // pinned staging is reused by the next chunk's host writes: fence on the previous upload
             if (ci > 0)
@@ -1250,6 +1328,8 @@ int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
         if (value != 0 && value != 16 && value != 32)
             return fail(ctx, GNX_EARG, "lanes_per_pair must be 0 (auto), 16 or 32");
         ctx->opt_lpp = (int)value;
+    } else if (k == "fill16") {
+        ctx->opt_fill16 = value ? 1 : 0;
     } else if (k == "skew") {
         if (value != 1 && value != 2)
             return fail(ctx, GNX_EARG, "skew must be 1 or 2");

@@ -1,0 +1,175 @@
+// gnx_fill16.cuh -- packed 16-bit score-only affine fill: FOUR pairs per warp.
+//
+// Same wavefront as affine_fill3_kernel<C=10, LPP=16> (two half-warps, 10 columns per lane), but every
+// 32-bit register carries the same DP cell of TWO different pairs: pair "A" in bits 15:0 and pair "B"
+// in bits 31:16.  The three maxes of a cell become one VIMNMX3.U16x2 and two VIADDMNMX.U16x2 (DPX, ALU
+// pipe, same issue cost as their 32-bit forms -- profiles/r01_microbench_pipes.txt), i.e. half the ALU
+// work per cell.  Halves are kept BIASED-UNSIGNED (u = v + 32768) so that
+//   * maxes are the unsigned 16x2 forms, and
+//   * the plain adds (M = H_diag + s, H + O + E) stay ordinary 32-bit integer adds on the FMA pipe:
+//     X = uB*65536 + uA, so X + (dB*65536 + dA) = (uB+dB)*65536 + (uA+dA) exactly as long as each half
+//     stays inside [0, 65535] -- which the host proves before dispatching this kernel (analyse16()).
+// Score-only needs no -inf at all: row 0 is I(0,j), column 0 is D(i,0) and every other state is a max
+// that contains a finite candidate (DESIGN.md "Arithmetic width"), so there is no sentinel to keep
+// away from the range limits.  Padding columns (j > m) get zero substitution scores, which keeps their
+// (unused) values within one gap-open of real cells.
+// Requires: uniform batch (all pairs n x m), m <= 160, dim <= 5, O <= 0, score only.
+#pragma once
+#include "gnx_fill3.cuh"
+
+namespace gnx {
+
+__device__ __forceinline__ unsigned pack16(int v) { return (unsigned)(v + 32768) * 65537u; } // same v in both halves
+__device__ __forceinline__ unsigned wrap16x2(int d) { return ((unsigned)d & 0xffffu) * 65537u; } // per-half wrapping addend
+__device__ __forceinline__ unsigned umax3_16x2(unsigned a, unsigned b, unsigned c) { return __vimax3_u16x2(a, b, c); }
+__device__ __forceinline__ unsigned uaddmax_16x2(unsigned a, unsigned b, unsigned c) { return __viaddmax_u16x2(a, b, c); }
+
+template <bool FREE>
+__global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams P)
+{
+    constexpr int C = 10, LPP = 16;
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ short s_tabA[C * kDimP * 32]; // [c][a][thread], pair A: s as int16 (sign-extending LDS)
+    __shared__ int s_tabB[C * kDimP * 32];   // [c][a][thread], pair B: s * 65536
+    const int tid = threadIdx.x;
+    const int lane = tid % LPP, half = tid / LPP;
+    const int one = P.one;
+    const int O = P.gap_open, E = P.gap_extend;
+    const int oe_i = (O + E) * 65537;          // integer addend: +O+E in both halves
+    const unsigned e_w = wrap16x2(E);          // per-half wrapping addend for VIADDMNMX.U16x2
+    const int64_t n_quads = (P.pair_end - P.pair_begin + 3) / 4;
+
+    for (int64_t quad = blockIdx.x; quad < n_quads; quad += gridDim.x) {
+        const int64_t pA0 = P.pair_begin + quad * 4 + half * 2, pB0 = pA0 + 1;
+        const int64_t pA = min(pA0, P.pair_end - 1), pB = min(pB0, P.pair_end - 1); // tail: recompute a valid pair
+        const int64_t a0A = P.alpha_off[pA], b0A = P.beta_off[pA];
+        const int n = (int)(P.alpha_off[pA + 1] - a0A);
+        const int m = (int)(P.beta_off[pA + 1] - b0A); // uniform batch: same n, m for every pair
+        const uint8_t *__restrict__ alA = P.alpha + a0A;
+        const uint8_t *__restrict__ alB = P.alpha + P.alpha_off[pB];
+        const uint8_t *__restrict__ beA = P.beta + b0A;
+        const uint8_t *__restrict__ beB = P.beta + P.beta_off[pB];
+        const int T = n + LPP - 1;
+        const int jbase = lane * C;
+        unsigned aD[C];
+        int aH[C]; // D-plane addends: (E, O+E) regular, (0, 0) in the freeEndGaps last column
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int j = jbase + c + 1;
+            const bool real = j <= m;
+            const int qA = real ? (int)beA[j - 1] : 0, qB = real ? (int)beB[j - 1] : 0;
+#pragma unroll
+            for (int a = 0; a < kDimP; ++a) {
+                int vA = 0, vB = 0;
+                if (real && a < P.dim) { // padding columns score 0 against everything
+                    vA = P.scores[a * P.dim + qA];
+                    vB = P.scores[a * P.dim + qB];
+                }
+                s_tabA[(c * kDimP + a) * 32 + tid] = (short)vA;
+                s_tabB[(c * kDimP + a) * 32 + tid] = vB * 65536;
+            }
+            const bool last = FREE && (j == m);
+            aD[c] = last ? 0u : e_w;
+            aH[c] = last ? 0 : oe_i;
+        }
+        unsigned Dt[C], Hc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int j = jbase + c + 1;
+            const unsigned h0 = pack16(O + j * E); // H(0,j) = I(0,j)
+            Hc[c] = h0;
+            Dt[c] = h0 + (unsigned)aH[c];          // D(1,j) = I(0,j) + O + E   (or I(0,m) in the free last column)
+        }
+        unsigned hpL = (jbase == 0) ? pack16(P.h00) : pack16(O + jbase * E);
+        unsigned edgeI = 0, edgeH = 0;
+        unsigned bI = 0, bH = 0;
+        auto boundary = [&](int r) {
+            const int d0 = FREE ? 0 : (O + r * E);
+            bI = pack16(d0 + O + E);
+            bH = pack16(d0);
+        };
+        if (lane == 0)
+            boundary(1);
+        int aA_next = 0, aB_next = 0;
+        if (lane == 0) {
+            aA_next = alA[0];
+            aB_next = alB[0];
+        }
+        __syncwarp();
+
+        auto step = [&](int t, auto check_tag) {
+            constexpr bool CHECK = decltype(check_tag)::value;
+            const int r = t - lane + 1;
+            unsigned inI = __shfl_up_sync(FULL, edgeI, 1, LPP);
+            unsigned inH = __shfl_up_sync(FULL, edgeH, 1, LPP);
+            if (lane == 0) {
+                inI = bI;
+                inH = bH;
+            }
+            const int aA = aA_next, aB = aB_next;
+            bool active = true;
+            if (CHECK) {
+                active = (unsigned)(r - 1) < (unsigned)n;
+                if ((unsigned)r < (unsigned)n) {
+                    aA_next = alA[r];
+                    aB_next = alB[r];
+                }
+            } else {
+                aA_next = alA[r];
+                aB_next = alB[r];
+            }
+            if (active) {
+                if (!FREE && lane == 0 && r < n)
+                    boundary(r + 1);
+                const short *rowA = s_tabA + aA * 32 + tid;
+                const int *rowB = s_tabB + aB * 32 + tid;
+                unsigned It = inI, hp = hpL;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int sA = rowA[c * kDimP * 32]; // sign-extended int16
+                    const int sB = rowB[c * kDimP * 32]; // s * 65536
+                    const unsigned MH = (unsigned)madd((int)hp, one, sA) + (unsigned)sB;
+                    const unsigned H = umax3_16x2(MH, It, Dt[c]);
+                    const unsigned Ho = (unsigned)madd((int)H, one, oe_i);
+                    It = uaddmax_16x2(It, e_w, Ho);                      // I' = max(I + E, H + O + E)
+                    if (FREE)
+                        Dt[c] = uaddmax_16x2(Dt[c], aD[c], (unsigned)madd((int)H, one, aH[c]));
+                    else
+                        Dt[c] = uaddmax_16x2(Dt[c], e_w, Ho);            // D' = max(D + E, H + O + E)
+                    hp = Hc[c];
+                    Hc[c] = H;
+                }
+                edgeI = It;
+                edgeH = Hc[C - 1];
+                hpL = inH;
+            }
+        };
+
+        int t = 0;
+#pragma unroll 1
+        for (; t < LPP - 1; ++t)
+            step(t, std::true_type{});
+#pragma unroll 2
+        for (; t < n - 1; ++t)
+            step(t, std::false_type{});
+#pragma unroll 1
+        for (; t < T; ++t)
+            step(t, std::true_type{});
+
+        const int lm = (m - 1) / C, cm = (m - 1) % C;
+        if (lane == lm) {
+            unsigned h = Hc[0];
+#pragma unroll
+            for (int c = 1; c < C; ++c)
+                if (c == cm)
+                    h = Hc[c];
+            if (pA0 < P.pair_end)
+                P.out_score[pA0] = (int64_t)(int)(h & 0xffffu) - 32768;
+            if (pB0 < P.pair_end)
+                P.out_score[pB0] = (int64_t)(int)(h >> 16) - 32768;
+        }
+        __syncwarp();
+    }
+}
+
+} // namespace gnx

@@ -73,10 +73,44 @@ __host__ __device__ inline int64_t trace_words(int64_t n, int64_t m, int C)
 // classify: per pair, the largest base value decides the kernel class (and the GNX_EBASE error).
 // One warp per pair, 16-byte vector loads where alignment allows.
 // ------------------------------------------------------------------------------------------------
+// maxbase: the largest base value of a byte range (one chunk's alpha or beta bytes), 16-byte loads,
+// HBM-bound.  When it is < dim (the normal case) no pair can be invalid and the per-pair classify pass
+// below returns at once (`gate`).
+__global__ void maxbase_kernel(const uint8_t *bytes, int64_t lo, int64_t hi, int *out_max)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    unsigned mx = 0;
+    // 16-byte aligned interior of the ADDRESS range (the base pointer itself may be biased/unaligned)
+    const uintptr_t base = reinterpret_cast<uintptr_t>(bytes);
+    const int64_t a_lo = min(hi, (int64_t)(((base + lo + 15) & ~uintptr_t(15)) - base));
+    const int64_t a_hi = max(a_lo, (int64_t)(((base + hi) & ~uintptr_t(15)) - base));
+    if (a_lo < a_hi) {
+        const uint4 *v = reinterpret_cast<const uint4 *>(bytes + a_lo);
+        const int64_t nv = (a_hi - a_lo) >> 4;
+        for (int64_t i = tid; i < nv; i += nth) {
+            const uint4 q = v[i];
+            mx = __vmaxu4(mx, __vmaxu4(__vmaxu4(q.x, q.y), __vmaxu4(q.z, q.w)));
+        }
+        for (int64_t i = lo + tid; i < a_lo; i += nth)
+            mx = max(mx, (unsigned)bytes[i]);
+        for (int64_t i = a_hi + tid; i < hi; i += nth)
+            mx = max(mx, (unsigned)bytes[i]);
+    } else {
+        for (int64_t i = lo + tid; i < hi; i += nth)
+            mx = max(mx, (unsigned)bytes[i]);
+    }
+    mx = max(max(mx & 0xffu, (mx >> 8) & 0xffu), max((mx >> 16) & 0xffu, mx >> 24));
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx > 0)
+        atomicMax(out_max, (int)mx);
+}
+
 __global__ void classify_kernel(const uint8_t *alpha, const int64_t *alpha_off, const uint8_t *beta,
                                 const int64_t *beta_off, int64_t pair_begin, int64_t pair_end, int dim,
-                                uint8_t *pair_class, int *status)
+                                uint8_t *pair_class, int *status, const int *gate)
 {
+    if (gate && *gate < dim)
+        return; // every base of the chunk is valid: pair_class stays all-zero
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
