@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -85,7 +86,7 @@ struct PinBuf {
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_total = nullptr, ev_done = nullptr;
-    DevBuf alpha, beta, aoff, boff, cls, trace, trace_off, slots, counts, score, cig_off, cigars, edge, misc;
+    DevBuf alpha, beta, aoff, boff, cls, trace, trace_off, slots, counts, score, cig_off, cigars, edge, misc, partials;
     PinBuf h_stage_a, h_stage_b, h_total, h_trace_off, h_score, h_off, h_cig;
     // chunk in flight
     int64_t begin = 0, end = 0;
@@ -113,6 +114,7 @@ struct gnx_ctx {
     int opt_blocks_per_sm = 8;
     int opt_fill_impl = 3;     // 1: affine_fill_kernel (v1, 4 warps/CTA), 2: affine_fill2_kernel, 3: affine_fill3_kernel
     int opt_lpp = 0;           // fill3 lanes per pair: 0 auto, 16 or 32
+    int opt_tb_impl = 2;       // 1: generic traceback_kernel, 2: traceback_affine_kernel for fill2/3 traces
     int opt_fill16 = 1;        // allow the packed 16-bit score-only kernel when its range proof holds
     int opt_skew = 1;          // fill3 row skew between lanes (1 or 2; 2 measured no faster, kept as an option)
     int opt_ctas_per_sm = 32;  // fill2/3 persistent grid = SMs * min(this, occupancy)
@@ -272,7 +274,10 @@ inline int64_t group_trace_words(const Problem &pb, int64_t n_eff, int64_t m)
     if (pb.kind == 2)
         return const_trace_words(n_eff, m, c.C);
     const int64_t strips = (m + (int64_t)c.lpp * c.C - 1) / ((int64_t)c.lpp * c.C);
-    return strips * (n_eff + c.skew * (c.lpp - 1)) * trace_wpl(c.C) * 32;
+    int64_t rows = n_eff + c.skew * (c.lpp - 1);
+    if (c.impl == 3)
+        rows = (rows + 3) & ~int64_t(3); // fill3 writes four steps per 16-byte piece
+    return strips * rows * trace_wpl(c.C) * 32;
 }
 
 // Per-pair trace offsets (32-bit words) of chunk [begin, begin+np); returns the chunk's total words.
@@ -294,7 +299,7 @@ int64_t compute_trace_offsets(const Problem &pb, const int64_t *aoff, const int6
                 len(k + 1, n1, m1);
             to[k] = acc;
             if (k + 1 < np)
-                to[k + 1] = acc + 16;
+                to[k + 1] = acc + 16 * 4; // second half-warp: 16 threads x 4 words per 16-byte piece
             acc += group_trace_words(pb, std::max(n0, n1), std::max(m0, m1));
         }
     } else {
@@ -604,7 +609,7 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         tp.trace = cd.trace;
         tp.trace_off = cd.trace_off;
         tp.C = C;
-        tp.layout = pb.cfg.impl >= 2 ? 2 : 1;
+        tp.layout = pb.cfg.impl == 3 ? 3 : (pb.cfg.impl == 2 ? 2 : 1);
         tp.lpp = pb.cfg.lpp;
         tp.skew = pb.cfg.skew;
         tp.kind = pb.kind == 2 ? 2 : 0;
@@ -613,7 +618,10 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         tp.slot_cap = kSlotCap;
         tp.counts = cd.counts;
         tp.pass = 0;
-        traceback_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
+        if (tp.kind == 0 && tp.layout >= 2 && ctx->opt_tb_impl == 2)
+            traceback_affine_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
+        else
+            traceback_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
         ctx->launches++;
     }
     cudaError_t e = cudaGetLastError();
@@ -621,6 +629,23 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         ctx->err = std::string("kernel launch failed: ") + cudaGetErrorString(e);
         return GNX_ECUDA;
     }
+    return GNX_OK;
+}
+
+// Exclusive scan of the chunk's cigar counts into `off` (np+1 entries), continuing from *running_total.
+// When `advance` is set the running total is moved forward on the device (device-resident batches).
+int enqueue_scan(gnx_ctx *ctx, DevBuf &partials, const int *counts, int64_t np, int64_t *off,
+                 const int64_t *running_total, int64_t *total_out, cudaStream_t st)
+{
+    const int blocks = (int)((np + kScanSeg - 1) / kScanSeg);
+    if (partials.ensure((size_t)blocks * 8) != cudaSuccess) {
+        ctx->err = "cudaMalloc failed (scan partials)";
+        return GNX_ECUDA;
+    }
+    scan_partial_kernel<<<blocks, 256, 0, st>>>(counts, np, partials.as<int64_t>());
+    // total_out must not alias running_total: other blocks may still be reading it
+    scan_apply_kernel<<<blocks, 256, 0, st>>>(counts, np, partials.as<int64_t>(), off, running_total, total_out);
+    ctx->launches += 2;
     return GNX_OK;
 }
 
@@ -645,7 +670,7 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
     tp.trace = cd.trace;
     tp.trace_off = cd.trace_off;
     tp.C = C;
-    tp.layout = pb.cfg.impl >= 2 ? 2 : 1;
+    tp.layout = pb.cfg.impl == 3 ? 3 : (pb.cfg.impl == 2 ? 2 : 1);
     tp.lpp = pb.cfg.lpp;
     tp.skew = pb.cfg.skew;
     tp.kind = pb.kind == 2 ? 2 : 0;
@@ -657,7 +682,10 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
     tp.out_cigar = cigars;
     tp.out_cap = cap;
     tp.pass = 1;
-    traceback_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
+    if (tp.kind == 0 && tp.layout >= 2 && ctx->opt_tb_impl == 2)
+        traceback_affine_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
+    else
+        traceback_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -678,15 +706,42 @@ struct Plan {
 int make_plan(gnx_ctx *ctx, Problem &pb, const int64_t *aoff, const int64_t *boff, int64_t n_pairs,
               int64_t budget_words, Plan &plan)
 {
-    for (int64_t p = 0; p < n_pairs; ++p) {
-        const int64_t n = aoff[p + 1] - aoff[p], m = boff[p + 1] - boff[p];
-        if (n < 0 || m < 0)
-            return fail(ctx, GNX_EARG, "offset arrays must be non-decreasing");
-        plan.max_n = std::max(plan.max_n, n);
-        plan.max_m = std::max(plan.max_m, m);
-        plan.min_n = std::min(plan.min_n, n);
-        plan.min_m = std::min(plan.min_m, m);
-        plan.cells += n * m;
+    { // length statistics (min/max/cells), split over a few host threads for 10^7-pair batches
+        struct Stat {
+            int64_t max_n = 0, max_m = 0, min_n = INT64_MAX, min_m = INT64_MAX, cells = 0;
+            bool bad = false;
+        };
+        const int nt = n_pairs >= (1 << 20) ? 8 : 1;
+        std::vector<Stat> st((size_t)nt);
+        auto work = [&](int t) {
+            Stat q;
+            const int64_t lo = n_pairs * t / nt, hi = n_pairs * (t + 1) / nt;
+            for (int64_t p = lo; p < hi; ++p) {
+                const int64_t n = aoff[p + 1] - aoff[p], m = boff[p + 1] - boff[p];
+                q.bad |= (n < 0) | (m < 0);
+                q.max_n = std::max(q.max_n, n);
+                q.max_m = std::max(q.max_m, m);
+                q.min_n = std::min(q.min_n, n);
+                q.min_m = std::min(q.min_m, m);
+                q.cells += n * m;
+            }
+            st[(size_t)t] = q;
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t)
+            th.emplace_back(work, t);
+        work(0);
+        for (auto &x : th)
+            x.join();
+        for (const Stat &q : st) {
+            if (q.bad)
+                return fail(ctx, GNX_EARG, "offset arrays must be non-decreasing");
+            plan.max_n = std::max(plan.max_n, q.max_n);
+            plan.max_m = std::max(plan.max_m, q.max_m);
+            plan.min_n = std::min(plan.min_n, q.min_n);
+            plan.min_m = std::min(plan.min_m, q.min_m);
+            plan.cells += q.cells;
+        }
     }
     pick_cfg(ctx, pb, plan.max_m, plan.max_n);
     if (fill16_ok(ctx, pb, plan.min_n, plan.max_n, plan.min_m, plan.max_m)) {
@@ -698,6 +753,20 @@ int make_plan(gnx_ctx *ctx, Problem &pb, const int64_t *aoff, const int64_t *bof
     }
     plan.any_long = pb.cfg.multi;
     plan.bounds.push_back(0);
+    if (plan.min_n == plan.max_n && plan.min_m == plan.max_m) { // uniform batch: chunk bounds are arithmetic
+        const int64_t gsz = 32 / pb.cfg.lpp; // pairs that share trace rows
+        const int64_t wg = pb.want_cigar ? group_trace_words(pb, (plan.max_n && plan.max_m) ? plan.max_n : 0, plan.max_m) : 0;
+        if (wg > budget_words)
+            return fail(ctx, GNX_ERANGE, "one pair's traceback matrix exceeds the context workspace");
+        int64_t per = ctx->opt_chunk_pairs;
+        if (wg > 0)
+            per = std::min(per, (budget_words / wg) * gsz);
+        per = std::max<int64_t>(4, per & ~int64_t(3)); // whole groups (and whole fill16 quads)
+        for (int64_t p = per; p < n_pairs; p += per)
+            plan.bounds.push_back(p);
+        plan.bounds.push_back(n_pairs);
+        return GNX_OK;
+    }
     // exact accounting of the trace words of the chunk being grown (groups of 32/lpp pairs share rows)
     int64_t words = 0, count = 0, prev_n = 0, prev_m = 0;
     for (int64_t p = 0; p < n_pairs; ++p) {
@@ -949,8 +1018,10 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
         if (pb.want_cigar) {
             CU(s.misc.ensure(64));
             CU(cudaMemsetAsync(s.misc.p, 0, 8, s.stream));
-            scan_counts_kernel<<<1, 1024, 0, s.stream>>>(cd.counts, np, s.cig_off.as<int64_t>(), s.misc.as<int64_t>());
-            ctx->launches++;
+            rc = enqueue_scan(ctx, s.partials, cd.counts, np, s.cig_off.as<int64_t>(), s.misc.as<int64_t>(), nullptr,
+                              s.stream);
+            if (rc != GNX_OK)
+                return rc;
             CU(s.h_total.ensure(8));
             CU(cudaMemcpyAsync(s.h_total.p, s.cig_off.as<int64_t>() + np, 8, cudaMemcpyDeviceToHost, s.stream));
             CU(cudaEventRecord(s.ev_total, s.stream));
@@ -1082,7 +1153,7 @@ void gnx_destroy(gnx_ctx *ctx)
     for (int k = 0; k < kSlots; ++k) {
         Slot &s = ctx->slot[k];
         DevBuf *d[] = {&s.alpha, &s.beta, &s.aoff, &s.boff, &s.cls, &s.trace, &s.trace_off, &s.slots,
-                       &s.counts, &s.score, &s.cig_off, &s.cigars, &s.edge, &s.misc};
+                       &s.counts, &s.score, &s.cig_off, &s.cigars, &s.edge, &s.misc, &s.partials};
         for (DevBuf *b : d)
             b->release();
         PinBuf *h[] = {&s.h_stage_a, &s.h_stage_b, &s.h_total, &s.h_trace_off, &s.h_score, &s.h_off, &s.h_cig};
@@ -1230,7 +1301,7 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
     const int nwarps_total = ctx->sm_count * std::max(ctx->opt_blocks_per_sm * 4, ctx->opt_ctas_per_sm);
     const int64_t edge_stride = plan.max_n + 2;
     CU(cudaMemsetAsync(ctx->status.p, 0, sizeof(int), st));
-    CU(cudaMemsetAsync(ctx->dr_misc.p, 0, 8, st)); // running cigar total
+    CU(cudaMemsetAsync(ctx->dr_misc.p, 0, 16, st)); // running cigar total (two ping-pong words)
     const int64_t n_chunks = (int64_t)plan.bounds.size() - 1;
     CU(s.cls.ensure((size_t)n_pairs));
     for (int64_t ci = 0; ci < n_chunks; ++ci) {
@@ -1274,8 +1345,11 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
         if (rc != GNX_OK)
             return rc;
         if (pb.want_cigar) {
-            scan_counts_kernel<<<1, 1024, 0, st>>>(cd.counts, np, d_out_cigar_off + begin, ctx->dr_misc.as<int64_t>());
-            ctx->launches++;
+            // the running cigar total ping-pongs between two device words from chunk to chunk
+            rc = enqueue_scan(ctx, s.partials, cd.counts, np, d_out_cigar_off + begin,
+                              ctx->dr_misc.as<int64_t>() + (ci & 1), ctx->dr_misc.as<int64_t>() + ((ci + 1) & 1), st);
+            if (rc != GNX_OK)
+                return rc;
             rc = enqueue_chunk_expand(ctx, pb, cd, begin, end, d_out_cigar_off + begin, d_out_cigar, cigar_cap, st);
             if (rc != GNX_OK)
                 return rc;
@@ -1328,6 +1402,8 @@ int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
         if (value != 0 && value != 16 && value != 32)
             return fail(ctx, GNX_EARG, "lanes_per_pair must be 0 (auto), 16 or 32");
         ctx->opt_lpp = (int)value;
+    } else if (k == "tb_impl") {
+        ctx->opt_tb_impl = (int)value;
     } else if (k == "fill16") {
         ctx->opt_fill16 = value ? 1 : 0;
     } else if (k == "skew") {

@@ -16,6 +16,9 @@ namespace gnx {
 #ifndef GNX_FILL3_MINB
 #define GNX_FILL3_MINB 12
 #endif
+#ifndef GNX_F3_GROUP4
+#define GNX_F3_GROUP4 1
+#endif
 #ifndef GNX_F3_STAGE
 #define GNX_F3_STAGE 1
 #endif
@@ -37,6 +40,8 @@ __host__ __device__ inline int64_t trace_words3(int64_t n_max_of_group, int64_t 
 
 constexpr int kDimP = 5; // rows of the per-lane score table (bases 0..4); matrices with dim > 5 use fill2
 constexpr int kUnrollTrace = GNX_F3_UNROLL_TRACE, kUnrollScore = GNX_F3_UNROLL_SCORE;
+constexpr bool kBlock4 = true; // trace rows are blocked four steps per 16-byte piece (layout 3)
+constexpr bool kGroup4 = GNX_F3_GROUP4 != 0; // traced steady loop processes aligned groups of 4 steps (no window shift)
 constexpr int kRing = 1024; // single-strip kernels stage the whole target (alpha) in shared memory: n <= kRing
 // MODE 0: score only (untagged, needs O <= 0)   1: tagged arithmetic, no stores   2: tagged + trace stores
 // SK   row skew between neighbouring lanes.  With SK = 2 lane l is two rows behind lane l-1, so the edge
@@ -114,8 +119,10 @@ __global__ void __launch_bounds__(32, (C == 5 ? 20 : GNX_FILL3_MINB)) affine_fil
         }
         if (nmax == 0)
             continue;
-        const int T = nmax + SK * (LPP - 1); // steps per strip for the whole warp
-        const int Tp = n + SK * (LPP - 1);   // strip pitch of MY pair's trace (MULTI only, G == 1)
+        // steps per strip for the whole warp; with STORE the trace rows are written four steps at a time
+        // (one 16-byte store per lane), so the step count is padded to a multiple of 4
+        const int T = (STORE && kBlock4) ? ((nmax + SK * (LPP - 1) + 3) & ~3) : nmax + SK * (LPP - 1);
+        const int Tp = kBlock4 ? ((n + SK * (LPP - 1) + 3) & ~3) : n + SK * (LPP - 1); // strip pitch (rows), MULTI only
         const int strips = MULTI ? (mmax + LPP * C - 1) / (LPP * C) : 1;
         uint32_t *tbase = (STORE && mine) ? P.trace + P.trace_off[pair - P.pair_begin] : nullptr;
 
@@ -151,7 +158,14 @@ __global__ void __launch_bounds__(32, (C == 5 ? 20 : GNX_FILL3_MINB)) affine_fil
             int edgeI1 = 0, edgeH1 = 0; // SK == 2: the values produced one step ago
             const int2 *ein = (p & 1) ? edge_b : edge_a;
             int2 *eout = (p & 1) ? edge_a : edge_b;
-            uint32_t *tp = STORE ? tbase + ((size_t)p * Tp * WPL) * 32 + lane : nullptr;
+            // blocked trace layout: uint4 index ((t/4)*WPL + k)*32 + thread, word t%4 inside it, so that the
+            // four consecutive steps of one lane share a 16-byte piece of one sector (the traceback walks
+            // mostly along a lane: 4x fewer sectors touched than with one word per (step, lane) row)
+            uint4 *tp4 = STORE ? reinterpret_cast<uint4 *>(tbase + ((size_t)p * Tp * WPL) * 32) + lane : nullptr;
+            uint4 wq[WPL];
+#pragma unroll
+            for (int k = 0; k < WPL; ++k)
+                wq[k] = make_uint4(0, 0, 0, 0);
             const bool store_edge = MULTI && (lane == LPP - 1) && (p + 1 < strips);
 
             int bI = 0, bH = 0;
@@ -177,7 +191,7 @@ __global__ void __launch_bounds__(32, (C == 5 ? 20 : GNX_FILL3_MINB)) affine_fil
             __syncwarp();
             int a_next = (lane == 0 && mine) ? (int)tg[0] : 0;
 
-            auto step = [&](int t, auto check_tag) {
+            auto step = [&](int t, auto check_tag, auto slot_tag) {
                 constexpr bool CHECK = decltype(check_tag)::value;
                 const int r = t - SK * lane + 1;
                 int inI = __shfl_up_sync(FULL, edgeI, 1, LPP);
@@ -199,15 +213,15 @@ __global__ void __launch_bounds__(32, (C == 5 ? 20 : GNX_FILL3_MINB)) affine_fil
                 } else {
                     a_next = tg[r];
                 }
+                unsigned w[WPL];
+#pragma unroll
+                for (int k = 0; k < WPL; ++k)
+                    w[k] = 0;
                 if (active) {
                     if (lane == 0 && r < n)
                         boundary(r + 1);
                     const int *row = s_tab + a * 32 + tid; // &s_tab[(0*kDimP + a)*32 + tid]
                     int It = inI, hp = hpL;
-                    unsigned w[WPL];
-#pragma unroll
-                    for (int k = 0; k < WPL; ++k)
-                        w[k] = 0;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         const int s = row[c * kDimP * 32]; // LDS at an immediate offset, bank = thread
@@ -240,34 +254,75 @@ __global__ void __launch_bounds__(32, (C == 5 ? 20 : GNX_FILL3_MINB)) affine_fil
                         edgeH = Hc[C - 1];
                     }
                     hpL = inH;
-                    if (STORE) {
-#pragma unroll
-                        for (int k = 0; k < WPL; ++k)
-                            tp[(size_t)k * 32] = w[k];
-                    }
                     if (store_edge)
                         eout[r] = make_int2(It, Hc[C - 1]);
                 }
-                if (STORE)
-                    tp += WPL * 32;
+                if (STORE) {
+                    constexpr int SLOT = decltype(slot_tag)::value; // 0..3: aligned group position, -1: runtime
+                    if (SLOT < 0) { // age the 4-step window
+#pragma unroll
+                        for (int k = 0; k < WPL; ++k) {
+                            wq[k].x = wq[k].y;
+                            wq[k].y = wq[k].z;
+                            wq[k].z = wq[k].w;
+                            wq[k].w = w[k];
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < WPL; ++k) {
+                            if (SLOT == 0)
+                                wq[k].x = w[k];
+                            if (SLOT == 1)
+                                wq[k].y = w[k];
+                            if (SLOT == 2)
+                                wq[k].z = w[k];
+                            if (SLOT == 3)
+                                wq[k].w = w[k];
+                        }
+                    }
+                    if (SLOT == 3 || (SLOT < 0 && (t & 3) == 3)) { // every fourth step: 16 B per lane
+                        if (tbase) {
+#pragma unroll
+                            for (int k = 0; k < WPL; ++k)
+                                tp4[(size_t)k * 32] = wq[k];
+                        }
+                        tp4 += WPL * 32;
+                    }
+                }
             };
 
+            using RT = std::integral_constant<int, -1>;
             int t = 0;
+            if (STORE && kGroup4) {
+                // ramp-up to a multiple of 4, then aligned groups of four steady steps (the 4-step trace
+                // window is filled in place, one 16-byte store per group), then the checked remainder
 #pragma unroll 1
-            for (; t < SK * (LPP - 1); ++t)
-                step(t, std::true_type{});
-            if (TRACE) {
-#pragma unroll kUnrollTrace
-                for (; t < nmin - 1; ++t) // steady: every lane of every pair in the warp is on a valid row < n
-                    step(t, std::false_type{});
+                for (; t < ((SK * (LPP - 1) + 3) & ~3); ++t)
+                    step(t, std::true_type{}, RT{});
+#pragma unroll 1
+                for (; t + 3 < nmin - 1; t += 4) {
+                    step(t, std::false_type{}, std::integral_constant<int, 0>{});
+                    step(t + 1, std::false_type{}, std::integral_constant<int, 1>{});
+                    step(t + 2, std::false_type{}, std::integral_constant<int, 2>{});
+                    step(t + 3, std::false_type{}, std::integral_constant<int, 3>{});
+                }
             } else {
+#pragma unroll 1
+                for (; t < SK * (LPP - 1); ++t)
+                    step(t, std::true_type{}, RT{});
+                if (TRACE) {
+#pragma unroll kUnrollTrace
+                    for (; t < nmin - 1; ++t) // steady: every lane of every pair in the warp is on a valid row < n
+                        step(t, std::false_type{}, RT{});
+                } else {
 #pragma unroll kUnrollScore
-                for (; t < nmin - 1; ++t)
-                    step(t, std::false_type{});
+                    for (; t < nmin - 1; ++t)
+                        step(t, std::false_type{}, RT{});
+                }
             }
 #pragma unroll 1
             for (; t < T; ++t)
-                step(t, std::true_type{});
+                step(t, std::true_type{}, RT{});
 
             if (mine) {
                 const int pm = (m - 1) / (LPP * C), lm = ((m - 1) % (LPP * C)) / C, cm = (m - 1) % C;

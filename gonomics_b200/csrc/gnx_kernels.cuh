@@ -498,7 +498,8 @@ struct TraceParams {
     const uint32_t *trace;
     const int64_t *trace_off;
     int C;          // columns per lane the fill kernel used
-    int layout;     // 1: affine_fill_kernel word layout, 2: affine_fill2/3_kernel (codes shifted in from the top)
+    int layout;     // 1: affine_fill_kernel word layout, 2: affine_fill2_kernel (codes shifted in from the top),
+                    // 3: affine_fill3_kernel (as 2, rows blocked four steps per 16-byte piece)
     int lpp;        // lanes per pair of the fill kernel (32, or 16 for fill3's two-pairs-per-warp form)
     int skew;       // rows between neighbouring lanes (1, or 2 for fill3's pipelined form)
     int kind;       // 0 affine, 2 const gap
@@ -528,6 +529,10 @@ __device__ __forceinline__ unsigned affine_code(const uint32_t *tr, int T, int C
     const int lane = within / C, c = within - lane * C;
     const int t = (i - 1) + skew * lane;
     const int nin = (c / 5 == wpl - 1) ? (C - 5 * (wpl - 1)) : 5; // codes held by this word
+    if (layout == 3) { // T is the padded (multiple of 4) row count; [t/4][word][thread][t%4]
+        const uint32_t w3 = tr[((((size_t)strip * (T >> 2) + (t >> 2)) * wpl + c / 5) * 32 + lane) * 4 + (t & 3)];
+        return (w3 >> (32 - kTagBits * (nin - (c % 5)))) & (kScale - 1);
+    }
     const uint32_t w = tr[(((size_t)strip * T + t) * wpl + c / 5) * 32 + lane];
     if (layout == 2) // codes funnel-shifted in from the top (gnx_fill2.cuh)
         return (w >> (32 - kTagBits * (nin - (c % 5)))) & (kScale - 1);
@@ -586,7 +591,10 @@ __global__ void traceback_kernel(const TraceParams P)
         return;
     }
     const uint32_t *tr = P.trace + P.trace_off[idx];
-    const int T = n + (P.kind == 0 ? P.skew * (P.lpp - 1) : 31), C = P.C;
+    int T = n + (P.kind == 0 ? P.skew * (P.lpp - 1) : 31);
+    if (P.kind == 0 && P.layout == 3)
+        T = (T + 3) & ~3;
+    const int C = P.C;
     int i = n, j = m, cur = -1, run = 0;
     if (P.kind == 0) {
         // start plane: T(M,I,D)(n,m) = the H tag of cell (n,m); boundaries are closed-form
@@ -664,6 +672,117 @@ __global__ void traceback_kernel(const TraceParams P)
         P.counts[idx] = cnt;
 }
 
+// Branch-light traceback for the affine kernels' packed traces (layouts 2 and 3, C = 5 or 10).
+// One thread per pair, exactly one trace load per step, the same instruction sequence for every
+// thread whatever plane it is in (the generic kernel above diverges three ways per step; ncu showed
+// 12.7 of 32 lanes active).  The cell's (strip, lane, column) coordinates are walked incrementally
+// instead of re-derived with integer divisions.  Boundary cells are given pseudo-codes:
+//   (0,0): H tag = plane of T(0,O,D(0,0));  (0,j>0): every tag = I;  (i>0,0): every tag = D.
+__global__ void traceback_affine_kernel(const TraceParams P)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t pair = P.pair_begin + idx;
+    if (pair >= P.pair_end)
+        return;
+    const int n = (int)(P.alpha_off[pair + 1] - P.alpha_off[pair]);
+    const int m = (int)(P.beta_off[pair + 1] - P.beta_off[pair]);
+    if (P.pass == 1 && P.counts[idx] <= P.slot_cap)
+        return;
+    uint32_t *slot = P.slots + (size_t)idx * P.slot_cap;
+    CigarOut *dst = nullptr;
+    int total = 0;
+    if (P.pass == 1) {
+        total = P.counts[idx];
+        if (P.cigar_off[idx] + total > P.out_cap)
+            return;
+        dst = (CigarOut *)P.out_cigar + P.cigar_off[idx];
+    }
+    int cnt = 0;
+    auto emit = [&](int op, int run) {
+        if (P.pass == 0) {
+            if (cnt < P.slot_cap)
+                slot[cnt] = ((uint32_t)run << 2) | (uint32_t)op;
+        } else {
+            CigarOut o;
+            o.run_length = run;
+            o.op = (unsigned char)op;
+            dst[total - 1 - cnt] = o;
+        }
+        ++cnt;
+    };
+    if (n == 0 && m == 0) {
+        emit(0, 0);
+        if (P.pass == 0)
+            P.counts[idx] = cnt;
+        return;
+    }
+    const uint32_t *__restrict__ tr = P.trace + P.trace_off[idx];
+    const int C = P.C, lpp = P.lpp, skew = P.skew, wpl = trace_wpl(C);
+    const bool blocked = P.layout == 3;
+    int T = n + skew * (lpp - 1);
+    if (blocked)
+        T = (T + 3) & ~3;
+    const size_t strip_words = (size_t)T * wpl * 32;
+    // coordinates of column j = m
+    int strip = 0, lane = 0, c = 0;
+    if (m > 0) {
+        const int jj = m - 1;
+        strip = jj / (lpp * C);
+        const int within = jj - strip * lpp * C;
+        lane = within / C;
+        c = within - lane * C;
+    }
+    auto load = [&](int i) -> unsigned { // code of cell (i, j) whose column coordinates are (strip, lane, c)
+        const int t = (i - 1) + skew * lane;
+        const int wi = c >= 5 ? 1 : 0, cc = c - 5 * wi;
+        const int nin = (wi == wpl - 1) ? (C - 5 * (wpl - 1)) : 5;
+        size_t a;
+        if (blocked)
+            a = (size_t)strip * strip_words + ((((size_t)(t >> 2)) * wpl + wi) * 32 + lane) * 4 + (t & 3);
+        else
+            a = (size_t)strip * strip_words + (((size_t)t) * wpl + wi) * 32 + lane;
+        return (__ldg(tr + a) >> (32 - kTagBits * (nin - cc))) & (kScale - 1);
+    };
+    const unsigned code00 = (unsigned)(2 - P.h00_plane) << 4;
+    int i = n, j = m;
+    unsigned cur = (i > 0 && j > 0) ? load(i) : (i == 0 ? 0x15u : 0x00u);
+    int k = 2 - (int)((cur >> 4) & 3u);
+    int run = 0, cur_op = k;
+    while (i > 0 || j > 0) {
+        if (k == cur_op) {
+            ++run;
+        } else {
+            emit(cur_op, run);
+            cur_op = k;
+            run = 1;
+        }
+        // next plane when the current one is I or D: its tag in the CURRENT cell's code
+        const int kn = 2 - (int)((cur >> (k == 1 ? 0 : 2)) & 3u);
+        const int di = k != 1, dj = k != 2;
+        i -= di;
+        if (dj) { // step one column to the left
+            --j;
+            if (--c < 0) {
+                c = C - 1;
+                if (--lane < 0) {
+                    lane = lpp - 1;
+                    --strip;
+                }
+            }
+        }
+        unsigned nw;
+        if (i > 0 && j > 0)
+            nw = load(i);
+        else
+            nw = (i == 0) ? (j == 0 ? code00 : 0x15u) : 0x00u;
+        k = (k == 0) ? 2 - (int)((nw >> 4) & 3u) : kn; // M: argmax(M,I,D) of the diagonal neighbour
+        cur = nw;
+    }
+    emit(cur_op, run);
+    if (P.pass == 0)
+        P.counts[idx] = cnt;
+}
+
 // Expand the per-pair slots into gnx_cigar records at the scanned offsets (reversing to start->end
 // order, align/align.go:86-90 reverseCigar).  One thread per pair; cigars are short.
 __global__ void expand_kernel(const uint32_t *slots, int slot_cap, const int *counts, const int64_t *cigar_off,
@@ -690,6 +809,90 @@ __global__ void expand_kernel(const uint32_t *slots, int slot_cap, const int *co
     }
 }
 
+// Exclusive scan of int counts into int64 offsets (n+1 entries) in two launches:
+//   scan_partial_kernel: each 256-thread block sums its kScanSeg-pair segment into partial[block];
+//   scan_apply_kernel:   each block adds the partials before it (a few hundred values) to *running_total
+//                        and scans its own segment; the last block publishes off[n] and the new total.
+constexpr int kScanSeg = 2048;
+
+__global__ void scan_partial_kernel(const int *counts, int64_t n, int64_t *partial)
+{
+    __shared__ int64_t s_sum[8];
+    const int64_t lo = (int64_t)blockIdx.x * kScanSeg;
+    int64_t sum = 0;
+    for (int64_t i = lo + threadIdx.x; i < min(n, lo + kScanSeg); i += blockDim.x)
+        sum += counts[i];
+    for (int o = 16; o > 0; o >>= 1)
+        sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0)
+        s_sum[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+            t += s_sum[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
+__global__ void scan_apply_kernel(const int *counts, int64_t n, const int64_t *partial, int64_t *off,
+                                  const int64_t *running_total, int64_t *total_out)
+{
+    __shared__ int64_t s_base;
+    __shared__ int64_t s_warp[8];
+    // base of this block = running total + sum of the partials of the blocks before it
+    int64_t b = 0;
+    for (int k = threadIdx.x; k < (int)blockIdx.x; k += blockDim.x)
+        b += partial[k];
+    for (int o = 16; o > 0; o >>= 1)
+        b += __shfl_down_sync(0xffffffffu, b, o);
+    if ((threadIdx.x & 31) == 0)
+        s_warp[threadIdx.x >> 5] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t t = *running_total;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+            t += s_warp[w];
+        s_base = t;
+    }
+    __syncthreads();
+    // each thread scans kScanSeg / blockDim consecutive counts
+    const int per = kScanSeg / 256;
+    const int64_t lo = (int64_t)blockIdx.x * kScanSeg + (int64_t)threadIdx.x * per;
+    int64_t mine = 0;
+    for (int k = 0; k < per; ++k)
+        if (lo + k < n)
+            mine += counts[lo + k];
+    // exclusive scan of `mine` across the block
+    int64_t incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o)
+            incl += v;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 31)
+        s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int64_t wbase = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w)
+        wbase += s_warp[w];
+    int64_t run = s_base + wbase + incl - mine;
+    for (int k = 0; k < per; ++k) {
+        if (lo + k < n) {
+            off[lo + k] = run;
+            run += counts[lo + k];
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) { // holds the grand total
+        off[n] = run;
+        if (total_out)
+            *total_out = run;
+    }
+}
+
+// Legacy single-block scan (kept for reference / tiny inputs): n+1 entries, offsets continue from
+// *running_total.
 // Exclusive scan of int counts into int64 offsets (n+1 entries), single block, chunk-sized inputs.
 // Chunks are at most a few hundred thousand pairs, so one 1024-thread block striding is enough.
 __global__ void scan_counts_kernel(const int *counts, int64_t n, int64_t *off, int64_t *running_total)
