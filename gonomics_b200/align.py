@@ -149,6 +149,28 @@ class Context:
         return self._batch(1 if free_end_gaps else 0, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_open,
                            gap_extend, want_cigar, cigar_cap, out)
 
+    def affine_gap_chunk_batch(self, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_open, gap_extend, chunk,
+                               cigar_cap=None):
+        """Batched AffineGapChunk (align/affineGap_highMem.go:227): DP over chunk-sized blocks."""
+        alpha_cat = np.ascontiguousarray(alpha_cat, dtype=np.uint8)
+        beta_cat = np.ascontiguousarray(beta_cat, dtype=np.uint8)
+        alpha_off = np.ascontiguousarray(alpha_off, dtype=np.int64)
+        beta_off = np.ascontiguousarray(beta_off, dtype=np.int64)
+        scores = np.ascontiguousarray(scores, dtype=np.int64)
+        n_pairs = len(alpha_off) - 1
+        out_score = np.zeros(n_pairs, dtype=np.int64)
+        out_off = np.zeros(n_pairs + 1, dtype=np.int64)
+        out_cig = np.zeros(max(int(cigar_cap or 16 * n_pairs + 64), 1), dtype=CIGAR_DTYPE)
+        rc = self._L.gnx_affine_chunk_batch(self._h, _addr(alpha_cat), _addr(alpha_off), _addr(beta_cat),
+                                            _addr(beta_off), n_pairs, _addr(scores), int(scores.shape[0]),
+                                            int(gap_open), int(gap_extend), int(chunk), _addr(out_score), _addr(out_cig),
+                                            _addr(out_off), len(out_cig))
+        if rc == GNX_ECAP:
+            out_cig = np.zeros(max(int(out_off[-1]), 1), dtype=CIGAR_DTYPE)
+            rc = self._L.gnx_copy_last_cigars(self._h, _addr(out_cig), len(out_cig))
+        self._check(rc)
+        return out_score, out_off, out_cig[:int(out_off[-1])]
+
     def const_gap_batch(self, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_pen, want_cigar=True,
                         cigar_cap=None, out=None):
         """Batched ConstGap_highMem."""
@@ -258,6 +280,15 @@ def ConstGap_customizeCheckersize(alpha, beta, scores, gapPen, checkersize_i, ch
 def ConstGap(alpha, beta, scores, gapPen, ctx=None):
     """align.ConstGap (align/constGap.go:13)."""
     return ConstGap_customizeCheckersize(alpha, beta, scores, gapPen, 10000, 10000, ctx)
+
+
+def AffineGapChunk(alpha, beta, scores, gapOpen, gapExtend, chunkSize, ctx=None):
+    """align.AffineGapChunk (align/affineGap_highMem.go:227)."""
+    ctx = ctx or default_context()
+    ac, ao = _concat([alpha])
+    bc, bo = _concat([beta])
+    sc, off, cig = ctx.affine_gap_chunk_batch(ac, ao, bc, bo, scores, gapOpen, gapExtend, chunkSize)
+    return int(sc[0]), _split(off, cig)[0]
 
 
 # ---- pretty printers (align/view.go) -------------------------------------------------------

@@ -169,6 +169,7 @@ struct Problem {
     int h00, h00_plane;
     bool prmt_ok;  // 16-bit PRMT tables usable for ACGT-only pairs
     bool tagged;   // run the tagged (scaled) arithmetic: traceback wanted, or score only with O > 0
+    int64_t chunk = 1; // AffineGapChunk: bases per DP cell
 };
 
 // Exact-arithmetic range analysis for the scaled int32 kernels (DESIGN.md "Arithmetic width").
@@ -183,6 +184,8 @@ int analyse(gnx_ctx *ctx, Problem &pb, int64_t max_n, int64_t max_m)
         smin = std::min(smin, pb.scores[i]);
         smax = std::max(smax, pb.scores[i]);
     }
+    smin *= pb.chunk; // AffineGapChunk: a cell's match score is a sum over `chunk` bases
+    smax *= pb.chunk; // (gap_extend already carries the factor)
     const int64_t O = pb.gap_open, E = pb.gap_extend;
     const int64_t absO = O < 0 ? -O : O, absE = E < 0 ? -E : E;
     const int64_t sabs = std::max(-smin, smax);
@@ -218,7 +221,7 @@ int analyse(gnx_ctx *ctx, Problem &pb, int64_t max_n, int64_t max_m)
 void pick_cfg(const gnx_ctx *ctx, Problem &pb, int64_t max_m, int64_t max_n)
 {
     FillCfg &c = pb.cfg;
-    c.impl = pb.kind == 2 ? 1 : ctx->opt_fill_impl;
+    c.impl = (pb.kind == 2 || pb.chunk > 1) ? 1 : ctx->opt_fill_impl;
     if (c.impl == 3 && pb.dim > kDimP)
         c.impl = 2;
     c.lpp = 32;
@@ -469,6 +472,13 @@ void dispatch_fill3(const Problem &pb, const FillParams &fp, int64_t groups, int
 
 void dispatch_fill(const Problem &pb, const FillParams &fp, int C, int lookup, int grid, cudaStream_t st)
 {
+    if (lookup == 2) { // AffineGapChunk: global affine with traceback only
+        if (C == 5)
+            launch_affine<5, true, false, 2>(fp, grid, st);
+        else
+            launch_affine<10, true, false, 2>(fp, grid, st);
+        return;
+    }
     if (C == 5) {
         if (lookup == 0)
             dispatch_fill_cl<5, 0>(pb, fp, grid, st);
@@ -550,11 +560,12 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     fp.edge_stride = cd.edge_stride;
     fp.out_score = cd.score;
     fp.one = 1;
+    fp.chunk = (int)pb.chunk;
 
     // class 0 (ACGT only) with the PRMT tables when the matrix fits 16 bits, else the smem lookup
     FillEvent &fe = next_fill_event(ctx);
     cudaEventRecord(fe.a, st);
-    const int lookup0 = (ctx->opt_force_lookup == 1 || !pb.prmt_ok) ? 1 : 0;
+    const int lookup0 = pb.chunk > 1 ? 2 : ((ctx->opt_force_lookup == 1 || !pb.prmt_ok) ? 1 : 0);
     const int grid2 = (int)std::min<int64_t>(np, (int64_t)ctx->sm_count * std::min(ctx->opt_ctas_per_sm, 20));
     if (pb.cfg.impl == 16) {
         static int occ16[2] = {0, 0};
@@ -593,7 +604,7 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         if (v2)
             dispatch_fill2(pb, fp, C, 1, any_long, grid2, st);
         else
-            dispatch_fill(pb, fp, C, 1, grid, st);
+            dispatch_fill(pb, fp, C, pb.chunk > 1 ? 2 : 1, grid, st);
         ctx->launches++;
         ctx->last_fill_launches++;
     }
@@ -612,6 +623,7 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         tp.layout = pb.cfg.impl == 3 ? 3 : (pb.cfg.impl == 2 ? 2 : 1);
         tp.lpp = pb.cfg.lpp;
         tp.skew = pb.cfg.skew;
+        tp.chunk = (int)pb.chunk;
         tp.kind = pb.kind == 2 ? 2 : 0;
         tp.h00_plane = pb.h00_plane;
         tp.slots = cd.slots;
@@ -673,6 +685,7 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
     tp.layout = pb.cfg.impl == 3 ? 3 : (pb.cfg.impl == 2 ? 2 : 1);
     tp.lpp = pb.cfg.lpp;
     tp.skew = pb.cfg.skew;
+    tp.chunk = (int)pb.chunk;
     tp.kind = pb.kind == 2 ? 2 : 0;
     tp.h00_plane = pb.h00_plane;
     tp.slots = cd.slots;
@@ -1128,7 +1141,7 @@ gnx_ctx *gnx_create(int device, size_t workspace_bytes)
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     if (workspace_bytes == 0)
-        workspace_bytes = std::min<size_t>(free_b / 4, (size_t)32 << 30);
+        workspace_bytes = std::min<size_t>(free_b / 2, (size_t)96 << 30);
     ctx->workspace = workspace_bytes;
     for (int k = 0; k < kSlots; ++k) {
         cudaStreamCreateWithFlags(&ctx->slot[k].stream, cudaStreamNonBlocking);
@@ -1231,12 +1244,27 @@ int gnx_const_batch(gnx_ctx *ctx, const uint8_t *alpha_cat, const int64_t *alpha
                           out_cigar_off, out_cigar ? cigar_cap : 0);
 }
 
-int gnx_affine_chunk_batch(gnx_ctx *ctx, const uint8_t *, const int64_t *, const uint8_t *, const int64_t *, int64_t,
-                           const int64_t *, int, int64_t, int64_t, int64_t, int64_t *, gnx_cigar *, int64_t *, int64_t)
+int gnx_affine_chunk_batch(gnx_ctx *ctx, const uint8_t *alpha_cat, const int64_t *alpha_off, const uint8_t *beta_cat,
+                           const int64_t *beta_off, int64_t n_pairs, const int64_t *scores, int dim, int64_t gap_open,
+                           int64_t gap_extend, int64_t chunk, int64_t *out_score, gnx_cigar *out_cigar,
+                           int64_t *out_cigar_off, int64_t cigar_cap)
 {
     if (!ctx)
         return GNX_EARG;
-    return fail(ctx, GNX_EARG, "gnx_affine_chunk_batch: not built yet");
+    if (n_pairs < 0 || !alpha_off || !beta_off || !out_score || !out_cigar_off)
+        return fail(ctx, GNX_EARG, "bad argument to gnx_affine_chunk_batch");
+    if (chunk <= 0 || chunk > 4096)
+        return fail(ctx, GNX_ECHUNK, "chunkSize must be in 1..4096");
+    for (int64_t p = 0; p < n_pairs; ++p) // align/affineGap_highMem.go:229-234: log.Fatalf on a ragged length
+        if ((alpha_off[p + 1] - alpha_off[p]) % chunk != 0 || (beta_off[p + 1] - beta_off[p]) % chunk != 0)
+            return fail(ctx, GNX_ECHUNK, "a sequence length is not a multiple of chunkSize");
+    Problem pb;
+    int rc = fill_problem(ctx, pb, 0, 1, scores, dim, gap_open, gap_extend * chunk);
+    if (rc != GNX_OK)
+        return rc;
+    pb.chunk = chunk;
+    return run_host_batch(ctx, pb, alpha_cat, alpha_off, beta_cat, beta_off, n_pairs, out_score, out_cigar,
+                          out_cigar_off, out_cigar ? cigar_cap : 0);
 }
 
 int gnx_copy_last_cigars(gnx_ctx *ctx, gnx_cigar *out_cigar, int64_t cigar_cap)

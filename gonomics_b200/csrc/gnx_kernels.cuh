@@ -44,6 +44,7 @@ struct FillParams {
     int2 *edge;                   // per-warp strip hand-off buffers: 2 * edge_stride int2 per warp
     int64_t edge_stride;
     int64_t *out_score;           // indexed by global pair id
+    int chunk;                    // AffineGapChunk: bases per DP cell (1 otherwise); LOOKUP == 2 kernels only
     int one;                      // always 1: an opaque multiplier that keeps adds on the FMA pipe (IMAD)
 };
 
@@ -141,6 +142,9 @@ __global__ void classify_kernel(const uint8_t *alpha, const int64_t *alpha_off, 
 //   FREE   freeEndGaps (AffineGapLocal): D(i,0) = 0 and an un-penalised D in the last column
 //   LOOKUP 0: ACGT-only pairs, substitution scores from per-column 16-bit tables via PRMT
 //          1: any base < dim, scores from a shared-memory copy of the matrix
+//          2: AffineGapChunk (align/affineGap_highMem.go:227-272): a DP cell is a block of P.chunk bases,
+//             its match score the sum of the chunk's substitution scores (ungappedRegionScore,
+//             align/ungapped.go:7-13); the host passes gap_extend * chunk as the gap step
 // ------------------------------------------------------------------------------------------------
 template <int C, bool TRACE, bool FREE, int LOOKUP>
 __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
@@ -152,11 +156,12 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
     constexpr unsigned FULL = 0xffffffffu;
 
     __shared__ int s_scores[64];
-    if (LOOKUP == 1) {
+    if (LOOKUP >= 1) {
         if (threadIdx.x < 64)
             s_scores[threadIdx.x] = P.scores[threadIdx.x] * SC;
         __syncthreads();
     }
+    const int chunk = LOOKUP == 2 ? P.chunk : 1;
 
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -176,8 +181,8 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
         if (P.pair_class && P.pair_class[pair] != P.want_class)
             continue;
         const int64_t a0 = P.alpha_off[pair], b0 = P.beta_off[pair];
-        const int n = (int)(P.alpha_off[pair + 1] - a0);
-        const int m = (int)(P.beta_off[pair + 1] - b0);
+        const int n = (int)(P.alpha_off[pair + 1] - a0) / chunk; // DP rows / columns (chunks when LOOKUP == 2)
+        const int m = (int)(P.beta_off[pair + 1] - b0) / chunk;
         const uint8_t *__restrict__ alpha = P.alpha + a0;
         const uint8_t *__restrict__ beta = P.beta + b0;
 
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const int j = jbase + c + 1;
-                q[c] = (j <= m) ? (int)beta[j - 1] : 0;
+                q[c] = (j <= m) ? (LOOKUP == 2 ? (j - 1) * chunk : (int)beta[j - 1]) : 0; // LOOKUP 2: chunk start
                 if (LOOKUP == 0) {
                     const int s0 = P.scores[0 * P.dim + q[c]] * SC, s1 = P.scores[1 * P.dim + q[c]] * SC;
                     const int s2 = P.scores[2 * P.dim + q[c]] * SC, s3 = P.scores[3 * P.dim + q[c]] * SC;
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
             if (lane == 0)
                 boundary(1);
             int a_next = 0;
-            if (lane == 0)
+            if (lane == 0 && LOOKUP != 2)
                 a_next = alpha[0];
 
             for (int t = 0; t < T; ++t) {
@@ -267,7 +272,7 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
                 }
                 const bool active = (r >= 1) && (r <= n);
                 const int a = a_next;
-                if (r + 1 >= 1 && r + 1 <= n)
+                if (LOOKUP != 2 && r + 1 >= 1 && r + 1 <= n)
                     a_next = alpha[r]; // prefetch the next row's base
                 if (active) {
                     if (lane == 0 && r < n)
@@ -286,10 +291,18 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         int s;
-                        if (LOOKUP == 0)
+                        if (LOOKUP == 0) {
                             s = prmt(t01[c], t23[c], sel);
-                        else
+                        } else if (LOOKUP == 1) {
                             s = s_scores[rowoff + q[c]];
+                        } else { // sum over the chunk (columns past m read nothing)
+                            s = 0;
+                            if (jbase + c + 1 <= m) {
+                                const uint8_t *pa = alpha + (size_t)(r - 1) * chunk, *pb = beta + q[c];
+                                for (int u = 0; u < chunk; ++u)
+                                    s += s_scores[(int)pa[u] * P.dim + (int)pb[u]];
+                            }
+                        }
                         const int Mc = hp + s; // M(r,j) = s + H(r-1,j-1)
                         int cI, cD, Ht, cH;
                         if (TRACE) {
@@ -502,6 +515,7 @@ struct TraceParams {
                     // 3: affine_fill3_kernel (as 2, rows blocked four steps per 16-byte piece)
     int lpp;        // lanes per pair of the fill kernel (32, or 16 for fill3's two-pairs-per-warp form)
     int skew;       // rows between neighbouring lanes (1, or 2 for fill3's pipelined form)
+    int chunk;      // AffineGapChunk: bases per DP cell (run lengths are multiplied by it), else 1
     int kind;       // 0 affine, 2 const gap
     int h00_plane;  // plane of T(0, O, D(0,0)) (affine)
     uint32_t *slots; // per pair in chunk: slot_cap entries, run<<2 | op, traceback order
@@ -558,8 +572,9 @@ __global__ void traceback_kernel(const TraceParams P)
     const int64_t pair = P.pair_begin + idx;
     if (pair >= P.pair_end)
         return;
-    const int n = (int)(P.alpha_off[pair + 1] - P.alpha_off[pair]);
-    const int m = (int)(P.beta_off[pair + 1] - P.beta_off[pair]);
+    const int chunk = P.chunk > 1 ? P.chunk : 1;
+    const int n = (int)(P.alpha_off[pair + 1] - P.alpha_off[pair]) / chunk;
+    const int m = (int)(P.beta_off[pair + 1] - P.beta_off[pair]) / chunk;
     if (P.pass == 1 && P.counts[idx] <= P.slot_cap)
         return;
     uint32_t *slot = P.slots + (size_t)idx * P.slot_cap;
@@ -573,6 +588,7 @@ __global__ void traceback_kernel(const TraceParams P)
     }
     int cnt = 0;
     auto emit = [&](int op, int run) {
+        run *= chunk; // expandCigarRunLength (align/affineGap_highMem.go:91-95)
         if (P.pass == 0) {
             if (cnt < P.slot_cap)
                 slot[cnt] = ((uint32_t)run << 2) | (uint32_t)op;

@@ -60,7 +60,8 @@ enum {
 /* ---- lifetime ------------------------------------------------------------------------------ */
 int gnx_device_count(void);
 /* workspace_bytes: device memory the context may use for traceback matrices of the chunks in
- * flight (0 = default, 1/4 of the device's free memory at creation, capped at 32 GiB). */
+ * flight (0 = default, 1/2 of the device's free memory at creation, capped at 96 GiB: long pairs need
+ * ~0.8 byte per DP cell and enough pairs in flight to fill the SMs). */
 gnx_ctx *gnx_create(int device, size_t workspace_bytes);
 void gnx_destroy(gnx_ctx *ctx);
 const char *gnx_last_error(gnx_ctx *ctx); /* ctx may be NULL: error of the last failed gnx_create */

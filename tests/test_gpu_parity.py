@@ -103,6 +103,43 @@ def test_golden_cigar_to_bed_10kb(ctx):
         assert (score, [tuple(x) for x in cig]) == orc.affine_gap_highmem(a, b, S, g["gap_open"], g["gap_extend"])
 
 
+def test_golden_affine_chunk(ctx):
+    g = load("affine_chunk")  # align/affineGap_test.go:83-93 TestAffineGapChunk
+    S = MATRICES[g["matrix"]]
+    for c in g["cases"]:
+        a, b = bases(c["alpha"]), bases(c["beta"])
+        score, cig = align.AffineGapChunk(a, b, S, g["gap_open"], g["gap_extend"], g["chunk"], ctx)
+        assert align.View(a, b, cig) == c["view"]
+        assert (score, [tuple(x) for x in cig]) == orc.affine_gap_chunk(a, b, S, g["gap_open"], g["gap_extend"], g["chunk"])
+    with pytest.raises(_lib.GnxError) as ei:  # ragged length: the reference log.Fatalf's
+        align.AffineGapChunk(bases("ACGT"), bases("ACG"), S, -400, -30, 3, ctx)
+    assert ei.value.code == _lib.GNX_ECHUNK
+
+
+def test_random_affine_chunk(ctx):
+    rng = np.random.default_rng(800)
+    S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX
+    for chunk in (1, 2, 3, 7):
+        al, be = [], []
+        for _ in range(120):
+            n, m = int(rng.integers(0, 60)) * chunk, int(rng.integers(0, 60)) * chunk
+            unit = rng.integers(0, 4, chunk, dtype=np.uint8)
+            a, b = np.resize(unit, n).copy(), np.resize(unit, m).copy()  # tandem repeats of a chunk-sized unit
+            for arr in (a, b):
+                if len(arr):
+                    k = max(1, len(arr) // 15)
+                    arr[rng.integers(0, len(arr), k)] = rng.integers(0, 4, k)
+            al.append(a)
+            be.append(b)
+        ac, ao = concat(al)
+        bc, bo = concat(be)
+        sc, off, cig = ctx.affine_gap_chunk_batch(ac, ao, bc, bo, S, -600, -150, chunk)
+        for p in range(len(al)):
+            want = orc.affine_gap_chunk(al[p], be[p], S, -600, -150, chunk)
+            got = (int(sc[p]), [(int(r), int(o)) for r, o in cig[off[p]:off[p + 1]]])
+            assert got == want, (chunk, p, len(al[p]), len(be[p]))
+
+
 def test_engine_fifo(ctx):
     cases = load("affine_local")["cases"][:4]
     inputs, outputs = align.GoAffineGapLocalEngine(MATRICES["Default"], -600, -150)

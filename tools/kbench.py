@@ -20,7 +20,10 @@ ap.add_argument("--pairs", type=int, default=500_000)
 ap.add_argument("--n", type=int, default=500)
 ap.add_argument("--m", type=int, default=150)
 ap.add_argument("--kind", type=int, default=1)
-ap.add_argument("--check", action="store_true", help="diff the first 5000 pairs against the oracle")
+ap.add_argument("--check", action="store_true", help="diff the first --check-pairs pairs against the oracle")
+ap.add_argument("--check-pairs", type=int, default=5000)
+ap.add_argument("--workspace-gb", type=float, default=0)
+ap.add_argument("--cap-per-pair", type=int, default=16)
 ap.add_argument("configs", nargs="*", default=["fill_impl=1", "fill_impl=2"])
 args = ap.parse_args()
 P = args.pairs
@@ -30,7 +33,7 @@ ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
 tao, tbo = torch.from_numpy(ao).to(dev), torch.from_numpy(bo).to(dev)
 score = torch.zeros(P, dtype=torch.int64, device=dev)
 off = torch.zeros(P + 1, dtype=torch.int64, device=dev)
-cap = P * 16
+cap = P * args.cap_per_pair
 cig = torch.zeros(cap * 16, dtype=torch.uint8, device=dev)
 status = torch.zeros(1, dtype=torch.int32, device=dev)
 S = align.HumanChimpTwoScoreMatrix
@@ -38,11 +41,11 @@ cells = P * args.n * args.m
 ref = None
 if args.check:
     import oracle as orc
-    k = min(P, 5000)
+    k = min(P, args.check_pairs)
     ref = orc.batch(a[:k * args.n], ao[:k + 1], b[:k * args.m], bo[:k + 1], orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, -600, -150,
                     args.kind, True, os.cpu_count())
 for cfg in args.configs:
-    ctx = align.Context(0)
+    ctx = align.Context(0, int(args.workspace_gb * (1 << 30)))
     for kv in cfg.split(","):
         if kv:
             k_, v_ = kv.split("=")
