@@ -35,6 +35,16 @@ BYTES_PER_PAIR_SCORE = (N_LEN + 3) // 4 + (M_LEN + 3) // 4 + 16 + 8
 BYTES_PER_CELL_TRACE = 0.75
 
 
+def ncu_traffic(kernel: str, pairs_per_launch: float):
+    """DRAM bytes per launch measured by ncu (profiles/ncu_traffic.json), scaled to this run's launch size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        return t[kernel]["dram_bytes"] * pairs_per_launch / t["pairs_per_launch"]
+    except Exception:
+        return None
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -138,6 +148,7 @@ def main():
     ap.add_argument("--no-traceback", action="store_true", help="skip the C3 (traceback) block")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C1 / C4-sample / const-gap block")
     ap.add_argument("--quick", action="store_true", help="profiling runs: no e2e/cpu legs, warm-up not clamped")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -252,7 +263,9 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "frac": (achieved / peak) if achieved else None,
+                     "traffic": ncu_traffic("affine_fill16_kernel", P / max(fill_n, 1)),
+                     "algorithmic_bytes_per_launch": alg_bytes / max(fill_n, 1),
                      "peak_source": peak_src, "kernel": "affine_fill16_kernel<FREE=1> (packed 16-bit, 4 pairs/warp)",
                      "fill_ms_per_step": fill_ms, "fill_launches_per_step": fill_n,
                      "algorithmic_bytes_per_step": alg_bytes,
@@ -279,9 +292,54 @@ def main():
             "workload": "C3 (configs[2]): same pairs, full traceback + CIGAR", "value": g3, "unit": "GCUPS",
             "ms_per_step": ms3 / args.steps, "gpu_launches": launches3, "clocks": clocks3,
             "roofline": {"bound": "hbm", "achieved": ach3, "peak": peak, "unit": "GB/s",
-                         "frac": (ach3 / peak) if ach3 else None, "traffic": None, "peak_source": peak_src,
+                         "frac": (ach3 / peak) if ach3 else None,
+                         "traffic": ncu_traffic("affine_fill3_kernel_trace", P / max(filln3, 1)),
+                         "algorithmic_bytes_per_launch": alg3 / max(filln3, 1), "peak_source": peak_src,
                          "kernel": "affine_fill3_kernel<C=10,LPP=16,MODE=2,FREE=1>", "fill_ms_per_step": fill3,
                          "fill_launches_per_step": filln3, "algorithmic_bytes_per_step": alg3}}
+
+    # ---- other BASELINE shapes (device-resident, fewer steps): C1, a C4-shaped sample, constant gap ----
+    if not args.quick and not args.no_extra:
+        def run_shape(kind, n_len, m_len, pairs, want_cigar, cap_per_pair, steps=3):
+            a, sao, b, sbo = synth_pairs(SEED + 7, pairs, n_len, m_len, first_pair=rank * pairs)
+            ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+            tao, tbo = torch.from_numpy(sao).to(dev), torch.from_numpy(sbo).to(dev)
+            sc = torch.zeros(pairs, dtype=torch.int64, device=dev)
+            off = torch.zeros(pairs + 1, dtype=torch.int64, device=dev)
+            cg = torch.zeros(pairs * cap_per_pair * 16, dtype=torch.uint8, device=dev)
+
+            def one():
+                ctx.batch_device(kind, ta.data_ptr(), tao.data_ptr(), tb.data_ptr(), tbo.data_ptr(), sao, sbo, pairs, S,
+                                 GAP_OPEN if kind != 2 else -430, GAP_EXTEND, want_cigar, sc.data_ptr(), cg.data_ptr(),
+                                 off.data_ptr(), pairs * cap_per_pair, d_status.data_ptr(), stream)
+            one()
+            one()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                one()
+            e1.record()
+            barrier()
+            ms_ = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms_], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_ = float(t.item())
+            assert int(d_status.item()) == 0
+            return world * pairs * n_len * m_len * steps / (ms_ * 1e-3) / 1e9, ms_ / steps
+
+        g1, ms1 = run_shape(0, 1000, 150, 100_000, True, 16)
+        g4, ms4 = run_shape(0, 10_000, 10_000, 512, True, 4096, steps=2)
+        gc, msc = run_shape(2, N_LEN, M_LEN, 1_000_000, True, 400)
+        line["other_workloads"] = {
+            "c1_global_1000x150_traceback": {"value": g1, "unit": "GCUPS", "pairs_per_gpu": 100_000, "ms_per_step": ms1,
+                                             "note": "AffineGap (global) + CIGAR, configs[0] shape x100"},
+            "c4_global_10kx10k_traceback": {"value": g4, "unit": "GCUPS", "pairs_per_gpu": 512, "ms_per_step": ms4,
+                                            "note": "AffineGap (global) + CIGAR, one warp per pair through 32 strips; "
+                                                    "sample of configs[3]"},
+            "const_gap_500x150_traceback": {"value": gc, "unit": "GCUPS", "pairs_per_gpu": 1_000_000,
+                                            "ms_per_step": msc, "note": "ConstGap_highMem + CIGAR, g=-430"}}
 
     # ---- e2e: the public host-buffer API, pinned host inputs, H2D + D2H inside the timed region --
     if not args.no_e2e:

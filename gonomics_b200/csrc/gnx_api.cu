@@ -6,7 +6,6 @@
 // host] -> expand -> D2H, so copies of one chunk overlap the DP fill of another.
 #include "../../include/gnxalign.h"
 #include "gnx_kernels.cuh"
-#include "gnx_fill2.cuh"
 #include "gnx_fill3.cuh"
 #include "gnx_fill16.cuh"
 
@@ -112,11 +111,10 @@ struct gnx_ctx {
     int opt_cols = 0;          // 0 = auto
     int64_t opt_chunk_pairs = 1 << 18;
     int opt_blocks_per_sm = 8;
-    int opt_fill_impl = 3;     // 1: affine_fill_kernel (v1, 4 warps/CTA), 2: affine_fill2_kernel, 3: affine_fill3_kernel
+    int opt_fill_impl = 3;     // 1: first-generation affine_fill_kernel (4 warps/CTA), 3: affine_fill3/fill16 kernels
     int opt_lpp = 0;           // fill3 lanes per pair: 0 auto, 16 or 32
     int opt_tb_impl = 2;       // 1: generic traceback_kernel, 2: traceback_affine_kernel for fill2/3 traces
     int opt_fill16 = 1;        // allow the packed 16-bit score-only kernel when its range proof holds
-    int opt_skew = 1;          // fill3 row skew between lanes (1 or 2; 2 measured no faster, kept as an option)
     int opt_ctas_per_sm = 32;  // fill2/3 persistent grid = SMs * min(this, occupancy)
     int opt_force_lookup = -1; // -1 auto; 0/1 force the PRMT / shared-memory score lookup for ACGT pairs
     int sm_count = 148;
@@ -151,7 +149,7 @@ int fail(gnx_ctx *ctx, int code, const char *msg)
 }
 
 struct FillCfg {
-    int impl = 1; // 1 affine_fill_kernel / const_fill_kernel, 2 affine_fill2_kernel, 3 affine_fill3_kernel,
+    int impl = 1; // 1 affine_fill_kernel / const_fill_kernel, 3 affine_fill3_kernel,
                   // 16 affine_fill16_kernel (packed 16-bit, score only, uniform batch)
     int C = 5;    // columns per lane
     int lpp = 32; // lanes per pair
@@ -221,28 +219,23 @@ int analyse(gnx_ctx *ctx, Problem &pb, int64_t max_n, int64_t max_m)
 void pick_cfg(const gnx_ctx *ctx, Problem &pb, int64_t max_m, int64_t max_n)
 {
     FillCfg &c = pb.cfg;
-    c.impl = (pb.kind == 2 || pb.chunk > 1) ? 1 : ctx->opt_fill_impl;
-    if (c.impl == 3 && pb.dim > kDimP)
-        c.impl = 2;
+    // fill3 (int32, per-lane smem score tables for bases 0..4) is the production affine kernel; the
+    // first-generation kernels serve the constant-gap DP, AffineGapChunk and matrices with dim > 5.
+    c.impl = (pb.kind == 2 || pb.chunk > 1 || pb.dim > kDimP || ctx->opt_fill_impl == 1) ? 1 : 3;
     c.lpp = 32;
-    c.skew = c.impl == 3 ? ctx->opt_skew : 1;
+    c.skew = 1;
     if (c.impl == 3) {
-        c.C = ctx->opt_cols == 5 ? 5 : 10;
-        if (c.C == 10 && ctx->opt_lpp != 32 && max_m <= 16 * c.C)
-            c.lpp = 16;
-        if (c.C == 5 && max_m > 32 * c.C)
-            c.C = 10;
+        c.C = 10;
+        if (ctx->opt_lpp != 32 && max_m <= 16 * c.C)
+            c.lpp = 16; // two pairs per warp
+        c.multi = max_m > (int64_t)c.lpp * c.C || max_n > kRing; // single-strip kernels stage the target in smem
+        if (c.multi)
+            c.lpp = 32;
     } else {
         c.C = (ctx->opt_cols == 5 || ctx->opt_cols == 10) ? ctx->opt_cols : (max_m <= 160 ? 5 : 10);
-    }
-    c.multi = max_m > (int64_t)c.lpp * c.C;
-    if (c.impl == 3 && max_n > kRing) { // single-strip fill3 kernels stage the target in shared memory
-        c.multi = true;
-        c.lpp = 32;
-        c.C = 10;
+        c.multi = max_m > 32 * (int64_t)c.C;
     }
 }
-
 
 // Range proof for the packed 16-bit score-only kernel (gnx_fill16.cuh): every state it ever holds,
 // including the padding columns up to 160, lies in [LB, UB]; with the +32768 bias both must fit 16 bits.
@@ -360,56 +353,6 @@ void dispatch_fill_cl(const Problem &pb, const FillParams &fp, int grid, cudaStr
     }
 }
 
-template <int C, int LOOKUP, bool MULTI>
-void dispatch_fill2_clm(const Problem &pb, const FillParams &fp, int grid, cudaStream_t st)
-{
-    const bool store = pb.want_cigar;
-    if (pb.kind == 1) {
-        if (!pb.tagged)
-            affine_fill2_kernel<C, false, false, true, LOOKUP, MULTI><<<grid, 32, 0, st>>>(fp);
-        else if (store)
-            affine_fill2_kernel<C, true, true, true, LOOKUP, MULTI><<<grid, 32, 0, st>>>(fp);
-        else
-            affine_fill2_kernel<C, true, false, true, LOOKUP, MULTI><<<grid, 32, 0, st>>>(fp);
-    } else {
-        if (!pb.tagged)
-            affine_fill2_kernel<C, false, false, false, LOOKUP, MULTI><<<grid, 32, 0, st>>>(fp);
-        else if (store)
-            affine_fill2_kernel<C, true, true, false, LOOKUP, MULTI><<<grid, 32, 0, st>>>(fp);
-        else
-            affine_fill2_kernel<C, true, false, false, LOOKUP, MULTI><<<grid, 32, 0, st>>>(fp);
-    }
-}
-
-void dispatch_fill2(const Problem &pb, const FillParams &fp, int C, int lookup, bool multi, int grid, cudaStream_t st)
-{
-    if (C == 5) {
-        if (multi) {
-            if (lookup == 0)
-                dispatch_fill2_clm<5, 0, true>(pb, fp, grid, st);
-            else
-                dispatch_fill2_clm<5, 1, true>(pb, fp, grid, st);
-        } else {
-            if (lookup == 0)
-                dispatch_fill2_clm<5, 0, false>(pb, fp, grid, st);
-            else
-                dispatch_fill2_clm<5, 1, false>(pb, fp, grid, st);
-        }
-    } else {
-        if (multi) {
-            if (lookup == 0)
-                dispatch_fill2_clm<10, 0, true>(pb, fp, grid, st);
-            else
-                dispatch_fill2_clm<10, 1, true>(pb, fp, grid, st);
-        } else {
-            if (lookup == 0)
-                dispatch_fill2_clm<10, 0, false>(pb, fp, grid, st);
-            else
-                dispatch_fill2_clm<10, 1, false>(pb, fp, grid, st);
-        }
-    }
-}
-
 // Persistent grid: every CTA must be resident at once (pairs are statically strided over CTAs), so the grid
 // is SMs x min(requested CTAs/SM, what the kernel's registers/shared memory allow).
 template <int C, int LPP, int MODE, bool FREE, bool MULTI, int SK>
@@ -430,10 +373,8 @@ void launch_fill3_sk(const FillParams &fp, int64_t groups, int sm_count, int cta
 template <int C, int LPP, int MODE, bool FREE, bool MULTI>
 void launch_fill3(const FillParams &fp, int64_t groups, int sm_count, int ctas_per_sm, cudaStream_t st, int skew)
 {
-    if (skew == 2)
-        launch_fill3_sk<C, LPP, MODE, FREE, MULTI, 2>(fp, groups, sm_count, ctas_per_sm, st);
-    else
-        launch_fill3_sk<C, LPP, MODE, FREE, MULTI, 1>(fp, groups, sm_count, ctas_per_sm, st);
+    (void)skew; // the two-row skew (SK = 2) variant measured no faster and is not instantiated
+    launch_fill3_sk<C, LPP, MODE, FREE, MULTI, 1>(fp, groups, sm_count, ctas_per_sm, st);
 }
 
 template <int C, int LPP, bool MULTI>
@@ -460,9 +401,7 @@ void dispatch_fill3_t(const Problem &pb, const FillParams &fp, int64_t groups, i
 void dispatch_fill3(const Problem &pb, const FillParams &fp, int64_t groups, int sms, int cps, cudaStream_t st)
 {
     const FillCfg &c = pb.cfg;
-    if (c.C == 5)
-        dispatch_fill3_t<5, 32, false>(pb, fp, groups, sms, cps, st);
-    else if (c.lpp == 16)
+    if (c.lpp == 16)
         dispatch_fill3_t<10, 16, false>(pb, fp, groups, sms, cps, st);
     else if (c.multi)
         dispatch_fill3_t<10, 32, true>(pb, fp, groups, sms, cps, st);
@@ -566,7 +505,6 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     FillEvent &fe = next_fill_event(ctx);
     cudaEventRecord(fe.a, st);
     const int lookup0 = pb.chunk > 1 ? 2 : ((ctx->opt_force_lookup == 1 || !pb.prmt_ok) ? 1 : 0);
-    const int grid2 = (int)std::min<int64_t>(np, (int64_t)ctx->sm_count * std::min(ctx->opt_ctas_per_sm, 20));
     if (pb.cfg.impl == 16) {
         static int occ16[2] = {0, 0};
         const int fi = pb.kind == 1 ? 1 : 0;
@@ -591,20 +529,13 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         ctx->launches++;
         ctx->last_fill_launches++;
     } else {
-        const bool v2 = pb.cfg.impl == 2;
         fp.want_class = 0;
-        if (v2)
-            dispatch_fill2(pb, fp, C, lookup0, any_long, grid2, st);
-        else
-            dispatch_fill(pb, fp, C, lookup0, grid, st);
+        dispatch_fill(pb, fp, C, lookup0, grid, st);
         ctx->launches++;
         ctx->last_fill_launches++;
         // class 1 (contains N or other bases < dim): generic lookup.  Warps skip pairs of the other class.
         fp.want_class = 1;
-        if (v2)
-            dispatch_fill2(pb, fp, C, 1, any_long, grid2, st);
-        else
-            dispatch_fill(pb, fp, C, pb.chunk > 1 ? 2 : 1, grid, st);
+        dispatch_fill(pb, fp, C, pb.chunk > 1 ? 2 : 1, grid, st);
         ctx->launches++;
         ctx->last_fill_launches++;
     }
@@ -620,7 +551,7 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         tp.trace = cd.trace;
         tp.trace_off = cd.trace_off;
         tp.C = C;
-        tp.layout = pb.cfg.impl == 3 ? 3 : (pb.cfg.impl == 2 ? 2 : 1);
+        tp.layout = pb.cfg.impl == 3 ? 3 : 1;
         tp.lpp = pb.cfg.lpp;
         tp.skew = pb.cfg.skew;
         tp.chunk = (int)pb.chunk;
@@ -682,7 +613,7 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
     tp.trace = cd.trace;
     tp.trace_off = cd.trace_off;
     tp.C = C;
-    tp.layout = pb.cfg.impl == 3 ? 3 : (pb.cfg.impl == 2 ? 2 : 1);
+    tp.layout = pb.cfg.impl == 3 ? 3 : 1;
     tp.lpp = pb.cfg.lpp;
     tp.skew = pb.cfg.skew;
     tp.chunk = (int)pb.chunk;
@@ -1423,8 +1354,8 @@ int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
             return fail(ctx, GNX_EARG, "blocks_per_sm must be in 1..32");
         ctx->opt_blocks_per_sm = (int)value;
     } else if (k == "fill_impl") {
-        if (value < 1 || value > 3)
-            return fail(ctx, GNX_EARG, "fill_impl must be 1, 2 or 3");
+        if (value != 1 && value != 3)
+            return fail(ctx, GNX_EARG, "fill_impl must be 1 (first-generation kernels) or 3 (fill3/fill16)");
         ctx->opt_fill_impl = (int)value;
     } else if (k == "lanes_per_pair") {
         if (value != 0 && value != 16 && value != 32)
@@ -1434,10 +1365,6 @@ int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
         ctx->opt_tb_impl = (int)value;
     } else if (k == "fill16") {
         ctx->opt_fill16 = value ? 1 : 0;
-    } else if (k == "skew") {
-        if (value != 1 && value != 2)
-            return fail(ctx, GNX_EARG, "skew must be 1 or 2");
-        ctx->opt_skew = (int)value;
     } else if (k == "force_lookup") {
         ctx->opt_force_lookup = (int)value;
     } else if (k == "ctas_per_sm") {

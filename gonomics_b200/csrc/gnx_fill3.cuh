@@ -1,5 +1,13 @@
-// gnx_fill3.cuh -- third-generation affine fill kernel.  Same recurrence, tie-break and 6-bit trace
-// codes as fill2 (gnx_fill2.cuh); what is new:
+// gnx_fill3.cuh -- the production affine fill kernel (int32, tagged max).  Same recurrence, tie-break and
+// 6-bit trace codes as the first-generation affine_fill_kernel (gnx_kernels.cuh), restructured after
+// measuring the SM's pipes (profiles/r01_microbench_pipes.txt, profiles/r01a_fill.md):
+//   * every integer max / logic / permute instruction issues on the ALU pipe (64 lanes/clk/SM) while IMAD
+//     issues on the FMA pipe (64 lanes/clk/SM) in parallel; the first kernel was ALU-bound (81 % vs 31 %).
+//     The cell update is "plain adds + one VIMNMX3 per plane", the adds forced onto the FMA pipe (madd()),
+//     leaving per cell on the ALU pipe: 3 tag-clears, 3 maxes, XOR3 + funnel shift (trace code).
+//   * one warp per CTA and a persistent, occupancy-sized grid: pair index, lengths and base pointers are
+//     CTA-uniform; the step loop is split into ramp-up / steady / ramp-down so the steady phase carries no
+//     activity predicate; score-only uses H directly (I' = max(I+E, H+O+E), D' likewise; needs O <= 0).
 //   * LPP lanes per pair (32 or 16).  With LPP = 16 a warp carries two pairs side by side (lanes 0-15 and
 //     16-31), each lane owning C = 10 columns: a 150-column read fills 15 of 16 lanes, the row skew is
 //     15 steps instead of 31, and the per-step overhead (shuffles, base fetch, loop control, stores) is
@@ -9,9 +17,33 @@
 //     conflict-free).  The lookup therefore costs no ALU- or FMA-pipe slot (the PRMT of fill2 was an
 //     ALU op) and handles N (dim 5) in the same kernel -- no ACGT/N class split.
 #pragma once
-#include "gnx_fill2.cuh"
+#include "gnx_kernels.cuh"
+#include <type_traits>
 
 namespace gnx {
+
+__device__ __forceinline__ unsigned shf_r_wrap(unsigned lo, unsigned hi, unsigned n)
+{
+    unsigned d;
+    asm("shf.r.wrap.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(n));
+    return d;
+}
+__device__ __forceinline__ int xor3(int a, int b, int c)
+{
+    int d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// a + b issued as IMAD a, one, b: the FMA pipe runs in parallel with the ALU pipe that all the integer
+// max / logic ops share.  `one` is a kernel parameter so ptxas cannot fold the multiply and re-fuse the
+// add into a VIADDMNMX (which would put it back on the saturated ALU pipe).
+__device__ __forceinline__ int madd(int a, int one, int b)
+{
+    int d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
+}
 
 #ifndef GNX_FILL3_MINB
 #define GNX_FILL3_MINB 12

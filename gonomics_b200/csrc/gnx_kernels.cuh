@@ -511,8 +511,8 @@ struct TraceParams {
     const uint32_t *trace;
     const int64_t *trace_off;
     int C;          // columns per lane the fill kernel used
-    int layout;     // 1: affine_fill_kernel word layout, 2: affine_fill2_kernel (codes shifted in from the top),
-                    // 3: affine_fill3_kernel (as 2, rows blocked four steps per 16-byte piece)
+    int layout;     // 1: affine_fill_kernel word layout (codes shifted in from the bottom, one word per step),
+                    // 3: affine_fill3_kernel (codes shifted in from the top, rows blocked four steps per 16-byte piece)
     int lpp;        // lanes per pair of the fill kernel (32, or 16 for fill3's two-pairs-per-warp form)
     int skew;       // rows between neighbouring lanes (1, or 2 for fill3's pipelined form)
     int chunk;      // AffineGapChunk: bases per DP cell (run lengths are multiplied by it), else 1
