@@ -221,7 +221,7 @@ void pick_cfg(const gnx_ctx *ctx, Problem &pb, int64_t max_m, int64_t max_n)
     FillCfg &c = pb.cfg;
     // fill3 (int32, per-lane smem score tables for bases 0..4) is the production affine kernel; the
     // first-generation kernels serve the constant-gap DP, AffineGapChunk and matrices with dim > 5.
-    c.impl = (pb.kind == 2 || pb.chunk > 1 || pb.dim > kDimP || ctx->opt_fill_impl == 1) ? 1 : 3;
+    c.impl = (pb.chunk > 1 || pb.dim > kDimP || ctx->opt_fill_impl == 1) ? 1 : 3;
     c.lpp = 32;
     c.skew = 1;
     if (c.impl == 3) {
@@ -267,13 +267,13 @@ inline int64_t group_trace_words(const Problem &pb, int64_t n_eff, int64_t m)
     if (n_eff <= 0 || m <= 0)
         return 0;
     const FillCfg &c = pb.cfg;
-    if (pb.kind == 2)
+    if (pb.kind == 2 && c.impl != 3)
         return const_trace_words(n_eff, m, c.C);
     const int64_t strips = (m + (int64_t)c.lpp * c.C - 1) / ((int64_t)c.lpp * c.C);
     int64_t rows = n_eff + c.skew * (c.lpp - 1);
     if (c.impl == 3)
         rows = (rows + 3) & ~int64_t(3); // fill3 writes four steps per 16-byte piece
-    return strips * rows * trace_wpl(c.C) * 32;
+    return strips * rows * (pb.kind == 2 ? 1 : trace_wpl(c.C)) * 32; // const_fill3: one word per lane per step
 }
 
 // Per-pair trace offsets (32-bit words) of chunk [begin, begin+np); returns the chunk's total words.
@@ -398,9 +398,48 @@ void dispatch_fill3_t(const Problem &pb, const FillParams &fp, int64_t groups, i
     }
 }
 
+template <int LPP, bool STORE, bool MULTI>
+void launch_const3(const FillParams &fp, int64_t groups, int sms, int cps, cudaStream_t st)
+{
+    static int occ = 0;
+    if (occ == 0) {
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, const_fill3_kernel<10, LPP, STORE, MULTI>, 32, 0) !=
+                cudaSuccess || o < 1)
+            o = 8;
+        occ = o;
+    }
+    const int grid = (int)std::min<int64_t>(groups, (int64_t)sms * std::min(occ, cps));
+    const_fill3_kernel<10, LPP, STORE, MULTI><<<grid, 32, 0, st>>>(fp);
+}
+
+void dispatch_const3(const Problem &pb, const FillParams &fp, int64_t groups, int sms, int cps, cudaStream_t st)
+{
+    const FillCfg &c = pb.cfg;
+    if (pb.want_cigar) {
+        if (c.lpp == 16)
+            launch_const3<16, true, false>(fp, groups, sms, cps, st);
+        else if (c.multi)
+            launch_const3<32, true, true>(fp, groups, sms, cps, st);
+        else
+            launch_const3<32, true, false>(fp, groups, sms, cps, st);
+    } else {
+        if (c.lpp == 16)
+            launch_const3<16, false, false>(fp, groups, sms, cps, st);
+        else if (c.multi)
+            launch_const3<32, false, true>(fp, groups, sms, cps, st);
+        else
+            launch_const3<32, false, false>(fp, groups, sms, cps, st);
+    }
+}
+
 void dispatch_fill3(const Problem &pb, const FillParams &fp, int64_t groups, int sms, int cps, cudaStream_t st)
 {
     const FillCfg &c = pb.cfg;
+    if (pb.kind == 2) {
+        dispatch_const3(pb, fp, groups, sms, cps, st);
+        return;
+    }
     if (c.lpp == 16)
         dispatch_fill3_t<10, 16, false>(pb, fp, groups, sms, cps, st);
     else if (c.multi)
@@ -561,7 +600,9 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         tp.slot_cap = kSlotCap;
         tp.counts = cd.counts;
         tp.pass = 0;
-        if (tp.kind == 0 && tp.layout >= 2 && ctx->opt_tb_impl == 2)
+        if (tp.kind == 2 && tp.layout == 3)
+            traceback_const3_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
+        else if (tp.kind == 0 && tp.layout >= 2 && ctx->opt_tb_impl == 2)
             traceback_affine_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
         else
             traceback_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
@@ -626,7 +667,9 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
     tp.out_cigar = cigars;
     tp.out_cap = cap;
     tp.pass = 1;
-    if (tp.kind == 0 && tp.layout >= 2 && ctx->opt_tb_impl == 2)
+    if (tp.kind == 2 && tp.layout == 3)
+        traceback_const3_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
+    else if (tp.kind == 0 && tp.layout >= 2 && ctx->opt_tb_impl == 2)
         traceback_affine_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
     else
         traceback_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);

@@ -372,4 +372,179 @@ __global__ void __launch_bounds__(32, (C == 5 ? 20 : GNX_FILL3_MINB)) affine_fil
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Constant-gap (Needleman-Wunsch) fill on the same wavefront (align/constGap_highMem.go:23-40):
+//   m(i,j), tr = T(m(i-1,j-1)+s, m(i,j-1)+g, m(i-1,j)+g),  boundaries m(0,j) = j*g, m(i,0) = i*g.
+// One plane, values carried as 4*v + tag (diag 2 = ColM, left 1 = ColI, up 0 = ColD), so a cell is one
+// VIMNMX3 + one tag-clear + one funnel shift on the ALU pipe, three IMAD adds on the FMA pipe and one LDS.
+// Trace: 2 bits per cell, the lane's 10 codes per step in one word, rows blocked four steps per 16 bytes
+// (layout [strip][step/4][thread][step%4]); code k of a word sits at bit 32 - 2*(10 - k).
+// ------------------------------------------------------------------------------------------------
+template <int C, int LPP, bool STORE, bool MULTI>
+__global__ void __launch_bounds__(32, 16) const_fill3_kernel(const FillParams P)
+{
+    constexpr int G = 32 / LPP;
+    constexpr int SC = STORE ? 4 : 1;
+    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(!(MULTI && LPP != 32), "multi-strip pairs use one pair per warp");
+    static_assert(C <= 16, "one trace word per lane per step");
+    __shared__ int s_tab[C * kDimP * 32];
+    constexpr bool STAGE = !MULTI;
+    constexpr int kTgtPitch = kRing + 64;
+    __shared__ uint8_t s_tgt[STAGE ? G * kTgtPitch : 4];
+    const int tid = threadIdx.x;
+    const int lane = tid % LPP, half = tid / LPP;
+    const int one = P.one;
+    const int g = P.gap_open; // the single gap penalty
+    const int g_left = g * SC + (STORE ? 1 : 0), g_up = g * SC;
+    int2 *edge_a = MULTI ? P.edge + (size_t)blockIdx.x * 2 * P.edge_stride : nullptr;
+    int2 *edge_b = MULTI ? edge_a + P.edge_stride : nullptr;
+    const int64_t n_groups = (P.pair_end - P.pair_begin + G - 1) / G;
+
+    for (int64_t group = blockIdx.x; group < n_groups; group += gridDim.x) {
+        const int64_t pair = P.pair_begin + group * G + half;
+        int n = 0, m = 0;
+        const uint8_t *__restrict__ alpha = P.alpha;
+        const uint8_t *__restrict__ beta = P.beta;
+        bool mine = pair < P.pair_end && (!P.pair_class || P.pair_class[pair] <= 1);
+        if (mine) {
+            const int64_t a0 = P.alpha_off[pair], b0 = P.beta_off[pair];
+            n = (int)(P.alpha_off[pair + 1] - a0);
+            m = (int)(P.beta_off[pair + 1] - b0);
+            alpha += a0;
+            beta += b0;
+            if (n == 0 || m == 0) { // boundary row / column (constGap_highMem.go:27-32)
+                if (lane == 0)
+                    P.out_score[pair] = (int64_t)g * (n + m);
+                mine = false;
+            }
+        }
+        if (!mine)
+            n = 0, m = 0;
+        int nmax = n, nmin = n, mmax = m;
+        if (G > 1) {
+            nmax = max(n, __shfl_xor_sync(FULL, n, 16));
+            nmin = min(n, __shfl_xor_sync(FULL, n, 16));
+            mmax = max(m, __shfl_xor_sync(FULL, m, 16));
+        }
+        if (nmax == 0)
+            continue;
+        const int T = STORE ? ((nmax + LPP - 1 + 3) & ~3) : nmax + LPP - 1;
+        const int Tp = (n + LPP - 1 + 3) & ~3;
+        const int strips = MULTI ? (mmax + LPP * C - 1) / (LPP * C) : 1;
+        uint32_t *tbase = (STORE && mine) ? P.trace + P.trace_off[pair - P.pair_begin] : nullptr;
+
+        for (int p = 0; p < strips; ++p) {
+            const int jbase = p * LPP * C + lane * C;
+            int Hc[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int j = jbase + c + 1;
+                const int q = (mine && j <= m) ? (int)beta[j - 1] : 0;
+#pragma unroll
+                for (int a = 0; a < kDimP; ++a) {
+                    int v = 0;
+                    if (a < P.dim && q < P.dim)
+                        v = P.scores[a * P.dim + q] * SC + (STORE ? 2 : 0);
+                    s_tab[(c * kDimP + a) * 32 + tid] = v;
+                }
+                Hc[c] = j * g * SC; // row 0
+            }
+            int hpL = jbase * g * SC;
+            int edgeH = 0;
+            const int2 *ein = (p & 1) ? edge_b : edge_a;
+            int2 *eout = (p & 1) ? edge_a : edge_b;
+            uint4 *tp4 = STORE ? reinterpret_cast<uint4 *>(tbase + ((size_t)p * Tp) * 32) + lane : nullptr;
+            uint4 wq = make_uint4(0, 0, 0, 0);
+            const bool store_edge = MULTI && (lane == LPP - 1) && (p + 1 < strips);
+            int bH = 0;
+            auto boundary = [&](int r) { bH = (!MULTI || p == 0) ? r * g * SC : ein[r].x; };
+            if (lane == 0)
+                boundary(1);
+            const uint8_t *tg = alpha;
+            if (STAGE) {
+                for (int i = lane; i < n; i += LPP)
+                    s_tgt[half * kTgtPitch + i] = alpha[i];
+                tg = s_tgt + half * kTgtPitch;
+            }
+            __syncwarp();
+            int a_next = (lane == 0 && mine) ? (int)tg[0] : 0;
+
+            auto step = [&](int t, auto check_tag) {
+                constexpr bool CHECK = decltype(check_tag)::value;
+                const int r = t - lane + 1;
+                int inH = __shfl_up_sync(FULL, edgeH, 1, LPP);
+                if (lane == 0)
+                    inH = bH;
+                const int a = a_next;
+                bool active = true;
+                if (CHECK) {
+                    active = (unsigned)(r - 1) < (unsigned)n;
+                    if ((unsigned)r < (unsigned)n)
+                        a_next = tg[r];
+                } else {
+                    a_next = tg[r];
+                }
+                unsigned w = 0;
+                if (active) {
+                    if (lane == 0 && r < n)
+                        boundary(r + 1);
+                    const int *row = s_tab + a * 32 + tid;
+                    int left = inH, hp = hpL;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int s = row[c * kDimP * 32];
+                        const int ht = max3(madd(hp, one, s), madd(left, one, g_left), madd(Hc[c], one, g_up));
+                        int cH = ht;
+                        if (STORE) {
+                            w = shf_r_wrap(w, (unsigned)ht, 2);
+                            cH = ht & ~3;
+                        }
+                        hp = Hc[c];
+                        Hc[c] = cH;
+                        left = cH;
+                    }
+                    edgeH = left;
+                    hpL = inH;
+                    if (store_edge)
+                        eout[r] = make_int2(left, 0);
+                }
+                if (STORE) {
+                    wq.x = wq.y;
+                    wq.y = wq.z;
+                    wq.z = wq.w;
+                    wq.w = w;
+                    if ((t & 3) == 3) {
+                        if (tbase)
+                            *tp4 = wq;
+                        tp4 += 32;
+                    }
+                }
+            };
+            int t = 0;
+#pragma unroll 1
+            for (; t < LPP - 1; ++t)
+                step(t, std::true_type{});
+#pragma unroll 4
+            for (; t < nmin - 1; ++t)
+                step(t, std::false_type{});
+#pragma unroll 1
+            for (; t < T; ++t)
+                step(t, std::true_type{});
+            if (mine) {
+                const int pm = (m - 1) / (LPP * C), lm = ((m - 1) % (LPP * C)) / C, cm = (m - 1) % C;
+                if (p == pm && lane == lm) {
+                    int h = Hc[0];
+#pragma unroll
+                    for (int c = 1; c < C; ++c)
+                        if (c == cm)
+                            h = Hc[c];
+                    P.out_score[pair] = (int64_t)(h / SC);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 } // namespace gnx

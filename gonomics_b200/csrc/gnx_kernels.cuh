@@ -799,6 +799,93 @@ __global__ void traceback_affine_kernel(const TraceParams P)
         P.counts[idx] = cnt;
 }
 
+// Traceback of const_fill3_kernel traces (2-bit codes, 10 per word, rows blocked by four): one load per
+// step, no plane state (the code IS the op).  Reference: constGap_highMem.go:43-65.
+__global__ void traceback_const3_kernel(const TraceParams P)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t pair = P.pair_begin + idx;
+    if (pair >= P.pair_end)
+        return;
+    const int n = (int)(P.alpha_off[pair + 1] - P.alpha_off[pair]);
+    const int m = (int)(P.beta_off[pair + 1] - P.beta_off[pair]);
+    if (P.pass == 1 && P.counts[idx] <= P.slot_cap)
+        return;
+    uint32_t *slot = P.slots + (size_t)idx * P.slot_cap;
+    CigarOut *dst = nullptr;
+    int total = 0;
+    if (P.pass == 1) {
+        total = P.counts[idx];
+        if (P.cigar_off[idx] + total > P.out_cap)
+            return;
+        dst = (CigarOut *)P.out_cigar + P.cigar_off[idx];
+    }
+    int cnt = 0;
+    auto emit = [&](int op, int run) {
+        if (P.pass == 0) {
+            if (cnt < P.slot_cap)
+                slot[cnt] = ((uint32_t)run << 2) | (uint32_t)op;
+        } else {
+            CigarOut o;
+            o.run_length = run;
+            o.op = (unsigned char)op;
+            dst[total - 1 - cnt] = o;
+        }
+        ++cnt;
+    };
+    if (n == 0 && m == 0) {
+        emit(0, 0);
+        if (P.pass == 0)
+            P.counts[idx] = cnt;
+        return;
+    }
+    const uint32_t *__restrict__ tr = P.trace + P.trace_off[idx];
+    const int C = P.C, lpp = P.lpp;
+    const int T = (n + lpp - 1 + 3) & ~3;
+    const size_t strip_words = (size_t)T * 32;
+    int strip = 0, lane = 0, c = 0;
+    if (m > 0) {
+        const int jj = m - 1;
+        strip = jj / (lpp * C);
+        const int within = jj - strip * lpp * C;
+        lane = within / C;
+        c = within - lane * C;
+    }
+    int i = n, j = m, cur_op = -1, run = 0;
+    while (i > 0 || j > 0) {
+        int k;
+        if (i > 0 && j > 0) {
+            const int t = (i - 1) + lane;
+            const uint32_t w = __ldg(tr + (size_t)strip * strip_words + (((size_t)(t >> 2)) * 32 + lane) * 4 + (t & 3));
+            k = 2 - (int)((w >> (32 - 2 * (C - c))) & 3u);
+        } else {
+            k = (i == 0) ? 1 : 2; // row 0: I, column 0: D (constGap_highMem.go:28,31)
+        }
+        if (k == cur_op) {
+            ++run;
+        } else {
+            if (cur_op >= 0)
+                emit(cur_op, run);
+            cur_op = k;
+            run = 1;
+        }
+        i -= (k != 1);
+        if (k != 2) {
+            --j;
+            if (--c < 0) {
+                c = C - 1;
+                if (--lane < 0) {
+                    lane = lpp - 1;
+                    --strip;
+                }
+            }
+        }
+    }
+    emit(cur_op, run);
+    if (P.pass == 0)
+        P.counts[idx] = cnt;
+}
+
 // Expand the per-pair slots into gnx_cigar records at the scanned offsets (reversing to start->end
 // order, align/align.go:86-90 reverseCigar).  One thread per pair; cigars are short.
 __global__ void expand_kernel(const uint32_t *slots, int slot_cap, const int *counts, const int64_t *cigar_off,
