@@ -168,6 +168,7 @@ struct Problem {
     bool prmt_ok;  // 16-bit PRMT tables usable for ACGT-only pairs
     bool tagged;   // run the tagged (scaled) arithmetic: traceback wanted, or score only with O > 0
     int64_t chunk = 1; // AffineGapChunk: bases per DP cell
+    bool wide = false; // int64 plane values (the int32 range proof failed)
 };
 
 // Exact-arithmetic range analysis for the scaled int32 kernels (DESIGN.md "Arithmetic width").
@@ -198,8 +199,21 @@ int analyse(gnx_ctx *ctx, Problem &pb, int64_t max_n, int64_t max_m)
     const int64_t bound = core + 2 * (absO + absE) + sabs + 64;
     pb.tagged = pb.want_cigar || (pb.kind != 2 && O > 0);
     const int64_t scale = pb.tagged ? (pb.kind == 2 ? 4 : kScale) : 1;
-    if (2 * bound * scale >= (int64_t(1) << 30) || max_n >= (1 << 24) || max_m >= (1 << 24))
-        return fail(ctx, GNX_ERANGE, "scores/penalties x lengths exceed the exact int32 range of the DP kernels");
+    if (max_n >= (1 << 24) || max_m >= (1 << 24))
+        return fail(ctx, GNX_ERANGE, "sequence longer than 2^24 bases");
+    if (2 * bound * scale >= (int64_t(1) << 30)) {
+        // the int32 proof fails: the affine DP falls back to the int64 instantiation (exact for any input
+        // whose finite values stay below 2^55, i.e. always in practice); other kernels have no wide form yet
+        if (pb.kind == 2 || pb.chunk > 1 || bound >= (int64_t(1) << 54))
+            return fail(ctx, GNX_ERANGE, "scores/penalties x lengths exceed the exact range of the DP kernels");
+        pb.wide = true;
+        pb.tagged = true; // the wide kernel is instantiated in its tagged form only
+        pb.cfg.impl = 1;
+        pb.cfg.C = 5;
+        pb.cfg.lpp = 32;
+        pb.cfg.skew = 1;
+        pb.cfg.multi = max_m > 32 * 5;
+    }
     pb.prmt_ok = sabs * scale + 4 <= 32767;
     // H(0,0) = tripleMaxTrace(0, O, D(0,0))  (affineGap_highMem.go:185-192 + affineTrace :62)
     const int64_t d00 = pb.kind == 1 ? 0 : O;
@@ -567,6 +581,15 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         dispatch_fill3(pb, fp, groups, ctx->sm_count, ctx->opt_ctas_per_sm, st);
         ctx->launches++;
         ctx->last_fill_launches++;
+    } else if (pb.wide) {
+        // int64 plane values: one launch over every valid pair (shared-memory score lookup)
+        fp.want_class = -1;
+        if (pb.kind == 1)
+            affine_fill_kernel<5, true, true, 1, long long><<<grid, 128, 0, st>>>(fp);
+        else
+            affine_fill_kernel<5, true, false, 1, long long><<<grid, 128, 0, st>>>(fp);
+        ctx->launches++;
+        ctx->last_fill_launches++;
     } else {
         fp.want_class = 0;
         dispatch_fill(pb, fp, C, lookup0, grid, st);
@@ -731,7 +754,12 @@ int make_plan(gnx_ctx *ctx, Problem &pb, const int64_t *aoff, const int64_t *bof
         }
     }
     pick_cfg(ctx, pb, plan.max_m, plan.max_n);
-    if (fill16_ok(ctx, pb, plan.min_n, plan.max_n, plan.min_m, plan.max_m)) {
+    {   // range proof first: it may switch the configuration to the int64 kernel, which changes the trace layout
+        const int rc = analyse(ctx, pb, plan.max_n, plan.max_m);
+        if (rc != GNX_OK)
+            return rc;
+    }
+    if (!pb.wide && fill16_ok(ctx, pb, plan.min_n, plan.max_n, plan.min_m, plan.max_m)) {
         pb.cfg.impl = 16;
         pb.cfg.C = 10;
         pb.cfg.lpp = 16;
@@ -829,9 +857,6 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
     Plan plan;
     const int64_t budget_words = (int64_t)(ctx->workspace / kSlots / 4);
     int rc = make_plan(ctx, pb, aoff, boff, n_pairs, budget_words, plan);
-    if (rc != GNX_OK)
-        return rc;
-    rc = analyse(ctx, pb, plan.max_n, plan.max_m);
     if (rc != GNX_OK)
         return rc;
     ctx->last_cells = plan.cells;
@@ -995,7 +1020,7 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
             cd.counts = s.counts.as<int>();
         }
         if (plan.any_long) {
-            CU(s.edge.ensure((size_t)nwarps_total * 2 * edge_stride * sizeof(int2)));
+            CU(s.edge.ensure((size_t)nwarps_total * 2 * edge_stride * sizeof(int2) * (pb.wide ? 2 : 1)));
             cd.edge = s.edge.as<int2>();
             cd.edge_stride = edge_stride;
         }
@@ -1295,9 +1320,6 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
     rc = make_plan(ctx, pb, alpha_off_host, beta_off_host, n_pairs, budget_words, plan);
     if (rc != GNX_OK)
         return rc;
-    rc = analyse(ctx, pb, plan.max_n, plan.max_m);
-    if (rc != GNX_OK)
-        return rc;
     ctx->last_cells = plan.cells;
     Slot &s = ctx->slot[0];
     const int nwarps_total = ctx->sm_count * std::max(ctx->opt_blocks_per_sm * 4, ctx->opt_ctas_per_sm);
@@ -1339,7 +1361,7 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
             cd.counts = s.counts.as<int>();
         }
         if (plan.any_long) {
-            CU(s.edge.ensure((size_t)nwarps_total * 2 * edge_stride * sizeof(int2)));
+            CU(s.edge.ensure((size_t)nwarps_total * 2 * edge_stride * sizeof(int2) * (pb.wide ? 2 : 1)));
             cd.edge = s.edge.as<int2>();
             cd.edge_stride = edge_stride;
         }

@@ -50,6 +50,8 @@ struct FillParams {
 
 __device__ __forceinline__ int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); } // max(a+b, c)
 __device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
+__device__ __forceinline__ long long addmax(long long a, long long b, long long c) { return max(a + b, c); }
+__device__ __forceinline__ long long max3(long long a, long long b, long long c) { return max(max(a, b), c); }
 // PRMT in its default mode: selector nibble bit 3 replicates the sign of the selected byte.
 // (__byte_perm masks that bit off, so the sign-extending 16-bit table lookup needs the PTX form.)
 __device__ __forceinline__ int prmt(int a, int b, int sel)
@@ -146,13 +148,18 @@ __global__ void classify_kernel(const uint8_t *alpha, const int64_t *alpha_off, 
 //             its match score the sum of the chunk's substitution scores (ungappedRegionScore,
 //             align/ungapped.go:7-13); the host passes gap_extend * chunk as the gap step
 // ------------------------------------------------------------------------------------------------
-template <int C, bool TRACE, bool FREE, int LOOKUP>
+//   V      plane value type: int (exact while analyse() proves the range) or long long (any input)
+template <int C, bool TRACE, bool FREE, int LOOKUP, typename V = int>
 __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
 {
+    struct EdgeT {
+        V x, y;
+    };
     constexpr int SC = TRACE ? kScale : 1;
     constexpr int FI = TRACE ? kFI : 0, FD = TRACE ? kFD : 0, FH = TRACE ? kFH : 0;
     constexpr int WPL = trace_wpl(C);
-    constexpr int NEG = kNeg32;
+    const V NEG = sizeof(V) == 8 ? (V)(-(1LL << 61)) : (V)kNeg32;
+    const V CLRV = ~(V)(kScale - 1);
     constexpr unsigned FULL = 0xffffffffu;
 
     __shared__ int s_scores[64];
@@ -168,18 +175,18 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
 
     const int O = P.gap_open, E = P.gap_extend;
-    const int oe_s = (O + E) * SC, e_s = E * SC;
+    const V oe_s = (V)(O + E) * SC, e_s = (V)E * SC;
     // addends of the I-plane max (candidates M, I, D of the cell to the left)
-    const int iM = oe_s + 2 * FI, iI = e_s + FI, iD = oe_s;
+    const V iM = oe_s + 2 * FI, iI = e_s + FI, iD = oe_s;
     // addends of the D-plane max (candidates M, I, D of the cell above), regular columns
-    const int dM = oe_s + 2 * FD, dI = oe_s + FD, dD = e_s;
+    const V dM = oe_s + 2 * FD, dI = oe_s + FD, dD = e_s;
 
-    int2 *edge_a = P.edge ? P.edge + (size_t)warp * 2 * P.edge_stride : nullptr;
-    int2 *edge_b = P.edge ? edge_a + P.edge_stride : nullptr;
+    EdgeT *edge_a = P.edge ? reinterpret_cast<EdgeT *>(P.edge) + (size_t)warp * 2 * P.edge_stride : nullptr;
+    EdgeT *edge_b = P.edge ? edge_a + P.edge_stride : nullptr;
 
     for (int64_t pair = P.pair_begin + warp; pair < P.pair_end; pair += nwarps) {
-        if (P.pair_class && P.pair_class[pair] != P.want_class)
-            continue;
+        if (P.pair_class && (P.want_class < 0 ? P.pair_class[pair] > 1 : P.pair_class[pair] != P.want_class))
+            continue; // want_class -1: every valid pair (classes 0 and 1)
         const int64_t a0 = P.alpha_off[pair], b0 = P.beta_off[pair];
         const int n = (int)(P.alpha_off[pair + 1] - a0) / chunk; // DP rows / columns (chunks when LOOKUP == 2)
         const int m = (int)(P.beta_off[pair + 1] - b0) / chunk;
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
             // ---- per-column constants -----------------------------------------------------------
             int q[C];
             int t01[C], t23[C];       // LOOKUP 0: packed int16 score tables for target base 0,1 | 2,3
-            int aM[C], aI[C], aD[C];  // D-plane addends (FREE: zero in the last column)
+            V aM[C], aI[C], aD[C];    // D-plane addends (FREE: zero in the last column)
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const int j = jbase + c + 1;
@@ -223,35 +230,35 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
                     t23[c] = (s2 & 0xffff) | (s3 << 16);
                 }
                 const bool last = FREE && (j == m);
-                aM[c] = last ? 2 * FD : dM;
-                aI[c] = last ? FD : dI;
-                aD[c] = last ? 0 : dD;
+                aM[c] = last ? (V)(2 * FD) : dM;
+                aI[c] = last ? (V)FD : dI;
+                aD[c] = last ? (V)0 : dD;
             }
             // ---- row 0 state (affineGap_highMem.go:193-197): M=-inf, I=O+jE, D=-inf --------------
-            int Dt[C];   // D(r, col) for the row about to be processed (tagged when TRACE)
-            int Hc[C];   // clean H(r-1, col) of the previous row
+            V Dt[C];     // D(r, col) for the row about to be processed (tagged when TRACE)
+            V Hc[C];     // clean H(r-1, col) of the previous row
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const int j = jbase + c + 1;
-                const int i0 = (O + j * E) * SC;
+                const V i0 = ((V)O + (V)j * E) * SC;
                 Hc[c] = i0; // T(-inf, I, -inf) = I
                 Dt[c] = addmax(NEG, aM[c], addmax(i0, aI[c], NEG + aD[c]));
             }
-            int hpL = (jbase == 0) ? P.h00 * SC : (O + jbase * E) * SC; // H(0, jbase)
-            int edgeI = 0, edgeH = 0;                                   // what lane+1 consumes
-            const int2 *ein = (p & 1) ? edge_b : edge_a;                // written by strip p-1
-            int2 *eout = (p & 1) ? edge_a : edge_b;
+            V hpL = (jbase == 0) ? (V)P.h00 * SC : ((V)O + (V)jbase * E) * SC; // H(0, jbase)
+            V edgeI = 0, edgeH = 0;                                     // what lane+1 consumes
+            const EdgeT *ein = (p & 1) ? edge_b : edge_a;               // written by strip p-1
+            EdgeT *eout = (p & 1) ? edge_a : edge_b;
             uint32_t *tp = (TRACE && tbase) ? tbase + ((size_t)p * T * WPL) * 32 + lane : nullptr;
 
             // lane 0 boundary stream for its next row (column jbase): I'(r, jbase+1) and H(r, jbase)
-            int bI = 0, bH = 0;
+            V bI = 0, bH = 0;
             auto boundary = [&](int r) {
                 if (p == 0) {
-                    const int d0 = FREE ? 0 : (O + r * E) * SC; // D(r,0); M(r,0)=I(r,0)=-inf
+                    const V d0 = FREE ? (V)0 : ((V)O + (V)r * E) * SC; // D(r,0); M(r,0)=I(r,0)=-inf
                     bI = d0 + iD;                               // T(-inf, -inf, D+oe): tag D (0)
                     bH = d0;
                 } else {
-                    const int2 v = ein[r];
+                    const EdgeT v = ein[r];
                     bI = v.x;
                     bH = v.y;
                 }
@@ -264,8 +271,8 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
 
             for (int t = 0; t < T; ++t) {
                 const int r = t - lane + 1; // my row this step
-                int inI = __shfl_up_sync(FULL, edgeI, 1);
-                int inH = __shfl_up_sync(FULL, edgeH, 1);
+                V inI = __shfl_up_sync(FULL, edgeI, 1);
+                V inH = __shfl_up_sync(FULL, edgeH, 1);
                 if (lane == 0) {
                     inI = bI;
                     inH = bH;
@@ -282,8 +289,8 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
                         sel = a * 0x2222 + 0x9910; // PRMT selector: sign-extended 16-bit entry a
                     else
                         rowoff = a * P.dim;
-                    int It = inI;
-                    int hp = hpL;
+                    V It = inI;
+                    V hp = hpL;
                     uint32_t w[WPL];
 #pragma unroll
                     for (int k = 0; k < WPL; ++k)
@@ -303,14 +310,14 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
                                     s += s_scores[(int)pa[u] * P.dim + (int)pb[u]];
                             }
                         }
-                        const int Mc = hp + s; // M(r,j) = s + H(r-1,j-1)
-                        int cI, cD, Ht, cH;
+                        const V Mc = hp + s; // M(r,j) = s + H(r-1,j-1)
+                        V cI, cD, Ht, cH;
                         if (TRACE) {
-                            cI = It & ~(kScale - 1);
-                            cD = Dt[c] & ~(kScale - 1);
+                            cI = It & CLRV;
+                            cD = Dt[c] & CLRV;
                             Ht = max3(Mc + 2 * FH, cI + FH, cD);
-                            cH = Ht & ~(kScale - 1);
-                            const unsigned code = (unsigned)(It + Dt[c] + Ht) & (kScale - 1);
+                            cH = Ht & CLRV;
+                            const unsigned code = (unsigned)((It + Dt[c] + Ht) & (V)(kScale - 1));
                             w[c / 5] = (w[c / 5] << kTagBits) | code;
                         } else {
                             cI = It;
@@ -334,7 +341,7 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
                             tp[(size_t)k * 32] = w[k];
                     }
                     if (lane == 31 && p + 1 < strips)
-                        eout[r] = make_int2(edgeI, edgeH);
+                        eout[r] = EdgeT{edgeI, edgeH};
                 }
                 if (TRACE && tp)
                     tp += WPL * 32;
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
             // ---- score: H(n, m) sits in Hc[] of the lane that owns column m ----------------------
             const int pm = (m - 1) / (32 * C), lm = ((m - 1) % (32 * C)) / C, cm = (m - 1) % C;
             if (p == pm && lane == lm) {
-                int h = Hc[0];
+                V h = Hc[0];
 #pragma unroll
                 for (int c = 1; c < C; ++c)
                     if (c == cm)

@@ -297,6 +297,23 @@ def test_many_ops_overflow_slot(ctx):
     check_batch(ctx, al, be, S, -30, 0, 2)
 
 
+def test_wide_int64_fallback(ctx):
+    """Scores/penalties too large for the int32 range proof take the int64 instantiation: still bit-exact."""
+    rng = np.random.default_rng(900)
+    S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX * 1000
+    al, be = [], []
+    for _ in range(200):
+        n, m = int(rng.integers(0, 400)), int(rng.integers(0, 400))
+        a, b = random_pair(rng, n, m, identity=float(rng.uniform(0.6, 1.0)))
+        if rng.random() < 0.3 and n:
+            a[rng.integers(0, n)] = 4
+        al.append(a)
+        be.append(b)
+    for mode in (0, 1):
+        check_batch(ctx, al, be, S, -600_000, -150_000, mode)
+        check_batch(ctx, al, be, S, -600_000, -150_000, mode, want_cigar=False)
+
+
 def test_invalid_base_is_an_error(ctx):
     a = np.array([0, 1, 7, 3], dtype=np.uint8)  # LowerG: Go panics with index out of range
     b = np.array([0, 1, 2, 3], dtype=np.uint8)
