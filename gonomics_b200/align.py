@@ -9,6 +9,9 @@ gonomics tree):
     ConstGap, ConstGap_customizeCheckersize        align/constGap.go:13,73
     ConstGap_highMem                               align/constGap_highMem.go:11
     AffineGapChunk                                 align/affineGap_highMem.go:227
+    multipleAffineGap, multipleAffineGapChunk      align/affineGap_highMem.go:272,308
+    nearestGroups[Chunk], AllSeqAffine[Chunk],
+    mergeMultipleAlignments                        align/multiAlign.go:27-78,112-153
 
 Every call goes through the CUDA library; there is no CPU path here.  Single-pair functions are
 thin wrappers over the batched entry points (`affine_gap_batch`, `const_gap_batch`), which are the
@@ -176,6 +179,37 @@ class Context:
         """Batched ConstGap_highMem."""
         return self._batch(2, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_pen, 0, want_cigar, cigar_cap, out)
 
+    def multi_affine_chunk_batch(self, groups, pair_x, pair_y, scores, gap_open, gap_extend, chunk=1,
+                                 want_cigar=True, cigar_cap=None):
+        """Batched multipleAffineGap (chunk=1) / multipleAffineGapChunk (align/affineGap_highMem.go:272-353):
+        DP p aligns the sub-alignment groups[pair_x[p]] against groups[pair_y[p]].  groups: 2-D uint8 arrays
+        (sequences x columns; dna.Base incl. lowercase 5..9 and Gap = 10)."""
+        mats = [np.ascontiguousarray(g, dtype=np.uint8).reshape(len(g), -1) for g in groups]
+        nseq = np.array([m.shape[0] for m in mats], dtype=np.int64)
+        goff = np.zeros(len(mats) + 1, dtype=np.int64)
+        if mats:
+            np.cumsum([m.size for m in mats], out=goff[1:])
+        cat = np.concatenate([m.ravel() for m in mats] + [np.zeros(0, dtype=np.uint8)])
+        px = np.ascontiguousarray(pair_x, dtype=np.int64)
+        py = np.ascontiguousarray(pair_y, dtype=np.int64)
+        scores = np.ascontiguousarray(scores, dtype=np.int64)
+        n_pairs = len(px)
+        out_score = np.zeros(n_pairs, dtype=np.int64)
+        out_off = np.zeros(n_pairs + 1, dtype=np.int64) if want_cigar else None
+        out_cig = np.zeros(max(int(cigar_cap or 32 * n_pairs + 64), 1), dtype=CIGAR_DTYPE) if want_cigar else None
+        rc = self._L.gnx_multi_affine_chunk_batch(self._h, _addr(cat), _addr(goff), _addr(nseq), len(mats), _addr(px),
+                                                  _addr(py), n_pairs, _addr(scores), int(scores.shape[0]),
+                                                  int(gap_open), int(gap_extend), int(chunk), int(bool(want_cigar)),
+                                                  _addr(out_score), _addr(out_cig), _addr(out_off),
+                                                  0 if out_cig is None else len(out_cig))
+        if rc == GNX_ECAP:
+            out_cig = np.zeros(max(int(out_off[-1]), 1), dtype=CIGAR_DTYPE)
+            rc = self._L.gnx_copy_last_cigars(self._h, _addr(out_cig), len(out_cig))
+        self._check(rc)
+        if want_cigar:
+            return out_score, out_off, out_cig[:int(out_off[-1])]
+        return out_score, None, None
+
     # ---- device-resident entry point (raw device addresses, e.g. torch tensor .data_ptr()) ----
     def batch_device(self, kind, d_alpha_cat, d_alpha_off, d_beta_cat, d_beta_off, alpha_off_host, beta_off_host,
                      n_pairs, scores, gap_open, gap_extend, want_cigar, d_out_score, d_out_cigar=0, d_out_cigar_off=0,
@@ -289,6 +323,88 @@ def AffineGapChunk(alpha, beta, scores, gapOpen, gapExtend, chunkSize, ctx=None)
     bc, bo = _concat([beta])
     sc, off, cig = ctx.affine_gap_chunk_batch(ac, ao, bc, bo, scores, gapOpen, gapExtend, chunkSize)
     return int(sc[0]), _split(off, cig)[0]
+
+
+# ---- profile DP and the progressive multiple alignment (align/multiAlign.go) --------------------
+class Fasta(NamedTuple):
+    """fasta.Fasta{Name, Seq} as far as the align package uses it."""
+    Name: str
+    Seq: np.ndarray
+
+
+Gap = 10  # dna.Gap
+
+
+def _stack(group: Sequence[Fasta]) -> np.ndarray:
+    return np.stack([np.asarray(f.Seq, dtype=np.uint8) for f in group])
+
+
+def multipleAffineGapChunk(alpha: Sequence[Fasta], beta: Sequence[Fasta], scores, gapOpen, gapExtend, chunkSize,
+                           ctx=None):
+    """align.multipleAffineGapChunk (align/affineGap_highMem.go:308-353)."""
+    ctx = ctx or default_context()
+    sc, off, cig = ctx.multi_affine_chunk_batch([_stack(alpha), _stack(beta)], [0], [1], scores, gapOpen, gapExtend,
+                                                chunkSize)
+    return int(sc[0]), _split(off, cig)[0]
+
+
+def multipleAffineGap(alpha: Sequence[Fasta], beta: Sequence[Fasta], scores, gapOpen, gapExtend, ctx=None):
+    """align.multipleAffineGap (align/affineGap_highMem.go:272-306)."""
+    return multipleAffineGapChunk(alpha, beta, scores, gapOpen, gapExtend, 1, ctx)
+
+
+def nearestGroupsChunk(groups: List[List[Fasta]], scoreMatrix, gapOpen, gapExtend, chunkSize, ctx=None):
+    """align.nearestGroupsChunk (align/multiAlign.go:43-57): every x < y group pair is aligned -- here as ONE
+    GPU batch -- and the first pair (in the reference's loop order) with the strictly best score wins.
+    Returns (bestX, bestY, bestScore, bestRoute)."""
+    ctx = ctx or default_context()
+    xs = [x for x in range(len(groups) - 1) for _ in range(x + 1, len(groups))]
+    ys = [y for x in range(len(groups) - 1) for y in range(x + 1, len(groups))]
+    if not xs:
+        return 0, 0, -(1 << 63), []  # bestScore = math.MinInt64, nothing compared
+    sc, off, cig = ctx.multi_affine_chunk_batch([_stack(g) for g in groups], xs, ys, scoreMatrix, gapOpen, gapExtend,
+                                                chunkSize)
+    k = int(np.argmax(sc))  # first occurrence of the maximum == the reference's strict '>' scan
+    route = [Cigar(int(r), int(o)) for r, o in cig[int(off[k]):int(off[k + 1])]]
+    return xs[k], ys[k], int(sc[k]), route
+
+
+def nearestGroups(groups, scoreMatrix, gapOpen, gapExtend, ctx=None):
+    """align.nearestGroups (align/multiAlign.go:27-41)."""
+    return nearestGroupsChunk(groups, scoreMatrix, gapOpen, gapExtend, 1, ctx)
+
+
+def mergeMultipleAlignments(alpha: Sequence[Fasta], beta: Sequence[Fasta], route) -> List[Fasta]:
+    """align.mergeMultipleAlignments (align/multiAlign.go:112-153): host-side column gather."""
+    ops = np.repeat(np.array([c[1] for c in route], dtype=np.int64), np.array([c[0] for c in route], dtype=np.int64))
+    a_idx = np.cumsum(ops != ColI) - 1  # alpha column consumed by M and D
+    b_idx = np.cumsum(ops != ColD) - 1  # beta column consumed by M and I
+    out = []
+    for f in alpha:
+        seq = np.full(len(ops), Gap, dtype=np.uint8)
+        seq[ops != ColI] = np.asarray(f.Seq, dtype=np.uint8)[a_idx[ops != ColI]]
+        out.append(Fasta(f.Name, seq))
+    for f in beta:
+        seq = np.full(len(ops), Gap, dtype=np.uint8)
+        seq[ops != ColD] = np.asarray(f.Seq, dtype=np.uint8)[b_idx[ops != ColD]]
+        out.append(Fasta(f.Name, seq))
+    return out
+
+
+def AllSeqAffineChunk(records: Sequence[Fasta], scoreMatrix, gapOpen, gapExtend, chunkSize, ctx=None) -> List[Fasta]:
+    """align.AllSeqAffineChunk (align/multiAlign.go:70-78) incl. mergeFastaGroups' swap-with-last (:20-25)."""
+    groups = [[Fasta(r[0], np.asarray(r[1], dtype=np.uint8))] for r in records]
+    while len(groups) > 1:
+        x, y, _, route = nearestGroupsChunk(groups, scoreMatrix, gapOpen, gapExtend, chunkSize, ctx)
+        groups[x] = mergeMultipleAlignments(groups[x], groups[y], route)
+        groups[y] = groups[-1]
+        groups.pop()
+    return groups[0]
+
+
+def AllSeqAffine(records, scoreMatrix, gapOpen, gapExtend, ctx=None) -> List[Fasta]:
+    """align.AllSeqAffine (align/multiAlign.go:59-66)."""
+    return AllSeqAffineChunk(records, scoreMatrix, gapOpen, gapExtend, 1, ctx)
 
 
 # ---- pretty printers (align/view.go) -------------------------------------------------------

@@ -8,6 +8,7 @@
 #include "gnx_kernels.cuh"
 #include "gnx_fill3.cuh"
 #include "gnx_fill16.cuh"
+#include "gnx_profile.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -105,6 +106,9 @@ struct gnx_ctx {
     Slot slot[kSlots];
     DevBuf status;       // int32 device status word
     DevBuf dr_misc;      // device-resident path scratch (running total, counters)
+    // profile (group-vs-group) batches: groups, profiles, pair lists, dense cell-score matrices
+    DevBuf pf_cat, pf_goff, pf_nseq, pf_coloff, pf_scores, pf_px, pf_py, pf_aoff, pf_boff, pf_soff, pf_prof, pf_vb,
+        pf_smat, pf_err;
     int64_t launches = 0;
     int gate_rr = 0;     // round-robin slot of the per-chunk max-base gate words (status[1..8])
     // options
@@ -169,6 +173,8 @@ struct Problem {
     bool tagged;   // run the tagged (scaled) arithmetic: traceback wanted, or score only with O > 0
     int64_t chunk = 1; // AffineGapChunk: bases per DP cell
     bool wide = false; // int64 plane values (the int32 range proof failed)
+    bool profile = false;               // match scores come from a dense per-pair matrix (gnx_profile.cuh)
+    const int64_t *extra_words = nullptr; // profile: per-pair workspace words besides the trace (the S matrix)
 };
 
 // Exact-arithmetic range analysis for the scaled int32 kernels (DESIGN.md "Arithmetic width").
@@ -204,7 +210,7 @@ int analyse(gnx_ctx *ctx, Problem &pb, int64_t max_n, int64_t max_m)
     if (2 * bound * scale >= (int64_t(1) << 30)) {
         // the int32 proof fails: the affine DP falls back to the int64 instantiation (exact for any input
         // whose finite values stay below 2^55, i.e. always in practice); other kernels have no wide form yet
-        if (pb.kind == 2 || pb.chunk > 1 || bound >= (int64_t(1) << 54))
+        if (pb.kind == 2 || pb.chunk > 1 || pb.profile || bound >= (int64_t(1) << 54))
             return fail(ctx, GNX_ERANGE, "scores/penalties x lengths exceed the exact range of the DP kernels");
         pb.wide = true;
         pb.tagged = true; // the wide kernel is instantiated in its tagged form only
@@ -235,7 +241,7 @@ void pick_cfg(const gnx_ctx *ctx, Problem &pb, int64_t max_m, int64_t max_n)
     FillCfg &c = pb.cfg;
     // fill3 (int32, per-lane smem score tables for bases 0..4) is the production affine kernel; the
     // first-generation kernels serve the constant-gap DP, AffineGapChunk and matrices with dim > 5.
-    c.impl = (pb.chunk > 1 || pb.dim > kDimP || ctx->opt_fill_impl == 1) ? 1 : 3;
+    c.impl = (pb.profile || pb.chunk > 1 || pb.dim > kDimP || ctx->opt_fill_impl == 1) ? 1 : 3;
     c.lpp = 32;
     c.skew = 1;
     if (c.impl == 3) {
@@ -497,6 +503,8 @@ struct ChunkDev {
     int *counts;                      // chunk-local
     int64_t *score;                   // biased by -begin (global pair index)
     int64_t a_lo, a_hi, b_lo, b_hi;   // absolute byte ranges of the chunk inside alpha / beta
+    const int *smat;                  // profile batches: biased so that smat + smat_off[pair] is the pair's matrix
+    const int64_t *smat_off;          // indexed by global pair id
 };
 
 // classify + fill (+ traceback pass 0) for chunk [begin, end) on stream st.
@@ -512,7 +520,9 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     const int warps_per_block = 4;
     const int max_grid = ctx->sm_count * ctx->opt_blocks_per_sm;
     const int grid = (int)std::min<int64_t>((np + warps_per_block - 1) / warps_per_block, max_grid);
-    if (pb.cfg.impl == 3 || pb.cfg.impl == 16) {
+    if (pb.profile) {
+        // no sequence bytes on this path: invalid bases were found while the profiles were built
+    } else if (pb.cfg.impl == 3 || pb.cfg.impl == 16) {
         // these kernels take any base < dim, so the per-pair pass is only needed to find WHICH pair is
         // invalid; gate it on the chunk's largest base (vectorised, HBM-bound)
         int *gate = status + 1 + ctx->gate_rr;
@@ -539,7 +549,9 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     fp.beta_off = cd.boff;
     fp.pair_begin = begin;
     fp.pair_end = end;
-    fp.pair_class = cd.cls;
+    fp.pair_class = pb.profile ? nullptr : cd.cls;
+    fp.smat = cd.smat;
+    fp.smat_off = cd.smat_off;
     fp.gap_open = (int)pb.gap_open;
     fp.gap_extend = (int)pb.gap_extend;
     fp.h00 = pb.h00;
@@ -579,6 +591,21 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         // one launch: the per-lane score tables cover every base < dim, so there is no class split
         const int64_t groups = (np + (32 / pb.cfg.lpp) - 1) / (32 / pb.cfg.lpp);
         dispatch_fill3(pb, fp, groups, ctx->sm_count, ctx->opt_ctas_per_sm, st);
+        ctx->launches++;
+        ctx->last_fill_launches++;
+    } else if (pb.profile) {
+        fp.want_class = -1;
+        if (pb.tagged) {
+            if (C == 5)
+                launch_affine<5, true, false, 3>(fp, grid, st);
+            else
+                launch_affine<10, true, false, 3>(fp, grid, st);
+        } else {
+            if (C == 5)
+                launch_affine<5, false, false, 3>(fp, grid, st);
+            else
+                launch_affine<10, false, false, 3>(fp, grid, st);
+        }
         ctx->launches++;
         ctx->last_fill_launches++;
     } else if (pb.wide) {
@@ -768,7 +795,7 @@ int make_plan(gnx_ctx *ctx, Problem &pb, const int64_t *aoff, const int64_t *bof
     }
     plan.any_long = pb.cfg.multi;
     plan.bounds.push_back(0);
-    if (plan.min_n == plan.max_n && plan.min_m == plan.max_m) { // uniform batch: chunk bounds are arithmetic
+    if (!pb.extra_words && plan.min_n == plan.max_n && plan.min_m == plan.max_m) { // uniform batch: chunk bounds are arithmetic
         const int64_t gsz = 32 / pb.cfg.lpp; // pairs that share trace rows
         const int64_t wg = pb.want_cigar ? group_trace_words(pb, (plan.max_n && plan.max_m) ? plan.max_n : 0, plan.max_m) : 0;
         if (wg > budget_words)
@@ -788,13 +815,14 @@ int make_plan(gnx_ctx *ctx, Problem &pb, const int64_t *aoff, const int64_t *bof
         int64_t n = aoff[p + 1] - aoff[p], m = boff[p + 1] - boff[p];
         if (n == 0 || m == 0)
             n = 0;
-        int64_t w = 0;
+        const int64_t extra = pb.extra_words ? pb.extra_words[p] : 0;
+        int64_t w = extra;
         if (pb.want_cigar) {
             if (pb.cfg.lpp == 16 && (count & 1)) // second pair of a group: the group grows to the larger one
-                w = group_trace_words(pb, std::max(n, prev_n), std::max(m, prev_m)) -
-                    group_trace_words(pb, prev_n, prev_m);
+                w += group_trace_words(pb, std::max(n, prev_n), std::max(m, prev_m)) -
+                     group_trace_words(pb, prev_n, prev_m);
             else
-                w = group_trace_words(pb, n, m);
+                w += group_trace_words(pb, n, m);
         }
         if (w > budget_words)
             return fail(ctx, GNX_ERANGE, "one pair's traceback matrix exceeds the context workspace");
@@ -802,7 +830,7 @@ int make_plan(gnx_ctx *ctx, Problem &pb, const int64_t *aoff, const int64_t *bof
             plan.bounds.push_back(p);
             words = 0;
             count = 0;
-            w = pb.want_cigar ? group_trace_words(pb, n, m) : 0;
+            w = extra + (pb.want_cigar ? group_trace_words(pb, n, m) : 0);
         }
         words += w;
         ++count;
@@ -1096,6 +1124,212 @@ int fill_problem(gnx_ctx *ctx, Problem &pb, int kind, int want_cigar, const int6
     return GNX_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Profile (group-vs-group) batch: the inner loop of nearestGroups[Chunk] (align/multiAlign.go:27-57).
+// Groups are uploaded and reduced to column profiles once; the pair list is cut into sub-batches whose
+// cell-score matrices + traceback matrices fit the workspace; each sub-batch runs
+//   profile_score_kernel -> affine_fill_kernel<LOOKUP 3> -> traceback -> scan -> expand
+// on one stream (these batches are small next to the read-alignment ones; no copy/compute overlap).
+// ---------------------------------------------------------------------------------------------
+int run_profile_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *group_cat, const int64_t *group_off,
+                      const int64_t *group_nseq, int64_t n_groups, const int64_t *pair_x, const int64_t *pair_y,
+                      int64_t n_pairs, int64_t *out_score, gnx_cigar *out_cigar, int64_t *out_cigar_off,
+                      int64_t cigar_cap)
+{
+    CU(cudaSetDevice(ctx->device));
+    ctx->fill_events_used = 0;
+    ctx->last_fill_launches = 0;
+    ctx->last_fill_ms = 0;
+    ctx->last_cells = 0;
+    ctx->have_retained = false;
+    ctx->retained.clear();
+    if (out_cigar_off)
+        out_cigar_off[0] = 0;
+    if (n_pairs == 0)
+        return GNX_OK;
+    const int64_t chunk = pb.chunk;
+    std::vector<int64_t> col_off((size_t)n_groups + 1, 0), len((size_t)n_groups, 0);
+    for (int64_t g = 0; g < n_groups; ++g) {
+        const int64_t bytes = group_off[g + 1] - group_off[g], ns = group_nseq[g];
+        if (ns <= 0 || bytes < 0 || bytes % ns != 0) // Go: alpha[0] of an empty group is an index-out-of-range panic
+            return fail(ctx, GNX_EARG, "every group needs >= 1 sequence and a byte count divisible by its sequence count");
+        len[(size_t)g] = bytes / ns;
+        col_off[(size_t)g + 1] = col_off[(size_t)g] + len[(size_t)g];
+    }
+    if (n_pairs >= (int64_t(1) << 23))
+        return fail(ctx, GNX_EARG, "at most 2^23 - 1 group pairs per call");
+    std::vector<int64_t> aoff((size_t)n_pairs + 1, 0), boff((size_t)n_pairs + 1, 0), soff((size_t)n_pairs + 1, 0),
+        extra((size_t)n_pairs, 0);
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        const int64_t x = pair_x[p], y = pair_y[p];
+        if (x < 0 || x >= n_groups || y < 0 || y >= n_groups)
+            return fail(ctx, GNX_EARG, "pair_x / pair_y index out of range");
+        const int64_t n = len[(size_t)x], m = len[(size_t)y];
+        if (n % chunk != 0 || m % chunk != 0) // affineGap_highMem.go:310-315: log.Fatalf
+            return fail(ctx, GNX_ECHUNK, "a subalignment length is not a multiple of chunkSize");
+        aoff[(size_t)p + 1] = aoff[(size_t)p] + n;
+        boff[(size_t)p + 1] = boff[(size_t)p] + m;
+        extra[(size_t)p] = (n / chunk) * (m / chunk);
+        if (extra[(size_t)p] >= (int64_t(1) << 36))
+            return fail(ctx, GNX_ERANGE, "a profile DP has 2^36 or more cells");
+        soff[(size_t)p + 1] = soff[(size_t)p] + extra[(size_t)p];
+    }
+    pb.extra_words = extra.data();
+    Plan plan;
+    const int64_t budget_words = (int64_t)(ctx->workspace / 4);
+    int rc = make_plan(ctx, pb, aoff.data(), boff.data(), n_pairs, budget_words, plan);
+    pb.extra_words = nullptr;
+    if (rc != GNX_OK)
+        return rc;
+    ctx->last_cells = soff[(size_t)n_pairs];
+
+    Slot &s = ctx->slot[0];
+    cudaStream_t st = s.stream;
+    auto up = [&](DevBuf &d, const void *src, size_t bytes) -> int {
+        CU(d.ensure(std::max<size_t>(bytes, 8)));
+        if (bytes)
+            CU(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, st));
+        return GNX_OK;
+    };
+    const int64_t total_cols = col_off[(size_t)n_groups];
+    if ((rc = up(ctx->pf_cat, group_cat, (size_t)(group_off[n_groups] - group_off[0]))) != GNX_OK ||
+        (rc = up(ctx->pf_goff, group_off, (size_t)(n_groups + 1) * 8)) != GNX_OK ||
+        (rc = up(ctx->pf_nseq, group_nseq, (size_t)n_groups * 8)) != GNX_OK ||
+        (rc = up(ctx->pf_coloff, col_off.data(), (size_t)(n_groups + 1) * 8)) != GNX_OK ||
+        (rc = up(ctx->pf_scores, pb.scores, sizeof pb.scores)) != GNX_OK ||
+        (rc = up(ctx->pf_px, pair_x, (size_t)n_pairs * 8)) != GNX_OK ||
+        (rc = up(ctx->pf_py, pair_y, (size_t)n_pairs * 8)) != GNX_OK ||
+        (rc = up(ctx->pf_aoff, aoff.data(), (size_t)(n_pairs + 1) * 8)) != GNX_OK ||
+        (rc = up(ctx->pf_boff, boff.data(), (size_t)(n_pairs + 1) * 8)) != GNX_OK ||
+        (rc = up(ctx->pf_soff, soff.data(), (size_t)(n_pairs + 1) * 8)) != GNX_OK)
+        return rc;
+    CU(ctx->pf_prof.ensure((size_t)std::max<int64_t>(total_cols, 1) * kProfW * 4));
+    CU(ctx->pf_vb.ensure((size_t)std::max<int64_t>(total_cols, 1) * 8 * 8));
+    CU(ctx->pf_err.ensure(8));
+    CU(cudaMemsetAsync(ctx->pf_err.p, 0xff, 8, st));
+    CU(cudaMemsetAsync(ctx->status.p, 0, sizeof(int), st));
+    if (total_cols > 0) {
+        // group_off is absolute inside the caller's group_cat; pf_cat holds it from group_off[0] on
+        profile_count_kernel<<<(int)((total_cols + 255) / 256), 256, 0, st>>>(
+            ctx->pf_cat.as<uint8_t>() - group_off[0], ctx->pf_goff.as<int64_t>(), ctx->pf_nseq.as<int64_t>(),
+            ctx->pf_coloff.as<int64_t>(), (int)n_groups, pb.dim, ctx->pf_scores.as<int64_t>(), ctx->pf_prof.as<int>(),
+            ctx->pf_vb.as<long long>());
+        ctx->launches++;
+    }
+    const int nwarps_total = ctx->sm_count * std::max(ctx->opt_blocks_per_sm * 4, ctx->opt_ctas_per_sm);
+    const int64_t edge_stride = plan.max_n + 2;
+    int64_t cig_total = 0;
+    bool overflow = false;
+    const int64_t n_chunks = (int64_t)plan.bounds.size() - 1;
+    for (int64_t ci = 0; ci < n_chunks; ++ci) {
+        const int64_t begin = plan.bounds[(size_t)ci], end = plan.bounds[(size_t)ci + 1], np = end - begin;
+        const int64_t cells = soff[(size_t)end] - soff[(size_t)begin];
+        CU(ctx->pf_smat.ensure((size_t)std::max<int64_t>(cells, 1) * 4));
+        if (cells > 0) {
+            ProfileScoreParams pp;
+            pp.prof = ctx->pf_prof.as<int>();
+            pp.vb = ctx->pf_vb.as<long long>();
+            pp.col_off = ctx->pf_coloff.as<int64_t>();
+            pp.pair_x = ctx->pf_px.as<int64_t>();
+            pp.pair_y = ctx->pf_py.as<int64_t>();
+            pp.smat_off = ctx->pf_soff.as<int64_t>();
+            pp.pair_begin = begin;
+            pp.pair_end = end;
+            pp.smat_base = soff[(size_t)begin];
+            pp.chunk = (int)chunk;
+            pp.smat = ctx->pf_smat.as<int>();
+            pp.first_error = ctx->pf_err.as<unsigned long long>();
+            profile_score_kernel<<<(int)((cells + 255) / 256), 256, 0, st>>>(pp);
+            ctx->launches++;
+        }
+        ChunkDev cd;
+        memset(&cd, 0, sizeof cd);
+        cd.aoff = ctx->pf_aoff.as<int64_t>();
+        cd.boff = ctx->pf_boff.as<int64_t>();
+        CU(s.score.ensure((size_t)np * 8));
+        cd.score = s.score.as<int64_t>() - begin;
+        cd.smat = ctx->pf_smat.as<int>() - soff[(size_t)begin];
+        cd.smat_off = ctx->pf_soff.as<int64_t>();
+        if (pb.want_cigar) {
+            CU(s.h_trace_off.ensure((size_t)(np + 1) * 8));
+            int64_t *to = s.h_trace_off.as<int64_t>();
+            const int64_t acc = compute_trace_offsets(pb, aoff.data(), boff.data(), begin, np, to);
+            CU(s.trace.ensure((size_t)std::max<int64_t>(acc, 1) * 4));
+            CU(s.trace_off.ensure((size_t)(np + 1) * 8));
+            CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, st));
+            CU(s.slots.ensure((size_t)np * kSlotCap * 4));
+            CU(s.counts.ensure((size_t)np * 4));
+            CU(s.cig_off.ensure((size_t)(np + 1) * 8));
+            cd.trace = s.trace.as<uint32_t>();
+            cd.trace_off = s.trace_off.as<int64_t>();
+            cd.slots = s.slots.as<uint32_t>();
+            cd.counts = s.counts.as<int>();
+        }
+        if (plan.any_long) {
+            CU(s.edge.ensure((size_t)nwarps_total * 2 * edge_stride * sizeof(int2)));
+            cd.edge = s.edge.as<int2>();
+            cd.edge_stride = edge_stride;
+        }
+        rc = enqueue_chunk_compute(ctx, pb, cd, begin, end, st);
+        if (rc != GNX_OK)
+            return rc;
+        CU(s.h_score.ensure((size_t)np * 8));
+        CU(cudaMemcpyAsync(s.h_score.p, s.score.p, (size_t)np * 8, cudaMemcpyDeviceToHost, st));
+        if (pb.want_cigar) {
+            CU(s.misc.ensure(64));
+            CU(cudaMemsetAsync(s.misc.p, 0, 8, st));
+            rc = enqueue_scan(ctx, s.partials, cd.counts, np, s.cig_off.as<int64_t>(), s.misc.as<int64_t>(), nullptr, st);
+            if (rc != GNX_OK)
+                return rc;
+            CU(s.h_off.ensure((size_t)(np + 1) * 8));
+            CU(cudaMemcpyAsync(s.h_off.p, s.cig_off.p, (size_t)(np + 1) * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st)); // also fences the pinned trace-offset staging for the next sub-batch
+            const int64_t *ho = s.h_off.as<int64_t>();
+            const int64_t total = ho[np];
+            CU(s.cigars.ensure((size_t)std::max<int64_t>(total, 1) * sizeof(gnx_cigar)));
+            rc = enqueue_chunk_expand(ctx, pb, cd, begin, end, s.cig_off.as<int64_t>(), s.cigars.as<gnx_cigar>(), total, st);
+            if (rc != GNX_OK)
+                return rc;
+            CU(s.h_cig.ensure((size_t)std::max<int64_t>(total, 1) * sizeof(gnx_cigar)));
+            CU(cudaMemcpyAsync(s.h_cig.p, s.cigars.p, (size_t)total * sizeof(gnx_cigar), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            const bool fits = !overflow && out_cigar && cig_total + total <= cigar_cap;
+            if (!fits && !overflow) {
+                overflow = true;
+                ctx->retained.resize((size_t)cig_total);
+                if (out_cigar && cig_total > 0)
+                    memcpy(ctx->retained.data(), out_cigar, (size_t)cig_total * sizeof(gnx_cigar));
+            }
+            if (fits) {
+                memcpy(out_cigar + cig_total, s.h_cig.p, (size_t)total * sizeof(gnx_cigar));
+            } else {
+                ctx->retained.resize((size_t)(cig_total + total));
+                memcpy(ctx->retained.data() + cig_total, s.h_cig.p, (size_t)total * sizeof(gnx_cigar));
+            }
+            for (int64_t k = 0; k < np; ++k)
+                out_cigar_off[begin + k] = cig_total + ho[k];
+            cig_total += total;
+            out_cigar_off[end] = cig_total;
+        } else {
+            CU(cudaStreamSynchronize(st));
+        }
+        memcpy(out_score + begin, s.h_score.p, (size_t)np * 8);
+    }
+    collect_fill_stats(ctx);
+    unsigned long long first = 0;
+    CU(cudaMemcpy(&first, ctx->pf_err.p, 8, cudaMemcpyDeviceToHost));
+    if (first != ~0ull) { // the panic the reference would hit first (pair order, then row-major cell order)
+        if ((first & 15) == (unsigned)kEBase)
+            return fail(ctx, GNX_EBASE, "a group holds a base >= dim opposite an ungapped base (Go: index out of range)");
+        return fail(ctx, GNX_EDIVZERO, "a column pair has no ungapped base pair (Go: integer divide by zero in scoreColumnMatch)");
+    }
+    if (overflow) {
+        ctx->have_retained = true;
+        return fail(ctx, GNX_ECAP, "cigar_cap too small; call gnx_copy_last_cigars with a larger buffer");
+    }
+    return GNX_OK;
+}
+
 } // namespace
 
 // =================================================================================================
@@ -1184,6 +1418,10 @@ void gnx_destroy(gnx_ctx *ctx)
     }
     ctx->status.release();
     ctx->dr_misc.release();
+    DevBuf *pf[] = {&ctx->pf_cat, &ctx->pf_goff, &ctx->pf_nseq, &ctx->pf_coloff, &ctx->pf_scores, &ctx->pf_px, &ctx->pf_py,
+                    &ctx->pf_aoff, &ctx->pf_boff, &ctx->pf_soff, &ctx->pf_prof, &ctx->pf_vb, &ctx->pf_smat, &ctx->pf_err};
+    for (DevBuf *b : pf)
+        b->release();
     delete ctx;
 }
 
@@ -1264,6 +1502,31 @@ int gnx_affine_chunk_batch(gnx_ctx *ctx, const uint8_t *alpha_cat, const int64_t
     pb.chunk = chunk;
     return run_host_batch(ctx, pb, alpha_cat, alpha_off, beta_cat, beta_off, n_pairs, out_score, out_cigar,
                           out_cigar_off, out_cigar ? cigar_cap : 0);
+}
+
+int gnx_multi_affine_chunk_batch(gnx_ctx *ctx, const uint8_t *group_cat, const int64_t *group_off,
+                                 const int64_t *group_nseq, int64_t n_groups, const int64_t *pair_x,
+                                 const int64_t *pair_y, int64_t n_pairs, const int64_t *scores, int dim,
+                                 int64_t gap_open, int64_t gap_extend, int64_t chunk, int want_cigar,
+                                 int64_t *out_score, gnx_cigar *out_cigar, int64_t *out_cigar_off, int64_t cigar_cap)
+{
+    if (!ctx)
+        return GNX_EARG;
+    if (n_groups < 0 || n_pairs < 0 || !group_off || (n_groups > 0 && !group_nseq) || !out_score ||
+        (n_pairs > 0 && (!pair_x || !pair_y)))
+        return fail(ctx, GNX_EARG, "bad argument to gnx_multi_affine_chunk_batch");
+    if (want_cigar && !out_cigar_off)
+        return fail(ctx, GNX_EARG, "out_cigar_off is required when want_cigar != 0");
+    if (chunk <= 0 || chunk > 4096)
+        return fail(ctx, GNX_ECHUNK, "chunkSize must be in 1..4096");
+    Problem pb;
+    int rc = fill_problem(ctx, pb, 0, want_cigar, scores, dim, gap_open, gap_extend * chunk);
+    if (rc != GNX_OK)
+        return rc;
+    pb.chunk = chunk;
+    pb.profile = true;
+    return run_profile_batch(ctx, pb, group_cat, group_off, group_nseq, n_groups, pair_x, pair_y, n_pairs, out_score,
+                             out_cigar, out_cigar_off, out_cigar ? cigar_cap : 0);
 }
 
 int gnx_copy_last_cigars(gnx_ctx *ctx, gnx_cigar *out_cigar, int64_t cigar_cap)

@@ -46,6 +46,8 @@ struct FillParams {
     int64_t *out_score;           // indexed by global pair id
     int chunk;                    // AffineGapChunk: bases per DP cell (1 otherwise); LOOKUP == 2 kernels only
     int one;                      // always 1: an opaque multiplier that keeps adds on the FMA pipe (IMAD)
+    const int *smat;              // LOOKUP == 3: dense per-pair cell scores S[i][j] (gnx_profile.cuh), unscaled
+    const int64_t *smat_off;      // LOOKUP == 3: first cell of pair p's matrix inside smat, indexed by global pair id
 };
 
 __device__ __forceinline__ int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); } // max(a+b, c)
@@ -147,6 +149,9 @@ __global__ void classify_kernel(const uint8_t *alpha, const int64_t *alpha_off, 
 //          2: AffineGapChunk (align/affineGap_highMem.go:227-272): a DP cell is a block of P.chunk bases,
 //             its match score the sum of the chunk's substitution scores (ungappedRegionScore,
 //             align/ungapped.go:7-13); the host passes gap_extend * chunk as the gap step
+//          3: profile DP (multipleAffineGap[Chunk], align/affineGap_highMem.go:274-353): the cell's match
+//             score is read from the dense matrix P.smat that profile_score_kernel produced; lengths are
+//             in bases and divided by P.chunk like LOOKUP 2; alpha/beta are not read
 // ------------------------------------------------------------------------------------------------
 //   V      plane value type: int (exact while analyse() proves the range) or long long (any input)
 template <int C, bool TRACE, bool FREE, int LOOKUP, typename V = int>
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
             s_scores[threadIdx.x] = P.scores[threadIdx.x] * SC;
         __syncthreads();
     }
-    const int chunk = LOOKUP == 2 ? P.chunk : 1;
+    const int chunk = LOOKUP >= 2 ? P.chunk : 1;
 
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -192,6 +197,7 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
         const int m = (int)(P.beta_off[pair + 1] - b0) / chunk;
         const uint8_t *__restrict__ alpha = P.alpha + a0;
         const uint8_t *__restrict__ beta = P.beta + b0;
+        const int *__restrict__ smat = LOOKUP == 3 ? P.smat + P.smat_off[pair] : nullptr;
 
         if (n == 0 || m == 0) { // closed forms of the boundary rows (affineGap_highMem.go:185-206)
             if (lane == 0) {
@@ -222,7 +228,10 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const int j = jbase + c + 1;
-                q[c] = (j <= m) ? (LOOKUP == 2 ? (j - 1) * chunk : (int)beta[j - 1]) : 0; // LOOKUP 2: chunk start
+                if (LOOKUP == 3)
+                    q[c] = j - 1;
+                else
+                    q[c] = (j <= m) ? (LOOKUP == 2 ? (j - 1) * chunk : (int)beta[j - 1]) : 0; // LOOKUP 2: chunk start
                 if (LOOKUP == 0) {
                     const int s0 = P.scores[0 * P.dim + q[c]] * SC, s1 = P.scores[1 * P.dim + q[c]] * SC;
                     const int s2 = P.scores[2 * P.dim + q[c]] * SC, s3 = P.scores[3 * P.dim + q[c]] * SC;
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
             if (lane == 0)
                 boundary(1);
             int a_next = 0;
-            if (lane == 0 && LOOKUP != 2)
+            if (lane == 0 && LOOKUP < 2)
                 a_next = alpha[0];
 
             for (int t = 0; t < T; ++t) {
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
                 }
                 const bool active = (r >= 1) && (r <= n);
                 const int a = a_next;
-                if (LOOKUP != 2 && r + 1 >= 1 && r + 1 <= n)
+                if (LOOKUP < 2 && r + 1 >= 1 && r + 1 <= n)
                     a_next = alpha[r]; // prefetch the next row's base
                 if (active) {
                     if (lane == 0 && r < n)
@@ -302,6 +311,8 @@ __global__ void __launch_bounds__(128) affine_fill_kernel(const FillParams P)
                             s = prmt(t01[c], t23[c], sel);
                         } else if (LOOKUP == 1) {
                             s = s_scores[rowoff + q[c]];
+                        } else if (LOOKUP == 3) {
+                            s = (jbase + c + 1 <= m) ? smat[(size_t)(r - 1) * m + q[c]] * SC : 0;
                         } else { // sum over the chunk (columns past m read nothing)
                             s = 0;
                             if (jbase + c + 1 <= m) {

@@ -48,7 +48,9 @@ enum {
     GNX_EEMPTY = 4, /* low-mem entry point called with an empty sequence (reference undefined)       */
     GNX_ECUDA = 5,  /* CUDA runtime failure, text in gnx_last_error                                  */
     GNX_EARG = 6,   /* bad argument (NULL pointer, dim out of range, ...)                            */
-    GNX_ERANGE = 7  /* scores/penalties/lengths exceed the exact-arithmetic range of every kernel    */
+    GNX_ERANGE = 7, /* scores/penalties/lengths exceed the exact-arithmetic range of every kernel    */
+    GNX_EDIVZERO = 8 /* profile DP: a column pair with no ungapped base pair (Go: integer divide by zero
+                        in scoreColumnMatch, align/multiAlign.go:101)                                 */
 };
 
 /* mode for gnx_affine_batch */
@@ -106,6 +108,25 @@ int gnx_affine_chunk_batch(gnx_ctx *ctx, const uint8_t *alpha_cat, const int64_t
                            const int64_t *scores, int dim, int64_t gap_open, int64_t gap_extend,
                            int64_t chunk, int64_t *out_score, gnx_cigar *out_cigar,
                            int64_t *out_cigar_off, int64_t cigar_cap);
+
+/* ---- profile (group-vs-group) affine gap: the progressive-MSA inner loop ----------------------- *
+ * Replaces multipleAffineGap / multipleAffineGapChunk (align/affineGap_highMem.go:274-353) with their
+ * match score scoreColumnMatch / ungappedRegionColumnScore (align/multiAlign.go:82-110: truncated
+ * integer mean of scores[a][b] over the ungapped base pairs of two alignment columns, lowercase folded),
+ * batched over the (x, y) group pairs that nearestGroups / nearestGroupsChunk (multiAlign.go:27-57)
+ * evaluate; chunk = 1 is multipleAffineGap.
+ * Group g is a sub-alignment of group_nseq[g] (>= 1) sequences of equal length
+ * L_g = (group_off[g+1] - group_off[g]) / group_nseq[g], stored row after row in group_cat (the
+ * fasta.Fasta.Seq bytes: dna.Base incl. lowercase 5..9 and dna.Gap = 10).  DP p aligns
+ * alpha = group pair_x[p] against beta = group pair_y[p]; run lengths are in bases (already x chunk).
+ * Errors in the reference's order: GNX_ECHUNK (log.Fatalf, :310-315), then the first panic in pair /
+ * row-major cell order: GNX_EBASE (a base >= dim opposite an ungapped base) or GNX_EDIVZERO. */
+int gnx_multi_affine_chunk_batch(gnx_ctx *ctx, const uint8_t *group_cat, const int64_t *group_off,
+                                 const int64_t *group_nseq, int64_t n_groups, const int64_t *pair_x,
+                                 const int64_t *pair_y, int64_t n_pairs, const int64_t *scores, int dim,
+                                 int64_t gap_open, int64_t gap_extend, int64_t chunk, int want_cigar,
+                                 int64_t *out_score, gnx_cigar *out_cigar, int64_t *out_cigar_off,
+                                 int64_t cigar_cap);
 
 /* After a GNX_ECAP return: copy the retained cigars of the last batch call (total = the last
  * entry of that call's out_cigar_off). */

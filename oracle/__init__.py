@@ -83,6 +83,10 @@ def lib():
         L.orc_const_lowmem.argtypes = [u8p, i64, u8p, i64, i64p, ci, i64, i64, i64, i64p, cgp, i64, i64p]
         L.orc_affine_chunk.argtypes = [u8p, i64, u8p, i64, i64p, ci, i64, i64, i64, i64p, cgp, i64, i64p]
         L.orc_multi_affine_chunk.argtypes = [u8p, i64, i64, u8p, i64, i64, i64p, ci, i64, i64, i64, i64p, cgp, i64, i64p]
+        L.orc_left_dynamic_aln.argtypes = [u8p, i64, u8p, i64, i64p, ci, i64, i64p, cgp, i64, i64p, i64p, i64p]
+        L.orc_right_dynamic_aln.argtypes = [u8p, i64, u8p, i64, i64p, ci, i64, i64p, cgp, i64, i64p, i64p, i64p]
+        L.orc_left_dynamic_aln.restype = ci
+        L.orc_right_dynamic_aln.restype = ci
         L.orc_batch.argtypes = [u8p, i64p, u8p, i64p, i64, i64p, ci, i64, i64, ci, ci, ci, i64p, cgp, i64p, i64p]
         for f in ("orc_affine_highmem", "orc_const_highmem", "orc_affine_lowmem", "orc_const_lowmem",
                   "orc_affine_chunk", "orc_multi_affine_chunk", "orc_batch"):
@@ -177,6 +181,31 @@ def multi_affine_gap_chunk(group_a: np.ndarray, group_b: np.ndarray, scores, gap
     if rc != ORC_OK:
         raise OracleError(rc, "multi_affine_chunk")
     return score.value, [(int(buf["run_length"][i]), int(buf["op"][i])) for i in range(n_out.value)]
+
+
+def _extend(fn, what, alpha, beta, scores, gap_pen):
+    a, ap = _u8(alpha)
+    b, bp = _u8(beta)
+    s, sp = _i64(scores)
+    cap = len(a) + len(b) + 2
+    buf = np.zeros(cap, dtype=CIGAR_DTYPE)
+    score, n_out, ri, rj = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    rc = fn(ap, len(a), bp, len(b), sp, int(s.shape[0]), int(gap_pen), C.byref(score),
+            buf.ctypes.data_as(C.POINTER(OrcCigar)), cap, C.byref(n_out), C.byref(ri), C.byref(rj))
+    if rc != ORC_OK:
+        raise OracleError(rc, what)
+    route = [(int(buf["run_length"][k]), chr(int(buf["op"][k]))) for k in range(n_out.value)]
+    return score.value, route, ri.value, rj.value
+
+
+def left_dynamic_aln(alpha, beta, scores, gap_pen):
+    """genomeGraph.LeftDynamicAln (genomeGraph/search.go:234): (score, route in traceback order, i, j)."""
+    return _extend(lib().orc_left_dynamic_aln, "left_dynamic_aln", alpha, beta, scores, gap_pen)
+
+
+def right_dynamic_aln(alpha, beta, scores, gap_pen):
+    """genomeGraph.RightDynamicAln (genomeGraph/search.go:276): (score, route in traceback order, maxI, maxJ)."""
+    return _extend(lib().orc_right_dynamic_aln, "right_dynamic_aln", alpha, beta, scores, gap_pen)
 
 
 def batch(alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_open, gap_extend, mode, want_cigar=True, n_threads=1):

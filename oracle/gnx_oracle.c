@@ -850,6 +850,159 @@ done:
 }
 
 /* =====================================================================================
+ * gsw extend step: LeftDynamicAln / RightDynamicAln, genomeGraph/search.go:234-321.
+ * cigar.TripleMaxTrace (cigar/tools.go:58-66) has the same M >= I >= D tie order with ops 'M','I','D'.
+ * ===================================================================================== */
+static const uint8_t kOpChar[3] = {'M', 'I', 'D'};
+
+/* the reference's route idiom here differs from align's: `len(route)==0 -> append` (search.go:250-257) */
+static void ext_push(route_t *r, int64_t *idx, uint8_t op)
+{
+    if (r->oom)
+        return;
+    if (r->len == 0) {
+        route_append(r, 1, op);
+    } else if (r->v[*idx].op == op) {
+        r->v[*idx].run_length += 1;
+    } else {
+        route_append(r, 1, op);
+        (*idx)++;
+    }
+}
+
+static int ext_fill(const uint8_t *alpha, int64_t n, const uint8_t *beta, int64_t m, const int64_t *scores, int dim,
+                    int64_t g, int left, int64_t **m_out, uint8_t **t_out, int64_t *max_v, int64_t *max_i,
+                    int64_t *max_j)
+{
+    const int64_t W = m + 1;
+    int64_t *mm = (int64_t *)calloc((size_t)((n + 1) * W), sizeof(int64_t));
+    uint8_t *tr = (uint8_t *)calloc((size_t)((n + 1) * W), 1);
+    if (!mm || !tr) {
+        free(mm);
+        free(tr);
+        return ORC_ENOMEM;
+    }
+    int64_t cur_max = 0, bi = 0, bj = 0;
+    for (int64_t i = 0; i <= n; i++) {
+        for (int64_t j = 0; j <= m; j++) {
+            int64_t v;
+            uint8_t k = 0;
+            if (left) { /* search.go:236-251: zero boundaries, clip at 0 after recording the trace */
+                if (i == 0 || j == 0) {
+                    v = 0;
+                } else {
+                    v = tmt(mm[(i - 1) * W + j - 1] + scores[(int64_t)alpha[i - 1] * dim + beta[j - 1]],
+                            mm[i * W + j - 1] + g, mm[(i - 1) * W + j] + g, &k);
+                    tr[i * W + j] = kOpChar[k];
+                    if (v < 0)
+                        v = 0;
+                }
+            } else { /* search.go:280-299 */
+                if (i == 0 && j == 0) {
+                    v = 0;
+                } else if (i == 0) {
+                    v = mm[j - 1] + g;
+                    tr[j] = 'I';
+                } else if (j == 0) {
+                    v = mm[(i - 1) * W] + g;
+                    tr[i * W] = 'D';
+                } else {
+                    v = tmt(mm[(i - 1) * W + j - 1] + scores[(int64_t)alpha[i - 1] * dim + beta[j - 1]],
+                            mm[i * W + j - 1] + g, mm[(i - 1) * W + j] + g, &k);
+                    tr[i * W + j] = kOpChar[k];
+                }
+                if (v > cur_max) { /* strict: the first arg-max in row-major order (:295-299) */
+                    cur_max = v;
+                    bi = i;
+                    bj = j;
+                }
+            }
+            mm[i * W + j] = v;
+        }
+    }
+    *m_out = mm;
+    *t_out = tr;
+    *max_v = cur_max;
+    *max_i = bi;
+    *max_j = bj;
+    return ORC_OK;
+}
+
+int orc_left_dynamic_aln(const uint8_t *alpha, int64_t n, const uint8_t *beta, int64_t m,
+                         const int64_t *scores, int dim, int64_t gap_pen, int64_t *score, orc_cigar *out,
+                         int64_t cap, int64_t *n_out, int64_t *end_i, int64_t *end_j)
+{
+    if (n > 0 && m > 0 && (!bases_ok(alpha, n, dim) || !bases_ok(beta, m, dim)))
+        return ORC_EBASE;
+    int64_t *mm;
+    uint8_t *tr;
+    int64_t mv, mi, mj;
+    int rc = ext_fill(alpha, n, beta, m, scores, dim, gap_pen, 1, &mm, &tr, &mv, &mi, &mj);
+    if (rc != ORC_OK)
+        return rc;
+    const int64_t W = m + 1;
+    route_t r;
+    route_init(&r);
+    r.len = 0; /* the extend functions start from an empty route */
+    int64_t idx = 0, i = n, j = m;
+    while (mm[i * W + j] > 0) { /* search.go:252-272 */
+        const uint8_t op = tr[i * W + j];
+        ext_push(&r, &idx, op);
+        if (op == 'M') {
+            i--;
+            j--;
+        } else if (op == 'I') {
+            j--;
+        } else {
+            i--;
+        }
+    }
+    *score = mm[n * W + m];
+    *end_i = i;
+    *end_j = j;
+    free(mm);
+    free(tr);
+    return route_emit(&r, out, cap, n_out);
+}
+
+int orc_right_dynamic_aln(const uint8_t *alpha, int64_t n, const uint8_t *beta, int64_t m,
+                          const int64_t *scores, int dim, int64_t gap_pen, int64_t *score, orc_cigar *out,
+                          int64_t cap, int64_t *n_out, int64_t *max_i, int64_t *max_j)
+{
+    if (n > 0 && m > 0 && (!bases_ok(alpha, n, dim) || !bases_ok(beta, m, dim)))
+        return ORC_EBASE;
+    int64_t *mm;
+    uint8_t *tr;
+    int64_t mv, mi, mj;
+    int rc = ext_fill(alpha, n, beta, m, scores, dim, gap_pen, 0, &mm, &tr, &mv, &mi, &mj);
+    if (rc != ORC_OK)
+        return rc;
+    const int64_t W = m + 1;
+    route_t r;
+    route_init(&r);
+    r.len = 0;
+    int64_t idx = 0, i = mi, j = mj;
+    while (i > 0 || j > 0) { /* search.go:301-319 */
+        const uint8_t op = tr[i * W + j];
+        ext_push(&r, &idx, op);
+        if (op == 'M') {
+            i--;
+            j--;
+        } else if (op == 'I') {
+            j--;
+        } else {
+            i--;
+        }
+    }
+    *score = mm[mi * W + mj];
+    *max_i = mi;
+    *max_j = mj;
+    free(mm);
+    free(tr);
+    return route_emit(&r, out, cap, n_out);
+}
+
+/* =====================================================================================
  * Batched, threaded driver (CPU baseline shape: one worker per core over disjoint pair
  * ranges, cmd/gsw/pairedEndFastqs.go:33-35).
  * ===================================================================================== */

@@ -82,6 +82,19 @@ int orc_multi_affine_chunk(const uint8_t *ga, int64_t na_seq, int64_t n, const u
                            int64_t gap_open, int64_t gap_extend, int64_t chunk, int64_t *score,
                            orc_cigar *out, int64_t cap, int64_t *n_out);
 
+/* ---- "next" row 8f-1: the gsw extend step (genomeGraph/search.go:234-321), linear gap, cigar.Cigar ops
+ * 'M','I','D' (cigar/cigar.go:15-18, tie-break cigar/tools.go:58-66), route in TRACEBACK order (the
+ * reference does not reverse it here).  Restated for a clean dynamicScoreKeeper (empty route, currMax 0):
+ * resetDynamicScore takes its argument by value (search.go:104-107), so in the reference a non-empty
+ * route leaks in from the caller; that caller-side quirk is outside these functions.
+ * PARITY UNPINNED: the reference has no asserting test for these two functions. */
+int orc_left_dynamic_aln(const uint8_t *alpha, int64_t n, const uint8_t *beta, int64_t m,
+                         const int64_t *scores, int dim, int64_t gap_pen, int64_t *score, orc_cigar *out,
+                         int64_t cap, int64_t *n_out, int64_t *end_i, int64_t *end_j);
+int orc_right_dynamic_aln(const uint8_t *alpha, int64_t n, const uint8_t *beta, int64_t m,
+                          const int64_t *scores, int dim, int64_t gap_pen, int64_t *score, orc_cigar *out,
+                          int64_t cap, int64_t *n_out, int64_t *max_i, int64_t *max_j);
+
 /* Batched driver used as the CPU baseline: one affineGap_highMem (or ConstGap_highMem when
  * mode==2) per pair, pairs split into contiguous ranges over n_threads pthreads -- the
  * goroutine-per-worker shape of cmd/gsw/pairedEndFastqs.go:33-35.  Cigars are written to

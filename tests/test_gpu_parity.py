@@ -398,3 +398,109 @@ def test_config_c1_global_1kb(ctx):
     al = [a[ao[p]:ao[p + 1]] for p in range(1000)]
     be = [b[bo[p]:bo[p + 1]] for p in range(1000)]
     check_batch(ctx, al, be, orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, -600, -150, 0)
+
+
+# ---- profile DP / progressive multiple alignment ---------------------------------
+def _random_group(rng, nseq, length, gap_frac=0.15, lower_frac=0.1, with_n=True):
+    g = rng.integers(0, 5 if with_n else 4, size=(nseq, length), dtype=np.uint8)
+    low = rng.random((nseq, length)) < lower_frac
+    g[low] += 5  # lowercase bases fold to uppercase in scoreColumnMatch
+    gaps = rng.random((nseq, length)) < gap_frac
+    g[gaps] = 10
+    g[0, :][g[0, :] == 10] = 1  # keep one ungapped base per column: no division by zero
+    return g
+
+
+def test_multi_affine_golden_fixtures(ctx):  # align/multiAlign_test.go:17-37 TestMultiAlignGap
+    g = load("multi_align")
+    S = MATRICES[g["matrix"]]
+    for c in g["cases"]:
+        recs = [(n, bases(s)) for n, s in c["input"]]
+        want = sorted((n, s) for n, s in c["expected"])
+        for chunk in (1, g["chunk"]):
+            got = align.AllSeqAffineChunk(recs, S, g["gap_open"], g["gap_extend"], chunk, ctx)
+            assert sorted((f.Name, orc.bases_to_string(f.Seq)) for f in got) == want, chunk
+    g = load("affine_global")  # TestAffineGapMulti (affineGap_test.go:95-108): groups of one sequence
+    S = MATRICES[g["matrix"]]
+    for c in g["cases"]:
+        a, b = bases(c["alpha"]), bases(c["beta"])
+        sc, cig = align.multipleAffineGap([align.Fasta("one", a)], [align.Fasta("two", b)], S, g["gap_open"],
+                                          g["gap_extend"], ctx)
+        assert (sc, cig) == align.AffineGap_highMem(a, b, S, g["gap_open"], g["gap_extend"], ctx)
+        assert align.View(a, b, cig) == c["view"]
+
+
+def test_multi_affine_random_groups(ctx):
+    rng = np.random.default_rng(815)
+    for chunk in (1, 2, 3, 5):
+        groups = []
+        for _ in range(9):
+            L = int(rng.integers(0, 70)) * chunk
+            groups.append(_random_group(rng, int(rng.integers(1, 7)), L))
+        groups.append(_random_group(rng, 3, 230 * chunk))  # more than one 160-column strip
+        groups.append(_random_group(rng, 2, 400 * chunk))
+        xs = [x for x in range(len(groups) - 1) for _ in range(x + 1, len(groups))]
+        ys = [y for x in range(len(groups) - 1) for y in range(x + 1, len(groups))]
+        for S, O, E in ((orc.DEFAULT_SCORE_MATRIX, -400, -30), (orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, -600, -150)):
+            sc, off, cig = ctx.multi_affine_chunk_batch(groups, xs, ys, S, O, E, chunk)
+            sc2, _, _ = ctx.multi_affine_chunk_batch(groups, xs, ys, S, O, E, chunk, want_cigar=False)
+            assert np.array_equal(sc, sc2)
+            for p, (x, y) in enumerate(zip(xs, ys)):
+                want = orc.multi_affine_gap_chunk(groups[x], groups[y], S, O, E, chunk)
+                got = (int(sc[p]), [(int(r), int(o)) for r, o in cig[off[p]:off[p + 1]]])
+                assert got == want, (chunk, x, y, groups[x].shape, groups[y].shape)
+
+
+def test_multi_affine_small_workspace_and_errors(ctx):
+    rng = np.random.default_rng(816)
+    groups = [_random_group(rng, 3, 120) for _ in range(8)]
+    xs = [x for x in range(7) for _ in range(x + 1, 8)]
+    ys = [y for x in range(7) for y in range(x + 1, 8)]
+    S = orc.DEFAULT_SCORE_MATRIX
+    want = [orc.multi_affine_gap_chunk(groups[x], groups[y], S, -400, -30, 1) for x, y in zip(xs, ys)]
+    c2 = align.Context(0, workspace_bytes=1 << 20)  # forces many sub-batches
+    try:
+        sc, off, cig = c2.multi_affine_chunk_batch(groups, xs, ys, S, -400, -30, 1, cigar_cap=8)  # + GNX_ECAP path
+        got = [(int(sc[p]), [(int(r), int(o)) for r, o in cig[off[p]:off[p + 1]]]) for p in range(len(xs))]
+        assert got == want
+    finally:
+        c2.close()
+    # all-gap column pair: Go divides by zero
+    bad = [g.copy() for g in groups]
+    bad[2][:, 7] = 10
+    bad[5][:, 3] = 10
+    with pytest.raises(_lib.GnxError) as ei:
+        ctx.multi_affine_chunk_batch(bad, xs, ys, S, -400, -30, 1)
+    assert ei.value.code == _lib.GNX_EDIVZERO
+    # a base outside the matrix (dna.Dot = 11) opposite an ungapped base: index out of range
+    bad = [g.copy() for g in groups]
+    bad[1][1, 5] = 11
+    with pytest.raises(_lib.GnxError) as ei:
+        ctx.multi_affine_chunk_batch(bad, xs, ys, S, -400, -30, 1)
+    assert ei.value.code == _lib.GNX_EBASE
+    with pytest.raises(orc.OracleError):
+        orc.multi_affine_gap_chunk(bad[1], bad[0], S, -400, -30, 1)
+    with pytest.raises(_lib.GnxError) as ei:  # length not a multiple of chunkSize: log.Fatalf
+        ctx.multi_affine_chunk_batch(groups, xs, ys, S, -400, -30, 7)
+    assert ei.value.code == _lib.GNX_ECHUNK
+
+
+def test_all_seq_affine_random_families(ctx):
+    """Whole progressive alignments (AllSeqAffine / AllSeqAffineChunk) against the oracle's driver."""
+    from oracle import msa
+    rng = np.random.default_rng(817)
+    S = orc.DEFAULT_SCORE_MATRIX
+    for chunk in (1, 4):
+        root = rng.integers(0, 4, size=30 * chunk, dtype=np.uint8)
+        recs = []
+        for k in range(6):
+            s = root.copy()
+            for _ in range(int(rng.integers(0, 3))):  # delete / duplicate whole chunk-sized units
+                u = int(rng.integers(0, len(s) // chunk)) * chunk
+                s = np.delete(s, np.s_[u:u + chunk]) if rng.random() < 0.5 else np.insert(s, u, s[u:u + chunk])
+            sub = rng.random(len(s)) < 0.05
+            s[sub] = rng.integers(0, 4, size=int(sub.sum()), dtype=np.uint8)
+            recs.append((f"s{k}", s))
+        got = align.AllSeqAffineChunk(recs, S, -400, -30, chunk, ctx)
+        want = msa.all_seq_affine_chunk(recs, S, -400, -30, chunk)
+        assert [(f.Name, f.Seq.tolist()) for f in got] == [(n, s.tolist()) for n, s in want]
