@@ -15,12 +15,13 @@ LIB_PATH = os.path.join(_HERE, "libgnxalign.so")
 
 GNX_OK, GNX_EBASE, GNX_ECAP, GNX_ECHUNK, GNX_EEMPTY, GNX_ECUDA, GNX_EARG, GNX_ERANGE, GNX_EDIVZERO = range(9)
 GNX_GLOBAL, GNX_FREE_END = 0, 1
+GNX_EXT_LEFT, GNX_EXT_RIGHT = 1, 2
 
 # every symbol include/gnxalign.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "gnx_device_count", "gnx_create", "gnx_destroy", "gnx_last_error", "gnx_version", "gnx_host_alloc",
     "gnx_host_free", "gnx_affine_batch", "gnx_const_batch", "gnx_affine_chunk_batch", "gnx_copy_last_cigars",
-    "gnx_multi_affine_chunk_batch", "gnx_batch_device", "gnx_launch_count", "gnx_last_fill_stats", "gnx_set_option",
+    "gnx_multi_affine_chunk_batch", "gnx_extend_batch", "gnx_batch_device", "gnx_launch_count", "gnx_last_fill_stats", "gnx_set_option",
 ]
 
 
@@ -73,6 +74,8 @@ def load() -> C.CDLL:
     L.gnx_multi_affine_chunk_batch.argtypes = [vp, u8p, i64p, i64p, i64, i64p, i64p, i64, i64p, ci, i64, i64, i64, ci,
                                                i64p, cgp, i64p, i64]
     L.gnx_multi_affine_chunk_batch.restype = ci
+    L.gnx_extend_batch.argtypes = [vp, ci, u8p, i64p, u8p, i64p, i64, i64p, ci, i64, ci, i64p, i64p, i64p, cgp, i64p, i64]
+    L.gnx_extend_batch.restype = ci
     L.gnx_copy_last_cigars.argtypes = [vp, cgp, i64]
     L.gnx_copy_last_cigars.restype = ci
     L.gnx_batch_device.argtypes = [vp, ci, u8p, i64p, u8p, i64p, i64p, i64p, i64, i64p, ci, i64, i64, ci, i64p, cgp,

@@ -87,7 +87,8 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_total = nullptr, ev_done = nullptr;
     DevBuf alpha, beta, aoff, boff, cls, trace, trace_off, slots, counts, score, cig_off, cigars, edge, misc, partials;
-    PinBuf h_stage_a, h_stage_b, h_total, h_trace_off, h_score, h_off, h_cig;
+    DevBuf best, endi, endj; // gsw extend step: first-maximum cell (right) and the traceback's end coordinates
+    PinBuf h_stage_a, h_stage_b, h_total, h_trace_off, h_score, h_off, h_cig, h_endi, h_endj;
     // chunk in flight
     int64_t begin = 0, end = 0;
     bool busy = false;
@@ -173,6 +174,7 @@ struct Problem {
     bool tagged;   // run the tagged (scaled) arithmetic: traceback wanted, or score only with O > 0
     int64_t chunk = 1; // AffineGapChunk: bases per DP cell
     bool wide = false; // int64 plane values (the int32 range proof failed)
+    int ext = 0;       // gsw extend step on the const-gap machinery (kind 2): 1 LeftDynamicAln, 2 RightDynamicAln
     bool profile = false;               // match scores come from a dense per-pair matrix (gnx_profile.cuh)
     const int64_t *extra_words = nullptr; // profile: per-pair workspace words besides the trace (the S matrix)
 };
@@ -204,7 +206,7 @@ int analyse(gnx_ctx *ctx, Problem &pb, int64_t max_n, int64_t max_m)
     }
     const int64_t bound = core + 2 * (absO + absE) + sabs + 64;
     pb.tagged = pb.want_cigar || (pb.kind != 2 && O > 0);
-    const int64_t scale = pb.tagged ? (pb.kind == 2 ? 4 : kScale) : 1;
+    const int64_t scale = pb.ext == 2 ? 16 : (pb.tagged ? (pb.kind == 2 ? 4 : kScale) : 1); // ext 2: 16*v + column keys
     if (max_n >= (1 << 24) || max_m >= (1 << 24))
         return fail(ctx, GNX_ERANGE, "sequence longer than 2^24 bases");
     if (2 * bound * scale >= (int64_t(1) << 30)) {
@@ -241,7 +243,7 @@ void pick_cfg(const gnx_ctx *ctx, Problem &pb, int64_t max_m, int64_t max_n)
     FillCfg &c = pb.cfg;
     // fill3 (int32, per-lane smem score tables for bases 0..4) is the production affine kernel; the
     // first-generation kernels serve the constant-gap DP, AffineGapChunk and matrices with dim > 5.
-    c.impl = (pb.profile || pb.chunk > 1 || pb.dim > kDimP || ctx->opt_fill_impl == 1) ? 1 : 3;
+    c.impl = (pb.profile || pb.chunk > 1 || pb.dim > kDimP || (ctx->opt_fill_impl == 1 && !pb.ext)) ? 1 : 3;
     c.lpp = 32;
     c.skew = 1;
     if (c.impl == 3) {
@@ -418,39 +420,50 @@ void dispatch_fill3_t(const Problem &pb, const FillParams &fp, int64_t groups, i
     }
 }
 
-template <int LPP, bool STORE, bool MULTI>
+template <int LPP, bool STORE, bool MULTI, int EXT>
 void launch_const3(const FillParams &fp, int64_t groups, int sms, int cps, cudaStream_t st)
 {
     static int occ = 0;
     if (occ == 0) {
         int o = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, const_fill3_kernel<10, LPP, STORE, MULTI>, 32, 0) !=
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, const_fill3_kernel<10, LPP, STORE, MULTI, EXT>, 32, 0) !=
                 cudaSuccess || o < 1)
             o = 8;
         occ = o;
     }
     const int grid = (int)std::min<int64_t>(groups, (int64_t)sms * std::min(occ, cps));
-    const_fill3_kernel<10, LPP, STORE, MULTI><<<grid, 32, 0, st>>>(fp);
+    const_fill3_kernel<10, LPP, STORE, MULTI, EXT><<<grid, 32, 0, st>>>(fp);
 }
 
-void dispatch_const3(const Problem &pb, const FillParams &fp, int64_t groups, int sms, int cps, cudaStream_t st)
+template <int EXT>
+void dispatch_const3_e(const Problem &pb, const FillParams &fp, int64_t groups, int sms, int cps, cudaStream_t st)
 {
     const FillCfg &c = pb.cfg;
     if (pb.want_cigar) {
         if (c.lpp == 16)
-            launch_const3<16, true, false>(fp, groups, sms, cps, st);
+            launch_const3<16, true, false, EXT>(fp, groups, sms, cps, st);
         else if (c.multi)
-            launch_const3<32, true, true>(fp, groups, sms, cps, st);
+            launch_const3<32, true, true, EXT>(fp, groups, sms, cps, st);
         else
-            launch_const3<32, true, false>(fp, groups, sms, cps, st);
+            launch_const3<32, true, false, EXT>(fp, groups, sms, cps, st);
     } else {
         if (c.lpp == 16)
-            launch_const3<16, false, false>(fp, groups, sms, cps, st);
+            launch_const3<16, false, false, EXT>(fp, groups, sms, cps, st);
         else if (c.multi)
-            launch_const3<32, false, true>(fp, groups, sms, cps, st);
+            launch_const3<32, false, true, EXT>(fp, groups, sms, cps, st);
         else
-            launch_const3<32, false, false>(fp, groups, sms, cps, st);
+            launch_const3<32, false, false, EXT>(fp, groups, sms, cps, st);
     }
+}
+
+void dispatch_const3(const Problem &pb, const FillParams &fp, int64_t groups, int sms, int cps, cudaStream_t st)
+{
+    if (pb.ext == 1)
+        dispatch_const3_e<1>(pb, fp, groups, sms, cps, st);
+    else if (pb.ext == 2)
+        dispatch_const3_e<2>(pb, fp, groups, sms, cps, st);
+    else
+        dispatch_const3_e<0>(pb, fp, groups, sms, cps, st);
 }
 
 void dispatch_fill3(const Problem &pb, const FillParams &fp, int64_t groups, int sms, int cps, cudaStream_t st)
@@ -503,9 +516,30 @@ struct ChunkDev {
     int *counts;                      // chunk-local
     int64_t *score;                   // biased by -begin (global pair index)
     int64_t a_lo, a_hi, b_lo, b_hi;   // absolute byte ranges of the chunk inside alpha / beta
+    int64_t *best;                    // ext 2: biased by -begin (global pair index)
+    int64_t *end_i, *end_j;           // ext: chunk-local
     const int *smat;                  // profile batches: biased so that smat + smat_off[pair] is the pair's matrix
     const int64_t *smat_off;          // indexed by global pair id
 };
+
+void launch_traceback_ext(const Problem &pb, const ChunkDev &cd, const TraceParams &tp, int64_t np, cudaStream_t st)
+{
+    ExtTraceParams ep;
+    memset(&ep, 0, sizeof ep);
+    ep.t = tp;
+    ep.side = pb.ext;
+    ep.alpha = cd.alpha;
+    ep.beta = cd.beta;
+    ep.dim = pb.dim;
+    ep.gap = (int)pb.gap_open;
+    for (int i = 0; i < pb.dim * pb.dim; ++i)
+        ep.scores[i] = (int)pb.scores[i];
+    ep.score = cd.score;
+    ep.best = cd.best;
+    ep.end_i = cd.end_i;
+    ep.end_j = cd.end_j;
+    traceback_ext_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(ep);
+}
 
 // classify + fill (+ traceback pass 0) for chunk [begin, end) on stream st.
 int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, int64_t begin, int64_t end,
@@ -552,6 +586,7 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     fp.pair_class = pb.profile ? nullptr : cd.cls;
     fp.smat = cd.smat;
     fp.smat_off = cd.smat_off;
+    fp.out_best = cd.best;
     fp.gap_open = (int)pb.gap_open;
     fp.gap_extend = (int)pb.gap_extend;
     fp.h00 = pb.h00;
@@ -650,7 +685,10 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         tp.slot_cap = kSlotCap;
         tp.counts = cd.counts;
         tp.pass = 0;
-        if (tp.kind == 2 && tp.layout == 3)
+        tp.pair_class = pb.profile ? nullptr : cd.cls;
+        if (pb.ext)
+            launch_traceback_ext(pb, cd, tp, np, st);
+        else if (tp.kind == 2 && tp.layout == 3)
             traceback_const3_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
         else if (tp.kind == 0 && tp.layout >= 2 && ctx->opt_tb_impl == 2)
             traceback_affine_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
@@ -693,7 +731,7 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
         return GNX_OK;
     int *status = ctx->status.as<int>();
     expand_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(cd.slots, kSlotCap, cd.counts, cig_off, np,
-                                                          (CigarOut *)cigars, cap, status);
+                                                          (CigarOut *)cigars, cap, status, pb.ext);
     ctx->launches++;
     TraceParams tp;
     memset(&tp, 0, sizeof tp);
@@ -717,7 +755,10 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
     tp.out_cigar = cigars;
     tp.out_cap = cap;
     tp.pass = 1;
-    if (tp.kind == 2 && tp.layout == 3)
+    tp.pair_class = pb.profile ? nullptr : cd.cls;
+    if (pb.ext)
+        launch_traceback_ext(pb, cd, tp, np, st);
+    else if (tp.kind == 2 && tp.layout == 3)
         traceback_const3_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
     else if (tp.kind == 0 && tp.layout >= 2 && ctx->opt_tb_impl == 2)
         traceback_affine_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
@@ -868,7 +909,7 @@ bool is_pinned(const void *p)
 // ---------------------------------------------------------------------------------------------
 int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const int64_t *aoff, const uint8_t *beta_cat,
                    const int64_t *boff, int64_t n_pairs, int64_t *out_score, gnx_cigar *out_cigar,
-                   int64_t *out_cigar_off, int64_t cigar_cap)
+                   int64_t *out_cigar_off, int64_t cigar_cap, int64_t *out_end_i = nullptr, int64_t *out_end_j = nullptr)
 {
     CU(cudaSetDevice(ctx->device));
     ctx->fill_events_used = 0;
@@ -930,6 +971,16 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
             CU(s.h_score.ensure((size_t)np * 8));
             CU(cudaMemcpyAsync(s.h_score.p, s.score.p, (size_t)np * 8, cudaMemcpyDeviceToHost, s.stream));
         }
+        if (pb.ext && out_end_i && out_end_j) {
+            CU(s.h_endi.ensure((size_t)np * 8));
+            CU(s.h_endj.ensure((size_t)np * 8));
+            if (pb.want_cigar) {
+                CU(cudaMemcpyAsync(s.h_endi.p, s.endi.p, (size_t)np * 8, cudaMemcpyDeviceToHost, s.stream));
+                CU(cudaMemcpyAsync(s.h_endj.p, s.endj.p, (size_t)np * 8, cudaMemcpyDeviceToHost, s.stream));
+            } else if (pb.ext == 2) {
+                CU(cudaMemcpyAsync(s.h_endi.p, s.best.p, (size_t)np * 8, cudaMemcpyDeviceToHost, s.stream));
+            }
+        }
         if (pb.want_cigar) {
             CU(s.h_off.ensure((size_t)(np + 1) * 8));
             CU(cudaMemcpyAsync(s.h_off.p, s.cig_off.p, (size_t)(np + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
@@ -970,6 +1021,18 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
         }
         if (!pin_score)
             memcpy(out_score + pd.begin, s.h_score.p, (size_t)np * 8);
+        if (pb.ext && out_end_i && out_end_j) { // the stream was synchronised above
+            const int64_t *hi = s.h_endi.as<int64_t>(), *hj = s.h_endj.as<int64_t>();
+            if (pb.want_cigar) {
+                memcpy(out_end_i + pd.begin, hi, (size_t)np * 8);
+                memcpy(out_end_j + pd.begin, hj, (size_t)np * 8);
+            } else {
+                for (int64_t k = 0; k < np; ++k) { // right: the packed first-maximum cell; left: unknown without a trace
+                    out_end_i[pd.begin + k] = pb.ext == 2 ? (hi[k] >> 32) : -1;
+                    out_end_j[pd.begin + k] = pb.ext == 2 ? (hi[k] & 0xffffffffll) : -1;
+                }
+            }
+        }
         s.busy = false;
         return GNX_OK;
     };
@@ -1032,6 +1095,14 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
         cd.a_hi = a_hi;
         cd.b_lo = b_lo;
         cd.b_hi = b_hi;
+        if (pb.ext) {
+            CU(s.best.ensure((size_t)np * 8));
+            CU(s.endi.ensure((size_t)np * 8));
+            CU(s.endj.ensure((size_t)np * 8));
+            cd.best = s.best.as<int64_t>() - begin;
+            cd.end_i = s.endi.as<int64_t>();
+            cd.end_j = s.endj.as<int64_t>();
+        }
         if (pb.want_cigar) {
             CU(s.h_trace_off.ensure((size_t)(np + 1) * 8));
             int64_t *to = s.h_trace_off.as<int64_t>();
@@ -1399,10 +1470,10 @@ void gnx_destroy(gnx_ctx *ctx)
     for (int k = 0; k < kSlots; ++k) {
         Slot &s = ctx->slot[k];
         DevBuf *d[] = {&s.alpha, &s.beta, &s.aoff, &s.boff, &s.cls, &s.trace, &s.trace_off, &s.slots,
-                       &s.counts, &s.score, &s.cig_off, &s.cigars, &s.edge, &s.misc, &s.partials};
+                       &s.counts, &s.score, &s.cig_off, &s.cigars, &s.edge, &s.misc, &s.partials, &s.best, &s.endi, &s.endj};
         for (DevBuf *b : d)
             b->release();
-        PinBuf *h[] = {&s.h_stage_a, &s.h_stage_b, &s.h_total, &s.h_trace_off, &s.h_score, &s.h_off, &s.h_cig};
+        PinBuf *h[] = {&s.h_stage_a, &s.h_stage_b, &s.h_total, &s.h_trace_off, &s.h_score, &s.h_off, &s.h_cig, &s.h_endi, &s.h_endj};
         for (PinBuf *b : h)
             b->release();
         if (s.stream)
@@ -1502,6 +1573,30 @@ int gnx_affine_chunk_batch(gnx_ctx *ctx, const uint8_t *alpha_cat, const int64_t
     pb.chunk = chunk;
     return run_host_batch(ctx, pb, alpha_cat, alpha_off, beta_cat, beta_off, n_pairs, out_score, out_cigar,
                           out_cigar_off, out_cigar ? cigar_cap : 0);
+}
+
+int gnx_extend_batch(gnx_ctx *ctx, int side, const uint8_t *alpha_cat, const int64_t *alpha_off, const uint8_t *beta_cat,
+                     const int64_t *beta_off, int64_t n_pairs, const int64_t *scores, int dim, int64_t gap_pen,
+                     int want_cigar, int64_t *out_score, int64_t *out_end_i, int64_t *out_end_j, gnx_cigar *out_cigar,
+                     int64_t *out_cigar_off, int64_t cigar_cap)
+{
+    if (!ctx)
+        return GNX_EARG;
+    if (n_pairs < 0 || !alpha_off || !beta_off || !out_score || (side != GNX_EXT_LEFT && side != GNX_EXT_RIGHT))
+        return fail(ctx, GNX_EARG, "bad argument to gnx_extend_batch");
+    if (want_cigar && !out_cigar_off)
+        return fail(ctx, GNX_EARG, "out_cigar_off is required when want_cigar != 0");
+    if (dim > kDimP)
+        return fail(ctx, GNX_EARG, "gnx_extend_batch supports score matrices up to 5 x 5");
+    if (side == GNX_EXT_RIGHT && gap_pen > 0)
+        return fail(ctx, GNX_EARG, "RightDynamicAln with a positive gap penalty is not supported");
+    Problem pb;
+    int rc = fill_problem(ctx, pb, 2, want_cigar, scores, dim, gap_pen, 0);
+    if (rc != GNX_OK)
+        return rc;
+    pb.ext = side;
+    return run_host_batch(ctx, pb, alpha_cat, alpha_off, beta_cat, beta_off, n_pairs, out_score, out_cigar,
+                          out_cigar_off, out_cigar ? cigar_cap : 0, out_end_i, out_end_j);
 }
 
 int gnx_multi_affine_chunk_batch(gnx_ctx *ctx, const uint8_t *group_cat, const int64_t *group_off,

@@ -380,7 +380,16 @@ __global__ void __launch_bounds__(32, (C == 5 ? 20 : GNX_FILL3_MINB)) affine_fil
 // Trace: 2 bits per cell, the lane's 10 codes per step in one word, rows blocked four steps per 16 bytes
 // (layout [strip][step/4][thread][step%4]); code k of a word sits at bit 32 - 2*(10 - k).
 // ------------------------------------------------------------------------------------------------
-template <int C, int LPP, bool STORE, bool MULTI>
+//
+// EXT selects the gsw extend step's variants of the same one-plane DP (genomeGraph/search.go:234-321):
+//   1  LeftDynamicAln  (:234-274): zero boundaries; a cell is clipped at 0 AFTER its trace is recorded; the score
+//      is m(n,m).  The traceback (traceback_ext_kernel) walks from (n,m) while the cell value is > 0.
+//   2  RightDynamicAln (:276-321): Needleman-Wunsch boundaries; the result is the first cell, in row-major
+//      order, holding the strict maximum (currMax starts at 0, so (0,0) wins when nothing is positive).  Each
+//      lane keeps key = 16*value + (15 - column) of its best cell and the row it was found in; rows are visited
+//      in increasing order and a later row replaces the best only on a strictly larger VALUE, so per lane the
+//      row-major-first maximum survives; lanes and strips are merged on (value, -row, -column).  Needs g <= 0.
+template <int C, int LPP, bool STORE, bool MULTI, int EXT = 0>
 __global__ void __launch_bounds__(32, 16) const_fill3_kernel(const FillParams P)
 {
     constexpr int G = 32 / LPP;
@@ -397,6 +406,7 @@ __global__ void __launch_bounds__(32, 16) const_fill3_kernel(const FillParams P)
     const int one = P.one;
     const int g = P.gap_open; // the single gap penalty
     const int g_left = g * SC + (STORE ? 1 : 0), g_up = g * SC;
+    const int k16 = one * (16 / SC); // EXT 2: clean value -> key multiplier (opaque, so the key is one IMAD)
     int2 *edge_a = MULTI ? P.edge + (size_t)blockIdx.x * 2 * P.edge_stride : nullptr;
     int2 *edge_b = MULTI ? edge_a + P.edge_stride : nullptr;
     const int64_t n_groups = (P.pair_end - P.pair_begin + G - 1) / G;
@@ -414,8 +424,12 @@ __global__ void __launch_bounds__(32, 16) const_fill3_kernel(const FillParams P)
             alpha += a0;
             beta += b0;
             if (n == 0 || m == 0) { // boundary row / column (constGap_highMem.go:27-32)
-                if (lane == 0)
-                    P.out_score[pair] = (int64_t)g * (n + m);
+                if (lane == 0) {
+                    // EXT: the boundaries are 0 (left) or never positive (right, g <= 0): score 0 at (0,0)
+                    P.out_score[pair] = EXT ? 0 : (int64_t)g * (n + m);
+                    if (EXT == 2)
+                        P.out_best[pair] = 0;
+                }
                 mine = false;
             }
         }
@@ -433,10 +447,12 @@ __global__ void __launch_bounds__(32, 16) const_fill3_kernel(const FillParams P)
         const int Tp = (n + LPP - 1 + 3) & ~3;
         const int strips = MULTI ? (mmax + LPP * C - 1) / (LPP * C) : 1;
         uint32_t *tbase = (STORE && mine) ? P.trace + P.trace_off[pair - P.pair_begin] : nullptr;
+        long long bestK = (long long)0xFFFFF << 20 | 0xFFFFF; // EXT 2: value 0 at (0,0)
 
         for (int p = 0; p < strips; ++p) {
             const int jbase = p * LPP * C + lane * C;
             int Hc[C];
+            int kadd[EXT == 2 ? C : 1];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const int j = jbase + c + 1;
@@ -448,9 +464,12 @@ __global__ void __launch_bounds__(32, 16) const_fill3_kernel(const FillParams P)
                         v = P.scores[a * P.dim + q] * SC + (STORE ? 2 : 0);
                     s_tab[(c * kDimP + a) * 32 + tid] = v;
                 }
-                Hc[c] = j * g * SC; // row 0
+                Hc[c] = EXT == 1 ? 0 : j * g * SC; // row 0
+                if (EXT == 2)
+                    kadd[c] = (mine && j <= m) ? 15 - c : kNeg32; // padding columns never hold the maximum
             }
-            int hpL = jbase * g * SC;
+            int bestkey = 15, brow = 0; // EXT 2: this lane's best cell in this strip (value 0, row 0 = "none yet")
+            int hpL = EXT == 1 ? 0 : jbase * g * SC;
             int edgeH = 0;
             const int2 *ein = (p & 1) ? edge_b : edge_a;
             int2 *eout = (p & 1) ? edge_a : edge_b;
@@ -458,7 +477,7 @@ __global__ void __launch_bounds__(32, 16) const_fill3_kernel(const FillParams P)
             uint4 wq = make_uint4(0, 0, 0, 0);
             const bool store_edge = MULTI && (lane == LPP - 1) && (p + 1 < strips);
             int bH = 0;
-            auto boundary = [&](int r) { bH = (!MULTI || p == 0) ? r * g * SC : ein[r].x; };
+            auto boundary = [&](int r) { bH = (!MULTI || p == 0) ? (EXT == 1 ? 0 : r * g * SC) : ein[r].x; };
             if (lane == 0)
                 boundary(1);
             const uint8_t *tg = alpha;
@@ -491,6 +510,7 @@ __global__ void __launch_bounds__(32, 16) const_fill3_kernel(const FillParams P)
                         boundary(r + 1);
                     const int *row = s_tab + a * 32 + tid;
                     int left = inH, hp = hpL;
+                    int rowkey = kNeg32;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         const int s = row[c * kDimP * 32];
@@ -500,9 +520,17 @@ __global__ void __launch_bounds__(32, 16) const_fill3_kernel(const FillParams P)
                             w = shf_r_wrap(w, (unsigned)ht, 2);
                             cH = ht & ~3;
                         }
+                        if (EXT == 1)
+                            cH = max(cH, 0); // search.go:247-249: clipped after the trace was recorded
+                        if (EXT == 2)
+                            rowkey = max(rowkey, madd(cH, k16, kadd[c]));
                         hp = Hc[c];
                         Hc[c] = cH;
                         left = cH;
+                    }
+                    if (EXT == 2 && (rowkey >> 4) > (bestkey >> 4)) {
+                        bestkey = rowkey;
+                        brow = r;
                     }
                     edgeH = left;
                     hpL = inH;
@@ -531,7 +559,14 @@ __global__ void __launch_bounds__(32, 16) const_fill3_kernel(const FillParams P)
 #pragma unroll 1
             for (; t < T; ++t)
                 step(t, std::true_type{});
-            if (mine) {
+            if (EXT == 2) {
+                if (brow > 0) { // merge this strip's best on (value, smaller row, smaller column)
+                    const int j = jbase + (15 - (bestkey & 15)) + 1;
+                    const long long K = ((long long)(bestkey >> 4) << 40) | ((long long)(0xFFFFF - brow) << 20) |
+                                        (long long)(0xFFFFF - j);
+                    bestK = max(bestK, K);
+                }
+            } else if (mine) {
                 const int pm = (m - 1) / (LPP * C), lm = ((m - 1) % (LPP * C)) / C, cm = (m - 1) % C;
                 if (p == pm && lane == lm) {
                     int h = Hc[0];
@@ -543,6 +578,16 @@ __global__ void __launch_bounds__(32, 16) const_fill3_kernel(const FillParams P)
                 }
             }
             __syncwarp();
+        }
+        if (EXT == 2) {
+#pragma unroll
+            for (int o = LPP / 2; o > 0; o >>= 1)
+                bestK = max(bestK, __shfl_xor_sync(FULL, bestK, o));
+            if (mine && lane == 0) {
+                P.out_score[pair] = bestK >> 40;
+                const long long bi = 0xFFFFF - ((bestK >> 20) & 0xFFFFF), bj = 0xFFFFF - (bestK & 0xFFFFF);
+                P.out_best[pair] = (bi << 32) | bj;
+            }
         }
     }
 }

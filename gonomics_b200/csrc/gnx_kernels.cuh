@@ -46,6 +46,7 @@ struct FillParams {
     int64_t *out_score;           // indexed by global pair id
     int chunk;                    // AffineGapChunk: bases per DP cell (1 otherwise); LOOKUP == 2 kernels only
     int one;                      // always 1: an opaque multiplier that keeps adds on the FMA pipe (IMAD)
+    int64_t *out_best;            // const_fill3_kernel<EXT 2>: (row << 32 | column) of the first maximal cell, per global pair
     const int *smat;              // LOOKUP == 3: dense per-pair cell scores S[i][j] (gnx_profile.cuh), unscaled
     const int64_t *smat_off;      // LOOKUP == 3: first cell of pair p's matrix inside smat, indexed by global pair id
 };
@@ -544,6 +545,7 @@ struct TraceParams {
     void *out_cigar;     // gnx_cigar* base that cigar_off indexes
     int64_t out_cap;     // entries available behind out_cigar
     int pass;            // 0: fill slots + counts, 1: rewrite pairs whose count > slot_cap
+    const uint8_t *pair_class; // per global pair (may be NULL): class 2 = invalid base, the fill skipped it
 };
 
 struct CigarOut {
@@ -590,6 +592,11 @@ __global__ void traceback_kernel(const TraceParams P)
     const int64_t pair = P.pair_begin + idx;
     if (pair >= P.pair_end)
         return;
+    if (P.pair_class && P.pair_class[pair] > 1) { // no trace was written for this pair (the call returns GNX_EBASE)
+        if (P.pass == 0)
+            P.counts[idx] = 0;
+        return;
+    }
     const int chunk = P.chunk > 1 ? P.chunk : 1;
     const int n = (int)(P.alpha_off[pair + 1] - P.alpha_off[pair]) / chunk;
     const int m = (int)(P.beta_off[pair + 1] - P.beta_off[pair]) / chunk;
@@ -718,6 +725,11 @@ __global__ void traceback_affine_kernel(const TraceParams P)
     const int64_t pair = P.pair_begin + idx;
     if (pair >= P.pair_end)
         return;
+    if (P.pair_class && P.pair_class[pair] > 1) { // no trace was written for this pair (the call returns GNX_EBASE)
+        if (P.pass == 0)
+            P.counts[idx] = 0;
+        return;
+    }
     const int n = (int)(P.alpha_off[pair + 1] - P.alpha_off[pair]);
     const int m = (int)(P.beta_off[pair + 1] - P.beta_off[pair]);
     if (P.pass == 1 && P.counts[idx] <= P.slot_cap)
@@ -825,6 +837,11 @@ __global__ void traceback_const3_kernel(const TraceParams P)
     const int64_t pair = P.pair_begin + idx;
     if (pair >= P.pair_end)
         return;
+    if (P.pair_class && P.pair_class[pair] > 1) { // no trace was written for this pair (the call returns GNX_EBASE)
+        if (P.pass == 0)
+            P.counts[idx] = 0;
+        return;
+    }
     const int n = (int)(P.alpha_off[pair + 1] - P.alpha_off[pair]);
     const int m = (int)(P.beta_off[pair + 1] - P.beta_off[pair]);
     if (P.pass == 1 && P.counts[idx] <= P.slot_cap)
@@ -904,10 +921,131 @@ __global__ void traceback_const3_kernel(const TraceParams P)
         P.counts[idx] = cnt;
 }
 
+// Traceback of the gsw extend step (genomeGraph/search.go:252-272 left, :301-319 right) over
+// const_fill3_kernel<EXT> traces.  The route stays in TRACEBACK order (the reference does not reverse it
+// here) and ops are the cigar package's bytes 'M','I','D' (cigar/cigar.go:15-18); expand_kernel is told so.
+//   left : from (n,m) while the cell's value is > 0.  Values are not stored: a cell with value > 0 was not
+//          clipped, so m(prev) = m(cur) - (substitution score | gap penalty) exactly; the walk starts from
+//          the pair's score m(n,m) and recomputes the value as it goes.  Returns where it stopped.
+//   right: from the first maximal cell (out_best) to (0,0); row 0 is 'I', column 0 is 'D' (:284-289).
+struct ExtTraceParams {
+    TraceParams t;
+    int side;                 // 1 left, 2 right
+    const uint8_t *alpha, *beta;
+    int dim, gap;
+    int scores[64];
+    const int64_t *score;     // per global pair (left: the starting value)
+    const int64_t *best;      // per global pair (right: row << 32 | column)
+    int64_t *end_i, *end_j;   // per pair in chunk
+};
+
+__global__ void traceback_ext_kernel(const ExtTraceParams E)
+{
+    const TraceParams &P = E.t;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t pair = P.pair_begin + idx;
+    if (pair >= P.pair_end)
+        return;
+    if (P.pair_class && P.pair_class[pair] > 1) { // no trace was written for this pair (the call returns GNX_EBASE)
+        if (P.pass == 0)
+            P.counts[idx] = 0;
+        return;
+    }
+    const int n = (int)(P.alpha_off[pair + 1] - P.alpha_off[pair]);
+    const int m = (int)(P.beta_off[pair + 1] - P.beta_off[pair]);
+    if (P.pass == 1 && P.counts[idx] <= P.slot_cap)
+        return;
+    uint32_t *slot = P.slots + (size_t)idx * P.slot_cap;
+    CigarOut *dst = nullptr;
+    if (P.pass == 1) {
+        if (P.cigar_off[idx] + P.counts[idx] > P.out_cap)
+            return;
+        dst = (CigarOut *)P.out_cigar + P.cigar_off[idx];
+    }
+    int cnt = 0;
+    auto emit = [&](int op, int run) {
+        if (P.pass == 0) {
+            if (cnt < P.slot_cap)
+                slot[cnt] = ((uint32_t)run << 2) | (uint32_t)op;
+        } else {
+            CigarOut o;
+            o.run_length = run;
+            o.op = (unsigned char)(op == 0 ? 'M' : (op == 1 ? 'I' : 'D'));
+            dst[cnt] = o; // traceback order is the final order
+        }
+        ++cnt;
+    };
+    int i = n, j = m;
+    long long v = 0;
+    if (E.side == 1) {
+        v = (n > 0 && m > 0) ? E.score[pair] : 0;
+    } else {
+        const long long b = (n > 0 && m > 0) ? E.best[pair] : 0;
+        i = (int)(b >> 32);
+        j = (int)(b & 0xffffffffll);
+    }
+    const int start_i = i, start_j = j;
+    const uint32_t *__restrict__ tr = P.trace + P.trace_off[idx];
+    const uint8_t *__restrict__ al = E.alpha + P.alpha_off[pair];
+    const uint8_t *__restrict__ be = E.beta + P.beta_off[pair];
+    const int C = P.C, lpp = P.lpp;
+    const int T = (n + lpp - 1 + 3) & ~3;
+    const size_t strip_words = (size_t)T * 32;
+    int strip = 0, lane = 0, c = 0;
+    if (j > 0) {
+        const int jj = j - 1;
+        strip = jj / (lpp * C);
+        const int within = jj - strip * lpp * C;
+        lane = within / C;
+        c = within - lane * C;
+    }
+    int cur_op = -1, run = 0;
+    int guard = n + m + 1; // a valid walk takes at most n + m steps: a corrupt trace must not spin forever
+    while ((E.side == 1 ? v > 0 : (i > 0 || j > 0)) && guard-- > 0) {
+        int k;
+        if (i > 0 && j > 0) {
+            const int t = (i - 1) + lane;
+            const uint32_t w = __ldg(tr + (size_t)strip * strip_words + (((size_t)(t >> 2)) * 32 + lane) * 4 + (t & 3));
+            k = 2 - (int)((w >> (32 - 2 * (C - c))) & 3u);
+        } else {
+            k = (i == 0) ? 1 : 2;
+        }
+        if (k == cur_op) {
+            ++run;
+        } else {
+            if (cur_op >= 0)
+                emit(cur_op, run);
+            cur_op = k;
+            run = 1;
+        }
+        if (E.side == 1)
+            v -= (k == 0) ? (long long)E.scores[(int)al[i - 1] * E.dim + (int)be[j - 1]] : (long long)E.gap;
+        i -= (k != 1);
+        if (k != 2) {
+            --j;
+            if (--c < 0) {
+                c = C - 1;
+                if (--lane < 0) {
+                    lane = lpp - 1;
+                    --strip;
+                }
+            }
+        }
+    }
+    if (cur_op >= 0)
+        emit(cur_op, run);
+    if (P.pass == 0) {
+        P.counts[idx] = cnt;
+        E.end_i[idx] = E.side == 1 ? i : start_i;
+        E.end_j[idx] = E.side == 1 ? j : start_j;
+    }
+}
+
 // Expand the per-pair slots into gnx_cigar records at the scanned offsets (reversing to start->end
 // order, align/align.go:86-90 reverseCigar).  One thread per pair; cigars are short.
+// ext != 0 (gsw extend step): keep the traceback order and write the ops as 'M','I','D'.
 __global__ void expand_kernel(const uint32_t *slots, int slot_cap, const int *counts, const int64_t *cigar_off,
-                              int64_t n_pairs, CigarOut *out, int64_t out_cap_remaining, int *status)
+                              int64_t n_pairs, CigarOut *out, int64_t out_cap_remaining, int *status, int ext)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_pairs)
@@ -926,7 +1064,12 @@ __global__ void expand_kernel(const uint32_t *slots, int slot_cap, const int *co
         CigarOut o;
         o.run_length = (long long)(v >> 2);
         o.op = (unsigned char)(v & 3u);
-        out[off + cnt - 1 - k] = o;
+        if (ext) {
+            o.op = (unsigned char)(o.op == 0 ? 'M' : (o.op == 1 ? 'I' : 'D'));
+            out[off + k] = o;
+        } else {
+            out[off + cnt - 1 - k] = o;
+        }
     }
 }
 

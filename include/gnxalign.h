@@ -128,6 +128,26 @@ int gnx_multi_affine_chunk_batch(gnx_ctx *ctx, const uint8_t *group_cat, const i
                                  int64_t *out_score, gnx_cigar *out_cigar, int64_t *out_cigar_off,
                                  int64_t cigar_cap);
 
+/* ---- gsw extend step ------------------------------------------------------------ *
+ * Replaces genomeGraph.LeftDynamicAln (genomeGraph/search.go:234-274) and RightDynamicAln (:276-321),
+ * the linear-gap DPs cmd/gsw's seed-and-extend runs on either side of a seed, called with a clean
+ * dynamicScoreKeeper (empty route, currMax 0 -- what the callers pass, since resetDynamicScore takes its
+ * argument by value, :104-107).  Tie-break cigar.TripleMaxTrace (cigar/tools.go:58-66), M >= I >= D.
+ *   GNX_EXT_LEFT : zero boundaries, cells clipped at 0 after their trace is recorded; score = m(n,m);
+ *                  the route is walked from (n,m) while the cell value is > 0; out_end_i/j = where it stopped.
+ *   GNX_EXT_RIGHT: Needleman-Wunsch boundaries; score = the first strict maximum in row-major order
+ *                  (0 at (0,0) if nothing is positive); route from there to (0,0); out_end_i/j = that cell.
+ *                  gap_pen must be <= 0.
+ * out_cigar holds cigar.Cigar{RunLength int; Op byte} records (same 16-byte layout as gnx_cigar) with
+ * Op = 'M', 'I' or 'D' (cigar/cigar.go:15-18), in TRACEBACK order -- the reference does not reverse the
+ * route inside these functions.  With want_cigar = 0 only scores (and, for the right side, the end cell;
+ * -1 for the left side) are produced.  dim <= 5. */
+enum { GNX_EXT_LEFT = 1, GNX_EXT_RIGHT = 2 };
+int gnx_extend_batch(gnx_ctx *ctx, int side, const uint8_t *alpha_cat, const int64_t *alpha_off,
+                     const uint8_t *beta_cat, const int64_t *beta_off, int64_t n_pairs, const int64_t *scores,
+                     int dim, int64_t gap_pen, int want_cigar, int64_t *out_score, int64_t *out_end_i,
+                     int64_t *out_end_j, gnx_cigar *out_cigar, int64_t *out_cigar_off, int64_t cigar_cap);
+
 /* After a GNX_ECAP return: copy the retained cigars of the last batch call (total = the last
  * entry of that call's out_cigar_off). */
 int gnx_copy_last_cigars(gnx_ctx *ctx, gnx_cigar *out_cigar, int64_t cigar_cap);

@@ -504,3 +504,60 @@ def test_all_seq_affine_random_families(ctx):
         got = align.AllSeqAffineChunk(recs, S, -400, -30, chunk, ctx)
         want = msa.all_seq_affine_chunk(recs, S, -400, -30, chunk)
         assert [(f.Name, f.Seq.tolist()) for f in got] == [(n, s.tolist()) for n, s in want]
+
+
+# ---- gsw extend step: LeftDynamicAln / RightDynamicAln ----------------------------
+def _check_extend(ctx, alphas, betas, S, g):
+    from gonomics_b200 import genomegraph as gg
+    for side, ofn in ((1, orc.left_dynamic_aln), (2, orc.right_dynamic_aln)):
+        got = gg.extend_pairs(side, alphas, betas, S, g, ctx)
+        ac, ao = concat(alphas)
+        bc, bo = concat(betas)
+        sc_only = ctx.extend_batch(side, ac, ao, bc, bo, S, g, want_cigar=False)
+        for p, (a, b) in enumerate(zip(alphas, betas)):
+            want = ofn(a, b, S, g)
+            assert (got[p][0], [tuple(c) for c in got[p][1]], got[p][2], got[p][3]) == want, \
+                (side, p, len(a), len(b), g, got[p], want)
+            assert int(sc_only[0][p]) == want[0]
+            if side == 2:
+                assert (int(sc_only[1][p]), int(sc_only[2][p])) == (want[2], want[3])
+
+
+def test_extend_random_read_sized(ctx):
+    rng = np.random.default_rng(2340)
+    S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX
+    alphas, betas = [], []
+    for _ in range(3000):  # the gsw shapes: target window <= ~175, read remainder <= 150
+        n, m = int(rng.integers(0, 180)), int(rng.integers(0, 151))
+        a, b = random_pair(rng, max(n, 1), max(m, 1), identity=float(rng.choice([0.7, 0.9, 0.97, 1.0])))
+        alphas.append(a[:n])
+        betas.append(b[:m])
+    _check_extend(ctx, alphas, betas, S, -600)
+    _check_extend(ctx, alphas[:500], betas[:500], S, -100)
+    _check_extend(ctx, alphas[:500], betas[:500], orc.DEFAULT_SCORE_MATRIX, 0)
+
+
+def test_extend_ties_n_and_long(ctx):
+    rng = np.random.default_rng(2341)
+    S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX
+    alphas, betas = [], []
+    for unit in ("A", "AC", "ACG", "AAC"):  # tie-heavy repeats
+        for n, m in ((30, 30), (64, 17), (17, 64), (150, 150)):
+            alphas.append(bases((unit * 200)[:n]))
+            betas.append(bases((unit * 200)[1:m + 1]))
+    for _ in range(40):  # N bases (dim 5)
+        a, b = random_pair(rng, int(rng.integers(1, 170)), int(rng.integers(1, 150)), alphabet=5)
+        alphas.append(a)
+        betas.append(b)
+    _check_extend(ctx, alphas, betas, S, -600)
+    _check_extend(ctx, alphas, betas, orc.DEFAULT_SCORE_MATRIX, -430)
+    # more than one 160- / 320-column strip, and targets longer than the shared-memory stage
+    alphas, betas = [], []
+    for n, m in ((400, 170), (170, 400), (1500, 700), (700, 1500), (2000, 330)):
+        a, b = random_pair(rng, n, m, identity=0.92)
+        alphas.append(a)
+        betas.append(b)
+    _check_extend(ctx, alphas, betas, S, -600)
+    with pytest.raises(_lib.GnxError) as ei:  # a base outside the matrix: Go panics
+        _check_extend(ctx, [np.array([0, 1, 7], np.uint8)], [np.array([0, 1], np.uint8)], S, -600)
+    assert ei.value.code == _lib.GNX_EBASE

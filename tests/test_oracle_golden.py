@@ -5,7 +5,7 @@ import pytest
 
 import oracle as orc
 from oracle import msa
-from golden_util import MATRICES, bases, cigar_to_beds, load
+from golden_util import MATRICES, bases, cigar_to_beds, load, random_pair
 
 
 def test_affine_global_views():  # align/affineGap_test.go:45-55 TestAffineGap
@@ -181,3 +181,72 @@ def test_batch_threads_match_single():
                 s, c = orc.affine_gap_highmem(al[p], be[p], S, -600, -150, mode == 1)
             got = [(int(r), int(o)) for r, o in cg[off[p]:off[p + 1]]]
             assert (int(sc[p]), got) == (s, c), (mode, p)
+
+
+# ---- gsw extend step: no reference test asserts these two functions ("parity unpinned"),
+# so the C oracle is cross-checked against a second, line-by-line Python transcription of the Go loops.
+def _py_extend(alpha, beta, S, g, left):
+    n, m = len(alpha), len(beta)
+    M = [[0] * (m + 1) for _ in range(n + 1)]
+    T = [[""] * (m + 1) for _ in range(n + 1)]
+
+    def tmt(a, b, c):  # cigar.TripleMaxTrace (cigar/tools.go:58-66)
+        if a >= b and a >= c:
+            return a, "M"
+        if b >= c:
+            return b, "I"
+        return c, "D"
+
+    cur_max, mi, mj = 0, 0, 0
+    if left:  # genomeGraph/search.go:236-251
+        for i in range(1, n + 1):
+            for j in range(1, m + 1):
+                M[i][j], T[i][j] = tmt(M[i - 1][j - 1] + int(S[alpha[i - 1]][beta[j - 1]]), M[i][j - 1] + g,
+                                       M[i - 1][j] + g)
+                if M[i][j] < 0:
+                    M[i][j] = 0
+    else:  # :280-299
+        for i in range(n + 1):
+            for j in range(m + 1):
+                if i == 0 and j == 0:
+                    M[i][j] = 0
+                elif i == 0:
+                    M[i][j], T[i][j] = M[i][j - 1] + g, "I"
+                elif j == 0:
+                    M[i][j], T[i][j] = M[i - 1][j] + g, "D"
+                else:
+                    M[i][j], T[i][j] = tmt(M[i - 1][j - 1] + int(S[alpha[i - 1]][beta[j - 1]]), M[i][j - 1] + g,
+                                           M[i - 1][j] + g)
+                if M[i][j] > cur_max:
+                    cur_max, mi, mj = M[i][j], i, j
+    route = []
+    i, j = (n, m) if left else (mi, mj)
+    while (M[i][j] > 0) if left else (i > 0 or j > 0):
+        op = T[i][j]
+        if route and route[-1][1] == op:
+            route[-1] = (route[-1][0] + 1, op)
+        else:
+            route.append((1, op))
+        if op == "M":
+            i, j = i - 1, j - 1
+        elif op == "I":
+            j -= 1
+        else:
+            i -= 1
+    return (M[n][m], route, i, j) if left else (M[mi][mj], route, mi, mj)
+
+
+def test_extend_oracle_against_python_transcription():
+    rng = np.random.default_rng(234)
+    S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX
+    cases = [(np.zeros(0, np.uint8), np.zeros(0, np.uint8)), (bases("ACGT"), np.zeros(0, np.uint8)),
+             (np.zeros(0, np.uint8), bases("ACGT")), (bases("ACGTACGT"), bases("ACGTACGT")),
+             (bases("AAAAAAAA"), bases("AAAA")), (bases("ACACACACAC"), bases("CACACA"))]
+    for _ in range(150):
+        n, m = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        a, b = random_pair(rng, n, m, identity=float(rng.choice([0.6, 0.9, 1.0])), alphabet=int(rng.choice([2, 4, 5])))
+        cases.append((a, b))
+    for a, b in cases:
+        for g in (-600, -100, 0):
+            assert orc.left_dynamic_aln(a, b, S, g) == _py_extend(a, b, S, g, True), (a, b, g)
+            assert orc.right_dynamic_aln(a, b, S, g) == _py_extend(a, b, S, g, False), (a, b, g)
