@@ -13,15 +13,19 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgnxalign.so")
 
-GNX_OK, GNX_EBASE, GNX_ECAP, GNX_ECHUNK, GNX_EEMPTY, GNX_ECUDA, GNX_EARG, GNX_ERANGE, GNX_EDIVZERO = range(9)
+GNX_OK, GNX_EBASE, GNX_ECAP, GNX_ECHUNK, GNX_EEMPTY, GNX_ECUDA, GNX_EARG, GNX_ERANGE, GNX_EDIVZERO, GNX_EOFFSET, GNX_EINDEX = range(11)
 GNX_GLOBAL, GNX_FREE_END = 0, 1
 GNX_EXT_LEFT, GNX_EXT_RIGHT = 1, 2
+GNX_MATCH_RIGHT, GNX_MATCH_LEFT = 0, 1
 
 # every symbol include/gnxalign.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "gnx_device_count", "gnx_create", "gnx_destroy", "gnx_last_error", "gnx_version", "gnx_host_alloc",
     "gnx_host_free", "gnx_affine_batch", "gnx_const_batch", "gnx_affine_chunk_batch", "gnx_copy_last_cigars",
     "gnx_multi_affine_chunk_batch", "gnx_extend_batch", "gnx_batch_device", "gnx_launch_count", "gnx_last_fill_stats", "gnx_set_option",
+    "gnx_twobit_new", "gnx_twobit_free", "gnx_twobit_info", "gnx_twobit_download", "gnx_twobit_unpack", "gnx_twobit_get_bases",
+    "gnx_twobit_count_matches", "gnx_twobit_pack_device", "gnx_seed_index_new", "gnx_seed_index_free", "gnx_seed_index_info",
+    "gnx_seed_index_download", "gnx_seed_batch",
 ]
 
 
@@ -31,6 +35,9 @@ class GnxCigar(C.Structure):
 
 
 CIGAR_DTYPE = np.dtype({"names": ["run_length", "op"], "formats": ["<i8", "u1"], "offsets": [0, 8], "itemsize": 16})
+# gnx_seed: genomeGraph.SeedDev without NextPart (genomeGraph/index.go:11-19)
+SEED_DTYPE = np.dtype([("target_id", "<u4"), ("target_start", "<u4"), ("query_start", "<u4"), ("length", "<u4"),
+                       ("pos_strand", "<u4"), ("total_length", "<u4")])
 
 _lib = None
 
@@ -87,5 +94,31 @@ def load() -> C.CDLL:
     L.gnx_last_fill_stats.restype = ci
     L.gnx_set_option.argtypes = [vp, C.c_char_p, i64]
     L.gnx_set_option.restype = ci
+    L.gnx_twobit_new.argtypes = [vp, u8p, i64p, i64, ci, C.POINTER(vp)]
+    L.gnx_twobit_new.restype = ci
+    L.gnx_twobit_free.argtypes = [vp]
+    L.gnx_twobit_free.restype = None
+    L.gnx_twobit_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.gnx_twobit_info.restype = ci
+    L.gnx_twobit_download.argtypes = [vp, vp, vp, i64p, i64p]
+    L.gnx_twobit_download.restype = ci
+    L.gnx_twobit_unpack.argtypes = [vp, vp, u8p, i64]
+    L.gnx_twobit_unpack.restype = ci
+    L.gnx_twobit_get_bases.argtypes = [vp, vp, i64p, i64p, i64, u8p]
+    L.gnx_twobit_get_bases.restype = ci
+    L.gnx_twobit_count_matches.argtypes = [vp, ci, vp, vp, i64p, i64p, i64p, i64p, i64, i64p]
+    L.gnx_twobit_count_matches.restype = ci
+    L.gnx_twobit_pack_device.argtypes = [vp, u8p, i64, ci, vp, vp]
+    L.gnx_twobit_pack_device.restype = ci
+    L.gnx_seed_index_new.argtypes = [vp, u8p, i64p, i64, ci, ci, C.POINTER(vp)]
+    L.gnx_seed_index_new.restype = ci
+    L.gnx_seed_index_free.argtypes = [vp]
+    L.gnx_seed_index_free.restype = None
+    L.gnx_seed_index_info.argtypes = [vp, C.POINTER(i64)]
+    L.gnx_seed_index_info.restype = ci
+    L.gnx_seed_index_download.argtypes = [vp, vp, vp, vp]
+    L.gnx_seed_index_download.restype = ci
+    L.gnx_seed_batch.argtypes = [vp, vp, u8p, i64p, i64, vp, i64p, i64]
+    L.gnx_seed_batch.restype = ci
     _lib = L
     return L

@@ -9,6 +9,10 @@
 #include "gnx_fill3.cuh"
 #include "gnx_fill16.cuh"
 #include "gnx_profile.cuh"
+#include "gnx_twobit.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cstdio>
@@ -1805,3 +1809,5 @@ int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
 }
 
 } // extern "C"
+
+#include "gnx_twobit_api.inl"

@@ -49,8 +49,11 @@ enum {
     GNX_ECUDA = 5,  /* CUDA runtime failure, text in gnx_last_error                                  */
     GNX_EARG = 6,   /* bad argument (NULL pointer, dim out of range, ...)                            */
     GNX_ERANGE = 7, /* scores/penalties/lengths exceed the exact-arithmetic range of every kernel    */
-    GNX_EDIVZERO = 8 /* profile DP: a column pair with no ungapped base pair (Go: integer divide by zero
-                        in scoreColumnMatch, align/multiAlign.go:101)                                 */
+    GNX_EDIVZERO = 8, /* profile DP: a column pair with no ungapped base pair (Go: integer divide by zero
+                         in scoreColumnMatch, align/multiAlign.go:101)                                */
+    GNX_EOFFSET = 9,  /* CountRight/LeftMatches: start offsets differ modulo 32 (Go: log.Fatalf "Different
+                         offsets", dna/dnaTwoBit/perfectAlign.go:24-26,63-65)                         */
+    GNX_EINDEX = 10   /* 2-bit sequences: position beyond the last word (Go: index out of range panic) */
 };
 
 /* mode for gnx_affine_batch */
@@ -147,6 +150,69 @@ int gnx_extend_batch(gnx_ctx *ctx, int side, const uint8_t *alpha_cat, const int
                      const uint8_t *beta_cat, const int64_t *beta_off, int64_t n_pairs, const int64_t *scores,
                      int dim, int64_t gap_pen, int want_cigar, int64_t *out_score, int64_t *out_end_i,
                      int64_t *out_end_j, gnx_cigar *out_cigar, int64_t *out_cigar_off, int64_t cigar_cap);
+
+/* ---- dna/dnaTwoBit on the device ------------------------------------------------ *
+ * A gnx_twobit is a SET of dnaTwoBit.TwoBit sequences resident in the context's device memory (a genome's
+ * nodes, a batch of reads): upload and pack once, query many times.
+ *
+ * gnx_twobit_new      dnaTwoBit.NewTwoBit (dna/dnaTwoBit/dnaTwoBit.go:68-78) of every sequence
+ *                     seq_cat[seq_off[s] .. seq_off[s+1]); lead = k (0..31) prepends k x dna.A first, i.e.
+ *                     element k of NewTwoBitRainbow (rainbow.go:8-25) with TwoBit.Len = len + k.  Bit-exact
+ *                     including bases > 3: BasesToUint64LeftAln ORs the raw dna.Base byte (:33-37), so N,
+ *                     lowercase and gap codes spill into the bits of the bases before them.
+ * gnx_twobit_download TwoBit.Seq of every sequence (concatenated; out_word_off has n_seqs+1 entries) and
+ *                     TwoBit.Len.  Any output pointer may be NULL.
+ * gnx_twobit_unpack   dnaTwoBit.GetBase (:59-65) for every position of every sequence, concatenated.
+ * gnx_twobit_get_bases GetBase(set[q_seq[q]], q_pos[q]) for a list of queries; GNX_EINDEX where Go panics.
+ * gnx_twobit_count_matches  dnaTwoBit.CountRightMatches (perfectAlign.go:10-47; dir GNX_MATCH_RIGHT) or
+ *                     CountLeftMatches (:49-85; GNX_MATCH_LEFT) of one[q_one[q]] from q_start_one[q] against
+ *                     two[q_two[q]] from q_start_two[q].  GNX_EOFFSET / GNX_EINDEX report the first query (in
+ *                     order) on which the reference would log.Fatalf / panic.
+ * gnx_twobit_pack_device  NewTwoBit of ONE sequence already in device memory, enqueued on cuda_stream
+ *                     without synchronising (d_words: (n_bases + lead + 31) / 32 words). */
+typedef struct gnx_twobit gnx_twobit;
+enum { GNX_MATCH_RIGHT = 0, GNX_MATCH_LEFT = 1 };
+int gnx_twobit_new(gnx_ctx *ctx, const uint8_t *seq_cat, const int64_t *seq_off, int64_t n_seqs, int lead,
+                   gnx_twobit **out);
+void gnx_twobit_free(gnx_twobit *tb);
+int gnx_twobit_info(const gnx_twobit *tb, int64_t *n_seqs, int64_t *total_words);
+int gnx_twobit_download(gnx_ctx *ctx, const gnx_twobit *tb, uint64_t *out_words, int64_t *out_word_off,
+                        int64_t *out_len);
+int gnx_twobit_unpack(gnx_ctx *ctx, const gnx_twobit *tb, uint8_t *out_cat, int64_t out_cap);
+int gnx_twobit_get_bases(gnx_ctx *ctx, const gnx_twobit *tb, const int64_t *q_seq, const int64_t *q_pos,
+                         int64_t n_q, uint8_t *out);
+int gnx_twobit_count_matches(gnx_ctx *ctx, int dir, const gnx_twobit *one, const gnx_twobit *two,
+                             const int64_t *q_one, const int64_t *q_start_one, const int64_t *q_two,
+                             const int64_t *q_start_two, int64_t n_q, int64_t *out_matches);
+int gnx_twobit_pack_device(gnx_ctx *ctx, const uint8_t *d_seq, int64_t n_bases, int lead, uint64_t *d_words,
+                           void *cuda_stream);
+
+/* ---- perfect-match seeds of cmd/gsw --------------------------------------------- *
+ * gnx_seed_index_new  genomeGraph.IndexGenomeIntoMap(genome, seedLen, seedStep) (genomeGraph/index.go:21-44)
+ *                     for a genome whose nodes have no edges (a linear reference: one node per chromosome):
+ *                     node s = genome_cat[node_off[s] .. node_off[s+1]).  The map is kept on the device as
+ *                     entries sorted by key (dnaToNumber, genomeGraph/align.go:170-177), each key's locations
+ *                     (ChromAndPosToNumber, :163-168) in the reference's insertion order, together with the
+ *                     nodes' TwoBit encoding.  seedLen outside 2..32 is the reference's log.Fatalf (GNX_EARG).
+ * gnx_seed_batch      genomeGraph.seedMapMemPool (genomeGraph/search.go:567-602) for every read
+ *                     reads_cat[read_off[r] .. read_off[r+1]): both strands (dna.ReverseComplement), every
+ *                     readStart, every hit extended with CountLeftMatches / extendToTheRightDev (:425-452).
+ *                     Read r's seeds are out_seeds[out_seed_off[r] .. out_seed_off[r+1]) in the reference's
+ *                     APPEND order, i.e. before its final SortSeedLen / heapSortSeeds (:596-600), which is an
+ *                     unstable sort the caller keeps applying on its side.  NextPart is always nil without
+ *                     edges, so gnx_seed carries the remaining SeedDev fields (genomeGraph/index.go:11-19).
+ *                     GNX_ECAP: seed_cap too small (out_seed_off is filled). GNX_EBASE: a read byte > 12. */
+typedef struct gnx_seed_index gnx_seed_index;
+typedef struct {
+    uint32_t target_id, target_start, query_start, length, pos_strand, total_length;
+} gnx_seed;
+int gnx_seed_index_new(gnx_ctx *ctx, const uint8_t *genome_cat, const int64_t *node_off, int64_t n_nodes,
+                       int seed_len, int seed_step, gnx_seed_index **out);
+void gnx_seed_index_free(gnx_seed_index *ix);
+int gnx_seed_index_info(const gnx_seed_index *ix, int64_t *n_entries);
+int gnx_seed_index_download(gnx_ctx *ctx, const gnx_seed_index *ix, uint64_t *out_key, uint64_t *out_loc);
+int gnx_seed_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8_t *reads_cat, const int64_t *read_off,
+                   int64_t n_reads, gnx_seed *out_seeds, int64_t *out_seed_off, int64_t seed_cap);
 
 /* After a GNX_ECAP return: copy the retained cigars of the last batch call (total = the last
  * entry of that call's out_cigar_off). */

@@ -72,7 +72,8 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "gnx_oracle.c")):
+        if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(
+                os.path.getmtime(os.path.join(_HERE, f)) for f in ("gnx_oracle.c", "gnx_twobit_oracle.c", "gnx_oracle.h")):
             build()
         L = C.CDLL(_SO)
         u8p, i64p, cgp = C.POINTER(C.c_uint8), C.POINTER(C.c_int64), C.POINTER(OrcCigar)
@@ -91,6 +92,18 @@ def lib():
         for f in ("orc_affine_highmem", "orc_const_highmem", "orc_affine_lowmem", "orc_const_lowmem",
                   "orc_affine_chunk", "orc_multi_affine_chunk", "orc_batch"):
             getattr(L, f).restype = ci
+        u64p, u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+        L.orc_new_twobit.argtypes = [u8p, i64, ci, u64p]
+        L.orc_new_twobit.restype = ci
+        L.orc_get_base.argtypes = [u64p, C.c_uint64]
+        L.orc_get_base.restype = C.c_uint8
+        for f in ("orc_count_right", "orc_count_left"):
+            getattr(L, f).argtypes = [u64p, i64, u64p, i64, i64, i64]
+            getattr(L, f).restype = i64
+        L.orc_seed_index.argtypes = [u8p, i64p, i64, ci, ci, u64p, u64p, i64]
+        L.orc_seed_index.restype = i64
+        L.orc_seeds_for_read.argtypes = [u64p, u64p, i64, u64p, i64p, i64p, u8p, u8p, i64, ci, u32p, i64]
+        L.orc_seeds_for_read.restype = i64
         _lib = L
     return _lib
 
@@ -262,3 +275,90 @@ def view(alpha, beta, cig: Cigar) -> str:
             else:
                 one.append(_RUNE_OF[int(alpha[i])]); two.append("-"); i += 1
     return "".join(one) + "\n" + "".join(two) + "\n"
+
+
+# ---- dna/dnaTwoBit and the perfect-match seed step (gnx_twobit_oracle.c) ----
+def _u64(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a, a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+def new_twobit(seq, lead: int = 0) -> Tuple[np.ndarray, int]:
+    """dnaTwoBit.NewTwoBit (lead=0) / NewTwoBitRainbow(seq)[lead]: (Seq []uint64, Len)."""
+    s, sp = _u8(seq)
+    total = len(s) + lead
+    out = np.zeros(max((total + 31) // 32, 1), dtype=np.uint64)
+    rc = lib().orc_new_twobit(sp, len(s), int(lead), out.ctypes.data_as(C.POINTER(C.c_uint64)))
+    if rc != ORC_OK:
+        raise OracleError(rc, "new_twobit")
+    return out[:(total + 31) // 32], total
+
+
+def get_base(words, pos: int) -> int:
+    """dnaTwoBit.GetBase."""
+    w, wp = _u64(words)
+    return int(lib().orc_get_base(wp, int(pos)))
+
+
+def count_right_matches(one, one_len, start_one, two, two_len, start_two) -> int:
+    """dnaTwoBit.CountRightMatches; -1 = Fatalf (different offsets), -2 = index-out-of-range panic."""
+    a, ap = _u64(one)
+    b, bp = _u64(two)
+    return int(lib().orc_count_right(ap, int(one_len), bp, int(two_len), int(start_one), int(start_two)))
+
+
+def count_left_matches(one, one_len, start_one, two, two_len, start_two) -> int:
+    """dnaTwoBit.CountLeftMatches; same error returns."""
+    a, ap = _u64(one)
+    b, bp = _u64(two)
+    return int(lib().orc_count_left(ap, int(one_len), bp, int(two_len), int(start_one), int(start_two)))
+
+
+def reverse_complement(seq) -> np.ndarray:
+    """dna.ReverseComplement (dna/modify.go:72,111-115)."""
+    comp = np.array([3, 2, 1, 0, 4, 8, 7, 6, 5, 9, 10, 11, 12], dtype=np.uint8)  # dna/modify.go:72 complementArray
+    return comp[np.asarray(seq, dtype=np.uint8)[::-1]].copy()
+
+
+def seed_index(genome_cat, node_off, seed_len: int, seed_step: int):
+    """genomeGraph.IndexGenomeIntoMap for edge-less nodes as a (key, loc)-sorted array."""
+    g, gp = _u8(genome_cat)
+    no, nop = _i64(node_off)
+    cap = max(int(len(g) // max(seed_step, 1)) + len(no) + 1, 1)
+    key = np.zeros(cap, dtype=np.uint64)
+    loc = np.zeros(cap, dtype=np.uint64)
+    k = lib().orc_seed_index(gp, nop, len(no) - 1, int(seed_len), int(seed_step),
+                             key.ctypes.data_as(C.POINTER(C.c_uint64)), loc.ctypes.data_as(C.POINTER(C.c_uint64)), cap)
+    if k < 0:
+        raise OracleError(int(k), "seed_index")
+    return key[:k].copy(), loc[:k].copy()
+
+
+def seeds_for_read(idx_key, idx_loc, genome_cat, node_off, read, seed_len: int) -> np.ndarray:
+    """genomeGraph.seedMapMemPool for one read, seeds in append order: uint32 [n, 6] =
+    (TargetId, TargetStart, QueryStart, Length, PosStrand, TotalLength)."""
+    g = np.ascontiguousarray(genome_cat, dtype=np.uint8)
+    no, nop = _i64(node_off)
+    n_nodes = len(no) - 1
+    wo = np.zeros(n_nodes + 1, dtype=np.int64)
+    np.cumsum((np.diff(no) + 31) // 32, out=wo[1:])
+    words = np.zeros(max(int(wo[-1]), 1), dtype=np.uint64)
+    for k in range(n_nodes):
+        w, _ = new_twobit(g[no[k]:no[k + 1]])
+        words[wo[k]:wo[k + 1]] = w
+    ik, ikp = _u64(idx_key)
+    il, ilp = _u64(idx_loc)
+    r, rp = _u8(read)
+    rc_, rcp = _u8(reverse_complement(r))
+    cap = 64
+    while True:
+        out = np.zeros((cap, 6), dtype=np.uint32)
+        k = lib().orc_seeds_for_read(ikp, ilp, len(ik), words.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                     wo.ctypes.data_as(C.POINTER(C.c_int64)), nop, rp, rcp, len(r), int(seed_len),
+                                     out.ctypes.data_as(C.POINTER(C.c_uint32)), cap)
+        if k == -1:
+            cap *= 4
+            continue
+        if k < 0:
+            raise OracleError(int(k), "seeds_for_read")
+        return out[:k].copy()

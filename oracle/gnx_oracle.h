@@ -95,6 +95,27 @@ int orc_right_dynamic_aln(const uint8_t *alpha, int64_t n, const uint8_t *beta, 
                           const int64_t *scores, int dim, int64_t gap_pen, int64_t *score, orc_cigar *out,
                           int64_t cap, int64_t *n_out, int64_t *max_i, int64_t *max_j);
 
+/* ---- "next" row 8f-2: dna/dnaTwoBit + the perfect-match seed step (gnx_twobit_oracle.c) ------------
+ * NewTwoBit / NewTwoBitRainbow element `lead` (dna/dnaTwoBit/dnaTwoBit.go:68-78, rainbow.go:8-25);
+ * GetBase (:59-65); CountRightMatches / CountLeftMatches (perfectAlign.go:10-85; -1 = log.Fatalf
+ * "Different offsets", -2 = Go index-out-of-range panic).  PINNED: perfectAlign_test.go:28-92,
+ * dnaTwoBit_test.go:9-42 (tests/golden/twobit.json). */
+int64_t orc_twobit_words(int64_t len);
+int orc_new_twobit(const uint8_t *seq, int64_t len, int lead, uint64_t *out);
+uint8_t orc_get_base(const uint64_t *words, uint64_t pos);
+int64_t orc_count_right(const uint64_t *one, int64_t one_len, const uint64_t *two, int64_t two_len,
+                        int64_t start_one, int64_t start_two);
+int64_t orc_count_left(const uint64_t *one, int64_t one_len, const uint64_t *two, int64_t two_len,
+                       int64_t start_one, int64_t start_two);
+/* IndexGenomeIntoMap (genomeGraph/index.go:21-44) and seedMapMemPool (genomeGraph/search.go:567-602) for
+ * edge-less nodes, seeds in append order (before the reference's unstable sort).  PARITY UNPINNED. */
+int64_t orc_seed_index(const uint8_t *genome_cat, const int64_t *node_off, int64_t n_nodes, int seed_len,
+                       int seed_step, uint64_t *out_key, uint64_t *out_loc, int64_t cap);
+int64_t orc_seeds_for_read(const uint64_t *idx_key, const uint64_t *idx_loc, int64_t n_idx,
+                           const uint64_t *node_words, const int64_t *node_word_off, const int64_t *node_off,
+                           const uint8_t *read, const uint8_t *read_rc, int64_t read_len, int seed_len,
+                           uint32_t *out, int64_t cap);
+
 /* Batched driver used as the CPU baseline: one affineGap_highMem (or ConstGap_highMem when
  * mode==2) per pair, pairs split into contiguous ranges over n_threads pthreads -- the
  * goroutine-per-worker shape of cmd/gsw/pairedEndFastqs.go:33-35.  Cigars are written to

@@ -15,6 +15,8 @@ Sources (relative to /root/reference):
   cmd/globalAlignmentAnchor/testdata      out_alignment.{1,2}.expected.tsv + toy genomes
   cmd/cigarToBed/testdata                 seth/raven, PanTro6/hg38 10 kb pair + ins/del BEDs
   cmd/globalAlignment/testdata            chelsea/eric + faOut_test.fa
+  dna/dnaTwoBit/perfectAlign_test.go:21-92 CountLeft/RightMatches known answers (seedTestsShort/Long)
+  dna/dnaTwoBit/dnaTwoBit_test.go:9-42    GetBase expectations on four packed strings
 """
 import json
 import os
@@ -143,6 +145,29 @@ def main():
         "matrix": "HumanChimpTwo", "gap_pen": -430,
         "alpha": read_fasta(d + "chelsea.fa")[0][1], "beta": read_fasta(d + "eric.fa")[0][1],
         "view": out[0][1] + "\n" + out[1][1] + "\n"})
+
+    twobit()
+
+
+def twobit():
+    """dna/dnaTwoBit known answers: the seedTest tables and the GetBase checks."""
+    src = read("dna/dnaTwoBit/perfectAlign_test.go")
+    seqs = dict(re.findall(r"var\s+(\w+)\s+\[\]dna\.Base\s*=\s*dna\.StringToBases\(\"(\w+)\"\)", src))
+    cases = []
+    for a, b, sa, sb, left, right in re.findall(
+            r"\{SeqA:\s*(\w+),.*?SeqB:\s*(\w+),.*?StartA:\s*(\d+),\s*StartB:\s*(\d+),\s*"
+            r"TrueMatchesLeft:\s*(\d+),\s*TrueMatchesRight:\s*(\d+),", src, re.S):
+        cases.append({"seq_a": seqs[a], "seq_b": seqs[b], "start_a": int(sa), "start_b": int(sb),
+                      "left": int(left), "right": int(right), "names": [a, b]})
+    assert len(cases) == 4, cases
+    t = read("dna/dnaTwoBit/dnaTwoBit_test.go")
+    strings = re.findall(r"\"([ACGT]+)\",", t[t.index("var dnaStrings"):t.index("func TestDnaToFromString")])
+    checks = [[int(pos), base] for pos, base in
+              re.findall(r"GetBase\(frag,\s*(\d+)\)\s*if\s+singleBase\s*!=\s*dna\.(\w)\b", t)]
+    assert len(strings) == 4 and len(checks) == 5, (strings, checks)
+    dump("twobit.json", {
+        "source": "dna/dnaTwoBit/perfectAlign_test.go:21-92 (TestCounting) + dnaTwoBit_test.go:9-42 (TestDnaToFromString)",
+        "count_cases": cases, "get_base_strings": strings, "get_base_checks": checks})
 
 
 if __name__ == "__main__":
