@@ -40,7 +40,7 @@ def ncu_traffic(kernel: str, pairs_per_launch: float):
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             t = json.load(f)
-        return t[kernel]["dram_bytes"] * pairs_per_launch / t["pairs_per_launch"]
+        return t[kernel]["dram_bytes"] * pairs_per_launch / t[kernel].get("units_per_launch", t["pairs_per_launch"])
     except Exception:
         return None
 
@@ -109,6 +109,98 @@ def cpu_reference_gcups(n_pairs: int, want_cigar: bool, threads: int):
     return n_pairs * N_LEN * M_LEN / dt / 1e9, dt
 
 
+def twobit_block(ctx, L, dev, stream, rank, world, barrier, args):
+    """dnaTwoBit.NewTwoBit of one long sequence (device-resident, HBM roofline) and genomeGraph.seedMapMemPool
+    over a synthetic linear reference (host-buffer API), with the oracle timed beside it on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from gonomics_b200 import genomegraph
+    out = {}
+    peak, peak_src = hbm_peak()
+    # -- pack: 2^31 bases in HBM -> 2^26 words; algorithmic bytes = 1 B/base in + 0.25 B/base out
+    n = 1 << 31
+    seq = torch.randint(0, 4, (n,), dtype=torch.uint8, device=dev)
+    words = torch.zeros(n // 32, dtype=torch.int64, device=dev)
+    for _ in range(3):
+        ctx._check(L.gnx_twobit_pack_device(ctx._h, seq.data_ptr(), n, 0, words.data_ptr(), stream))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        ctx._check(L.gnx_twobit_pack_device(ctx._h, seq.data_ptr(), n, 0, words.data_ptr(), stream))
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / reps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    gbs = 1.25 * n / (ms * 1e-3) / 1e9
+    # size-independent check at full size: base i of the packing is seq[i] (sampled) and a word checksum
+    idx = torch.randint(0, n, (1 << 16,), device=dev)
+    got = (words[idx // 32] >> (62 - 2 * (idx % 32))) & 3
+    assert torch.equal(got.to(torch.uint8), seq[idx]), "2-bit packing differs from the input bases"
+    out["twobit_pack_2Gbase"] = {
+        "value": world * n / (ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": ms,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                     "traffic": ncu_traffic("twobit_pack_kernel", n), "peak_source": peak_src, "kernel": "twobit_pack_kernel",
+                     "algorithmic_bytes_per_launch": 1.25 * n},
+        "note": "dnaTwoBit.NewTwoBit of one 2^31-base sequence resident in HBM (inputs exceed L2)"}
+    del seq, words, idx, got
+    torch.cuda.empty_cache()
+    # -- seeds: 1M reads x 150 bp against a 64 Mb linear reference, seedLen 32 / seedStep 32 (cmd/gsw defaults)
+    rng = np.random.default_rng(SEED + 11 + rank)
+    g_len, n_reads, r_len = 1 << 26, 1_000_000, 150
+    genome = rng.integers(0, 4, size=g_len, dtype=np.uint8)
+    t0 = time.perf_counter()
+    ix = genomegraph.SeedIndex([genome], 32, 32, ctx)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    starts = rng.integers(0, g_len - r_len, size=n_reads)
+    reads = genome[starts[:, None] + np.arange(r_len)[None, :]]
+    mut = rng.random(reads.shape) < 0.02
+    reads[mut] = (reads[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) % 4
+    flip = rng.random(n_reads) < 0.5
+    reads[flip] = (3 - reads[flip])[:, ::-1]
+    rcat = np.ascontiguousarray(reads.reshape(-1))
+    roff = np.arange(n_reads + 1, dtype=np.int64) * r_len
+    seeds, soff = ix.seed_batch(rcat, roff)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        seeds, soff = ix.seed_batch(rcat, roff)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 3
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    blk = {"value": world * n_reads / dt / 1e6, "unit": "Mreads/s", "ms_per_step": dt * 1e3,
+           "seeds_per_read": float(soff[-1]) / n_reads, "index_entries": ix.n_entries, "index_build_s": build_s,
+           "note": "genomeGraph.seedMapMemPool, host-buffer API (H2D reads + D2H seeds inside the timed region), "
+                   "1M reads x 150 bp, 2 % substitutions, both strands, 64 Mb reference, seedLen 32 / step 32"}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle as orc
+        key, loc = ix.entries()
+        off = np.array([0, g_len], dtype=np.int64)
+        k = 20000
+        packed = orc.pack_nodes(genome, off)  # Node.SeqTwoBit, built once like the reference's genome graph
+        t0 = time.perf_counter()
+        ok = True
+        for r in range(k):
+            want = orc.seeds_for_read(key, loc, genome, off, reads[r], 32, packed)
+            got = seeds[soff[r]:soff[r + 1]]
+            ok &= len(got) == len(want) and all(np.array_equal(got[f], want[:, c]) for c, f in enumerate(got.dtype.names))
+        blk["cpu_baseline"] = {"value": k / (time.perf_counter() - t0) / 1e6, "unit": "Mreads/s", "cores": 1, "kind": "port",
+                               "sample": f"first {k} reads, one thread (C restatement of seedMapMemPool incl. the read's rainbow "
+                                         "tables; ctypes call per read)"}
+        blk["parity_spot_check"] = bool(ok)
+    out["gsw_seeds_1M_reads_150bp"] = blk
+    ix.close()
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The Go toolchain is not in
     this image, so this is the C restatement (oracle/), all host threads, bounded sample per step."""
@@ -116,7 +208,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = max(2000, 1500 * threads)
+    sample = max(2000, 4000 * threads)  # ~3 s of host work per step
     vals = []
     for i in range(args.warmup + args.steps):
         g, dt = cpu_reference_gcups(sample, False, threads)
@@ -341,6 +433,10 @@ def main():
             "const_gap_500x150_traceback": {"value": gc, "unit": "GCUPS", "pairs_per_gpu": 1_000_000,
                                             "ms_per_step": msc, "note": "ConstGap_highMem + CIGAR, g=-430"}}
 
+    # ---- 2-bit packing (HBM-bound) and the perfect-match seed step ----------------------
+    if not args.quick and not args.no_extra:
+        line["other_workloads"].update(twobit_block(ctx, L, dev, stream, rank, world, barrier, args))
+
     # ---- e2e: the public host-buffer API, pinned host inputs, H2D + D2H inside the timed region --
     if not args.no_e2e:
         def e2e(want_cigar: bool):
@@ -375,7 +471,7 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores ----------------------
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        sample = max(2000, 1500 * threads)
+        sample = max(2000, 12000 * threads)  # ~10 s of host work
         g, dt = cpu_reference_gcups(sample, True, threads)
         line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": threads, "kind": "port",
                                 "sample": f"first {sample} pairs of the batch, traceback + cigar, {dt:.1f} s "

@@ -334,11 +334,10 @@ def seed_index(genome_cat, node_off, seed_len: int, seed_step: int):
     return key[:k].copy(), loc[:k].copy()
 
 
-def seeds_for_read(idx_key, idx_loc, genome_cat, node_off, read, seed_len: int) -> np.ndarray:
-    """genomeGraph.seedMapMemPool for one read, seeds in append order: uint32 [n, 6] =
-    (TargetId, TargetStart, QueryStart, Length, PosStrand, TotalLength)."""
+def pack_nodes(genome_cat, node_off):
+    """NewTwoBit of every node: (words concatenated, word offsets) -- what the reference keeps in Node.SeqTwoBit."""
     g = np.ascontiguousarray(genome_cat, dtype=np.uint8)
-    no, nop = _i64(node_off)
+    no = np.ascontiguousarray(node_off, dtype=np.int64)
     n_nodes = len(no) - 1
     wo = np.zeros(n_nodes + 1, dtype=np.int64)
     np.cumsum((np.diff(no) + 31) // 32, out=wo[1:])
@@ -346,6 +345,14 @@ def seeds_for_read(idx_key, idx_loc, genome_cat, node_off, read, seed_len: int) 
     for k in range(n_nodes):
         w, _ = new_twobit(g[no[k]:no[k + 1]])
         words[wo[k]:wo[k + 1]] = w
+    return words, wo
+
+
+def seeds_for_read(idx_key, idx_loc, genome_cat, node_off, read, seed_len: int, packed=None) -> np.ndarray:
+    """genomeGraph.seedMapMemPool for one read, seeds in append order: uint32 [n, 6] =
+    (TargetId, TargetStart, QueryStart, Length, PosStrand, TotalLength).  `packed` = pack_nodes(...) (cached)."""
+    no, nop = _i64(node_off)
+    words, wo = packed if packed is not None else pack_nodes(genome_cat, no)
     ik, ikp = _u64(idx_key)
     il, ilp = _u64(idx_loc)
     r, rp = _u8(read)
