@@ -126,6 +126,7 @@ struct gnx_ctx {
     int opt_fill16 = 1;        // allow the packed 16-bit score-only kernel when its range proof holds
     int opt_ctas_per_sm = 32;  // fill2/3 persistent grid = SMs * min(this, occupancy)
     int opt_force_lookup = -1; // -1 auto; 0/1 force the PRMT / shared-memory score lookup for ACGT pairs
+    int opt_wide_cta = -1;     // -1 auto; 0/1 never / always run multi-strip pairs on the 4-warp CTA-per-pair kernel
     int sm_count = 148;
     // stats of the last batch call
     std::vector<FillEvent> fill_events;
@@ -164,6 +165,7 @@ struct FillCfg {
     int lpp = 32; // lanes per pair
     int skew = 1; // rows between neighbouring lanes (fill3: 2)
     bool multi = false; // some pair needs more than one strip
+    int strips_max = 1; // fill3: strips of the widest pair
 };
 
 struct Problem {
@@ -257,6 +259,7 @@ void pick_cfg(const gnx_ctx *ctx, Problem &pb, int64_t max_m, int64_t max_n)
         c.multi = max_m > (int64_t)c.lpp * c.C || max_n > kRing; // single-strip kernels stage the target in smem
         if (c.multi)
             c.lpp = 32;
+        c.strips_max = (int)((max_m + 32 * c.C - 1) / (32 * c.C));
     } else {
         c.C = (ctx->opt_cols == 5 || ctx->opt_cols == 10) ? ctx->opt_cols : (max_m <= 160 ? 5 : 10);
         c.multi = max_m > 32 * (int64_t)c.C;
@@ -421,6 +424,43 @@ void dispatch_fill3_t(const Problem &pb, const FillParams &fp, int64_t groups, i
             launch_fill3<C, LPP, 1, false, MULTI>(fp, groups, sms, cps, st, pb.cfg.skew);
         else
             launch_fill3<C, LPP, 2, false, MULTI>(fp, groups, sms, cps, st, pb.cfg.skew);
+    }
+}
+
+// CTA-per-pair kernel for long pairs (affine_fill3w_kernel): persistent grid over the chunk's pairs.
+template <int MODE, bool FREE>
+void launch_fill3w(const FillParams &fp, int64_t np, int sm_count, cudaStream_t st)
+{
+    constexpr int NW = 4;
+    static int occ = 0;
+    if (occ == 0) {
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_fill3w_kernel<10, MODE, FREE, NW>, 32 * NW, 0) != cudaSuccess ||
+            o < 1)
+            o = 2;
+        occ = o;
+    }
+    const int grid = (int)std::min<int64_t>(np, (int64_t)sm_count * occ);
+    affine_fill3w_kernel<10, MODE, FREE, NW><<<grid, 32 * NW, 0, st>>>(fp);
+}
+
+void dispatch_fill3w(const Problem &pb, const FillParams &fp, int64_t np, int sms, cudaStream_t st)
+{
+    const int mode = !pb.tagged ? 0 : (pb.want_cigar ? 2 : 1);
+    if (pb.kind == 1) {
+        if (mode == 0)
+            launch_fill3w<0, true>(fp, np, sms, st);
+        else if (mode == 1)
+            launch_fill3w<1, true>(fp, np, sms, st);
+        else
+            launch_fill3w<2, true>(fp, np, sms, st);
+    } else {
+        if (mode == 0)
+            launch_fill3w<0, false>(fp, np, sms, st);
+        else if (mode == 1)
+            launch_fill3w<1, false>(fp, np, sms, st);
+        else
+            launch_fill3w<2, false>(fp, np, sms, st);
     }
 }
 
@@ -629,7 +669,20 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     } else if (pb.cfg.impl == 3) {
         // one launch: the per-lane score tables cover every base < dim, so there is no class split
         const int64_t groups = (np + (32 / pb.cfg.lpp) - 1) / (32 / pb.cfg.lpp);
-        dispatch_fill3(pb, fp, groups, ctx->sm_count, ctx->opt_ctas_per_sm, st);
+        // long pairs with few pairs in flight (the traceback matrix of a 10 kb x 10 kb pair is 82 MB, so a chunk
+        // holds ~1000 of them and the one-warp kernel leaves the SMs short of warps): four warps share one pair
+        // (affine_fill3w_kernel).  Measured at 10 kb x 10 kb (profiles/r01g_kbench_c4.txt): a wave of SMs x 3 pairs
+        // takes 0.75 x the time the one-warp kernel needs for its first pair, which then grows by 1/(2.6 waves)
+        // per extra pair -- so the CTA-per-pair kernel wins for up to one wave and again near two full waves.
+        const int64_t wave = (int64_t)ctx->sm_count * 3;
+        const int64_t waves = (np + wave - 1) / wave;
+        const bool w_faster = 0.75 * (double)waves < 1.0 + (double)np / (2.6 * (double)wave);
+        const bool wide_cta = pb.kind != 2 && pb.cfg.multi &&
+                              (ctx->opt_wide_cta == 1 || (ctx->opt_wide_cta < 0 && pb.cfg.strips_max >= 4 && w_faster));
+        if (wide_cta)
+            dispatch_fill3w(pb, fp, np, ctx->sm_count, st);
+        else
+            dispatch_fill3(pb, fp, groups, ctx->sm_count, ctx->opt_ctas_per_sm, st);
         ctx->launches++;
         ctx->last_fill_launches++;
     } else if (pb.profile) {
@@ -1794,6 +1847,8 @@ int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
         ctx->opt_fill16 = value ? 1 : 0;
     } else if (k == "force_lookup") {
         ctx->opt_force_lookup = (int)value;
+    } else if (k == "wide_cta") {
+        ctx->opt_wide_cta = (int)value;
     } else if (k == "ctas_per_sm") {
         if (value < 1 || value > 32)
             return fail(ctx, GNX_EARG, "ctas_per_sm must be in 1..32");

@@ -201,15 +201,30 @@ __global__ void __launch_bounds__(32, (C == 5 ? 20 : GNX_FILL3_MINB)) affine_fil
             const bool store_edge = MULTI && (lane == LPP - 1) && (p + 1 < strips);
 
             int bI = 0, bH = 0;
+            // MULTI, p > 0: the left boundary column comes from the previous strip's edge buffer (L2).  A load per
+            // step one step ahead sits on the critical path (L2 latency ~ 4 steps at low occupancy: long pairs
+            // are occupancy-bound), so the warp prefetches it 32 rows at a time, one block ahead: lane l holds
+            // row base + l and lane 0 picks its row up with two shuffles per step.
+            int2 eb_cur = make_int2(0, 0), eb_next = make_int2(0, 0);
+            int nbI = 0, nbH = 0;
+            auto edge_block = [&](int first_row) {
+                const int rho = first_row + lane;
+                return (MULTI && p > 0 && rho <= n) ? __ldcg(&ein[rho]) : make_int2(0, 0);
+            };
+            if (MULTI && p > 0) {
+                eb_cur = edge_block(1);
+                eb_next = edge_block(33);
+                nbI = eb_cur.x; // lane 0: row 1
+                nbH = eb_cur.y;
+            }
             auto boundary = [&](int r) {
                 if (!MULTI || p == 0) {
                     const int d0 = FREE ? 0 : (O + r * E) * SC;
                     bI = d0 + iD;
                     bH = d0;
                 } else {
-                    const int2 v = ein[r];
-                    bI = v.x;
-                    bH = v.y;
+                    bI = nbI;
+                    bH = nbH;
                 }
             };
             if (lane == 0)
@@ -226,6 +241,15 @@ __global__ void __launch_bounds__(32, (C == 5 ? 20 : GNX_FILL3_MINB)) affine_fil
             auto step = [&](int t, auto check_tag, auto slot_tag) {
                 constexpr bool CHECK = decltype(check_tag)::value;
                 const int r = t - SK * lane + 1;
+                if (MULTI && p > 0) { // lane 0 fetches row t + 2 for its next step (boundary(r + 1) below)
+                    const int idx = (t + 1) & 31;
+                    if (idx == 0) {
+                        eb_cur = eb_next;
+                        eb_next = edge_block(t + 34);
+                    }
+                    nbI = __shfl_sync(FULL, eb_cur.x, idx);
+                    nbH = __shfl_sync(FULL, eb_cur.y, idx);
+                }
                 int inI = __shfl_up_sync(FULL, edgeI, 1, LPP);
                 int inH = __shfl_up_sync(FULL, edgeH, 1, LPP);
                 if (SK == 2) { // age the pipeline: the one-step-old edge becomes visible to lane+1 next step
@@ -368,6 +392,358 @@ __global__ void __launch_bounds__(32, (C == 5 ? 20 : GNX_FILL3_MINB)) affine_fil
                 }
             }
             __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// affine_fill3w_kernel: one CTA of NW warps per LONG pair (BASELINE config C4: 10 kb x 10 kb).
+//
+// The one-warp-per-pair MULTI kernel above is occupancy-bound on long pairs: a 10 kb x 10 kb pair owns
+// 82 MB of traceback matrix, so only ~1000 pairs (= warps) fit in the workspace and each SM sees 3-7 warps.
+// Here the NW warps of a CTA sweep NW consecutive 320-column strips of the SAME pair concurrently: warp w
+// runs strip k*NW + w in round k and receives its left boundary column (I, H per row) from warp w-1 through
+// a shared-memory ring (8 stages of 16 rows, each stage guarded by a full/empty mbarrier pair -- no fence
+// instruction at all: MEMBAR.CTA per batch measured 2x slower, the GPU-scope fence of the L2 ring 2.9x).  Warp 0 of round k+1 reads
+// the column warp NW-1 wrote to the per-CTA global ping-pong buffer in round k; rounds are separated by
+// __syncthreads() (the pipeline drains for ~(NW-1)*40 of ~10 000 steps).  Cell arithmetic, tags, trace
+// layout and score output are identical to affine_fill3_kernel<C, 32, MODE, FREE, true, 1>.
+// ------------------------------------------------------------------------------------------------
+// mbarrier producer/consumer primitives (shared::cta): arrive has release.cta and try_wait acquire.cta
+// semantics, which orders the plain ring stores/loads around them without any MEMBAR.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+constexpr int kWBatch = 16, kWStages = 8, kWRing = kWBatch * kWStages;
+
+template <int C, int MODE, bool FREE, int NW>
+__global__ void __launch_bounds__(32 * NW, GNX_FILL3_MINB / NW) affine_fill3w_kernel(const FillParams P)
+{
+    constexpr bool TRACE = MODE >= 1, STORE = MODE == 2;
+    constexpr int LPP = 32;
+    constexpr int SC = TRACE ? kScale : 1;
+    constexpr int FI = TRACE ? kFI : 0, FD = TRACE ? kFD : 0, FH = TRACE ? kFH : 0;
+    constexpr int WPL = trace_wpl(C);
+    constexpr int NEG = kNeg32;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int CLR = ~(kScale - 1);
+
+    __shared__ int s_tab_all[NW][C * kDimP * 32]; // per warp: [c][a][lane]
+    __shared__ int2 s_ring[NW][kWRing];           // ring w: written by warp w (lane 31), read by warp w+1 (lane 0)
+    __shared__ uint64_t s_full[NW][kWStages], s_empty[NW][kWStages]; // one mbarrier pair per 8-row stage of ring w
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int *s_tab = s_tab_all[warp];
+    const int one = P.one;
+    const int O = P.gap_open, E = P.gap_extend;
+    const int oe_s = (O + E) * SC, e_s = E * SC;
+    const int kI = oe_s + 2 * FI - 2 * FH;
+    const int iI = e_s + FI, iD = oe_s;
+    const int dMn = oe_s + 2 * FD - 2 * FH, dIn = oe_s + FD - FH, dDn = e_s;
+    const int dMl = 2 * FD - 2 * FH, dIl = FD - FH, dDl = 0;
+    const int fh_reg = FH * one;
+    int2 *edge_a = P.edge + (size_t)blockIdx.x * 2 * P.edge_stride;
+    int2 *edge_b = edge_a + P.edge_stride;
+    if (threadIdx.x < NW * kWStages) { // one arriving thread each: lane 31 of the producer / lane 0 of the consumer
+        mbar_init(&s_full[0][0] + threadIdx.x, 1);
+        mbar_init(&s_empty[0][0] + threadIdx.x, 1);
+    }
+    __syncthreads();
+    // batches handed over so far on the ring this warp writes (g_out) / reads (g_in); both ends count the same
+    // batches, so stage = g % 8 and phase parity = (g / 8) & 1 stay in step for the whole kernel
+    unsigned g_out = 0, g_in = 0;
+
+    for (int64_t pair = P.pair_begin + blockIdx.x; pair < P.pair_end; pair += gridDim.x) {
+        if (P.pair_class && P.pair_class[pair] > 1)
+            continue; // CTA-uniform
+        const int64_t a0 = P.alpha_off[pair], b0 = P.beta_off[pair];
+        const int n = (int)(P.alpha_off[pair + 1] - a0);
+        const int m = (int)(P.beta_off[pair + 1] - b0);
+        const uint8_t *__restrict__ alpha = P.alpha + a0;
+        const uint8_t *__restrict__ beta = P.beta + b0;
+        if (n == 0 || m == 0) { // closed forms of the boundary row / column
+            if (threadIdx.x == 0) {
+                int64_t sc;
+                if (n == 0 && m == 0)
+                    sc = P.h00;
+                else if (n == 0)
+                    sc = (int64_t)O + (int64_t)m * E;
+                else
+                    sc = FREE ? 0 : (int64_t)O + (int64_t)n * E;
+                P.out_score[pair] = sc;
+            }
+            continue;
+        }
+        const int T = STORE ? ((n + LPP - 1 + 3) & ~3) : n + LPP - 1;
+        const int Tp = (n + LPP - 1 + 3) & ~3;
+        const int strips = (m + LPP * C - 1) / (LPP * C);
+        const int rounds = (strips + NW - 1) / NW;
+        uint32_t *tbase = STORE ? P.trace + P.trace_off[pair - P.pair_begin] : nullptr;
+
+        for (int k = 0; k < rounds; ++k) {
+            __syncthreads(); // the previous round is complete: its global edge column is visible, the rings are idle
+            const int p = k * NW + warp;
+            if (p >= strips)
+                continue;
+            const int jbase = p * LPP * C + lane * C;
+            int aM[C], aI[C], aD[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int j = jbase + c + 1;
+                const int q = (j <= m) ? (int)beta[j - 1] : 0;
+#pragma unroll
+                for (int a = 0; a < kDimP; ++a) {
+                    int v = 0;
+                    if (a < P.dim && q < P.dim)
+                        v = P.scores[a * P.dim + q] * SC + 2 * FH;
+                    s_tab[(c * kDimP + a) * 32 + lane] = v;
+                }
+                const bool last = FREE && (j == m);
+                aM[c] = last ? dMl : dMn;
+                aI[c] = last ? dIl : dIn;
+                aD[c] = last ? dDl : dDn;
+            }
+            int Dt[C], Hc[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int j = jbase + c + 1;
+                const int i0 = (O + j * E) * SC;
+                Hc[c] = i0;
+                Dt[c] = max3(NEG + 2 * FH + aM[c], i0 + FH + aI[c], NEG + aD[c]);
+            }
+            int hpL = (jbase == 0) ? P.h00 * SC : (O + jbase * E) * SC;
+            int edgeI = 0, edgeH = 0;
+            const int2 *ein = (k & 1) ? edge_b : edge_a;   // written by warp NW-1 in round k-1
+            int2 *eout = (k & 1) ? edge_a : edge_b;
+            uint4 *tp4 = STORE ? reinterpret_cast<uint4 *>(tbase + ((size_t)p * Tp * WPL) * 32) + lane : nullptr;
+            uint4 wq[WPL];
+#pragma unroll
+            for (int q = 0; q < WPL; ++q)
+                wq[q] = make_uint4(0, 0, 0, 0);
+            const bool has_next = p + 1 < strips;
+            const bool to_ring = has_next && warp < NW - 1, to_global = has_next && warp == NW - 1;
+            const int win = warp > 0 ? warp - 1 : 0;
+            const int2 *ring_in = s_ring[win];
+            const unsigned nb = (unsigned)(n + kWBatch - 1) / kWBatch; // batches per strip
+            const unsigned gi0 = g_in, go0 = g_out;
+            if (warp > 0)
+                g_in += nb; // this strip consumes nb batches from warp-1 ...
+            if (to_ring)
+                g_out += nb; // ... and hands nb batches to warp+1
+
+            int bI = 0, bH = 0;
+            // warp 0, p > 0: block prefetch of the global edge column (see affine_fill3_kernel)
+            const bool gin = warp == 0 && p > 0;
+            int2 eb_cur = make_int2(0, 0), eb_next = make_int2(0, 0);
+            int nbI = 0, nbH = 0;
+            auto edge_block = [&](int first_row) {
+                const int rho = first_row + lane;
+                return (gin && rho <= n) ? __ldcg(&ein[rho]) : make_int2(0, 0);
+            };
+            if (gin) {
+                eb_cur = edge_block(1);
+                eb_next = edge_block(33);
+                nbI = eb_cur.x;
+                nbH = eb_cur.y;
+            }
+            auto boundary = [&](int r) { // lane 0 only: (I, H) of the column left of this strip, row r
+                if (p == 0) {
+                    const int d0 = FREE ? 0 : (O + r * E) * SC;
+                    bI = d0 + iD;
+                    bH = d0;
+                } else if (warp == 0) {
+                    bI = nbI;
+                    bH = nbH;
+                } else {
+                    const unsigned g = gi0 + (unsigned)(r - 1) / kWBatch;
+                    const int2 v = ring_in[(r - 1) & (kWRing - 1)];
+                    bI = v.x;
+                    bH = v.y;
+                    if ((r & (kWBatch - 1)) == 0 || r == n) // last row of the batch: hand the stage back
+                        mbar_arrive(&s_empty[win][g % kWStages]);
+                }
+            };
+            // The ring waits are executed by the WHOLE warp (their conditions depend only on the step index):
+            // a spin loop inside the lane-0 / lane-31 branches leaves the warp split for the rest of the step
+            // (ncu: the cell loop issued twice, 16 active threads on average).
+            //   consumer: lane 0 fetches row t + 2 during step t; at the first row of a batch wait until the
+            //             producer has filled that batch AND the next one (batches complete in order), so that in
+            //             steady state the consumer is never polling a barrier that is about to flip;
+            //   producer: lane 31 writes row t - 30 during step t; at the first row of a batch the stage must
+            //             have been handed back by the consumer.
+            const bool rin = warp > 0;
+            auto wait_full = [&](int row) {
+                const unsigned g = gi0 + (unsigned)(row - 1) / kWBatch;
+                const unsigned gw = min(g + 1, gi0 + nb - 1);
+                mbar_wait(&s_full[win][gw % kWStages], (gw / kWStages) & 1);
+            };
+            if (rin)
+                wait_full(1);
+            if (lane == 0)
+                boundary(1);
+            int a_next = (lane == 0) ? (int)alpha[0] : 0;
+
+            auto step = [&](int t, auto check_tag, auto slot_tag) {
+                constexpr bool CHECK = decltype(check_tag)::value;
+                const int r = t - lane + 1;
+                if (rin && ((t + 1) & (kWBatch - 1)) == 0 && t + 2 <= n)
+                    wait_full(t + 2);
+                if (to_ring && ((t - 31) & (kWBatch - 1)) == 0 && t >= 31 && t - 30 <= n) {
+                    const unsigned g = go0 + (unsigned)(t - 31) / kWBatch;
+                    mbar_wait(&s_empty[warp][g % kWStages], ((g / kWStages) & 1) ^ 1);
+                }
+                if (gin) {
+                    const int idx = (t + 1) & 31;
+                    if (idx == 0) {
+                        eb_cur = eb_next;
+                        eb_next = edge_block(t + 34);
+                    }
+                    nbI = __shfl_sync(FULL, eb_cur.x, idx);
+                    nbH = __shfl_sync(FULL, eb_cur.y, idx);
+                }
+                int inI = __shfl_up_sync(FULL, edgeI, 1);
+                int inH = __shfl_up_sync(FULL, edgeH, 1);
+                if (lane == 0) {
+                    inI = bI;
+                    inH = bH;
+                }
+                const int a = a_next;
+                bool active = true;
+                if (CHECK) {
+                    active = (unsigned)(r - 1) < (unsigned)n;
+                    if ((unsigned)r < (unsigned)n)
+                        a_next = alpha[r];
+                } else {
+                    a_next = alpha[r];
+                }
+                unsigned w[WPL];
+#pragma unroll
+                for (int q = 0; q < WPL; ++q)
+                    w[q] = 0;
+                if (active) {
+                    if (lane == 0 && r < n)
+                        boundary(r + 1);
+                    const int *row = s_tab + a * 32 + lane;
+                    int It = inI, hp = hpL;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int s = row[c * kDimP * 32];
+                        const int MH = madd(hp, one, s);
+                        if (TRACE) {
+                            int cIh;
+                            asm("lop3.b32 %0, %1, %2, %3, 0xea;" : "=r"(cIh) : "r"(It), "r"(CLR), "r"(fh_reg));
+                            const int cD = Dt[c] & CLR;
+                            const int Ht = max3(MH, cIh, cD);
+                            if (STORE)
+                                w[c / 5] = shf_r_wrap(w[c / 5], (unsigned)xor3(It, Dt[c], Ht), kTagBits);
+                            It = max3(madd(MH, one, kI), madd(cIh, one, iI - FH), madd(cD, one, iD));
+                            Dt[c] = max3(madd(MH, one, aM[c]), madd(cIh, one, aI[c]), madd(cD, one, aD[c]));
+                            hp = Hc[c];
+                            Hc[c] = Ht & CLR;
+                        } else {
+                            const int H = max3(MH, It, Dt[c]);
+                            const int Ho = madd(H, one, oe_s);
+                            It = addmax(It, e_s, Ho);
+                            Dt[c] = FREE ? addmax(Dt[c], aD[c], madd(H, one, aI[c])) : addmax(Dt[c], e_s, Ho);
+                            hp = Hc[c];
+                            Hc[c] = H;
+                        }
+                    }
+                    edgeI = It;
+                    edgeH = Hc[C - 1];
+                    hpL = inH;
+                    if (lane == LPP - 1) {
+                        if (to_global) {
+                            eout[r] = make_int2(It, Hc[C - 1]);
+                        } else if (to_ring) {
+                            const unsigned g = go0 + (unsigned)(r - 1) / kWBatch;
+                            s_ring[warp][(r - 1) & (kWRing - 1)] = make_int2(It, Hc[C - 1]);
+                            if ((r & (kWBatch - 1)) == 0 || r == n)
+                                mbar_arrive(&s_full[warp][g % kWStages]);
+                        }
+                    }
+                }
+                if (STORE) {
+                    constexpr int SLOT = decltype(slot_tag)::value; // 0..3: aligned group position, -1: runtime
+                    if (SLOT < 0) {
+#pragma unroll
+                        for (int q = 0; q < WPL; ++q) {
+                            wq[q].x = wq[q].y;
+                            wq[q].y = wq[q].z;
+                            wq[q].z = wq[q].w;
+                            wq[q].w = w[q];
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < WPL; ++q) {
+                            if (SLOT == 0)
+                                wq[q].x = w[q];
+                            if (SLOT == 1)
+                                wq[q].y = w[q];
+                            if (SLOT == 2)
+                                wq[q].z = w[q];
+                            if (SLOT == 3)
+                                wq[q].w = w[q];
+                        }
+                    }
+                    if (SLOT == 3 || (SLOT < 0 && (t & 3) == 3)) {
+#pragma unroll
+                        for (int q = 0; q < WPL; ++q)
+                            tp4[(size_t)q * 32] = wq[q];
+                        tp4 += WPL * 32;
+                    }
+                }
+            };
+
+            using RT = std::integral_constant<int, -1>;
+            int t = 0;
+            if (STORE) {
+#pragma unroll 1
+                for (; t < ((LPP - 1 + 3) & ~3); ++t)
+                    step(t, std::true_type{}, RT{});
+#pragma unroll 1
+                for (; t + 3 < n - 1; t += 4) {
+                    step(t, std::false_type{}, std::integral_constant<int, 0>{});
+                    step(t + 1, std::false_type{}, std::integral_constant<int, 1>{});
+                    step(t + 2, std::false_type{}, std::integral_constant<int, 2>{});
+                    step(t + 3, std::false_type{}, std::integral_constant<int, 3>{});
+                }
+            } else {
+#pragma unroll 1
+                for (; t < LPP - 1; ++t)
+                    step(t, std::true_type{}, RT{});
+#pragma unroll 2
+                for (; t < n - 1; ++t)
+                    step(t, std::false_type{}, RT{});
+            }
+#pragma unroll 1
+            for (; t < T; ++t)
+                step(t, std::true_type{}, RT{});
+
+            const int pm = (m - 1) / (LPP * C), lm = ((m - 1) % (LPP * C)) / C, cm = (m - 1) % C;
+            if (p == pm && lane == lm) {
+                int h = Hc[0];
+#pragma unroll
+                for (int c = 1; c < C; ++c)
+                    if (c == cm)
+                        h = Hc[c];
+                P.out_score[pair] = (int64_t)(h / SC);
+            }
         }
     }
 }

@@ -255,6 +255,33 @@ def test_long_pairs_multi_strip(ctx):
         check_batch(ctx, al, be, orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, -600 if mode != 2 else -430, -150, mode)
 
 
+@pytest.mark.parametrize("wide", [0, 1])
+def test_long_pairs_cta_per_pair_kernel(wide):
+    """The 4-warp CTA-per-pair kernel (affine_fill3w_kernel: strips pipelined over warps through shared-memory
+    rings) and the one-warp multi-strip kernel give the oracle's result on ragged long pairs: 1..7 strips, more
+    pairs than resident CTAs is not needed (each CTA loops), N bases, empty sides, both modes, with/without trace."""
+    c = align.Context(0)
+    try:
+        c.set_option("wide_cta", wide)
+        rng = np.random.default_rng(601 + wide)
+        al, be = [], []
+        shapes = [(1500, 100), (1030, 321), (40, 700), (900, 640), (2000, 1281), (333, 1600), (2100, 2100), (5, 330),
+                  (1, 961), (1300, 0), (0, 1300), (64, 1990), (3000, 1000)]
+        for rep in range(3):
+            for n, m in shapes:
+                a, b = random_pair(rng, n, m, identity=0.9)
+                if rep == 1 and n and m:
+                    a[rng.integers(0, n, max(1, n // 50))] = 4
+                al.append(a)
+                be.append(b)
+        for mode in (0, 1):
+            check_batch(c, al, be, orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, -600, -150, mode)
+            check_batch(c, al, be, orc.DEFAULT_SCORE_MATRIX, -400, -30, mode, want_cigar=False)
+            check_batch(c, al, be, orc.DEFAULT_SCORE_MATRIX, 30, -40, mode, want_cigar=False)  # O > 0: tagged score-only
+    finally:
+        c.close()
+
+
 def test_chunking_and_small_workspace():
     """Force many chunks (tiny workspace / chunk_pairs) so chunk boundaries and slot reuse are exercised."""
     c = align.Context(0, workspace_bytes=8 << 20)
