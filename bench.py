@@ -227,7 +227,14 @@ def run_reference(args):
         "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_FD = 1
+
+
+def emit(line: dict):
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
 
 
 def main():
@@ -243,6 +250,12 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the C1 / C4-sample / const-gap block")
     ap.add_argument("--quick", action="store_true", help="profiling runs: no e2e/cpu legs, warm-up not clamped")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: everything libraries print there (e.g. "NCCL version ..."
+    # under torchrun) is sent to stderr by pointing fd 1 at fd 2 for the duration of the run.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -485,7 +498,7 @@ def main():
         line["parity_spot_check"] = bool(np.array_equal(osc, d_score[:k].cpu().numpy()))
 
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     L.gnx_host_free(pa)
     L.gnx_host_free(pb_)

@@ -166,6 +166,7 @@ struct FillCfg {
     int skew = 1; // rows between neighbouring lanes (fill3: 2)
     bool multi = false; // some pair needs more than one strip
     int strips_max = 1; // fill3: strips of the widest pair
+    int64_t m_uniform = 0; // fill16: the batch's (uniform) query length
 };
 
 struct Problem {
@@ -427,6 +428,37 @@ void dispatch_fill3_t(const Problem &pb, const FillParams &fp, int64_t groups, i
     }
 }
 
+template <bool FREE, int CM>
+void launch_fill16(const FillParams &fp, int64_t quads, int sm_count, int ctas_per_sm, cudaStream_t st)
+{
+    static int occ = 0; // per instantiation
+    if (occ == 0) {
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_fill16_kernel<FREE, CM>, 32, 0) != cudaSuccess || o < 1)
+            o = 8;
+        occ = o;
+    }
+    const int grid = (int)std::min<int64_t>(quads, (int64_t)sm_count * std::min(occ, ctas_per_sm));
+    affine_fill16_kernel<FREE, CM><<<grid, 32, 0, st>>>(fp);
+}
+
+// freeEndGaps: the in-lane index of the last column is a template parameter (uniform batches: one value per call)
+void launch_fill16_free(const FillParams &fp, int64_t quads, int cm, int sm_count, int ctas_per_sm, cudaStream_t st)
+{
+    switch (cm) {
+    case 0: launch_fill16<true, 0>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 1: launch_fill16<true, 1>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 2: launch_fill16<true, 2>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 3: launch_fill16<true, 3>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 4: launch_fill16<true, 4>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 5: launch_fill16<true, 5>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 6: launch_fill16<true, 6>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 7: launch_fill16<true, 7>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 8: launch_fill16<true, 8>(fp, quads, sm_count, ctas_per_sm, st); break;
+    default: launch_fill16<true, 9>(fp, quads, sm_count, ctas_per_sm, st); break;
+    }
+}
+
 // CTA-per-pair kernel for long pairs (affine_fill3w_kernel): persistent grid over the chunk's pairs.
 template <int MODE, bool FREE>
 void launch_fill3w(const FillParams &fp, int64_t np, int sm_count, cudaStream_t st)
@@ -650,20 +682,11 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     cudaEventRecord(fe.a, st);
     const int lookup0 = pb.chunk > 1 ? 2 : ((ctx->opt_force_lookup == 1 || !pb.prmt_ok) ? 1 : 0);
     if (pb.cfg.impl == 16) {
-        static int occ16[2] = {0, 0};
-        const int fi = pb.kind == 1 ? 1 : 0;
-        if (occ16[fi] == 0) {
-            int o = 0;
-            cudaError_t e = fi ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_fill16_kernel<true>, 32, 0)
-                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_fill16_kernel<false>, 32, 0);
-            occ16[fi] = (e == cudaSuccess && o > 0) ? o : 8;
-        }
         const int64_t quads = (np + 3) / 4;
-        const int g16 = (int)std::min<int64_t>(quads, (int64_t)ctx->sm_count * std::min(occ16[fi], ctx->opt_ctas_per_sm));
-        if (fi)
-            affine_fill16_kernel<true><<<g16, 32, 0, st>>>(fp);
+        if (pb.kind == 1)
+            launch_fill16_free(fp, quads, (int)((pb.cfg.m_uniform - 1) % 10), ctx->sm_count, ctx->opt_ctas_per_sm, st);
         else
-            affine_fill16_kernel<false><<<g16, 32, 0, st>>>(fp);
+            launch_fill16<false, -1>(fp, quads, ctx->sm_count, ctx->opt_ctas_per_sm, st);
         ctx->launches++;
         ctx->last_fill_launches++;
     } else if (pb.cfg.impl == 3) {
@@ -890,6 +913,7 @@ int make_plan(gnx_ctx *ctx, Problem &pb, const int64_t *aoff, const int64_t *bof
         pb.cfg.lpp = 16;
         pb.cfg.skew = 1;
         pb.cfg.multi = false;
+        pb.cfg.m_uniform = plan.max_m;
     }
     plan.any_long = pb.cfg.multi;
     plan.bounds.push_back(0);

@@ -24,9 +24,12 @@ __device__ __forceinline__ unsigned wrap16x2(int d) { return ((unsigned)d & 0xff
 __device__ __forceinline__ unsigned umax3_16x2(unsigned a, unsigned b, unsigned c) { return __vimax3_u16x2(a, b, c); }
 __device__ __forceinline__ unsigned uaddmax_16x2(unsigned a, unsigned b, unsigned c) { return __viaddmax_u16x2(a, b, c); }
 
-template <bool FREE>
+// CM >= 0 (FREE only): (m - 1) % C, the in-lane index of the freeEndGaps column, known at compile time -- only that
+// column then pays the extra add for its zero D-plane addends; every other cell shares H + O + E between I' and D'.
+template <bool FREE, int CM = -1>
 __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams P)
 {
+    static_assert(CM < 0 || FREE, "CM selects the free-end column");
     constexpr int C = 10, LPP = 16;
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ short s_tabA[C * kDimP * 32]; // [c][a][thread], pair A: s as int16 (sign-extending LDS)
@@ -80,6 +83,9 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
             Hc[c] = h0;
             Dt[c] = h0 + (unsigned)aH[c];          // D(1,j) = I(0,j) + O + E   (or I(0,m) in the free last column)
         }
+        const bool lastlane = FREE && lane == (m - 1) / C;
+        const unsigned aDl = lastlane ? 0u : e_w; // addends of column CM in this lane (zero in the free-end column)
+        const int aHl = lastlane ? 0 : oe_i;
         unsigned hpL = (jbase == 0) ? pack16(P.h00) : pack16(O + jbase * E);
         unsigned edgeI = 0, edgeH = 0;
         unsigned bI = 0, bH = 0;
@@ -128,12 +134,14 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
                 for (int c = 0; c < C; ++c) {
                     const int sA = rowA[c * kDimP * 32]; // sign-extended int16
                     const int sB = rowB[c * kDimP * 32]; // s * 65536
-                    const unsigned MH = (unsigned)madd((int)hp, one, sA) + (unsigned)sB;
+                    const unsigned MH = hp + (unsigned)sA + (unsigned)sB; // one IADD3
                     const unsigned H = umax3_16x2(MH, It, Dt[c]);
                     const unsigned Ho = (unsigned)madd((int)H, one, oe_i);
                     It = uaddmax_16x2(It, e_w, Ho);                      // I' = max(I + E, H + O + E)
-                    if (FREE)
+                    if (FREE && CM < 0)
                         Dt[c] = uaddmax_16x2(Dt[c], aD[c], (unsigned)madd((int)H, one, aH[c]));
+                    else if (FREE && c == CM)
+                        Dt[c] = uaddmax_16x2(Dt[c], aDl, (unsigned)madd((int)H, one, aHl));
                     else
                         Dt[c] = uaddmax_16x2(Dt[c], e_w, Ho);            // D' = max(D + E, H + O + E)
                     hp = Hc[c];
