@@ -8,6 +8,7 @@
 #include "gnx_kernels.cuh"
 #include "gnx_fill3.cuh"
 #include "gnx_fill16.cuh"
+#include "gnx_ckpt.cuh"
 #include "gnx_profile.cuh"
 #include "gnx_twobit.cuh"
 
@@ -126,6 +127,7 @@ struct gnx_ctx {
     int opt_fill16 = 1;        // allow the packed 16-bit score-only kernel when its range proof holds
     int opt_ctas_per_sm = 32;  // fill2/3 persistent grid = SMs * min(this, occupancy)
     int opt_force_lookup = -1; // -1 auto; 0/1 force the PRMT / shared-memory score lookup for ACGT pairs
+    int opt_ckpt = 1;          // allow the checkpoint-and-recompute traceback for uniform freeEndGaps batches
     int opt_wide_cta = -1;     // -1 auto; 0/1 never / always run multi-strip pairs on the 4-warp CTA-per-pair kernel
     int sm_count = 148;
     // stats of the last batch call
@@ -167,6 +169,7 @@ struct FillCfg {
     bool multi = false; // some pair needs more than one strip
     int strips_max = 1; // fill3: strips of the widest pair
     int64_t m_uniform = 0; // fill16: the batch's (uniform) query length
+    int64_t n_uniform = 0; // checkpoint path: the batch's (uniform) target length
 };
 
 struct Problem {
@@ -269,9 +272,17 @@ void pick_cfg(const gnx_ctx *ctx, Problem &pb, int64_t max_m, int64_t max_n)
 
 // Range proof for the packed 16-bit score-only kernel (gnx_fill16.cuh): every state it ever holds,
 // including the padding columns up to 160, lies in [LB, UB]; with the +32768 bias both must fit 16 bits.
-bool fill16_ok(const gnx_ctx *ctx, const Problem &pb, int64_t min_n, int64_t max_n, int64_t min_m, int64_t max_m)
+bool fill16_ok(const gnx_ctx *ctx, const Problem &pb, int64_t min_n, int64_t max_n, int64_t min_m, int64_t max_m,
+               bool for_ckpt = false)
 {
-    if (!ctx->opt_fill16 || ctx->opt_fill_impl != 3 || pb.kind == 2 || pb.want_cigar || pb.dim > kDimP)
+    if (!ctx->opt_fill16 || ctx->opt_fill_impl != 3 || pb.kind == 2 || pb.dim > kDimP)
+        return false;
+    if (!for_ckpt && pb.want_cigar)
+        return false;
+    // checkpoint-and-recompute traceback (gnx_ckpt.cuh): freeEndGaps only, target staged in shared memory, and
+    // worth it only when the target is well longer than the query (the path then skips most of the rows)
+    if (for_ckpt && (!pb.want_cigar || !ctx->opt_ckpt || pb.kind != 1 || pb.chunk > 1 || pb.profile || pb.ext || max_n > kRing ||
+                     max_n < 2 * max_m))
         return false;
     if (min_n != max_n || min_m != max_m || max_n < 1 || max_m < 1 || max_m > 160) // uniform batch only
         return false;
@@ -297,6 +308,8 @@ inline int64_t group_trace_words(const Problem &pb, int64_t n_eff, int64_t m)
     if (n_eff <= 0 || m <= 0)
         return 0;
     const FillCfg &c = pb.cfg;
+    if (c.impl == 17) // checkpoints: kCkRegs words per lane every kCkK steps; a group is half a quad
+        return ((n_eff + 16 - 2) / kCkK) * kCkRegs * 16;
     if (pb.kind == 2 && c.impl != 3)
         return const_trace_words(n_eff, m, c.C);
     const int64_t strips = (m + (int64_t)c.lpp * c.C - 1) / ((int64_t)c.lpp * c.C);
@@ -440,6 +453,68 @@ void launch_fill16(const FillParams &fp, int64_t quads, int sm_count, int ctas_p
     }
     const int grid = (int)std::min<int64_t>(quads, (int64_t)sm_count * std::min(occ, ctas_per_sm));
     affine_fill16_kernel<FREE, CM><<<grid, 32, 0, st>>>(fp);
+}
+
+inline int64_t ckpt_quad_words(int64_t n) { return ((n + 16 - 2) / kCkK) * kCkRegs * 32; }
+
+template <int CM>
+void launch_fill16_ckpt_t(const FillParams &fp, int64_t quads, int sm_count, int ctas_per_sm, cudaStream_t st)
+{
+    static int occ = 0;
+    if (occ == 0) {
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_fill16_kernel<true, CM, true>, 32, 0) != cudaSuccess || o < 1)
+            o = 8;
+        occ = o;
+    }
+    const int grid = (int)std::min<int64_t>(quads, (int64_t)sm_count * std::min(occ, ctas_per_sm));
+    affine_fill16_kernel<true, CM, true><<<grid, 32, 0, st>>>(fp);
+}
+
+void launch_fill16_ckpt(const FillParams &fp, int64_t quads, int cm, int sm_count, int ctas_per_sm, cudaStream_t st)
+{
+    switch (cm) {
+    case 0: launch_fill16_ckpt_t<0>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 1: launch_fill16_ckpt_t<1>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 2: launch_fill16_ckpt_t<2>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 3: launch_fill16_ckpt_t<3>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 4: launch_fill16_ckpt_t<4>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 5: launch_fill16_ckpt_t<5>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 6: launch_fill16_ckpt_t<6>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 7: launch_fill16_ckpt_t<7>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 8: launch_fill16_ckpt_t<8>(fp, quads, sm_count, ctas_per_sm, st); break;
+    default: launch_fill16_ckpt_t<9>(fp, quads, sm_count, ctas_per_sm, st); break;
+    }
+}
+
+// second pass of the checkpoint path: recompute + walk (pass 0: slots and counts; pass 1: overflowing pairs)
+void launch_ckpt_trace(gnx_ctx *ctx, const Problem &pb, const FillParams &fp, const uint32_t *ckpt, const int64_t *rstar,
+                       uint32_t *slots, int *counts, int pass, const int64_t *cig_off, gnx_cigar *cigars, int64_t cap,
+                       cudaStream_t st)
+{
+    static int occ = 0;
+    if (occ == 0) {
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_ckpt_trace_kernel, 32, 0) != cudaSuccess || o < 1)
+            o = 8;
+        occ = o;
+    }
+    CkptParams q;
+    memset(&q, 0, sizeof q);
+    q.ckpt = ckpt;
+    q.quad_words = ckpt_quad_words(pb.cfg.n_uniform);
+    q.rstar = rstar;
+    q.slots = slots;
+    q.slot_cap = kSlotCap;
+    q.counts = counts;
+    q.pass = pass;
+    q.cigar_off = cig_off;
+    q.out_cigar = (CigarOut *)cigars;
+    q.out_cap = cap;
+    q.h00_plane = pb.h00_plane;
+    const int64_t units = ((fp.pair_end - fp.pair_begin + 3) / 4) * 2;
+    const int grid = (int)std::min<int64_t>(units, (int64_t)ctx->sm_count * occ);
+    affine_ckpt_trace_kernel<<<grid, 32, 0, st>>>(fp, q);
 }
 
 // freeEndGaps: the in-lane index of the last column is a template parameter (uniform batches: one value per call)
@@ -632,7 +707,7 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     const int grid = (int)std::min<int64_t>((np + warps_per_block - 1) / warps_per_block, max_grid);
     if (pb.profile) {
         // no sequence bytes on this path: invalid bases were found while the profiles were built
-    } else if (pb.cfg.impl == 3 || pb.cfg.impl == 16) {
+    } else if (pb.cfg.impl == 3 || pb.cfg.impl == 16 || pb.cfg.impl == 17) {
         // these kernels take any base < dim, so the per-pair pass is only needed to find WHICH pair is
         // invalid; gate it on the chunk's largest base (vectorised, HBM-bound)
         int *gate = status + 1 + ctx->gate_rr;
@@ -681,7 +756,14 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     FillEvent &fe = next_fill_event(ctx);
     cudaEventRecord(fe.a, st);
     const int lookup0 = pb.chunk > 1 ? 2 : ((ctx->opt_force_lookup == 1 || !pb.prmt_ok) ? 1 : 0);
-    if (pb.cfg.impl == 16) {
+    if (pb.cfg.impl == 17) {
+        const int64_t quads = (np + 3) / 4;
+        fp.trace = cd.trace;                                   // checkpoint area
+        fp.edge_stride = ckpt_quad_words(pb.cfg.n_uniform);    // words per quad
+        launch_fill16_ckpt(fp, quads, (int)((pb.cfg.m_uniform - 1) % 10), ctx->sm_count, ctx->opt_ctas_per_sm, st);
+        ctx->launches++;
+        ctx->last_fill_launches++;
+    } else if (pb.cfg.impl == 16) {
         const int64_t quads = (np + 3) / 4;
         if (pb.kind == 1)
             launch_fill16_free(fp, quads, (int)((pb.cfg.m_uniform - 1) % 10), ctx->sm_count, ctx->opt_ctas_per_sm, st);
@@ -766,7 +848,9 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         tp.counts = cd.counts;
         tp.pass = 0;
         tp.pair_class = pb.profile ? nullptr : cd.cls;
-        if (pb.ext)
+        if (pb.cfg.impl == 17)
+            launch_ckpt_trace(ctx, pb, fp, cd.trace, cd.best, cd.slots, cd.counts, 0, nullptr, nullptr, 0, st);
+        else if (pb.ext)
             launch_traceback_ext(pb, cd, tp, np, st);
         else if (tp.kind == 2 && tp.layout == 3)
             traceback_const3_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
@@ -836,7 +920,25 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
     tp.out_cap = cap;
     tp.pass = 1;
     tp.pair_class = pb.profile ? nullptr : cd.cls;
-    if (pb.ext)
+    if (pb.cfg.impl == 17) {
+        FillParams fp;
+        memset(&fp, 0, sizeof fp);
+        fp.alpha = cd.alpha;
+        fp.alpha_off = cd.aoff;
+        fp.beta = cd.beta;
+        fp.beta_off = cd.boff;
+        fp.pair_begin = begin;
+        fp.pair_end = end;
+        fp.pair_class = cd.cls;
+        fp.gap_open = (int)pb.gap_open;
+        fp.gap_extend = (int)pb.gap_extend;
+        fp.h00 = pb.h00;
+        fp.dim = pb.dim;
+        for (int i = 0; i < pb.dim * pb.dim; ++i)
+            fp.scores[i] = (int)pb.scores[i];
+        fp.one = 1;
+        launch_ckpt_trace(ctx, pb, fp, cd.trace, cd.best, cd.slots, cd.counts, 1, cig_off, cigars, cap, st);
+    } else if (pb.ext)
         launch_traceback_ext(pb, cd, tp, np, st);
     else if (tp.kind == 2 && tp.layout == 3)
         traceback_const3_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
@@ -909,6 +1011,14 @@ int make_plan(gnx_ctx *ctx, Problem &pb, const int64_t *aoff, const int64_t *bof
     }
     if (!pb.wide && fill16_ok(ctx, pb, plan.min_n, plan.max_n, plan.min_m, plan.max_m)) {
         pb.cfg.impl = 16;
+        pb.cfg.C = 10;
+        pb.cfg.lpp = 16;
+        pb.cfg.skew = 1;
+        pb.cfg.multi = false;
+        pb.cfg.m_uniform = plan.max_m;
+    } else if (!pb.wide && fill16_ok(ctx, pb, plan.min_n, plan.max_n, plan.min_m, plan.max_m, true)) {
+        pb.cfg.impl = 17; // fill16 with checkpoints + affine_ckpt_trace_kernel
+        pb.cfg.n_uniform = plan.max_n;
         pb.cfg.C = 10;
         pb.cfg.lpp = 16;
         pb.cfg.skew = 1;
@@ -1187,7 +1297,12 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
         if (pb.want_cigar) {
             CU(s.h_trace_off.ensure((size_t)(np + 1) * 8));
             int64_t *to = s.h_trace_off.as<int64_t>();
-            const int64_t acc = compute_trace_offsets(pb, aoff, boff, begin, np, to);
+            int64_t acc = compute_trace_offsets(pb, aoff, boff, begin, np, to);
+            if (pb.cfg.impl == 17) { // checkpoint area: whole quads; r* per pair
+                acc = std::max(acc, ((np + 3) / 4) * ckpt_quad_words(pb.cfg.n_uniform));
+                CU(s.best.ensure((size_t)np * 8));
+                cd.best = s.best.as<int64_t>() - begin;
+            }
             CU(s.trace.ensure((size_t)std::max<int64_t>(acc, 1) * 4));
             CU(s.trace_off.ensure((size_t)(np + 1) * 8));
             CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
@@ -1787,7 +1902,12 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
                 CU(cudaEventSynchronize(s.ev_done));
             CU(s.h_trace_off.ensure((size_t)(np + 1) * 8));
             int64_t *to = s.h_trace_off.as<int64_t>();
-            const int64_t acc = compute_trace_offsets(pb, alpha_off_host, beta_off_host, begin, np, to);
+            int64_t acc = compute_trace_offsets(pb, alpha_off_host, beta_off_host, begin, np, to);
+            if (pb.cfg.impl == 17) { // checkpoint area: whole quads; r* per pair
+                acc = std::max(acc, ((np + 3) / 4) * ckpt_quad_words(pb.cfg.n_uniform));
+                CU(s.best.ensure((size_t)np * 8));
+                cd.best = s.best.as<int64_t>() - begin;
+            }
             CU(s.trace.ensure((size_t)std::max<int64_t>(acc, 1) * 4));
             CU(s.trace_off.ensure((size_t)(np + 1) * 8));
             CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -1871,6 +1991,8 @@ int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
         ctx->opt_fill16 = value ? 1 : 0;
     } else if (k == "force_lookup") {
         ctx->opt_force_lookup = (int)value;
+    } else if (k == "ckpt") {
+        ctx->opt_ckpt = value ? 1 : 0;
     } else if (k == "wide_cta") {
         ctx->opt_wide_cta = (int)value;
     } else if (k == "ctas_per_sm") {

@@ -26,10 +26,22 @@ __device__ __forceinline__ unsigned uaddmax_16x2(unsigned a, unsigned b, unsigne
 
 // CM >= 0 (FREE only): (m - 1) % C, the in-lane index of the freeEndGaps column, known at compile time -- only that
 // column then pays the extra add for its zero D-plane addends; every other cell shares H + O + E between I' and D'.
-template <bool FREE, int CM = -1>
+//
+// CKPT (needs FREE and CM >= 0): the first pass of the checkpoint-and-recompute traceback (affine_ckpt_trace_kernel
+// below).  Every kCkK steps the warp saves its 23 state registers per lane (Hc[10], Dt[10], hpL, edgeI, edgeH --
+// the complete wavefront state entering step kCkK*k) and the lane that owns the free-end column tracks
+//     r* = the LAST row r whose max(M(r,m), I(r,m)) equals the running maximum of the column (>= I(0,m)),
+// which is where the reference's traceback leaves the free-end column: walking up from (n,m) in plane D, the
+// source of D(i,m) is T(M, I, D)(i-1,m) with ties M >= I >= D (align/align.go:76-84), D(i,m) being the running
+// maximum itself, so the walk stays in D exactly until the last row that reached it.
+constexpr int kCkK = 32;   // steps between checkpoints
+constexpr int kCkRegs = 23; // 32-bit words per lane per checkpoint
+
+template <bool FREE, int CM = -1, bool CKPT = false>
 __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams P)
 {
     static_assert(CM < 0 || FREE, "CM selects the free-end column");
+    static_assert(!CKPT || (FREE && CM >= 0), "checkpoints are taken on the freeEndGaps path only");
     constexpr int C = 10, LPP = 16;
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ short s_tabA[C * kDimP * 32]; // [c][a][thread], pair A: s as int16 (sign-extending LDS)
@@ -89,6 +101,10 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
         unsigned hpL = (jbase == 0) ? pack16(P.h00) : pack16(O + jbase * E);
         unsigned edgeI = 0, edgeH = 0;
         unsigned bI = 0, bH = 0;
+        // CKPT: (value << 16 | row) of the last row that reached the free-end column's running maximum, per pair;
+        // row 0 stands for the boundary D(1,m) = I(0,m)
+        unsigned bestA = (unsigned)(O + m * E + 32768) << 16, bestB = bestA;
+        uint32_t *ck = CKPT ? P.trace + (size_t)quad * P.edge_stride : nullptr; // edge_stride: words per quad
         auto boundary = [&](int r) {
             const int d0 = FREE ? 0 : (O + r * E);
             bI = pack16(d0 + O + E);
@@ -135,6 +151,11 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
                     const int sA = rowA[c * kDimP * 32]; // sign-extended int16
                     const int sB = rowB[c * kDimP * 32]; // s * 65536
                     const unsigned MH = hp + (unsigned)sA + (unsigned)sB; // one IADD3
+                    if (CKPT && c == CM) { // max(M, I) of the free-end column (meaningful in its lane only)
+                        const unsigned mx = __vmaxu2(MH, It);
+                        bestA = max(bestA, __byte_perm((unsigned)r, mx, 0x5410)); // mxA << 16 | r: later rows win ties
+                        bestB = max(bestB, __byte_perm((unsigned)r, mx, 0x7610));
+                    }
                     const unsigned H = umax3_16x2(MH, It, Dt[c]);
                     const unsigned Ho = (unsigned)madd((int)H, one, oe_i);
                     It = uaddmax_16x2(It, e_w, Ho);                      // I' = max(I + E, H + O + E)
@@ -153,16 +174,42 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
             }
         };
 
+        auto save = [&](int s) { // state entering step s = kCkK * k, k >= 1
+            uint32_t *dst = ck + (size_t)(s / kCkK - 1) * (kCkRegs * 32) + tid;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                dst[c * 32] = Hc[c];
+                dst[(C + c) * 32] = Dt[c];
+            }
+            dst[20 * 32] = hpL;
+            dst[21 * 32] = edgeI;
+            dst[22 * 32] = edgeH;
+        };
         int t = 0;
 #pragma unroll 1
         for (; t < LPP - 1; ++t)
             step(t, std::true_type{});
-#pragma unroll 2
-        for (; t < n - 1; ++t)
-            step(t, std::false_type{});
+        if (CKPT) {
 #pragma unroll 1
-        for (; t < T; ++t)
-            step(t, std::true_type{});
+            for (; t < n - 1; ++t) {
+                if ((t & (kCkK - 1)) == 0 && t > 0)
+                    save(t);
+                step(t, std::false_type{});
+            }
+#pragma unroll 1
+            for (; t < T; ++t) {
+                if ((t & (kCkK - 1)) == 0 && t > 0)
+                    save(t);
+                step(t, std::true_type{});
+            }
+        } else {
+#pragma unroll 2
+            for (; t < n - 1; ++t)
+                step(t, std::false_type{});
+#pragma unroll 1
+            for (; t < T; ++t)
+                step(t, std::true_type{});
+        }
 
         const int lm = (m - 1) / C, cm = (m - 1) % C;
         if (lane == lm) {
@@ -175,6 +222,12 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
                 P.out_score[pA0] = (int64_t)(int)(h & 0xffffu) - 32768;
             if (pB0 < P.pair_end)
                 P.out_score[pB0] = (int64_t)(int)(h >> 16) - 32768;
+            if (CKPT) {
+                if (pA0 < P.pair_end)
+                    P.out_best[pA0] = (int64_t)(bestA & 0xffffu);
+                if (pB0 < P.pair_end)
+                    P.out_best[pB0] = (int64_t)(bestB & 0xffffu);
+            }
         }
         __syncwarp();
     }

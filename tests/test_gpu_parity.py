@@ -282,6 +282,64 @@ def test_long_pairs_cta_per_pair_kernel(wide):
         c.close()
 
 
+def _uniform_batch(rng, P, n, m, flavour):
+    al, be = [], []
+    for k in range(P):
+        if flavour == "related":
+            a, b = random_pair(rng, n, m, identity=float(rng.choice([0.6, 0.8, 0.9, 0.97, 1.0])))
+        elif flavour == "ties":  # homopolymers / short tandem repeats: ties everywhere
+            unit = rng.integers(0, 4, size=int(rng.integers(1, 4)), dtype=np.uint8)
+            a = np.resize(unit, n).astype(np.uint8)
+            b = np.resize(np.roll(unit, int(rng.integers(0, 3))), m).astype(np.uint8)
+            if k % 3 == 0:
+                b[rng.integers(0, m, 3)] = rng.integers(0, 4, 3)
+        elif flavour == "indels":  # many short runs: cigars longer than the 24-entry slot
+            a = rng.integers(0, 4, size=n, dtype=np.uint8)
+            src = a[int(rng.integers(0, n - m)):]
+            out, i = [], 0
+            while len(out) < m:
+                piece = src[i:i + 4].tolist()
+                out.extend(piece if piece else rng.integers(0, 4, size=4).tolist())
+                i += 4 + (1 if (len(out) // 4) % 2 else 0)
+                if (len(out) // 4) % 3 == 0:
+                    out.append(int(rng.integers(0, 4)))
+            b = np.array(out[:m], dtype=np.uint8)
+        else:  # unrelated
+            a = rng.integers(0, 4, size=n, dtype=np.uint8)
+            b = rng.integers(0, 4, size=m, dtype=np.uint8)
+        if flavour == "related" and k % 7 == 3:
+            a[rng.integers(0, n, 4)] = 4
+            b[rng.integers(0, m, 2)] = 4
+        al.append(a)
+        be.append(b)
+    return al, be
+
+
+@pytest.mark.parametrize("n,m", [(500, 150), (300, 141), (333, 142), (400, 143), (1024, 144), (290, 145), (292, 146),
+                                 (301, 147), (640, 148), (298, 149), (64, 30), (45, 9), (700, 160), (33, 1), (2, 1)])
+def test_checkpoint_recompute_traceback(n, m):
+    """Uniform freeEndGaps batches take the checkpoint-and-recompute path (fill16 + affine_ckpt_trace_kernel);
+    it must give the oracle's score and cigar, and the same as the trace-matrix path (ckpt = 0)."""
+    c = align.Context(0)
+    try:
+        rng = np.random.default_rng(7000 + n + m)
+        for flavour, P, O, E, S in (("related", 203, -600, -150, orc.HUMAN_CHIMP_TWO_SCORE_MATRIX),
+                                    ("ties", 101, -600, -150, orc.HUMAN_CHIMP_TWO_SCORE_MATRIX),
+                                    ("ties", 50, 0, -30, orc.DEFAULT_SCORE_MATRIX),
+                                    ("indels", 64, -100, -20, orc.DEFAULT_SCORE_MATRIX),
+                                    ("unrelated", 97, -400, -30, orc.DEFAULT_SCORE_MATRIX)):
+            if flavour == "indels" and n - m < 8:
+                continue
+            al, be = _uniform_batch(rng, P, n, m, flavour)
+            c.set_option("ckpt", 1)
+            sc = check_batch(c, al, be, S, O, E, 1)
+            c.set_option("ckpt", 0)
+            sc0 = check_batch(c, al, be, S, O, E, 1)
+            assert np.array_equal(sc, sc0)
+    finally:
+        c.close()
+
+
 def test_chunking_and_small_workspace():
     """Force many chunks (tiny workspace / chunk_pairs) so chunk boundaries and slot reuse are exercised."""
     c = align.Context(0, workspace_bytes=8 << 20)
