@@ -392,15 +392,20 @@ def main():
         ms3, launches3, fill3, filln3, clocks3 = timed_device(True)
         g3 = world * cells * args.steps / (ms3 * 1e-3) / 1e9
         alg3 = cells * BYTES_PER_CELL_TRACE + P * BYTES_PER_PAIR_SCORE
+        n_chunks3 = -(-P // (1 << 18))  # chunk_pairs default
+        ckpt_path = filln3 >= 2 * n_chunks3  # fill16+checkpoints and the recompute kernel: two fill launches per chunk
         ach3 = alg3 / (fill3 * 1e-3) / 1e9 if fill3 > 0 else None
         line["traceback"] = {
             "workload": "C3 (configs[2]): same pairs, full traceback + CIGAR", "value": g3, "unit": "GCUPS",
             "ms_per_step": ms3 / args.steps, "gpu_launches": launches3, "clocks": clocks3,
             "roofline": {"bound": "hbm", "achieved": ach3, "peak": peak, "unit": "GB/s",
                          "frac": (ach3 / peak) if ach3 else None,
-                         "traffic": ncu_traffic("affine_fill3_kernel_trace", P / max(filln3, 1)),
-                         "algorithmic_bytes_per_launch": alg3 / max(filln3, 1), "peak_source": peak_src,
-                         "kernel": "affine_fill3_kernel<C=10,LPP=16,MODE=2,FREE=1>", "fill_ms_per_step": fill3,
+                         "traffic": ncu_traffic("ckpt_path" if ckpt_path else "affine_fill3_kernel_trace",
+                                                P / max(n_chunks3, 1)),
+                         "algorithmic_bytes_per_launch": alg3 / max(n_chunks3, 1), "peak_source": peak_src,
+                         "kernel": ("affine_fill16_kernel<FREE,CM,CKPT> + affine_ckpt_trace_kernel (checkpoint-and-"
+                                    "recompute: two launches per chunk, traceback walk included)") if ckpt_path
+                         else "affine_fill3_kernel<C=10,LPP=16,MODE=2,FREE=1>", "fill_ms_per_step": fill3,
                          "fill_launches_per_step": filln3, "algorithmic_bytes_per_step": alg3}}
 
     # ---- other BASELINE shapes (device-resident, fewer steps): C1, a C4-shaped sample, constant gap ----

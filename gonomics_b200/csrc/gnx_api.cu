@@ -825,7 +825,8 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         ctx->launches++;
         ctx->last_fill_launches++;
     }
-    cudaEventRecord(fe.b, st);
+    if (!(pb.cfg.impl == 17 && pb.want_cigar)) // checkpoint path: the re-fill of the path's blocks is part of the DP fill
+        cudaEventRecord(fe.b, st);
 
     if (pb.want_cigar) {
         TraceParams tp;
@@ -848,9 +849,11 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         tp.counts = cd.counts;
         tp.pass = 0;
         tp.pair_class = pb.profile ? nullptr : cd.cls;
-        if (pb.cfg.impl == 17)
+        if (pb.cfg.impl == 17) {
             launch_ckpt_trace(ctx, pb, fp, cd.trace, cd.best, cd.slots, cd.counts, 0, nullptr, nullptr, 0, st);
-        else if (pb.ext)
+            cudaEventRecord(fe.b, st);
+            ctx->last_fill_launches++;
+        } else if (pb.ext)
             launch_traceback_ext(pb, cd, tp, np, st);
         else if (tp.kind == 2 && tp.layout == 3)
             traceback_const3_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);

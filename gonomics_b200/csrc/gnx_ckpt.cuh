@@ -59,7 +59,23 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
     const int64_t np = P.pair_end - P.pair_begin;
     const int64_t n_units = ((np + 3) / 4) * 2; // (quad, sel): the A pairs (low halves) or the B pairs of a quad
 
-    for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    // pass 1 (the rare cigars longer than the slot) first screens 32 units per warp, one per lane, so that a chunk
+    // without overflow costs a few coalesced loads instead of a full unit set-up each
+    const int G = Q.pass == 1 ? 32 : 1;
+    for (int64_t ubase = (int64_t)blockIdx.x * G; ubase < n_units; ubase += (int64_t)gridDim.x * G) {
+      unsigned todo = 1u;
+      if (Q.pass == 1) {
+          const int64_t u = ubase + tid;
+          bool need = false;
+          if (u < n_units) {
+              const int64_t p0 = (u >> 1) * 4 + (u & 1); // chunk-local index of the unit's first pair; second is p0 + 2
+              need = (p0 < np && Q.counts[p0] > Q.slot_cap) || (p0 + 2 < np && Q.counts[p0 + 2] > Q.slot_cap);
+          }
+          todo = __ballot_sync(FULL, need);
+      }
+      while (todo) {
+        const int64_t unit = ubase + (__ffs(todo) - 1);
+        todo &= todo - 1;
         const int64_t quad = unit >> 1;
         const int sel = (int)(unit & 1);
         const int64_t pair0 = P.pair_begin + quad * 4 + half * 2 + sel; // this half-warp's pair
@@ -353,6 +369,7 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
             __syncwarp();
         }
         __syncwarp();
+      }
     }
 }
 

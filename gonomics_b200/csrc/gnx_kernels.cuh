@@ -795,6 +795,19 @@ __global__ void traceback_affine_kernel(const TraceParams P)
     int k = 2 - (int)((cur >> 4) & 3u);
     int run = 0, cur_op = k;
     while (i > 0 || j > 0) {
+        // on the boundary the pseudo-codes point to themselves: column 0 stays in plane D up to (0,0), row 0 in
+        // plane I -- the rest of the route is one run (freeEndGaps alignments end with hundreds of such cells)
+        if ((j == 0 && k == 2) || (i == 0 && k == 1)) {
+            const int len = j == 0 ? i : j;
+            if (k == cur_op) {
+                run += len;
+            } else {
+                emit(cur_op, run);
+                cur_op = k;
+                run = len;
+            }
+            break;
+        }
         if (k == cur_op) {
             ++run;
         } else {
