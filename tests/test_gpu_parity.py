@@ -331,6 +331,11 @@ def test_checkpoint_recompute_traceback(n, m):
             if flavour == "indels" and n - m < 8:
                 continue
             al, be = _uniform_batch(rng, P, n, m, flavour)
+            if flavour == "indels" and m >= 140:  # these cigars must overflow the 24-entry slot (second pass)
+                ac, ao = concat(al)
+                bc, bo = concat(be)
+                _, ooff, _ = orc.batch(ac, ao, bc, bo, S, O, E, 1, True, 8)
+                assert int(np.diff(ooff).max()) > 24
             c.set_option("ckpt", 1)
             sc = check_batch(c, al, be, S, O, E, 1)
             c.set_option("ckpt", 0)
@@ -354,8 +359,9 @@ def test_chunking_and_small_workspace():
         c.close()
 
 
-def test_cigar_cap_overflow_and_fetch(ctx):
-    a, ao, b, bo = synth_pairs(12, 500, 120, 100)
+@pytest.mark.parametrize("n,m", [(120, 100), (300, 100)])  # trace-matrix path / checkpoint-and-recompute path
+def test_cigar_cap_overflow_and_fetch(ctx, n, m):
+    a, ao, b, bo = synth_pairs(12, 500, n, m)
     S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX
     want = ctx.affine_gap_batch(a, ao, b, bo, S, -600, -150, True)
     out_score = np.zeros(500, dtype=np.int64)
