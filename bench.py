@@ -197,6 +197,50 @@ def twobit_block(ctx, L, dev, stream, rank, world, barrier, args):
                                          "tables; ctypes call per read)"}
         blk["parity_spot_check"] = bool(ok)
     out["gsw_seeds_1M_reads_150bp"] = blk
+    # -- the gsw extend step on read-sized flanks: LeftDynamicAln / RightDynamicAln, 1M pairs each, target window
+    #    175 (extension = perfectScore/600 + len(read) - seed, genomeGraph/toGiraf.go:32) x read flank 100
+    from gonomics_b200 import align as _al
+    from gonomics_b200._lib import GNX_EXT_LEFT, GNX_EXT_RIGHT
+    n_ext, tn, qm = 1_000_000, 175, 100
+    est = rng.integers(0, g_len - tn - 8, size=n_ext)
+    tgt = genome[est[:, None] + np.arange(tn)[None, :]]
+    qry = tgt[:, tn - qm:].copy()  # left side: the flank ends where the window ends
+    mutq = rng.random(qry.shape) < 0.03
+    qry[mutq] = (qry[mutq] + rng.integers(1, 4, size=int(mutq.sum()), dtype=np.uint8)) % 4
+    tcat, toff = np.ascontiguousarray(tgt.reshape(-1)), np.arange(n_ext + 1, dtype=np.int64) * tn
+    qcat, qoff = np.ascontiguousarray(qry.reshape(-1)), np.arange(n_ext + 1, dtype=np.int64) * qm
+    ext = {}
+    for name, side in (("left", GNX_EXT_LEFT), ("right", GNX_EXT_RIGHT)):
+        if side == GNX_EXT_RIGHT:  # right side: the flank starts where the window starts
+            qry = tgt[:, :qm].copy()
+            qry[mutq] = (qry[mutq] + 1) % 4
+            qcat = np.ascontiguousarray(qry.reshape(-1))
+        ctx.extend_batch(side, tcat, toff, qcat, qoff, _al.HumanChimpTwoScoreMatrix, -600)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            sc, ei, ej, coff, cig = ctx.extend_batch(side, tcat, toff, qcat, qoff, _al.HumanChimpTwoScoreMatrix, -600)
+        torch.cuda.synchronize()
+        dte = (time.perf_counter() - t0) / 3
+        if world > 1:
+            t = torch.tensor([dte], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dte = float(t.item())
+        ext[name] = {"Mpairs_per_s": world * n_ext / dte / 1e6, "GCUPS": world * n_ext * tn * qm / dte / 1e9,
+                     "ms_per_step": dte * 1e3, "mean_score": float(sc.mean())}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            import oracle as orc
+            fn = orc.left_dynamic_aln if side == GNX_EXT_LEFT else orc.right_dynamic_aln
+            ok = True
+            for r in range(300):
+                w = fn(tgt[r], qry[r], orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, -600)
+                g = [(int(x["run_length"]), chr(int(x["op"]))) for x in cig[coff[r]:coff[r + 1]]]
+                ok &= (w[0] == int(sc[r]) and w[1] == g and w[2] == int(ei[r]) and w[3] == int(ej[r]))
+            ext[name]["parity_spot_check"] = bool(ok)
+    out["gsw_extend_1M_pairs_175x100"] = {
+        "value": ext["left"]["Mpairs_per_s"], "unit": "Mpairs/s (LeftDynamicAln)", "left": ext["left"], "right": ext["right"],
+        "note": "genomeGraph.LeftDynamicAln / RightDynamicAln with route, host-buffer API (pageable numpy buffers, "
+                "H2D + D2H inside the timed region), linear gap -600, HumanChimpTwo"}
     ix.close()
     return out
 
@@ -381,11 +425,19 @@ def main():
         sm = torch.cuda.get_device_properties(local).multi_processor_count
         slots = sm * 4 * clocks["sm_mhz"] * 1e6  # warp-instruction issue slots per second
         # 32 lanes x 2 packed pairs = 64 cells per warp-instruction slot in the packed kernel
-        line["issue_roofline"] = {"cells_per_s_fill": cells / (fill_ms * 1e-3),
-                                  "issue_slots_per_s": slots,
-                                  "issue_slots_per_64_cells": slots / (cells / 64 / (fill_ms * 1e-3)),
-                                  "note": "warp-instruction issue slots spent per 64 DP cells (one packed "
-                                          "warp-cell); the SASS of the steady loop needs ~10.7, see DESIGN.md"}
+        avail = slots / (cells / 64 / (fill_ms * 1e-3))
+        # instructions the kernel executes per 64 cells: smsp__inst_executed.sum of the ncu capture in
+        # profiles/r01i_ckpt_path.md (3.0786e9 for a 262,144-pair chunk of 75,000-cell pairs)
+        inst64 = 3.0786e9 / (262144 * 75000 / 64)
+        line["issue_roofline"] = {"bound": "issue", "cells_per_s_fill": cells / (fill_ms * 1e-3),
+                                  "issue_slots_per_s": slots, "issue_slots_per_64_cells": avail,
+                                  "inst_per_64_cells": inst64, "frac": inst64 / avail,
+                                  "steady_loop_inst_per_64_cells": 8.6,
+                                  "note": "the binding roof of this integer max-plus kernel: warp-instruction issue "
+                                          "slots available per 64 DP cells (one packed warp-cell) at the measured fill "
+                                          "rate vs the instructions the kernel executes for them (ncu); frac = issue "
+                                          "utilisation.  The steady loop itself needs 8.6 (7 per packed cell + per-step "
+                                          "overhead), see DESIGN.md"}
 
     # ---- C3: traceback + CIGAR on the same pairs -------------------------------------------------
     if not args.no_traceback:
