@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
     static_assert(!CKPT || (FREE && CM >= 0), "checkpoints are taken on the freeEndGaps path only");
     constexpr int C = 10, LPP = 16;
     constexpr unsigned FULL = 0xffffffffu;
-    __shared__ short s_tabA[C * kDimP * 32]; // [c][a][thread], pair A: s as int16 (sign-extending LDS)
+    __shared__ int s_tabA[C * kDimP * 32];   // [c][a][thread], pair A: s sign-extended (a 16-bit LDS costs two
+                                             // shared-memory wavefronts: ncu counted 30 per step instead of 20)
     __shared__ int s_tabB[C * kDimP * 32];   // [c][a][thread], pair B: s * 65536
     const int tid = threadIdx.x;
     const int lane = tid % LPP, half = tid / LPP;
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
                     vA = P.scores[a * P.dim + qA];
                     vB = P.scores[a * P.dim + qB];
                 }
-                s_tabA[(c * kDimP + a) * 32 + tid] = (short)vA;
+                s_tabA[(c * kDimP + a) * 32 + tid] = vA;
                 s_tabB[(c * kDimP + a) * 32 + tid] = vB * 65536;
             }
             const bool last = FREE && (j == m);
@@ -143,12 +144,12 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
             if (active) {
                 if (!FREE && lane == 0 && r < n)
                     boundary(r + 1);
-                const short *rowA = s_tabA + aA * 32 + tid;
+                const int *rowA = s_tabA + aA * 32 + tid;
                 const int *rowB = s_tabB + aB * 32 + tid;
                 unsigned It = inI, hp = hpL;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    const int sA = rowA[c * kDimP * 32]; // sign-extended int16
+                    const int sA = rowA[c * kDimP * 32];
                     const int sB = rowB[c * kDimP * 32]; // s * 65536
                     const unsigned MH = hp + (unsigned)sA + (unsigned)sB; // one IADD3
                     if (CKPT && c == CM) { // max(M, I) of the free-end column (meaningful in its lane only)
