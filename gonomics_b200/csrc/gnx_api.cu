@@ -28,6 +28,8 @@ using namespace gnx;
 
 constexpr int kSlots = 3;
 constexpr int kSlotCap = 24; // cigar elements kept per pair before the overflow pass
+constexpr int kSlotCapLong = 1024; // ... for multi-strip (long) pairs, whose cigars run to hundreds of elements and
+                                   // whose second traceback pass is a second walk of a 20 000-step route
 
 static_assert(sizeof(gnx_cigar) == 16, "gnx_cigar must match Go's align.Cigar layout");
 static_assert(sizeof(CigarOut) == 16, "device cigar record must match gnx_cigar");
@@ -188,6 +190,8 @@ struct Problem {
     bool profile = false;               // match scores come from a dense per-pair matrix (gnx_profile.cuh)
     const int64_t *extra_words = nullptr; // profile: per-pair workspace words besides the trace (the S matrix)
 };
+
+inline int slot_cap_of(const Problem &pb) { return (pb.cfg.multi && !pb.profile && !pb.ext) ? kSlotCapLong : kSlotCap; }
 
 // Exact-arithmetic range analysis for the scaled int32 kernels (DESIGN.md "Arithmetic width").
 // Every finite plane value v obeys |v| <= bound.  With values carried as scale*v and -inf = -2^30,
@@ -505,7 +509,7 @@ void launch_ckpt_trace(gnx_ctx *ctx, const Problem &pb, const FillParams &fp, co
     q.quad_words = ckpt_quad_words(pb.cfg.n_uniform);
     q.rstar = rstar;
     q.slots = slots;
-    q.slot_cap = kSlotCap;
+    q.slot_cap = slot_cap_of(pb);
     q.counts = counts;
     q.pass = pass;
     q.cigar_off = cig_off;
@@ -845,7 +849,7 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         tp.kind = pb.kind == 2 ? 2 : 0;
         tp.h00_plane = pb.h00_plane;
         tp.slots = cd.slots;
-        tp.slot_cap = kSlotCap;
+        tp.slot_cap = slot_cap_of(pb);
         tp.counts = cd.counts;
         tp.pass = 0;
         tp.pair_class = pb.profile ? nullptr : cd.cls;
@@ -857,7 +861,9 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
             launch_traceback_ext(pb, cd, tp, np, st);
         else if (tp.kind == 2 && tp.layout == 3)
             traceback_const3_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
-        else if (tp.kind == 0 && tp.layout >= 2 && ctx->opt_tb_impl == 2)
+        else if (tp.kind == 0 && tp.layout == 3 && (ctx->opt_tb_impl == 3 || (ctx->opt_tb_impl == 2 && pb.cfg.multi)))
+            traceback_affine_warp_kernel<<<(int)((np + 3) / 4), 128, 0, st>>>(tp); // long pairs: a warp per pair
+        else if (tp.kind == 0 && tp.layout >= 2 && ctx->opt_tb_impl >= 2)
             traceback_affine_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
         else
             traceback_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
@@ -897,7 +903,7 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
     if (np <= 0)
         return GNX_OK;
     int *status = ctx->status.as<int>();
-    expand_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(cd.slots, kSlotCap, cd.counts, cig_off, np,
+    expand_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(cd.slots, slot_cap_of(pb), cd.counts, cig_off, np,
                                                           (CigarOut *)cigars, cap, status, pb.ext);
     ctx->launches++;
     TraceParams tp;
@@ -916,7 +922,7 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
     tp.kind = pb.kind == 2 ? 2 : 0;
     tp.h00_plane = pb.h00_plane;
     tp.slots = cd.slots;
-    tp.slot_cap = kSlotCap;
+    tp.slot_cap = slot_cap_of(pb);
     tp.counts = cd.counts;
     tp.cigar_off = const_cast<int64_t *>(cig_off);
     tp.out_cigar = cigars;
@@ -945,7 +951,9 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
         launch_traceback_ext(pb, cd, tp, np, st);
     else if (tp.kind == 2 && tp.layout == 3)
         traceback_const3_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
-    else if (tp.kind == 0 && tp.layout >= 2 && ctx->opt_tb_impl == 2)
+    else if (tp.kind == 0 && tp.layout == 3 && (ctx->opt_tb_impl == 3 || (ctx->opt_tb_impl == 2 && pb.cfg.multi)))
+        traceback_affine_warp_kernel<<<(int)((np + 3) / 4), 128, 0, st>>>(tp);
+    else if (tp.kind == 0 && tp.layout >= 2 && ctx->opt_tb_impl >= 2)
         traceback_affine_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
     else
         traceback_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(tp);
@@ -1309,7 +1317,7 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
             CU(s.trace.ensure((size_t)std::max<int64_t>(acc, 1) * 4));
             CU(s.trace_off.ensure((size_t)(np + 1) * 8));
             CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
-            CU(s.slots.ensure((size_t)np * kSlotCap * 4));
+            CU(s.slots.ensure((size_t)np * slot_cap_of(pb) * 4));
             CU(s.counts.ensure((size_t)np * 4));
             CU(s.cig_off.ensure((size_t)(np + 1) * 8));
             cd.trace = s.trace.as<uint32_t>();
@@ -1527,7 +1535,7 @@ int run_profile_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *group_cat, const
             CU(s.trace.ensure((size_t)std::max<int64_t>(acc, 1) * 4));
             CU(s.trace_off.ensure((size_t)(np + 1) * 8));
             CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, st));
-            CU(s.slots.ensure((size_t)np * kSlotCap * 4));
+            CU(s.slots.ensure((size_t)np * slot_cap_of(pb) * 4));
             CU(s.counts.ensure((size_t)np * 4));
             CU(s.cig_off.ensure((size_t)(np + 1) * 8));
             cd.trace = s.trace.as<uint32_t>();
@@ -1644,7 +1652,7 @@ gnx_ctx *gnx_create(int device, size_t workspace_bytes)
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     if (workspace_bytes == 0)
-        workspace_bytes = std::min<size_t>(free_b / 2, (size_t)96 << 30);
+        workspace_bytes = std::min<size_t>(free_b / 3 * 2, (size_t)128 << 30);
     ctx->workspace = workspace_bytes;
     for (int k = 0; k < kSlots; ++k) {
         cudaStreamCreateWithFlags(&ctx->slot[k].stream, cudaStreamNonBlocking);
@@ -1915,7 +1923,7 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
             CU(s.trace_off.ensure((size_t)(np + 1) * 8));
             CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, st));
             CU(cudaEventRecord(s.ev_done, st));
-            CU(s.slots.ensure((size_t)np * kSlotCap * 4));
+            CU(s.slots.ensure((size_t)np * slot_cap_of(pb) * 4));
             CU(s.counts.ensure((size_t)np * 4));
             cd.trace = s.trace.as<uint32_t>();
             cd.trace_off = s.trace_off.as<int64_t>();

@@ -842,6 +842,151 @@ __global__ void traceback_affine_kernel(const TraceParams P)
         P.counts[idx] = cnt;
 }
 
+// Warp-per-pair form of traceback_affine_kernel for LONG pairs (layout 3).  A thread-per-pair walk is a chain
+// of ~n+m dependent L2/HBM loads (20 000 for a 10 kb x 10 kb pair: ~18 ms per chunk whatever the pair count).
+// Here every lane of the warp keeps the same walk state; while the path is in plane M, lane d-1 loads the code
+// of the diagonal cell (i-d, j-d) -- 32 independent loads in flight -- and the run of leading cells whose H tag
+// is M is consumed in one iteration (the code the walk lands on comes from the lane that loaded it), so a
+// match run of L cells costs L/32 round trips.  I / D steps take one broadcast load each.  Same RLE, same
+// boundary pseudo-codes, same two-pass protocol as traceback_affine_kernel.
+__global__ void __launch_bounds__(128) traceback_affine_warp_kernel(const TraceParams P)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane_id = threadIdx.x & 31;
+    const int64_t idx = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t pair = P.pair_begin + idx;
+    if (pair >= P.pair_end)
+        return;
+    if (P.pair_class && P.pair_class[pair] > 1) {
+        if (P.pass == 0 && lane_id == 0)
+            P.counts[idx] = 0;
+        return;
+    }
+    const int n = (int)(P.alpha_off[pair + 1] - P.alpha_off[pair]);
+    const int m = (int)(P.beta_off[pair + 1] - P.beta_off[pair]);
+    if (P.pass == 1 && P.counts[idx] <= P.slot_cap)
+        return;
+    uint32_t *slot = P.slots + (size_t)idx * P.slot_cap;
+    CigarOut *dst = nullptr;
+    int total = 0;
+    if (P.pass == 1) {
+        total = P.counts[idx];
+        if (P.cigar_off[idx] + total > P.out_cap)
+            return;
+        dst = (CigarOut *)P.out_cigar + P.cigar_off[idx];
+    }
+    int cnt = 0;
+    auto emit = [&](int op, int run) { // every lane counts, lane 0 stores
+        if (lane_id == 0) {
+            if (P.pass == 0) {
+                if (cnt < P.slot_cap)
+                    slot[cnt] = ((uint32_t)run << 2) | (uint32_t)op;
+            } else {
+                CigarOut o;
+                o.run_length = run;
+                o.op = (unsigned char)op;
+                dst[total - 1 - cnt] = o;
+            }
+        }
+        ++cnt;
+    };
+    if (n == 0 && m == 0) {
+        emit(0, 0);
+        if (P.pass == 0 && lane_id == 0)
+            P.counts[idx] = cnt;
+        return;
+    }
+    const uint32_t *__restrict__ tr = P.trace + P.trace_off[idx];
+    const int C = P.C, lpp = P.lpp, skew = P.skew, wpl = trace_wpl(C);
+    int T = (n + skew * (lpp - 1) + 3) & ~3; // layout 3: rows blocked four steps per 16-byte piece
+    const size_t strip_words = (size_t)T * wpl * 32;
+    const int strip_cols = lpp * C;
+    auto load = [&](int i, int j) -> unsigned { // code of interior cell (i, j)
+        const int jj = j - 1;
+        const int strip = jj / strip_cols, within = jj - strip * strip_cols;
+        const int lane = within / C, c = within - lane * C;
+        const int t = (i - 1) + skew * lane;
+        const int wi = c >= 5 ? 1 : 0, cc = c - 5 * wi;
+        const int nin = (wi == wpl - 1) ? (C - 5 * (wpl - 1)) : 5;
+        const size_t a = (size_t)strip * strip_words + ((((size_t)(t >> 2)) * wpl + wi) * 32 + lane) * 4 + (t & 3);
+        return (__ldg(tr + a) >> (32 - kTagBits * (nin - cc))) & (kScale - 1);
+    };
+    const unsigned code00 = (unsigned)(2 - P.h00_plane) << 4;
+    auto code_at = [&](int i, int j) -> unsigned {
+        return (i > 0 && j > 0) ? load(i, j) : ((i == 0) ? (j == 0 ? code00 : 0x15u) : 0x00u);
+    };
+    int i = n, j = m;
+    unsigned cur = code_at(i, j);
+    int k = 2 - (int)((cur >> 4) & 3u);
+    int run = 0, cur_op = k;
+    while (i > 0 || j > 0) {
+        if ((j == 0 && k == 2) || (i == 0 && k == 1)) { // boundary: the rest is one run
+            const int len = j == 0 ? i : j;
+            if (k == cur_op) {
+                run += len;
+            } else {
+                emit(cur_op, run);
+                cur_op = k;
+                run = len;
+            }
+            break;
+        }
+        if (k == 0) {
+            // look ahead along the diagonal: lane d-1 takes cell (i-d, j-d)
+            const int d = lane_id + 1, ci = i - d, cj = j - d;
+            const bool inside = ci > 0 && cj > 0;
+            const unsigned cd = inside ? load(ci, cj) : 0u;
+            const bool isM = inside && ((cd >> 4) & 3u) == 2u;
+            const int skip = __ffs(~__ballot_sync(FULL, isM)) - 1; // 0..32 leading diagonal cells in plane M
+            if (skip >= 1) {
+                // the current cell and the next skip-1 cells are M; land on cell d = skip (plane M, code known)
+                if (cur_op == 0) {
+                    run += skip;
+                } else {
+                    emit(cur_op, run);
+                    cur_op = 0;
+                    run = skip;
+                }
+                i -= skip;
+                j -= skip;
+                cur = __shfl_sync(FULL, cd, skip - 1);
+                continue;
+            }
+            // skip == 0: the diagonal neighbour is not an interior M cell -- one ordinary step, its code is in lane 0
+            if (cur_op == 0) {
+                ++run;
+            } else {
+                emit(cur_op, run);
+                cur_op = 0;
+                run = 1;
+            }
+            --i;
+            --j;
+            const unsigned c1 = __shfl_sync(FULL, cd, 0);
+            const unsigned nw = (i > 0 && j > 0) ? c1 : ((i == 0) ? (j == 0 ? code00 : 0x15u) : 0x00u);
+            k = 2 - (int)((nw >> 4) & 3u);
+            cur = nw;
+            continue;
+        }
+        // plane I or D: one step
+        if (k == cur_op) {
+            ++run;
+        } else {
+            emit(cur_op, run);
+            cur_op = k;
+            run = 1;
+        }
+        const int kn = 2 - (int)((cur >> (k == 1 ? 0 : 2)) & 3u);
+        i -= (k != 1);
+        j -= (k != 2);
+        cur = code_at(i, j);
+        k = kn;
+    }
+    emit(cur_op, run);
+    if (P.pass == 0 && lane_id == 0)
+        P.counts[idx] = cnt;
+}
+
 // Traceback of const_fill3_kernel traces (2-bit codes, 10 per word, rows blocked by four): one load per
 // step, no plane state (the code IS the op).  Reference: constGap_highMem.go:43-65.
 __global__ void traceback_const3_kernel(const TraceParams P)

@@ -65,8 +65,9 @@ enum {
 /* ---- lifetime ------------------------------------------------------------------------------ */
 int gnx_device_count(void);
 /* workspace_bytes: device memory the context may use for traceback matrices of the chunks in
- * flight (0 = default, 1/2 of the device's free memory at creation, capped at 96 GiB: long pairs need
- * ~0.8 byte per DP cell and enough pairs in flight to fill the SMs). */
+ * flight (0 = default, 2/3 of the device's free memory at creation, capped at 128 GiB: long pairs need
+ * ~0.8 byte per DP cell and enough pairs in flight to fill the SMs; buffers are grown on demand, so
+ * read-sized batches only ever use a few GB of it). */
 gnx_ctx *gnx_create(int device, size_t workspace_bytes);
 void gnx_destroy(gnx_ctx *ctx);
 const char *gnx_last_error(gnx_ctx *ctx); /* ctx may be NULL: error of the last failed gnx_create */

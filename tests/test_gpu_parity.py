@@ -345,6 +345,38 @@ def test_checkpoint_recompute_traceback(n, m):
         c.close()
 
 
+def test_warp_per_pair_traceback_kernel():
+    """traceback_affine_warp_kernel (a warp per pair, match runs consumed 32 cells at a time) is the default for
+    long pairs; forced here (tb_impl = 3) onto every fill3 trace so that short, ragged, tie-heavy and N-bearing
+    pairs, both modes, and cigars beyond the slot go through it too."""
+    c = align.Context(0)
+    try:
+        c.set_option("tb_impl", 3)
+        c.set_option("ckpt", 0)
+        rng = np.random.default_rng(811)
+        al, be = [], []
+        for k in range(300):
+            n, m = int(rng.integers(0, 700)), int(rng.integers(0, 700))
+            a, b = random_pair(rng, n, m, identity=float(rng.choice([0.5, 0.8, 0.95, 1.0])))
+            if k % 9 == 0 and n and m:
+                a[rng.integers(0, n, 3)] = 4
+            if k % 11 == 0:
+                unit = rng.integers(0, 4, size=2, dtype=np.uint8)
+                a, b = np.resize(unit, n).astype(np.uint8), np.resize(unit[::-1], m).astype(np.uint8)
+            al.append(a)
+            be.append(b)
+        al += [rng.integers(0, 4, 3000, dtype=np.uint8), rng.integers(0, 4, 40, dtype=np.uint8)]
+        be += [rng.integers(0, 4, 2500, dtype=np.uint8), rng.integers(0, 4, 1500, dtype=np.uint8)]
+        for mode in (0, 1):
+            check_batch(c, al, be, orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, -600, -150, mode)
+            check_batch(c, al, be, orc.DEFAULT_SCORE_MATRIX, -20, -5, mode)  # cheap gaps: dozens of ops per cigar
+        a, ao, b, bo = synth_pairs(5, 2000, 500, 150)
+        check_batch(c, [a[ao[p]:ao[p + 1]] for p in range(2000)], [b[bo[p]:bo[p + 1]] for p in range(2000)],
+                    orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, -600, -150, 1)
+    finally:
+        c.close()
+
+
 def test_chunking_and_small_workspace():
     """Force many chunks (tiny workspace / chunk_pairs) so chunk boundaries and slot reuse are exercised."""
     c = align.Context(0, workspace_bytes=8 << 20)
