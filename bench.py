@@ -493,9 +493,9 @@ def main():
 
         g1, ms1 = run_shape(0, 1000, 150, 100_000, True, 16)
         # C4: a 10 kb x 10 kb pair owns 82 MB of traceback matrix and the one-warp-per-pair kernel needs pairs in
-        # flight to fill the SMs, so this block gets its own context sized for the 180 GB part (80 % of what is free)
+        # flight to fill the SMs, so this block gets its own context sized for the 180 GB part (75 % of what is free)
         free_b, _ = torch.cuda.mem_get_info(dev)
-        ws4 = int(free_b * 0.8)
+        ws4 = int(free_b * 0.75)
         pairs4 = max(256, min(1776, ws4 // 82_300_000) // 4 * 4)
         ctx4 = align.Context(local, ws4)
         try:
@@ -511,7 +511,7 @@ def main():
                                             "workspace_gb": round(ws4 / 1e9, 1),
                                             "note": "AffineGap (global) + CIGAR, one warp per pair through 32 strips "
                                                     "(one workspace-sized chunk of configs[3]: 82 MB of traceback "
-                                                    "matrix per pair, dedicated context with 80 % of free HBM)"},
+                                                    "matrix per pair, dedicated context with 75 % of free HBM)"},
             "const_gap_500x150_traceback": {"value": gc, "unit": "GCUPS", "pairs_per_gpu": 1_000_000,
                                             "ms_per_step": msc, "note": "ConstGap_highMem + CIGAR, g=-430"}}
 

@@ -47,7 +47,8 @@ struct DevBuf {
             cudaFree(p);
         p = nullptr;
         cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
+        size_t want = bytes + std::min<size_t>(bytes / 8, (size_t)256 << 20) + 256; // growth slack, bounded for the
+                                                                                     // 100-GB trace buffers of long pairs
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess)
             cap = want;
