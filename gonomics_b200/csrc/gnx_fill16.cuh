@@ -192,10 +192,13 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
             step(t, std::true_type{});
         if (CKPT) {
 #pragma unroll 1
-            for (; t < n - 1; ++t) {
+            while (t < n - 1) { // steady phase in runs that end at the next checkpoint, each run unrolled by two
                 if ((t & (kCkK - 1)) == 0 && t > 0)
                     save(t);
-                step(t, std::false_type{});
+                const int tend = min(n - 1, (t | (kCkK - 1)) + 1);
+#pragma unroll 2
+                for (; t < tend; ++t)
+                    step(t, std::false_type{});
             }
 #pragma unroll 1
             for (; t < T; ++t) {
