@@ -96,6 +96,7 @@ struct Slot {
     cudaEvent_t ev_total = nullptr, ev_done = nullptr;
     DevBuf alpha, beta, aoff, boff, cls, trace, trace_off, slots, counts, score, cig_off, cigars, edge, misc, partials;
     DevBuf best, endi, endj; // gsw extend step: first-maximum cell (right) and the traceback's end coordinates
+    DevBuf work;             // checkpoint path: work list of the pairs that need the recompute walk (+ its counter)
     PinBuf h_stage_a, h_stage_b, h_total, h_trace_off, h_score, h_off, h_cig, h_endi, h_endj;
     // chunk in flight
     int64_t begin = 0, end = 0;
@@ -495,7 +496,7 @@ void launch_fill16_ckpt(const FillParams &fp, int64_t quads, int cm, int sm_coun
 // second pass of the checkpoint path: recompute + walk (pass 0: slots and counts; pass 1: overflowing pairs)
 void launch_ckpt_trace(gnx_ctx *ctx, const Problem &pb, const FillParams &fp, const uint32_t *ckpt, const int64_t *rstar,
                        uint32_t *slots, int *counts, int pass, const int64_t *cig_off, gnx_cigar *cigars, int64_t cap,
-                       cudaStream_t st)
+                       int *work, int *work_count, cudaStream_t st)
 {
     static int occ = 0;
     if (occ == 0) {
@@ -517,7 +518,15 @@ void launch_ckpt_trace(gnx_ctx *ctx, const Problem &pb, const FillParams &fp, co
     q.out_cigar = (CigarOut *)cigars;
     q.out_cap = cap;
     q.h00_plane = pb.h00_plane;
-    const int64_t units = ((fp.pair_end - fp.pair_begin + 3) / 4) * 2;
+    q.work = work;
+    q.work_count = work_count;
+    const int64_t np = fp.pair_end - fp.pair_begin;
+    if (pass == 0) { // screening: indel-free routes are written directly, the rest is queued
+        cudaMemsetAsync(work_count, 0, sizeof(int), st);
+        ckpt_classify_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(fp, q);
+        ctx->launches++;
+    }
+    const int64_t units = ((np + 3) / 4) * 2;
     const int grid = (int)std::min<int64_t>(units, (int64_t)ctx->sm_count * occ);
     affine_ckpt_trace_kernel<<<grid, 32, 0, st>>>(fp, q);
 }
@@ -674,6 +683,7 @@ struct ChunkDev {
     int64_t a_lo, a_hi, b_lo, b_hi;   // absolute byte ranges of the chunk inside alpha / beta
     int64_t *best;                    // ext 2: biased by -begin (global pair index)
     int64_t *end_i, *end_j;           // ext: chunk-local
+    int *work, *work_count;           // checkpoint path: work list (chunk-local pair indices) and its device counter
     const int *smat;                  // profile batches: biased so that smat + smat_off[pair] is the pair's matrix
     const int64_t *smat_off;          // indexed by global pair id
 };
@@ -855,7 +865,7 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         tp.pass = 0;
         tp.pair_class = pb.profile ? nullptr : cd.cls;
         if (pb.cfg.impl == 17) {
-            launch_ckpt_trace(ctx, pb, fp, cd.trace, cd.best, cd.slots, cd.counts, 0, nullptr, nullptr, 0, st);
+            launch_ckpt_trace(ctx, pb, fp, cd.trace, cd.best, cd.slots, cd.counts, 0, nullptr, nullptr, 0, cd.work, cd.work_count, st);
             cudaEventRecord(fe.b, st);
             ctx->last_fill_launches++;
         } else if (pb.ext)
@@ -947,7 +957,7 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
         for (int i = 0; i < pb.dim * pb.dim; ++i)
             fp.scores[i] = (int)pb.scores[i];
         fp.one = 1;
-        launch_ckpt_trace(ctx, pb, fp, cd.trace, cd.best, cd.slots, cd.counts, 1, cig_off, cigars, cap, st);
+        launch_ckpt_trace(ctx, pb, fp, cd.trace, cd.best, cd.slots, cd.counts, 1, cig_off, cigars, cap, cd.work, cd.work_count, st);
     } else if (pb.ext)
         launch_traceback_ext(pb, cd, tp, np, st);
     else if (tp.kind == 2 && tp.layout == 3)
@@ -1314,6 +1324,9 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
                 acc = std::max(acc, ((np + 3) / 4) * ckpt_quad_words(pb.cfg.n_uniform));
                 CU(s.best.ensure((size_t)np * 8));
                 cd.best = s.best.as<int64_t>() - begin;
+                CU(s.work.ensure((size_t)np * 4 + 64));
+                cd.work_count = s.work.as<int>();
+                cd.work = s.work.as<int>() + 16;
             }
             CU(s.trace.ensure((size_t)std::max<int64_t>(acc, 1) * 4));
             CU(s.trace_off.ensure((size_t)(np + 1) * 8));
@@ -1678,7 +1691,7 @@ void gnx_destroy(gnx_ctx *ctx)
     for (int k = 0; k < kSlots; ++k) {
         Slot &s = ctx->slot[k];
         DevBuf *d[] = {&s.alpha, &s.beta, &s.aoff, &s.boff, &s.cls, &s.trace, &s.trace_off, &s.slots,
-                       &s.counts, &s.score, &s.cig_off, &s.cigars, &s.edge, &s.misc, &s.partials, &s.best, &s.endi, &s.endj};
+                       &s.counts, &s.score, &s.cig_off, &s.cigars, &s.edge, &s.misc, &s.partials, &s.best, &s.endi, &s.endj, &s.work};
         for (DevBuf *b : d)
             b->release();
         PinBuf *h[] = {&s.h_stage_a, &s.h_stage_b, &s.h_total, &s.h_trace_off, &s.h_score, &s.h_off, &s.h_cig, &s.h_endi, &s.h_endj};
@@ -1919,6 +1932,9 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
                 acc = std::max(acc, ((np + 3) / 4) * ckpt_quad_words(pb.cfg.n_uniform));
                 CU(s.best.ensure((size_t)np * 8));
                 cd.best = s.best.as<int64_t>() - begin;
+                CU(s.work.ensure((size_t)np * 4 + 64));
+                cd.work_count = s.work.as<int>();
+                cd.work = s.work.as<int>() + 16;
             }
             CU(s.trace.ensure((size_t)std::max<int64_t>(acc, 1) * 4));
             CU(s.trace_off.ensure((size_t)(np + 1) * 8));

@@ -35,7 +35,56 @@ struct CkptParams {
     CigarOut *out_cigar;
     int64_t out_cap;
     int h00_plane;
+    int *work;                 // pass 0: chunk-local indices of the pairs that need the recompute walk
+    int *work_count;           // device counter of `work` (ckpt_classify_kernel)
 };
+
+// Screening pass between the two passes: one thread per pair.  If the pair's score equals the score of the
+// UNGAPPED diagonal that ends at (r*, m), its route is known without any trace code:
+//     D x (n - r*),  M x m,  D x (r* - m)          (traceback order; zero-length runs omitted)
+// Proof.  Let c_k = (r* - m + k, k) and P_k the diagonal's prefix score.  M(c_k) >= P_k (the diagonal is a valid
+// path: it starts from the free D(i,0) = 0 and M(c_{k+1}) >= s + M(c_k)), and M(r*,m) <= max(M,I)(r*,m) = S = P_m,
+// so M(r*,m) = S >= I(r*,m): the walk enters in plane M.  If some X in {I, D} had X(c_{k-1}) > M(c_{k-1}), then
+// M(c_k) >= s_k + X(c_{k-1}) > s_k + P_{k-1} = P_k and, propagating along the diagonal, M(c_m) > P_m = S:
+// impossible.  Hence tripleMaxTrace (ties M >= I >= D, align/align.go:76-84) picks M at every diagonal cell and
+// the walk stays on the diagonal down to column 0, where affineTrace's boundary is plane D up to (0,0).
+// Everything else is queued for affine_ckpt_trace_kernel.  Reads with no indel against their window are the
+// common case in practice; in the synthetic C3 workload they are ~45 % of the pairs.
+__global__ void __launch_bounds__(128) ckpt_classify_kernel(const FillParams P, const CkptParams Q)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t pair = P.pair_begin + idx;
+    if (pair >= P.pair_end)
+        return;
+    if (P.pair_class && P.pair_class[pair] > 1) {
+        Q.counts[idx] = 0;
+        return;
+    }
+    const int64_t a0 = P.alpha_off[pair], b0 = P.beta_off[pair];
+    const int n = (int)(P.alpha_off[pair + 1] - a0), m = (int)(P.beta_off[pair + 1] - b0);
+    const int rs = (int)Q.rstar[pair];
+    bool shortcut = false;
+    if (rs >= m && m >= 1) {
+        const uint8_t *__restrict__ al = P.alpha + a0 + (rs - m);
+        const uint8_t *__restrict__ be = P.beta + b0;
+        long long sum = 0;
+        for (int k = 0; k < m; ++k)
+            sum += P.scores[(int)al[k] * P.dim + (int)be[k]];
+        shortcut = sum == P.out_score[pair];
+    }
+    if (!shortcut) {
+        Q.work[atomicAdd(Q.work_count, 1)] = (int)idx;
+        return;
+    }
+    uint32_t *slot = Q.slots + (size_t)idx * Q.slot_cap; // slot_cap >= 3
+    int cnt = 0;
+    if (n > rs)
+        slot[cnt++] = ((uint32_t)(n - rs) << 2) | 2u;
+    slot[cnt++] = ((uint32_t)m << 2) | 0u;
+    if (rs > m)
+        slot[cnt++] = ((uint32_t)(rs - m) << 2) | 2u;
+    Q.counts[idx] = cnt;
+}
 
 __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillParams P, const CkptParams Q)
 {
@@ -57,10 +106,10 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
     const int dMl = 2 * FD - 2 * FH, dIl = FD - FH, dDl = 0;
     const int fh_reg = FH * one;
     const int64_t np = P.pair_end - P.pair_begin;
-    const int64_t n_units = ((np + 3) / 4) * 2; // (quad, sel): the A pairs (low halves) or the B pairs of a quad
-
-    // pass 1 (the rare cigars longer than the slot) first screens 32 units per warp, one per lane, so that a chunk
-    // without overflow costs a few coalesced loads instead of a full unit set-up each
+    // pass 0 takes two queued pairs per warp from the work list; pass 1 (the rare cigars longer than the slot) first
+    // screens 32 candidate units per warp, one per lane, a unit being two pairs (pl, pl + 2) of a quad
+    const int64_t n_work = Q.pass == 0 ? (int64_t)*Q.work_count : 0;
+    const int64_t n_units = Q.pass == 0 ? (n_work + 1) / 2 : ((np + 3) / 4) * 2;
     const int G = Q.pass == 1 ? 32 : 1;
     for (int64_t ubase = (int64_t)blockIdx.x * G; ubase < n_units; ubase += (int64_t)gridDim.x * G) {
       unsigned todo = 1u;
@@ -76,12 +125,19 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
       while (todo) {
         const int64_t unit = ubase + (__ffs(todo) - 1);
         todo &= todo - 1;
-        const int64_t quad = unit >> 1;
-        const int sel = (int)(unit & 1);
-        const int64_t pair0 = P.pair_begin + quad * 4 + half * 2 + sel; // this half-warp's pair
-        const bool valid = pair0 < P.pair_end;
-        const int64_t pair = valid ? pair0 : P.pair_end - 1;
-        const int64_t idx = pair - P.pair_begin;
+        // this half-warp's pair (chunk-local index pl) and where its checkpoint words live: quad pl / 4, lanes
+        // 16 * ((pl % 4) / 2) .. + 15 of each record, 16-bit half pl % 2
+        int64_t pl;
+        if (Q.pass == 0)
+            pl = (2 * unit + half < n_work) ? (int64_t)Q.work[2 * unit + half] : -1;
+        else
+            pl = (unit >> 1) * 4 + half * 2 + (unit & 1);
+        const bool valid = pl >= 0 && pl < np;
+        const int64_t idx = valid ? pl : 0;
+        const int64_t pair = P.pair_begin + idx;
+        const int64_t quad = idx >> 2;
+        const int src_lane = (int)(((idx >> 1) & 1) * LPP) + lane; // lane of the pass-1 warp that held these columns
+        const int sel = (int)(idx & 1);
         const int64_t a0 = P.alpha_off[pair], b0 = P.beta_off[pair];
         const int n = (int)(P.alpha_off[pair + 1] - a0), m = (int)(P.beta_off[pair + 1] - b0); // uniform batch
         bool want = valid && (!P.pair_class || P.pair_class[pair] <= 1);
@@ -179,7 +235,7 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
                 int Hc[C], Dt[C];
                 int hpL, edgeI = 0, edgeH = 0;
                 if (blk > 0 && recompute) {
-                    const uint32_t *src = Q.ckpt + (size_t)quad * Q.quad_words + (size_t)(blk - 1) * (kCkRegs * 32) + tid;
+                    const uint32_t *src = Q.ckpt + (size_t)quad * Q.quad_words + (size_t)(blk - 1) * (kCkRegs * 32) + src_lane;
                     auto val = [&](uint32_t x) { return ((int)((x >> (16 * sel)) & 0xffffu) - 32768) * SC; };
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
