@@ -9,8 +9,10 @@
 // kCkK = 32 steps: 11.8 KB per pair instead of a 66 KB trace matrix); pass 2 (here) walks the path backwards
 // block by block: restore the state entering step 32b, re-run 33 steps with the TAGGED arithmetic of
 // affine_fill3_kernel (identical cell code, so identical tie-breaks), keep the 6-bit codes of those steps in
-// shared memory, and let one lane per pair walk them until the path leaves the block.  On the C3 workload the
-// path touches ~6 of 16 blocks.
+// shared memory, and walk them (state in lane 0 of the half-warp, the other lanes look 16 diagonal cells ahead so
+// that match runs are consumed at once) until the path leaves the block.  On the C3 workload the path touches ~6
+// of 16 blocks.  Between the passes ckpt_classify_kernel settles the pairs whose route is provably the ungapped
+// diagonal (no trace needed at all) and queues the rest.
 //
 // Exactness: the checkpointed values are the clean plane values (H, D', edge I) the tagged kernel carries
 // between steps (score-only I' = max(I+E, H+O+E) equals the tagged three-way max's value when O <= 0, which
