@@ -521,10 +521,22 @@ def main():
 
     # ---- e2e: the public host-buffer API, pinned host inputs, H2D + D2H inside the timed region --
     if not args.no_e2e:
+        pinned = []
+
+        def pinned_array(count, dtype):
+            """Caller-owned result buffer in page-locked memory (gnx_host_alloc): results are DMA'd straight into it."""
+            dt = np.dtype(dtype)
+            ptr = L.gnx_host_alloc(max(count * dt.itemsize, 1))
+            if not ptr:
+                raise MemoryError("gnx_host_alloc failed")
+            pinned.append(ptr)
+            raw = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(max(count * dt.itemsize, 1),))
+            return raw[:count * dt.itemsize].view(dt)
+
         def e2e(want_cigar: bool):
-            out_score = np.zeros(P, dtype=np.int64)
-            out_off = np.zeros(P + 1, dtype=np.int64) if want_cigar else None
-            out_cig = np.zeros(cig_cap, dtype=CIGAR_DTYPE) if want_cigar else None
+            out_score = pinned_array(P, np.int64)
+            out_off = pinned_array(P + 1, np.int64) if want_cigar else None
+            out_cig = pinned_array(cig_cap, CIGAR_DTYPE) if want_cigar else None
             out = (out_score, out_off, out_cig)
             for _ in range(2):
                 ctx.affine_gap_batch(h_alpha, ao, h_beta, bo, S, GAP_OPEN, GAP_EXTEND, True, want_cigar, out=out)
@@ -543,12 +555,15 @@ def main():
             return world * cells * args.steps / dt / 1e9, h2d, d2h, out_score
         v, h2d, d2h, sc_host = e2e(False)
         line["e2e"] = {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "api": "gnx_affine_batch (host buffers, pinned), score only"}
+                       "api": "gnx_affine_batch (host buffers, inputs and results pinned), score only"}
         assert np.array_equal(sc_host, d_score.cpu().numpy()), "host-API scores differ from device-API scores"
         if not args.no_traceback:
             v3, h2d3, d2h3, _ = e2e(True)
             line["traceback"]["e2e"] = {"value": v3, "unit": "GCUPS", "h2d_bytes_per_step": h2d3,
                                         "d2h_bytes_per_step": d2h3}
+        sc_host = None
+        for ptr in pinned:
+            L.gnx_host_free(ptr)
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores ----------------------
     if rank == 0 and world == 1 and not args.no_cpu:
