@@ -552,15 +552,29 @@ def main():
                 dt = float(t.item())
             h2d = na + nb + 2 * (P + 1) * 8
             d2h = P * 8 + ((P + 1) * 8 + int(out_off[-1]) * 16 if want_cigar else 0)
-            return world * cells * args.steps / dt / 1e9, h2d, d2h, out_score
+            return world * cells * args.steps / dt / 1e9, h2d, d2h, (out_score if not want_cigar else out)
         v, h2d, d2h, sc_host = e2e(False)
         line["e2e"] = {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "api": "gnx_affine_batch (host buffers, inputs and results pinned), score only"}
         assert np.array_equal(sc_host, d_score.cpu().numpy()), "host-API scores differ from device-API scores"
         if not args.no_traceback:
-            v3, h2d3, d2h3, _ = e2e(True)
+            v3, h2d3, d2h3, out3 = e2e(True)
             line["traceback"]["e2e"] = {"value": v3, "unit": "GCUPS", "h2d_bytes_per_step": h2d3,
                                         "d2h_bytes_per_step": d2h3}
+            if rank == 0 and world == 1 and not args.no_cpu:
+                # the first pairs of the timed batch diffed against the oracle, score AND cigar
+                import oracle as orc
+                k = min(P, 20000)
+                osc, ooff, ocig = orc.batch(h_alpha[:k * N_LEN], ao[:k + 1], h_beta[:k * M_LEN], bo[:k + 1],
+                                            orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, GAP_OPEN, GAP_EXTEND, 1, True,
+                                            os.cpu_count() or 1)
+                gsc, goff, gcig = out3
+                t = int(ooff[-1])
+                line["traceback"]["parity_spot_check"] = bool(
+                    np.array_equal(gsc[:k], osc) and np.array_equal(goff[:k + 1], ooff)
+                    and np.array_equal(gcig["run_length"][:t], ocig["run_length"])
+                    and np.array_equal(gcig["op"][:t], ocig["op"]))
+            out3 = None
         sc_host = None
         for ptr in pinned:
             L.gnx_host_free(ptr)
