@@ -1,4 +1,4 @@
-"""The C++ host mirror (gonomics_b200/csrc/host/align.hpp): compiles on CPU, runs on the GPU box."""
+"""The C++ host mirrors (gonomics_b200/csrc/host/align.hpp, genomegraph.hpp): compile on CPU, run on the GPU box."""
 import os
 import subprocess
 
@@ -7,24 +7,26 @@ import pytest
 from gonomics_b200 import build
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = os.path.join(ROOT, "tests", "cpp", "test_align_host.cpp")
-EXE = os.path.join(ROOT, "tests", "cpp", "test_align_host")
+TESTS = ["test_align_host", "test_genomegraph_host"]
 
 
-def _compile():
+def _compile(name):
     build.build()
     libdir = os.path.join(ROOT, "gonomics_b200")
-    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-pthread", SRC, "-o", EXE, f"-L{libdir}", "-lgnxalign",
+    src = os.path.join(ROOT, "tests", "cpp", name + ".cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", name)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-pthread", src, "-o", exe, f"-L{libdir}", "-lgnxalign",
                     f"-Wl,-rpath,{libdir}", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"], check=True)
+    return exe
 
 
-def test_cpp_host_mirror_compiles_and_links():
-    _compile()
-    assert os.path.exists(EXE)
+@pytest.mark.parametrize("name", TESTS)
+def test_cpp_host_mirror_compiles_and_links(name):
+    assert os.path.exists(_compile(name))
 
 
 @pytest.mark.gpu
-def test_cpp_host_mirror_replays_reference_tests():
-    _compile()
-    r = subprocess.run([EXE], capture_output=True, text=True, timeout=300)
+@pytest.mark.parametrize("name", TESTS)
+def test_cpp_host_mirror_replays_reference_tests(name):
+    r = subprocess.run([_compile(name)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
