@@ -28,6 +28,7 @@ using namespace gnx;
 
 constexpr int kSlots = 3;
 constexpr int kSlotCap = 24; // cigar elements kept per pair before the overflow pass
+constexpr int kSlotCapCkpt = 64;
 constexpr int kSlotCapLong = 1024; // ... for multi-strip (long) pairs, whose cigars run to hundreds of elements and
                                    // whose second traceback pass is a second walk of a 20 000-step route
 
@@ -193,7 +194,12 @@ struct Problem {
     const int64_t *extra_words = nullptr; // profile: per-pair workspace words besides the trace (the S matrix)
 };
 
-inline int slot_cap_of(const Problem &pb) { return (pb.cfg.multi && !pb.profile && !pb.ext) ? kSlotCapLong : kSlotCap; }
+inline int slot_cap_of(const Problem &pb)
+{
+    if (pb.cfg.impl == 17)
+        return kSlotCapCkpt; // the checkpoint path's second pass is a second recompute, not a second walk of a stored trace
+    return (pb.cfg.multi && !pb.profile && !pb.ext) ? kSlotCapLong : kSlotCap;
+}
 
 // Exact-arithmetic range analysis for the scaled int32 kernels (DESIGN.md "Arithmetic width").
 // Every finite plane value v obeys |v| <= bound.  With values carried as scale*v and -inf = -2^30,

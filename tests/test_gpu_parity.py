@@ -327,15 +327,16 @@ def test_checkpoint_recompute_traceback(n, m):
                                     ("ties", 101, -600, -150, orc.HUMAN_CHIMP_TWO_SCORE_MATRIX),
                                     ("ties", 50, 0, -30, orc.DEFAULT_SCORE_MATRIX),
                                     ("indels", 64, -100, -20, orc.DEFAULT_SCORE_MATRIX),
+                                    ("unrelated", 64, -20, -5, orc.DEFAULT_SCORE_MATRIX),  # cheap gaps: > 64 ops
                                     ("unrelated", 97, -400, -30, orc.DEFAULT_SCORE_MATRIX)):
             if flavour == "indels" and n - m < 8:
                 continue
             al, be = _uniform_batch(rng, P, n, m, flavour)
-            if flavour == "indels" and m >= 140:  # these cigars must overflow the 24-entry slot (second pass)
+            if flavour == "unrelated" and O == -20 and m >= 140:  # these cigars must overflow the 64-entry slot
                 ac, ao = concat(al)
                 bc, bo = concat(be)
                 _, ooff, _ = orc.batch(ac, ao, bc, bo, S, O, E, 1, True, 8)
-                assert int(np.diff(ooff).max()) > 24
+                assert int(np.diff(ooff).max()) > 64
             c.set_option("ckpt", 1)
             sc = check_batch(c, al, be, S, O, E, 1)
             c.set_option("ckpt", 0)
