@@ -250,3 +250,42 @@ def test_extend_oracle_against_python_transcription():
         for g in (-600, -100, 0):
             assert orc.left_dynamic_aln(a, b, S, g) == _py_extend(a, b, S, g, True), (a, b, g)
             assert orc.right_dynamic_aln(a, b, S, g) == _py_extend(a, b, S, g, False), (a, b, g)
+
+
+def test_ungapped_diagonal_route_theorem():
+    """The screening pass of the checkpoint path (ckpt_classify_kernel) relies on: in freeEndGaps mode, if the score
+    equals the score of the ungapped diagonal that ends where the traceback leaves the last column (r*, m), the route
+    is D x (r* - m), M x m, D x (n - r*).  Checked here against the pinned oracle on random, mutated, tie-heavy and
+    unrelated pairs (CPU only)."""
+    rng = np.random.default_rng(99)
+    hits = 0
+    for trial in range(1500):
+        n, m = int(rng.integers(20, 220)), int(rng.integers(1, 60))
+        kind = trial % 4
+        if kind == 0:
+            a, b = random_pair(rng, n, m, identity=float(rng.choice([0.7, 0.9, 1.0])))
+        elif kind == 1:  # exact window, maybe with substitutions only
+            a = rng.integers(0, 4, size=n, dtype=np.uint8)
+            s = int(rng.integers(0, n - m + 1)) if n >= m else 0
+            b = a[s:s + m].copy() if n >= m else rng.integers(0, 4, size=m, dtype=np.uint8)
+            for k in rng.integers(0, m, size=int(rng.integers(0, 3))):
+                b[k] = (b[k] + 1) % 4
+        elif kind == 2:  # repeats: ties everywhere
+            unit = rng.integers(0, 4, size=int(rng.integers(1, 4)), dtype=np.uint8)
+            a, b = np.resize(unit, n).astype(np.uint8), np.resize(unit, m).astype(np.uint8)
+        else:
+            a, b = rng.integers(0, 4, size=n, dtype=np.uint8), rng.integers(0, 4, size=m, dtype=np.uint8)
+        S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX if trial % 2 else orc.DEFAULT_SCORE_MATRIX
+        O, E = ((-600, -150), (-400, -30), (0, -30))[trial % 3]
+        score, cig = orc.affine_gap_highmem(a, b, S, O, E, free_end_gaps=True)
+        tail_d = cig[-1][0] if cig and cig[-1][1] == 2 and len(cig) > 1 else 0  # D x (n - r*) closes the route
+        rs = n - tail_d
+        if rs < m:
+            continue
+        diag = int(sum(int(S[a[rs - m + k], b[k]]) for k in range(m)))
+        if diag != score:
+            continue
+        hits += 1
+        want = ([(rs - m, 2)] if rs > m else []) + [(m, 0)] + ([(n - rs, 2)] if n > rs else [])
+        assert cig == want, (trial, n, m, cig, want)
+    assert hits > 300
