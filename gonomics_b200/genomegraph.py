@@ -98,11 +98,18 @@ class SeedIndex:
         self.ctx._check(self._L.gnx_seed_index_download(self.ctx._h, self._h, key.ctypes.data, loc.ctypes.data))
         return key[:self.n_entries], loc[:self.n_entries]
 
-    def seed_batch(self, reads_cat: np.ndarray, read_off: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
-        """seedMapMemPool's seeds of every read in APPEND order: (seeds[SEED_DTYPE], offsets [n_reads+1])."""
+    def seed_batch(self, reads_cat: np.ndarray, read_off: np.ndarray, out=None) -> Tuple[np.ndarray, np.ndarray]:
+        """seedMapMemPool's seeds of every read in APPEND order: (seeds[SEED_DTYPE], offsets [n_reads+1]).
+        `out` = (seeds buffer, offsets buffer) lets the caller provide (e.g. page-locked) result arrays."""
         cat = np.ascontiguousarray(reads_cat, dtype=np.uint8)
         off = np.ascontiguousarray(read_off, dtype=np.int64)
         n = len(off) - 1
+        if out is not None:
+            seeds, soff = out
+            rc = self._L.gnx_seed_batch(self.ctx._h, self._h, cat.ctypes.data, off.ctypes.data, n, seeds.ctypes.data,
+                                        soff.ctypes.data, len(seeds))
+            self.ctx._check(rc)
+            return seeds[:int(soff[n])], soff
         soff = np.zeros(n + 1, dtype=np.int64)
         cap = max(8 * n, 64)
         while True:
