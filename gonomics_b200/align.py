@@ -180,7 +180,7 @@ class Context:
         return self._batch(2, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_pen, 0, want_cigar, cigar_cap, out)
 
     def extend_batch(self, side, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_pen, want_cigar=True,
-                     cigar_cap=None):
+                     cigar_cap=None, out=None):
         """Batched genomeGraph.LeftDynamicAln (side=1) / RightDynamicAln (side=2) (genomeGraph/search.go:234-321).
         Returns (scores, end_i, end_j, cigar_off | None, cigars | None); cigar ops are the bytes 'M','I','D' and
         the route is in traceback order, as in the reference."""
@@ -190,16 +190,19 @@ class Context:
         beta_off = np.ascontiguousarray(beta_off, dtype=np.int64)
         scores = np.ascontiguousarray(scores, dtype=np.int64)
         n_pairs = len(alpha_off) - 1
-        out_score = np.zeros(n_pairs, dtype=np.int64)
-        end_i = np.zeros(n_pairs, dtype=np.int64)
-        end_j = np.zeros(n_pairs, dtype=np.int64)
-        out_off = np.zeros(n_pairs + 1, dtype=np.int64) if want_cigar else None
-        out_cig = np.zeros(max(int(cigar_cap or 16 * n_pairs + 64), 1), dtype=CIGAR_DTYPE) if want_cigar else None
+        if out is not None:  # caller-provided (e.g. page-locked) result arrays
+            out_score, end_i, end_j, out_off, out_cig = out
+        else:
+            out_score = np.zeros(n_pairs, dtype=np.int64)
+            end_i = np.zeros(n_pairs, dtype=np.int64)
+            end_j = np.zeros(n_pairs, dtype=np.int64)
+            out_off = np.zeros(n_pairs + 1, dtype=np.int64) if want_cigar else None
+            out_cig = np.zeros(max(int(cigar_cap or 16 * n_pairs + 64), 1), dtype=CIGAR_DTYPE) if want_cigar else None
         rc = self._L.gnx_extend_batch(self._h, int(side), _addr(alpha_cat), _addr(alpha_off), _addr(beta_cat),
                                       _addr(beta_off), n_pairs, _addr(scores), int(scores.shape[0]), int(gap_pen),
                                       int(bool(want_cigar)), _addr(out_score), _addr(end_i), _addr(end_j),
                                       _addr(out_cig), _addr(out_off), 0 if out_cig is None else len(out_cig))
-        if rc == GNX_ECAP:
+        if rc == GNX_ECAP and out is None:
             out_cig = np.zeros(max(int(out_off[-1]), 1), dtype=CIGAR_DTYPE)
             rc = self._L.gnx_copy_last_cigars(self._h, _addr(out_cig), len(out_cig))
         self._check(rc)
