@@ -9,6 +9,7 @@
 #include "gnx_fill3.cuh"
 #include "gnx_fill16.cuh"
 #include "gnx_ckpt.cuh"
+#include "gnx_long.cuh"
 #include "gnx_profile.cuh"
 #include "gnx_twobit.cuh"
 
@@ -117,6 +118,12 @@ struct gnx_ctx {
     Slot slot[kSlots];
     DevBuf status;       // int32 device status word
     DevBuf dr_misc;      // device-resident path scratch (running total, counters)
+    // long-pair checkpoint path (gnx_long.cuh): per-warp scratch shared by the slots (its launches are chained on
+    // ev_long, so at most one of them runs at a time) + a ring of work counters in its first 256 bytes
+    DevBuf long_scratch;
+    cudaEvent_t ev_long = nullptr;
+    bool ev_long_set = false;
+    int long_rr = 0;
     // profile (group-vs-group) batches: groups, profiles, pair lists, dense cell-score matrices
     DevBuf pf_cat, pf_goff, pf_nseq, pf_coloff, pf_scores, pf_px, pf_py, pf_aoff, pf_boff, pf_soff, pf_prof, pf_vb,
         pf_smat, pf_err;
@@ -134,6 +141,9 @@ struct gnx_ctx {
     int opt_force_lookup = -1; // -1 auto; 0/1 force the PRMT / shared-memory score lookup for ACGT pairs
     int opt_ckpt = 1;          // allow the checkpoint-and-recompute traceback for uniform freeEndGaps batches
     int opt_wide_cta = -1;     // -1 auto; 0/1 never / always run multi-strip pairs on the 4-warp CTA-per-pair kernel
+    int opt_long = -1;         // -1 auto; 0/1 never / always run multi-strip traceback batches on the tile-checkpoint kernel
+    int opt_long_form = 0;     // cell formulation of its score-only pass (gnx_long.cuh FORM)
+    int64_t opt_long_pool = 0; // its run-pool entries per chunk (0 = auto; tests shrink it to force the re-run pass)
     int sm_count = 148;
     // stats of the last batch call
     std::vector<FillEvent> fill_events;
@@ -175,6 +185,7 @@ struct FillCfg {
     int strips_max = 1; // fill3: strips of the widest pair
     int64_t m_uniform = 0; // fill16: the batch's (uniform) query length
     int64_t n_uniform = 0; // checkpoint path: the batch's (uniform) target length
+    int64_t long_pool = 0; // impl 18: run-pool entries per chunk (0 = long_pool_entries())
 };
 
 struct Problem {
@@ -194,11 +205,26 @@ struct Problem {
     const int64_t *extra_words = nullptr; // profile: per-pair workspace words besides the trace (the S matrix)
 };
 
+inline int slot_cap_of(const Problem &pb);
+inline size_t slots_bytes(const Problem &pb, int64_t np);
 inline int slot_cap_of(const Problem &pb)
 {
     if (pb.cfg.impl == 17)
         return kSlotCapCkpt; // the checkpoint path's second pass is a second recompute, not a second walk of a stored trace
+    if (pb.cfg.impl == 18)
+        return kSlotCapLong;
     return (pb.cfg.multi && !pb.profile && !pb.ext) ? kSlotCapLong : kSlotCap;
+}
+
+inline int64_t pool_entries_of(const Problem &pb, int64_t np)
+{
+    return pb.cfg.long_pool > 0 ? pb.cfg.long_pool : long_pool_entries(np, pb.cfg.n_uniform, pb.cfg.m_uniform);
+}
+inline size_t slots_bytes(const Problem &pb, int64_t np)
+{
+    if (pb.cfg.impl == 18) // cursor + per-pair pool offsets + run pool (gnx_long.cuh)
+        return long_slot_bytes(np, pool_entries_of(pb, np));
+    return (size_t)np * slot_cap_of(pb) * 4;
 }
 
 // Exact-arithmetic range analysis for the scaled int32 kernels (DESIGN.md "Arithmetic width").
@@ -320,6 +346,8 @@ inline int64_t group_trace_words(const Problem &pb, int64_t n_eff, int64_t m)
     if (n_eff <= 0 || m <= 0)
         return 0;
     const FillCfg &c = pb.cfg;
+    if (c.impl == 18) // tile checkpoints live in per-warp scratch, not per pair
+        return 0;
     if (c.impl == 17) // checkpoints: kCkRegs words per lane every kCkK steps; a group is half a quad
         return ((n_eff + 16 - 2) / kCkK) * kCkRegs * 16;
     if (pb.kind == 2 && c.impl != 3)
@@ -674,6 +702,70 @@ void dispatch_fill(const Problem &pb, const FillParams &fp, int C, int lookup, i
     }
 }
 
+// Tile-checkpoint kernel for long pairs (gnx_long.cuh): one persistent launch per chunk, pairs taken from a device
+// counter.  pass 0: scores, cigar slots and counts; pass 1: pairs whose cigar overflowed the slot, re-run entirely.
+template <bool FREE, int FORM>
+int launch_long_t(gnx_ctx *ctx, const Problem &pb, const FillParams &fp, LongParams q, cudaStream_t st)
+{
+    static int occ = 0;
+    if (occ == 0) {
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_long_kernel<FREE, FORM>, 32, 0) != cudaSuccess || o < 1)
+            o = 8;
+        occ = o;
+    }
+    const LongGeom g = long_geom(pb.cfg.n_uniform, pb.cfg.m_uniform);
+    const int64_t np = fp.pair_end - fp.pair_begin;
+    int64_t grid = std::min<int64_t>(np, (int64_t)ctx->sm_count * std::min(occ, ctx->opt_ctas_per_sm));
+    const int64_t fit = ((int64_t)ctx->workspace - 256) / g.cta_stride;
+    if (fit < 1)
+        return fail(ctx, GNX_ERANGE, "one long pair's checkpoints exceed the context workspace");
+    grid = std::max<int64_t>(1, std::min(grid, fit));
+    CU(ctx->long_scratch.ensure((size_t)(256 + grid * g.cta_stride)));
+    int *counter = ctx->long_scratch.as<int>() + ctx->long_rr;
+    ctx->long_rr = (ctx->long_rr + 1) % 64;
+    q.scratch = ctx->long_scratch.as<uint8_t>() + 256;
+    q.cta_stride = g.cta_stride;
+    q.edge_stride = g.edge_stride;
+    q.ckpt_off = g.ckpt_off;
+    q.ckpt_strip_words = g.ckpt_strip_words;
+    q.tile_off = g.tile_off;
+    q.runs_off = g.runs_off;
+    q.next_pair = counter;
+    if (ctx->ev_long_set) // the scratch is shared by the slots' streams: chain the launches
+        CU(cudaStreamWaitEvent(st, ctx->ev_long, 0));
+    CU(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    affine_long_kernel<FREE, FORM><<<(int)grid, 32, 0, st>>>(fp, q);
+    CU(cudaEventRecord(ctx->ev_long, st));
+    ctx->ev_long_set = true;
+    ctx->launches++;
+    return GNX_OK;
+}
+
+int launch_long(gnx_ctx *ctx, const Problem &pb, const FillParams &fp, uint32_t *slots, int *counts, int pass,
+                const int64_t *cig_off, gnx_cigar *cigars, int64_t cap, cudaStream_t st)
+{
+    LongParams q;
+    memset(&q, 0, sizeof q);
+    const int64_t np = fp.pair_end - fp.pair_begin;
+    q.pool_cursor = reinterpret_cast<unsigned long long *>(slots); // layout: long_slot_bytes()
+    q.slot64 = reinterpret_cast<long long *>(slots) + 2;
+    q.pool = slots + 4 + 2 * np;
+    q.pool_cap = pool_entries_of(pb, np);
+    if (pass == 0)
+        CU(cudaMemsetAsync(q.pool_cursor, 0, 8, st));
+    q.counts = counts;
+    q.pass = pass;
+    q.cigar_off = cig_off;
+    q.out_cigar = (CigarOut *)cigars;
+    q.out_cap = cap;
+    q.h00_plane = pb.h00_plane;
+    const bool f1 = ctx->opt_long_form != 0;
+    if (pb.kind == 1)
+        return f1 ? launch_long_t<true, 1>(ctx, pb, fp, q, st) : launch_long_t<true, 0>(ctx, pb, fp, q, st);
+    return f1 ? launch_long_t<false, 1>(ctx, pb, fp, q, st) : launch_long_t<false, 0>(ctx, pb, fp, q, st);
+}
+
 // Device buffers of one chunk, all addressed with GLOBAL pair indices (pointers are pre-biased).
 struct ChunkDev {
     const uint8_t *alpha, *beta;      // biased so that absolute offsets index them
@@ -728,7 +820,7 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     const int grid = (int)std::min<int64_t>((np + warps_per_block - 1) / warps_per_block, max_grid);
     if (pb.profile) {
         // no sequence bytes on this path: invalid bases were found while the profiles were built
-    } else if (pb.cfg.impl == 3 || pb.cfg.impl == 16 || pb.cfg.impl == 17) {
+    } else if (pb.cfg.impl == 3 || pb.cfg.impl == 16 || pb.cfg.impl == 17 || pb.cfg.impl == 18) {
         // these kernels take any base < dim, so the per-pair pass is only needed to find WHICH pair is
         // invalid; gate it on the chunk's largest base (vectorised, HBM-bound)
         int *gate = status + 1 + ctx->gate_rr;
@@ -777,7 +869,12 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     FillEvent &fe = next_fill_event(ctx);
     cudaEventRecord(fe.a, st);
     const int lookup0 = pb.chunk > 1 ? 2 : ((ctx->opt_force_lookup == 1 || !pb.prmt_ok) ? 1 : 0);
-    if (pb.cfg.impl == 17) {
+    if (pb.cfg.impl == 18) { // long pairs: score, checkpoints, recompute and walk in one persistent launch
+        const int rc = launch_long(ctx, pb, fp, cd.slots, cd.counts, 0, nullptr, nullptr, 0, st);
+        if (rc != GNX_OK)
+            return rc;
+        ctx->last_fill_launches++;
+    } else if (pb.cfg.impl == 17) {
         const int64_t quads = (np + 3) / 4;
         fp.trace = cd.trace;                                   // checkpoint area
         fp.edge_stride = ckpt_quad_words(pb.cfg.n_uniform);    // words per quad
@@ -849,7 +946,7 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     if (!(pb.cfg.impl == 17 && pb.want_cigar)) // checkpoint path: the re-fill of the path's blocks is part of the DP fill
         cudaEventRecord(fe.b, st);
 
-    if (pb.want_cigar) {
+    if (pb.want_cigar && pb.cfg.impl != 18) {
         TraceParams tp;
         memset(&tp, 0, sizeof tp);
         tp.alpha_off = cd.aoff;
@@ -920,8 +1017,13 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
     if (np <= 0)
         return GNX_OK;
     int *status = ctx->status.as<int>();
-    expand_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(cd.slots, slot_cap_of(pb), cd.counts, cig_off, np,
-                                                          (CigarOut *)cigars, cap, status, pb.ext);
+    if (pb.cfg.impl == 18)
+        expand_pool_kernel<<<(int)((np + 3) / 4), 128, 0, st>>>(reinterpret_cast<const long long *>(cd.slots) + 2,
+                                                               cd.slots + 4 + 2 * np, cd.counts, cig_off, np,
+                                                               (CigarOut *)cigars, cap, status);
+    else
+        expand_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(cd.slots, slot_cap_of(pb), cd.counts, cig_off, np,
+                                                              (CigarOut *)cigars, cap, status, pb.ext);
     ctx->launches++;
     TraceParams tp;
     memset(&tp, 0, sizeof tp);
@@ -946,7 +1048,7 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
     tp.out_cap = cap;
     tp.pass = 1;
     tp.pair_class = pb.profile ? nullptr : cd.cls;
-    if (pb.cfg.impl == 17) {
+    if (pb.cfg.impl == 17 || pb.cfg.impl == 18) {
         FillParams fp;
         memset(&fp, 0, sizeof fp);
         fp.alpha = cd.alpha;
@@ -963,7 +1065,14 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
         for (int i = 0; i < pb.dim * pb.dim; ++i)
             fp.scores[i] = (int)pb.scores[i];
         fp.one = 1;
-        launch_ckpt_trace(ctx, pb, fp, cd.trace, cd.best, cd.slots, cd.counts, 1, cig_off, cigars, cap, cd.work, cd.work_count, st);
+        fp.out_score = cd.score;
+        if (pb.cfg.impl == 18) {
+            const int rc = launch_long(ctx, pb, fp, cd.slots, cd.counts, 1, cig_off, cigars, cap, st);
+            if (rc != GNX_OK)
+                return rc;
+            ctx->launches--; // counted below
+        } else
+            launch_ckpt_trace(ctx, pb, fp, cd.trace, cd.best, cd.slots, cd.counts, 1, cig_off, cigars, cap, cd.work, cd.work_count, st);
     } else if (pb.ext)
         launch_traceback_ext(pb, cd, tp, np, st);
     else if (tp.kind == 2 && tp.layout == 3)
@@ -1053,7 +1162,19 @@ int make_plan(gnx_ctx *ctx, Problem &pb, const int64_t *aoff, const int64_t *bof
         pb.cfg.multi = false;
         pb.cfg.m_uniform = plan.max_m;
     }
-    plan.any_long = pb.cfg.multi;
+    // long pairs with traceback: tile checkpoints + recompute of the route's tiles instead of a trace matrix.  The
+    // recompute costs ~(351 + kLongR) x 320 cells per strip crossed, i.e. a fraction ~610 / min(n, m) of the pair: worth
+    // it from a couple of million cells per pair; a batch of less than two pairs per SM is latency-bound and stays on
+    // the CTA-per-pair kernel.
+    if (pb.cfg.impl == 3 && pb.cfg.multi && pb.want_cigar && pb.kind != 2 && !pb.wide && !pb.ext && pb.gap_open <= 0 &&
+        ctx->opt_long != 0 &&
+        (ctx->opt_long == 1 || (plan.cells / n_pairs >= 2000000 && n_pairs >= 2 * (int64_t)ctx->sm_count))) {
+        pb.cfg.impl = 18;
+        pb.cfg.n_uniform = plan.max_n; // geometry of the per-warp scratch
+        pb.cfg.m_uniform = plan.max_m;
+        pb.cfg.long_pool = ctx->opt_long_pool;
+    }
+    plan.any_long = pb.cfg.multi && pb.cfg.impl != 18;
     plan.bounds.push_back(0);
     if (!pb.extra_words && plan.min_n == plan.max_n && plan.min_m == plan.max_m) { // uniform batch: chunk bounds are arithmetic
         const int64_t gsz = 32 / pb.cfg.lpp; // pairs that share trace rows
@@ -1337,7 +1458,7 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
             CU(s.trace.ensure((size_t)std::max<int64_t>(acc, 1) * 4));
             CU(s.trace_off.ensure((size_t)(np + 1) * 8));
             CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
-            CU(s.slots.ensure((size_t)np * slot_cap_of(pb) * 4));
+            CU(s.slots.ensure(slots_bytes(pb, np)));
             CU(s.counts.ensure((size_t)np * 4));
             CU(s.cig_off.ensure((size_t)(np + 1) * 8));
             cd.trace = s.trace.as<uint32_t>();
@@ -1555,7 +1676,7 @@ int run_profile_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *group_cat, const
             CU(s.trace.ensure((size_t)std::max<int64_t>(acc, 1) * 4));
             CU(s.trace_off.ensure((size_t)(np + 1) * 8));
             CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, st));
-            CU(s.slots.ensure((size_t)np * slot_cap_of(pb) * 4));
+            CU(s.slots.ensure(slots_bytes(pb, np)));
             CU(s.counts.ensure((size_t)np * 4));
             CU(s.cig_off.ensure((size_t)(np + 1) * 8));
             cd.trace = s.trace.as<uint32_t>();
@@ -1679,6 +1800,7 @@ gnx_ctx *gnx_create(int device, size_t workspace_bytes)
         cudaEventCreateWithFlags(&ctx->slot[k].ev_total, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->slot[k].ev_done, cudaEventDisableTiming);
     }
+    cudaEventCreateWithFlags(&ctx->ev_long, cudaEventDisableTiming);
     if (ctx->status.ensure(64) != cudaSuccess || ctx->dr_misc.ensure(256) != cudaSuccess) {
         g_create_error = "cudaMalloc failed at context creation";
         delete ctx;
@@ -1716,6 +1838,9 @@ void gnx_destroy(gnx_ctx *ctx)
     }
     ctx->status.release();
     ctx->dr_misc.release();
+    ctx->long_scratch.release();
+    if (ctx->ev_long)
+        cudaEventDestroy(ctx->ev_long);
     DevBuf *pf[] = {&ctx->pf_cat, &ctx->pf_goff, &ctx->pf_nseq, &ctx->pf_coloff, &ctx->pf_scores, &ctx->pf_px, &ctx->pf_py,
                     &ctx->pf_aoff, &ctx->pf_boff, &ctx->pf_soff, &ctx->pf_prof, &ctx->pf_vb, &ctx->pf_smat, &ctx->pf_err};
     for (DevBuf *b : pf)
@@ -1946,7 +2071,7 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
             CU(s.trace_off.ensure((size_t)(np + 1) * 8));
             CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, st));
             CU(cudaEventRecord(s.ev_done, st));
-            CU(s.slots.ensure((size_t)np * slot_cap_of(pb) * 4));
+            CU(s.slots.ensure(slots_bytes(pb, np)));
             CU(s.counts.ensure((size_t)np * 4));
             cd.trace = s.trace.as<uint32_t>();
             cd.trace_off = s.trace_off.as<int64_t>();
@@ -2029,6 +2154,12 @@ int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
         ctx->opt_ckpt = value ? 1 : 0;
     } else if (k == "wide_cta") {
         ctx->opt_wide_cta = (int)value;
+    } else if (k == "long_ckpt") {
+        ctx->opt_long = (int)value;
+    } else if (k == "long_form") {
+        ctx->opt_long_form = (int)value;
+    } else if (k == "long_pool") {
+        ctx->opt_long_pool = value;
     } else if (k == "ctas_per_sm") {
         if (value < 1 || value > 32)
             return fail(ctx, GNX_EARG, "ctas_per_sm must be in 1..32");

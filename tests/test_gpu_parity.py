@@ -282,6 +282,71 @@ def test_long_pairs_cta_per_pair_kernel(wide):
         c.close()
 
 
+@pytest.mark.parametrize("form", [0, 1])
+def test_long_pairs_tile_checkpoint_kernel(form):
+    """affine_long_kernel (gnx_long.cuh: score-only sweep with strip-edge columns + row checkpoints, then recompute of
+    the route's tiles) forced onto ragged pairs: 1..16 strips, several row-checkpoint blocks, pairs shorter than one
+    block, N bases, empty sides, both modes, both cell formulations of the score-only pass, cigars beyond the
+    1024-entry slot (second pass) and a tie-heavy matrix."""
+    c = align.Context(0)
+    try:
+        c.set_option("long_ckpt", 1)
+        c.set_option("long_form", form)
+        rng = np.random.default_rng(9100 + form)
+        al, be = [], []
+        shapes = [(1500, 100), (1030, 321), (40, 700), (900, 640), (2000, 1281), (333, 1600), (2100, 2100), (5, 330),
+                  (1, 961), (1300, 0), (0, 1300), (64, 1990), (3000, 1000), (257, 321), (256, 640), (255, 330),
+                  (513, 5000), (5000, 513), (226, 960), (289, 322)]
+        for rep in range(3):
+            for n, m in shapes:
+                a, b = random_pair(rng, n, m, identity=float(rng.choice([0.6, 0.9, 0.97])))
+                if rep == 1 and n and m:
+                    a[rng.integers(0, n, max(1, n // 50))] = 4
+                al.append(a)
+                be.append(b)
+        for mode in (0, 1):
+            check_batch(c, al, be, orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, -600, -150, mode)
+        # cheap gaps on unrelated sequences: thousands of cigar elements per pair (slot overflow pass), ties everywhere
+        al = [rng.integers(0, 4, 4000, dtype=np.uint8) for _ in range(6)] + [np.resize(np.array([0, 1], np.uint8), 3000)]
+        be = [rng.integers(0, 4, 3900, dtype=np.uint8) for _ in range(6)] + [np.resize(np.array([1, 0, 0], np.uint8), 2800)]
+        for mode in (0, 1):
+            check_batch(c, al, be, orc.DEFAULT_SCORE_MATRIX, -20, -5, mode)
+            check_batch(c, al, be, orc.DEFAULT_SCORE_MATRIX, 0, -30, mode)
+        # a run pool too small for the batch: the pairs that find it full are re-run by the kernel's second pass
+        c.set_option("long_pool", 3000)
+        check_batch(c, al, be, orc.DEFAULT_SCORE_MATRIX, -20, -5, 0)
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("path", ["tile_checkpoint", "trace_matrix_warp", "trace_matrix_cta"])
+def test_config_c4_10kb_pairs(path):
+    """BASELINE configs[3] shape: 64 random 10 kb x 10 kb global pairs (the SURVEY 8d recipe: related with
+    substitutions and indels, 10 % unrelated whose cigars run past the 1024-entry slot) + indel-heavy pairs + the
+    reference's own 9673 x 10000 PanTro6/hg38 pair, bit-exact against the oracle on every long-pair path."""
+    c = align.Context(0)
+    try:
+        c.set_option("long_ckpt", 1 if path == "tile_checkpoint" else 0)
+        if path != "tile_checkpoint":
+            c.set_option("wide_cta", 1 if path == "trace_matrix_cta" else 0)
+        a, ao, b, bo = synth_pairs(20260104, 56, 10_000, 10_000)
+        al = [a[ao[p]:ao[p + 1]] for p in range(56)]
+        be = [b[bo[p]:bo[p + 1]] for p in range(56)]
+        rng = np.random.default_rng(4242)
+        for k in range(8):
+            x, y = random_pair(rng, 10_000 - 7 * k, 10_000 - 13 * (k % 3), identity=0.7)
+            al.append(x)
+            be.append(y)
+        g = load("cigar_to_bed")
+        big = [cs for cs in g["cases"] if len(cs["alpha"]) > 9000][0]
+        al.append(bases(big["alpha"], upper=True))
+        be.append(bases(big["beta"], upper=True))
+        sc = check_batch(c, al, be, orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, -600, -150, 0, threads=16)
+        assert int(sc[-1]) == 790738
+    finally:
+        c.close()
+
+
 def _uniform_batch(rng, P, n, m, flavour):
     al, be = [], []
     for k in range(P):

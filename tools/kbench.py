@@ -24,6 +24,7 @@ ap.add_argument("--check", action="store_true", help="diff the first --check-pai
 ap.add_argument("--check-pairs", type=int, default=5000)
 ap.add_argument("--workspace-gb", type=float, default=0)
 ap.add_argument("--cap-per-pair", type=int, default=16)
+ap.add_argument("--score-only", action="store_true")
 ap.add_argument("configs", nargs="*", default=["fill_impl=1", "fill_impl=2"])
 args = ap.parse_args()
 P = args.pairs
@@ -50,7 +51,7 @@ for cfg in args.configs:
         if kv:
             k_, v_ = kv.split("=")
             ctx.set_option(k_, int(v_))
-    for want in (False, True):
+    for want in ((False,) if args.score_only else (False, True)):
         best_fill, best_tot = 1e9, 1e9
         for it in range(4):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
