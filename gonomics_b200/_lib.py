@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgnxalign.so")
+LIB_PATH = os.environ.get("GNX_LIB") or os.path.join(_HERE, "libgnxalign.so")  # GNX_LIB: A/B builds (tools/)
 
 GNX_OK, GNX_EBASE, GNX_ECAP, GNX_ECHUNK, GNX_EEMPTY, GNX_ECUDA, GNX_EARG, GNX_ERANGE, GNX_EDIVZERO, GNX_EOFFSET, GNX_EINDEX = range(11)
 GNX_GLOBAL, GNX_FREE_END = 0, 1
@@ -26,6 +26,8 @@ EXPORTS = [
     "gnx_twobit_new", "gnx_twobit_free", "gnx_twobit_info", "gnx_twobit_download", "gnx_twobit_unpack", "gnx_twobit_get_bases",
     "gnx_twobit_count_matches", "gnx_twobit_pack_device", "gnx_seed_index_new", "gnx_seed_index_free", "gnx_seed_index_info",
     "gnx_seed_index_download", "gnx_seed_batch",
+    "gnx_multi_create", "gnx_multi_destroy", "gnx_multi_device_count", "gnx_multi_last_error", "gnx_multi_context",
+    "gnx_multi_shard_bounds", "gnx_multi_affine_batch", "gnx_multi_const_batch", "gnx_multi_copy_last_cigars",
 ]
 
 
@@ -120,5 +122,23 @@ def load() -> C.CDLL:
     L.gnx_seed_index_download.restype = ci
     L.gnx_seed_batch.argtypes = [vp, vp, u8p, i64p, i64, vp, i64p, i64]
     L.gnx_seed_batch.restype = ci
+    L.gnx_multi_create.argtypes = [vp, ci, C.c_size_t]
+    L.gnx_multi_create.restype = vp
+    L.gnx_multi_destroy.argtypes = [vp]
+    L.gnx_multi_destroy.restype = None
+    L.gnx_multi_device_count.argtypes = [vp]
+    L.gnx_multi_device_count.restype = ci
+    L.gnx_multi_last_error.argtypes = [vp]
+    L.gnx_multi_last_error.restype = C.c_char_p
+    L.gnx_multi_context.argtypes = [vp, ci]
+    L.gnx_multi_context.restype = vp
+    L.gnx_multi_shard_bounds.argtypes = [vp, i64p, i64p, i64, i64p]
+    L.gnx_multi_shard_bounds.restype = ci
+    L.gnx_multi_affine_batch.argtypes = [vp, u8p, i64p, u8p, i64p, i64, i64p, ci, i64, i64, ci, ci, i64p, cgp, i64p, i64]
+    L.gnx_multi_affine_batch.restype = ci
+    L.gnx_multi_const_batch.argtypes = [vp, u8p, i64p, u8p, i64p, i64, i64p, ci, i64, ci, i64p, cgp, i64p, i64]
+    L.gnx_multi_const_batch.restype = ci
+    L.gnx_multi_copy_last_cigars.argtypes = [vp, cgp, i64]
+    L.gnx_multi_copy_last_cigars.restype = ci
     _lib = L
     return L

@@ -299,6 +299,99 @@ def const_gap_pairs(alphas, betas, scores, gapPen, ctx: Optional[Context] = None
     return list(zip((int(x) for x in sc), _split(off, cig)))
 
 
+
+class MultiContext:
+    """gnx_multi: one context per device behind ONE call (include/gnxalign.h "several GPUs behind one call").
+    `devices` may repeat a device (two contexts on it); None = every visible device."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None, workspace_bytes: int = 0):
+        self._L = _lib.load()
+        if devices is None:
+            self._h = self._L.gnx_multi_create(None, 0, int(workspace_bytes))
+        else:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self._h = self._L.gnx_multi_create(C.cast(arr, C.c_void_p), len(devices), int(workspace_bytes))
+        if not self._h:
+            raise GnxError(_lib.GNX_ECUDA, self._L.gnx_multi_last_error(None).decode())
+        self.n_devices = int(self._L.gnx_multi_device_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gnx_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != GNX_OK:
+            raise GnxError(rc, self._L.gnx_multi_last_error(self._h).decode())
+
+    def set_option(self, name: str, value: int):
+        for k in range(self.n_devices):
+            rc = self._L.gnx_set_option(self._L.gnx_multi_context(self._h, k), name.encode(), int(value))
+            if rc != GNX_OK:
+                raise GnxError(rc, f"gnx_set_option({name})")
+
+    def shard_bounds(self, alpha_off, beta_off) -> np.ndarray:
+        alpha_off = np.ascontiguousarray(alpha_off, dtype=np.int64)
+        beta_off = np.ascontiguousarray(beta_off, dtype=np.int64)
+        out = np.zeros(self.n_devices + 1, dtype=np.int64)
+        self._check(self._L.gnx_multi_shard_bounds(self._h, _addr(alpha_off), _addr(beta_off), len(alpha_off) - 1, _addr(out)))
+        return out
+
+    def _batch(self, kind, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_open, gap_extend, want_cigar,
+               cigar_cap=None, out=None):
+        alpha_cat = np.ascontiguousarray(alpha_cat, dtype=np.uint8)
+        beta_cat = np.ascontiguousarray(beta_cat, dtype=np.uint8)
+        alpha_off = np.ascontiguousarray(alpha_off, dtype=np.int64)
+        beta_off = np.ascontiguousarray(beta_off, dtype=np.int64)
+        scores = np.ascontiguousarray(scores, dtype=np.int64)
+        dim = int(scores.shape[0])
+        n_pairs = len(alpha_off) - 1
+        if out is not None:
+            out_score, out_off, out_cig = out
+        else:
+            out_score = np.zeros(n_pairs, dtype=np.int64)
+            out_off = np.zeros(n_pairs + 1, dtype=np.int64) if want_cigar else None
+            out_cig = np.zeros(max(int(cigar_cap or 16 * n_pairs + 64), 1), dtype=CIGAR_DTYPE) if want_cigar else None
+        cap = 0 if out_cig is None else len(out_cig)
+        if kind == 2:
+            rc = self._L.gnx_multi_const_batch(self._h, _addr(alpha_cat), _addr(alpha_off), _addr(beta_cat), _addr(beta_off),
+                                               n_pairs, _addr(scores), dim, int(gap_open), int(bool(want_cigar)),
+                                               _addr(out_score), _addr(out_cig), _addr(out_off), cap)
+        else:
+            rc = self._L.gnx_multi_affine_batch(self._h, _addr(alpha_cat), _addr(alpha_off), _addr(beta_cat), _addr(beta_off),
+                                                n_pairs, _addr(scores), dim, int(gap_open), int(gap_extend),
+                                                GNX_FREE_END if kind == 1 else GNX_GLOBAL, int(bool(want_cigar)),
+                                                _addr(out_score), _addr(out_cig), _addr(out_off), cap)
+        if rc == GNX_ECAP and out is None:
+            out_cig = np.zeros(max(int(out_off[-1]), 1), dtype=CIGAR_DTYPE)
+            rc = self._L.gnx_multi_copy_last_cigars(self._h, _addr(out_cig), len(out_cig))
+        self._check(rc)
+        if want_cigar:
+            return out_score, out_off, out_cig[:int(out_off[-1])] if out is None else out_cig
+        return out_score, None, None
+
+    def affine_gap_batch(self, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_open, gap_extend,
+                         free_end_gaps=False, want_cigar=True, cigar_cap=None, out=None):
+        return self._batch(1 if free_end_gaps else 0, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_open,
+                           gap_extend, want_cigar, cigar_cap, out)
+
+    def const_gap_batch(self, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_pen, want_cigar=True,
+                        cigar_cap=None, out=None):
+        return self._batch(2, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_pen, 0, want_cigar, cigar_cap, out)
+
+
 # ---- the reference's single-pair API -------------------------------------------------------
 def AffineGap_highMem(alpha, beta, scores, gapOpen, gapExtend, ctx=None):
     """align.AffineGap_highMem (align/affineGap_highMem.go:99)."""
@@ -316,19 +409,32 @@ def _require_nonempty(alpha, beta, what):
         raise GnxError(_lib.GNX_EEMPTY, f"{what}: empty sequence (undefined in the reference)")
 
 
-def AffineGap_customizeCheckersize(alpha, beta, scores, gapOpen, gapExtend, checkersize_i, checkersize_j, ctx=None):
+def _require_one_board(alpha, beta, checkersize_i, checkersize_j, multi_board, what):
+    """For inputs that fit one checkerboard the low-memory drivers equal the high-memory result (SURVEY.md 8a:
+    verified on 4075 random cases).  Past one board the reference's stitching has defects (cigars differ from
+    highMem in ~11 % of random cases and can be invalid) that this library does not reproduce: the caller has to
+    ask for the high-memory alignment explicitly instead of getting a silently different answer."""
+    if (len(alpha) > checkersize_i or len(beta) > checkersize_j) and multi_board != "highmem":
+        raise GnxError(_lib.GNX_EARG,
+                       f"{what}: {len(alpha)} x {len(beta)} spans more than one {checkersize_i} x {checkersize_j} "
+                       "checkerboard; the reference's multi-board stitching is not reproduced -- pass "
+                       "multi_board='highmem' (or call the _highMem function) for the high-memory alignment")
+
+
+def AffineGap_customizeCheckersize(alpha, beta, scores, gapOpen, gapExtend, checkersize_i, checkersize_j, ctx=None,
+                                   multi_board=None):
     """align.AffineGap_customizeCheckersize (align/affineGap.go:73).
 
-    The checkerboard is the reference's memory-saving device, not part of the result for inputs that
-    fit one board; for longer inputs this returns the AffineGap_highMem alignment (DESIGN.md,
-    "multi-board divergence")."""
+    The checkerboard is the reference's memory-saving device, not part of the result for inputs that fit one
+    board.  Longer inputs are an explicit error unless multi_board='highmem' (see _require_one_board)."""
     _require_nonempty(alpha, beta, "AffineGap_customizeCheckersize")
+    _require_one_board(alpha, beta, checkersize_i, checkersize_j, multi_board, "AffineGap_customizeCheckersize")
     return affine_gap_pairs([alpha], [beta], scores, gapOpen, gapExtend, False, ctx)[0]
 
 
-def AffineGap(alpha, beta, scores, gapOpen, gapExtend, ctx=None):
+def AffineGap(alpha, beta, scores, gapOpen, gapExtend, ctx=None, multi_board=None):
     """align.AffineGap (align/affineGap.go:59): checker size 10000 x 10000."""
-    return AffineGap_customizeCheckersize(alpha, beta, scores, gapOpen, gapExtend, 10000, 10000, ctx)
+    return AffineGap_customizeCheckersize(alpha, beta, scores, gapOpen, gapExtend, 10000, 10000, ctx, multi_board)
 
 
 def ConstGap_highMem(alpha, beta, scores, gapPen, ctx=None):
@@ -336,15 +442,16 @@ def ConstGap_highMem(alpha, beta, scores, gapPen, ctx=None):
     return const_gap_pairs([alpha], [beta], scores, gapPen, ctx)[0]
 
 
-def ConstGap_customizeCheckersize(alpha, beta, scores, gapPen, checkersize_i, checkersize_j, ctx=None):
-    """align.ConstGap_customizeCheckersize (align/constGap.go:73)."""
+def ConstGap_customizeCheckersize(alpha, beta, scores, gapPen, checkersize_i, checkersize_j, ctx=None, multi_board=None):
+    """align.ConstGap_customizeCheckersize (align/constGap.go:73); multi-board inputs: see _require_one_board."""
     _require_nonempty(alpha, beta, "ConstGap_customizeCheckersize")
+    _require_one_board(alpha, beta, checkersize_i, checkersize_j, multi_board, "ConstGap_customizeCheckersize")
     return const_gap_pairs([alpha], [beta], scores, gapPen, ctx)[0]
 
 
-def ConstGap(alpha, beta, scores, gapPen, ctx=None):
+def ConstGap(alpha, beta, scores, gapPen, ctx=None, multi_board=None):
     """align.ConstGap (align/constGap.go:13)."""
-    return ConstGap_customizeCheckersize(alpha, beta, scores, gapPen, 10000, 10000, ctx)
+    return ConstGap_customizeCheckersize(alpha, beta, scores, gapPen, 10000, 10000, ctx, multi_board)
 
 
 def AffineGapChunk(alpha, beta, scores, gapOpen, gapExtend, chunkSize, ctx=None):
@@ -480,7 +587,9 @@ def GoAffineGapLocalEngine(scores, gapOpen, gapExtend, max_batch: int = 1 << 16,
     Returns (inputs, outputs) queues (the Go channels, capacity 1000).  A worker thread drains
     whatever is queued (up to max_batch pairs), aligns it as ONE GPU batch with AffineGapLocal
     semantics and emits results in input order (FIFO, as the single reference goroutine does).
-    Put `engine_close` (or call inputs.close()) to end the stream; outputs then yields None."""
+    Put `engine_close` (or call inputs.close()) to end the stream; outputs then yields None.  If a batch fails
+    (e.g. GNX_EBASE: the reference goroutine would panic), the exception object is put on `outputs` in place of
+    that batch's results, the stream is closed (None) and the worker ends -- consumers never block forever."""
     inputs: "queue.Queue" = queue.Queue(maxsize=1000)
     outputs: "queue.Queue" = queue.Queue(maxsize=1000)
 
@@ -508,8 +617,10 @@ def GoAffineGapLocalEngine(scores, gapOpen, gapExtend, max_batch: int = 1 << 16,
                     for p, (s, c) in zip(batch, res):
                         p.Score, p.Cigar = s, c
                         outputs.put(p)
-            outputs.put(None)  # close(outputs)
+        except BaseException as exc:  # noqa: BLE001 -- forwarded to the consumer, never swallowed
+            outputs.put(exc)
         finally:
+            outputs.put(None)  # close(outputs), on success and on failure alike
             ctx.close()
 
     threading.Thread(target=worker, daemon=True).start()

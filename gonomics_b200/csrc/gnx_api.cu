@@ -17,6 +17,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -103,6 +104,7 @@ struct Slot {
     // chunk in flight
     int64_t begin = 0, end = 0;
     bool busy = false;
+    bool ev_done_set = false; // ev_done has been recorded: h_trace_off may still be the source of a pending upload
 };
 
 struct FillEvent {
@@ -120,6 +122,10 @@ struct gnx_ctx {
     DevBuf dr_misc;      // device-resident path scratch (running total, counters)
     // long-pair checkpoint path (gnx_long.cuh): per-warp scratch shared by the slots (its launches are chained on
     // ev_long, so at most one of them runs at a time) + a ring of work counters in its first 256 bytes
+    // gnx_batch_device calls share slot[0]'s scratch and the status / running-total words: each call is ordered
+    // after the previous one on this context (ev_dev, recorded at the end of every call), whatever stream it uses
+    cudaEvent_t ev_dev = nullptr;
+    bool ev_dev_set = false;
     DevBuf long_scratch;
     cudaEvent_t ev_long = nullptr;
     bool ev_long_set = false;
@@ -441,7 +447,7 @@ void dispatch_fill_cl(const Problem &pb, const FillParams &fp, int grid, cudaStr
 template <int C, int LPP, int MODE, bool FREE, bool MULTI, int SK>
 void launch_fill3_sk(const FillParams &fp, int64_t groups, int sm_count, int ctas_per_sm, cudaStream_t st)
 {
-    static int occ = 0; // per instantiation
+    static std::atomic<int> occ{0}; // per instantiation; contexts on different threads may race to fill it
     if (occ == 0) {
         int o = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_fill3_kernel<C, LPP, MODE, FREE, MULTI, SK>, 32,
@@ -449,7 +455,7 @@ void launch_fill3_sk(const FillParams &fp, int64_t groups, int sm_count, int cta
             o = 8;
         occ = o;
     }
-    const int grid = (int)std::min<int64_t>(groups, (int64_t)sm_count * std::min(occ, ctas_per_sm));
+    const int grid = (int)std::min<int64_t>(groups, (int64_t)sm_count * std::min(occ.load(), ctas_per_sm));
     affine_fill3_kernel<C, LPP, MODE, FREE, MULTI, SK><<<grid, 32, 0, st>>>(fp);
 }
 
@@ -484,14 +490,14 @@ void dispatch_fill3_t(const Problem &pb, const FillParams &fp, int64_t groups, i
 template <bool FREE, int CM>
 void launch_fill16(const FillParams &fp, int64_t quads, int sm_count, int ctas_per_sm, cudaStream_t st)
 {
-    static int occ = 0; // per instantiation
+    static std::atomic<int> occ{0}; // per instantiation; contexts on different threads may race to fill it
     if (occ == 0) {
         int o = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_fill16_kernel<FREE, CM>, 32, 0) != cudaSuccess || o < 1)
             o = 8;
         occ = o;
     }
-    const int grid = (int)std::min<int64_t>(quads, (int64_t)sm_count * std::min(occ, ctas_per_sm));
+    const int grid = (int)std::min<int64_t>(quads, (int64_t)sm_count * std::min(occ.load(), ctas_per_sm));
     affine_fill16_kernel<FREE, CM><<<grid, 32, 0, st>>>(fp);
 }
 
@@ -500,14 +506,14 @@ inline int64_t ckpt_quad_words(int64_t n) { return ((n + 16 - 2) / kCkK) * kCkRe
 template <int CM>
 void launch_fill16_ckpt_t(const FillParams &fp, int64_t quads, int sm_count, int ctas_per_sm, cudaStream_t st)
 {
-    static int occ = 0;
+    static std::atomic<int> occ{0};
     if (occ == 0) {
         int o = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_fill16_kernel<true, CM, true>, 32, 0) != cudaSuccess || o < 1)
             o = 8;
         occ = o;
     }
-    const int grid = (int)std::min<int64_t>(quads, (int64_t)sm_count * std::min(occ, ctas_per_sm));
+    const int grid = (int)std::min<int64_t>(quads, (int64_t)sm_count * std::min(occ.load(), ctas_per_sm));
     affine_fill16_kernel<true, CM, true><<<grid, 32, 0, st>>>(fp);
 }
 
@@ -532,7 +538,7 @@ void launch_ckpt_trace(gnx_ctx *ctx, const Problem &pb, const FillParams &fp, co
                        uint32_t *slots, int *counts, int pass, const int64_t *cig_off, gnx_cigar *cigars, int64_t cap,
                        int *work, int *work_count, cudaStream_t st)
 {
-    static int occ = 0;
+    static std::atomic<int> occ{0};
     if (occ == 0) {
         int o = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_ckpt_trace_kernel, 32, 0) != cudaSuccess || o < 1)
@@ -561,7 +567,7 @@ void launch_ckpt_trace(gnx_ctx *ctx, const Problem &pb, const FillParams &fp, co
         ctx->launches++;
     }
     const int64_t units = ((np + 3) / 4) * 2;
-    const int grid = (int)std::min<int64_t>(units, (int64_t)ctx->sm_count * occ);
+    const int grid = (int)std::min<int64_t>(units, (int64_t)ctx->sm_count * occ.load());
     affine_ckpt_trace_kernel<<<grid, 32, 0, st>>>(fp, q);
 }
 
@@ -587,7 +593,7 @@ template <int MODE, bool FREE>
 void launch_fill3w(const FillParams &fp, int64_t np, int sm_count, cudaStream_t st)
 {
     constexpr int NW = 4;
-    static int occ = 0;
+    static std::atomic<int> occ{0};
     if (occ == 0) {
         int o = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_fill3w_kernel<10, MODE, FREE, NW>, 32 * NW, 0) != cudaSuccess ||
@@ -595,7 +601,7 @@ void launch_fill3w(const FillParams &fp, int64_t np, int sm_count, cudaStream_t 
             o = 2;
         occ = o;
     }
-    const int grid = (int)std::min<int64_t>(np, (int64_t)sm_count * occ);
+    const int grid = (int)std::min<int64_t>(np, (int64_t)sm_count * occ.load());
     affine_fill3w_kernel<10, MODE, FREE, NW><<<grid, 32 * NW, 0, st>>>(fp);
 }
 
@@ -622,7 +628,7 @@ void dispatch_fill3w(const Problem &pb, const FillParams &fp, int64_t np, int sm
 template <int LPP, bool STORE, bool MULTI, int EXT>
 void launch_const3(const FillParams &fp, int64_t groups, int sms, int cps, cudaStream_t st)
 {
-    static int occ = 0;
+    static std::atomic<int> occ{0};
     if (occ == 0) {
         int o = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, const_fill3_kernel<10, LPP, STORE, MULTI, EXT>, 32, 0) !=
@@ -630,7 +636,7 @@ void launch_const3(const FillParams &fp, int64_t groups, int sms, int cps, cudaS
             o = 8;
         occ = o;
     }
-    const int grid = (int)std::min<int64_t>(groups, (int64_t)sms * std::min(occ, cps));
+    const int grid = (int)std::min<int64_t>(groups, (int64_t)sms * std::min(occ.load(), cps));
     const_fill3_kernel<10, LPP, STORE, MULTI, EXT><<<grid, 32, 0, st>>>(fp);
 }
 
@@ -707,7 +713,7 @@ void dispatch_fill(const Problem &pb, const FillParams &fp, int C, int lookup, i
 template <bool FREE, int FORM>
 int launch_long_t(gnx_ctx *ctx, const Problem &pb, const FillParams &fp, LongParams q, cudaStream_t st)
 {
-    static int occ = 0;
+    static std::atomic<int> occ{0};
     if (occ == 0) {
         int o = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_long_kernel<FREE, FORM>, 32, 0) != cudaSuccess || o < 1)
@@ -716,7 +722,7 @@ int launch_long_t(gnx_ctx *ctx, const Problem &pb, const FillParams &fp, LongPar
     }
     const LongGeom g = long_geom(pb.cfg.n_uniform, pb.cfg.m_uniform);
     const int64_t np = fp.pair_end - fp.pair_begin;
-    int64_t grid = std::min<int64_t>(np, (int64_t)ctx->sm_count * std::min(occ, ctx->opt_ctas_per_sm));
+    int64_t grid = std::min<int64_t>(np, (int64_t)ctx->sm_count * std::min(occ.load(), ctx->opt_ctas_per_sm));
     const int64_t fit = ((int64_t)ctx->workspace - 256) / g.cta_stride;
     if (fit < 1)
         return fail(ctx, GNX_ERANGE, "one long pair's checkpoints exceed the context workspace");
@@ -1801,6 +1807,7 @@ gnx_ctx *gnx_create(int device, size_t workspace_bytes)
         cudaEventCreateWithFlags(&ctx->slot[k].ev_done, cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&ctx->ev_long, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_dev, cudaEventDisableTiming);
     if (ctx->status.ensure(64) != cudaSuccess || ctx->dr_misc.ensure(256) != cudaSuccess) {
         g_create_error = "cudaMalloc failed at context creation";
         delete ctx;
@@ -1841,6 +1848,8 @@ void gnx_destroy(gnx_ctx *ctx)
     ctx->long_scratch.release();
     if (ctx->ev_long)
         cudaEventDestroy(ctx->ev_long);
+    if (ctx->ev_dev)
+        cudaEventDestroy(ctx->ev_dev);
     DevBuf *pf[] = {&ctx->pf_cat, &ctx->pf_goff, &ctx->pf_nseq, &ctx->pf_coloff, &ctx->pf_scores, &ctx->pf_px, &ctx->pf_py,
                     &ctx->pf_aoff, &ctx->pf_boff, &ctx->pf_soff, &ctx->pf_prof, &ctx->pf_vb, &ctx->pf_smat, &ctx->pf_err};
     for (DevBuf *b : pf)
@@ -2034,6 +2043,8 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
     Slot &s = ctx->slot[0];
     const int nwarps_total = ctx->sm_count * std::max(ctx->opt_blocks_per_sm * 4, ctx->opt_ctas_per_sm);
     const int64_t edge_stride = plan.max_n + 2;
+    if (ctx->ev_dev_set) // the previous call's kernels still own the slot scratch, status and running-total words
+        CU(cudaStreamWaitEvent(st, ctx->ev_dev, 0));
     CU(cudaMemsetAsync(ctx->status.p, 0, sizeof(int), st));
     CU(cudaMemsetAsync(ctx->dr_misc.p, 0, 16, st)); // running cigar total (two ping-pong words)
     const int64_t n_chunks = (int64_t)plan.bounds.size() - 1;
@@ -2053,8 +2064,9 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
         cd.b_lo = beta_off_host[begin];
         cd.b_hi = beta_off_host[end];
         if (pb.want_cigar) {
-            // pinned staging is reused by the next chunk's host writes: fence on the previous upload
-            if (ci > 0)
+            // the pinned staging is about to be rewritten by the host: fence on the upload that last read it -- the
+            // previous chunk's, or the last chunk's of an earlier call that may still be queued behind other work
+            if (s.ev_done_set)
                 CU(cudaEventSynchronize(s.ev_done));
             CU(s.h_trace_off.ensure((size_t)(np + 1) * 8));
             int64_t *to = s.h_trace_off.as<int64_t>();
@@ -2071,6 +2083,7 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
             CU(s.trace_off.ensure((size_t)(np + 1) * 8));
             CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, st));
             CU(cudaEventRecord(s.ev_done, st));
+            s.ev_done_set = true;
             CU(s.slots.ensure(slots_bytes(pb, np)));
             CU(s.counts.ensure((size_t)np * 4));
             cd.trace = s.trace.as<uint32_t>();
@@ -2099,6 +2112,8 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
     }
     if (d_status)
         CU(cudaMemcpyAsync(d_status, ctx->status.p, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    CU(cudaEventRecord(ctx->ev_dev, st));
+    ctx->ev_dev_set = true;
     return GNX_OK;
 }
 
@@ -2177,3 +2192,4 @@ int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
 } // extern "C"
 
 #include "gnx_twobit_api.inl"
+#include "gnx_multi.inl"

@@ -69,8 +69,11 @@ struct LongParams {
 //         instructions per cell.
 // FORM 1: X = max(M, D) + O + E first (independent of I), then I' = max(I + E, X): ONE dependent instruction per
 //         cell on the chain; H + O + E = max(I + O + E, X).  4 ALU + 2 FMA; H is carried as H + O + E.
+#ifndef GNX_LONG_MINB
+#define GNX_LONG_MINB 20 // 96 registers, no spills: 2594 vs 2517 GCUPS at 16 (24: no further gain), profiles/r02d
+#endif
 template <bool FREE, int FORM>
-__global__ void __launch_bounds__(32, FREE ? 12 : 16) affine_long_kernel(const FillParams P, const LongParams Q)
+__global__ void __launch_bounds__(32, FREE ? 12 : GNX_LONG_MINB) affine_long_kernel(const FillParams P, const LongParams Q)
 {
     constexpr int C = 10, R = kLongR;
     constexpr unsigned FULL = 0xffffffffu;

@@ -227,13 +227,47 @@ int gnx_copy_last_cigars(gnx_ctx *ctx, gnx_cigar *out_cigar, int64_t cigar_cap);
  * read offsets back.  kind: 0 affine global, 1 affine free-end, 2 const gap (gap_open = penalty).
  * d_out_cigar_off (n_pairs+1) and d_out_cigar (cigar_cap entries) may be NULL when want_cigar=0.
  * d_status (one int32, may be NULL) receives a GNX_E* code discovered on the device
- * (GNX_EBASE, GNX_ECAP). */
+ * (GNX_EBASE, GNX_ECAP).
+ * Ordering: successive calls on one context share its scratch, so the library orders each call after the
+ * previous one (an event wait on `cuda_stream`), whatever streams they use; device buffers growing between
+ * calls (cudaFree) synchronise the device.  Calls on DIFFERENT contexts are independent.  The host-buffer
+ * entry points must not run concurrently with a device-resident call on the same context. */
 int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const int64_t *d_alpha_off,
                      const uint8_t *d_beta_cat, const int64_t *d_beta_off,
                      const int64_t *alpha_off_host, const int64_t *beta_off_host, int64_t n_pairs,
                      const int64_t *scores, int dim, int64_t gap_open, int64_t gap_extend,
                      int want_cigar, int64_t *d_out_score, gnx_cigar *d_out_cigar,
                      int64_t *d_out_cigar_off, int64_t cigar_cap, int32_t *d_status, void *cuda_stream);
+
+/* ---- several GPUs behind one call --------------------------------------------------- *
+ * A gnx_multi owns one context per listed device.  A batch is cut into contiguous shards balanced by DP
+ * cells (sum of n*m), shard r runs on device r from its own host thread, scores land directly in the
+ * caller's array and the cigars are stitched into the caller's buffer in pair order: the result is
+ * identical to the single-device call (same arguments, same error codes -- when several shards fail, the
+ * one holding the lowest pair indices reports).  There is no data-path collective: pairs are independent.
+ * This is what a Go process binds to use a whole box from ONE cgo call (align.AffineGap batches of
+ * cmd/gsw-style callers); `devices` may list a device more than once (two contexts on it).
+ *   gnx_multi_create      devices == NULL or n_devices <= 0: every visible device.  workspace: per device,
+ *                         0 = the default of gnx_create.
+ *   gnx_multi_shard_bounds  the n_devices + 1 pair indices a call with these offsets would cut at.
+ *   gnx_multi_context     the context of shard `index` (options, statistics); owned by the gnx_multi. */
+typedef struct gnx_multi gnx_multi;
+gnx_multi *gnx_multi_create(const int *devices, int n_devices, size_t workspace_bytes_per_device);
+void gnx_multi_destroy(gnx_multi *mg);
+int gnx_multi_device_count(const gnx_multi *mg);
+const char *gnx_multi_last_error(gnx_multi *mg); /* mg may be NULL: error of the last failed gnx_multi_create */
+gnx_ctx *gnx_multi_context(gnx_multi *mg, int index);
+int gnx_multi_shard_bounds(const gnx_multi *mg, const int64_t *alpha_off, const int64_t *beta_off, int64_t n_pairs,
+                           int64_t *out_bounds);
+int gnx_multi_affine_batch(gnx_multi *mg, const uint8_t *alpha_cat, const int64_t *alpha_off, const uint8_t *beta_cat,
+                           const int64_t *beta_off, int64_t n_pairs, const int64_t *scores, int dim, int64_t gap_open,
+                           int64_t gap_extend, int mode, int want_cigar, int64_t *out_score, gnx_cigar *out_cigar,
+                           int64_t *out_cigar_off, int64_t cigar_cap);
+int gnx_multi_const_batch(gnx_multi *mg, const uint8_t *alpha_cat, const int64_t *alpha_off, const uint8_t *beta_cat,
+                          const int64_t *beta_off, int64_t n_pairs, const int64_t *scores, int dim, int64_t gap_pen,
+                          int want_cigar, int64_t *out_score, gnx_cigar *out_cigar, int64_t *out_cigar_off,
+                          int64_t cigar_cap);
+int gnx_multi_copy_last_cigars(gnx_multi *mg, gnx_cigar *out_cigar, int64_t cigar_cap);
 
 /* ---- introspection (used by bench.py / tests) ------------------------------------------------ */
 /* Kernel launches issued by this context since creation (every launch of a libgnxalign kernel). */

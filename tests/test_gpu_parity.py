@@ -57,8 +57,14 @@ def test_golden_affine_global(ctx):
         _, cig = align.AffineGap_highMem(a, b, S, g["gap_open"], g["gap_extend"], ctx)
         assert align.View(a, b, cig) == c["view"]
         _, cig2 = align.AffineGap(a, b, S, g["gap_open"], g["gap_extend"], ctx)
-        _, cig3 = align.AffineGap_customizeCheckersize(a, b, S, g["gap_open"], g["gap_extend"], 3, 3, ctx)
+        # TestAffineGap_lowMem (affineGap_test.go:57-81) asserts lowMem == highMem on these vectors with a 3 x 3 checker;
+        # the multi-board driver itself is not reproduced: without the explicit opt-in the call is an error
+        _, cig3 = align.AffineGap_customizeCheckersize(a, b, S, g["gap_open"], g["gap_extend"], 3, 3, ctx,
+                                                       multi_board="highmem")
         assert cig2 == cig and cig3 == cig
+        if len(a) > 3 or len(b) > 3:
+            with pytest.raises(_lib.GnxError):
+                align.AffineGap_customizeCheckersize(a, b, S, g["gap_open"], g["gap_extend"], 3, 3, ctx)
 
 
 def test_golden_affine_local(ctx):
@@ -154,6 +160,78 @@ def test_engine_fifo(ctx):
         assert (r.Score, align.PrintCigar(r.Cigar)) == (c["score"], c["cigar"])
     inputs.close()
     assert outputs.get(timeout=120) is None
+
+
+def test_engine_forwards_errors_and_closes():
+    """A failing batch (a base >= dim: the reference goroutine would panic) must not leave consumers blocked: the
+    error comes out of `outputs`, followed by the close sentinel."""
+    inputs, outputs = align.GoAffineGapLocalEngine(MATRICES["Default"], -600, -150)
+    inputs.put(align.TargetQueryPair(np.array([0, 1, 9, 3], dtype=np.uint8), np.array([0, 1, 2], dtype=np.uint8)))
+    r = outputs.get(timeout=120)
+    assert isinstance(r, _lib.GnxError) and r.code == _lib.GNX_EBASE
+    assert outputs.get(timeout=120) is None
+
+
+# ---- several GPUs behind one C call (gnx_multi_*) ---------------------------------------------
+def _multi_devices(k):
+    import ctypes as C
+    n = _lib.load().gnx_device_count()
+    return [d % max(n, 1) for d in range(k)]  # fewer GPUs than shards: several contexts share a device
+
+
+@pytest.mark.parametrize("shards", [2, 3])
+def test_multi_gpu_abi_matches_single_device(ctx, shards):
+    """gnx_multi_affine_batch / gnx_multi_const_batch: contiguous cell-balanced shards on one context per device
+    (the same device repeated when the box has fewer), results stitched in pair order == the oracle, for ragged
+    batches, both modes, with and without cigars, tiny staging (GNX_ECAP inside a shard) and a too-small caller
+    buffer (GNX_ECAP + gnx_multi_copy_last_cigars)."""
+    rng = np.random.default_rng(77 + shards)
+    al, be = [], []
+    for k in range(997):
+        n, m = int(rng.integers(0, 400)), int(rng.integers(0, 200))
+        a, b = random_pair(rng, n, m, identity=float(rng.choice([0.7, 0.9, 1.0])))
+        al.append(a)
+        be.append(b)
+    al.append(rng.integers(0, 4, 3000, dtype=np.uint8))  # one heavy pair at the end: unbalanced cuts
+    be.append(rng.integers(0, 4, 2500, dtype=np.uint8))
+    ac, ao = concat(al)
+    bc, bo = concat(be)
+    S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX
+    with align.MultiContext(_multi_devices(shards)) as mc:
+        assert mc.n_devices == shards
+        cuts = mc.shard_bounds(ao, bo)
+        from gonomics_b200 import shard as shard_mod
+        assert [(int(cuts[r]), int(cuts[r + 1])) for r in range(shards)] == shard_mod.shard_bounds(ao, bo, shards)
+        for mode in (0, 1, 2):
+            O = -600 if mode != 2 else -430
+            osc, ooff, ocig = orc.batch(ac, ao, bc, bo, S, O, -150, mode, True, 8)
+            if mode == 2:
+                sc, off, cig = mc.const_gap_batch(ac, ao, bc, bo, S, O, True)
+                sc0, _, _ = mc.const_gap_batch(ac, ao, bc, bo, S, O, False)
+            else:
+                sc, off, cig = mc.affine_gap_batch(ac, ao, bc, bo, S, O, -150, mode == 1, True)
+                sc0, _, _ = mc.affine_gap_batch(ac, ao, bc, bo, S, O, -150, mode == 1, False)
+            assert np.array_equal(sc, osc) and np.array_equal(sc0, osc) and np.array_equal(off, ooff)
+            assert np.array_equal(cig["run_length"], ocig["run_length"]) and np.array_equal(cig["op"], ocig["op"])
+        # caller buffer too small: GNX_ECAP with scores and offsets filled, cigars fetched afterwards
+        osc, ooff, ocig = orc.batch(ac, ao, bc, bo, S, -600, -150, 0, True, 8)
+        out = (np.zeros(len(al), np.int64), np.zeros(len(al) + 1, np.int64), np.zeros(5, _lib.CIGAR_DTYPE))
+        with pytest.raises(_lib.GnxError) as ei:
+            mc.affine_gap_batch(ac, ao, bc, bo, S, -600, -150, False, True, out=out)
+        assert ei.value.code == _lib.GNX_ECAP and np.array_equal(out[0], osc) and np.array_equal(out[1], ooff)
+        big = np.zeros(int(out[1][-1]), dtype=_lib.CIGAR_DTYPE)
+        assert mc._L.gnx_multi_copy_last_cigars(mc._h, big.ctypes.data, len(big)) == 0
+        assert np.array_equal(big["run_length"], ocig["run_length"]) and np.array_equal(big["op"], ocig["op"])
+        # an invalid base in the second shard is reported like the single-device call reports it
+        bad = ac.copy()
+        bad[ao[len(al) - 2] + 1] = 9
+        with pytest.raises(_lib.GnxError) as ei:
+            mc.affine_gap_batch(bad, ao, bc, bo, S, -600, -150, False, True)
+        assert ei.value.code == _lib.GNX_EBASE
+        # empty batch
+        sc, off, cig = mc.affine_gap_batch(np.zeros(0, np.uint8), np.zeros(1, np.int64), np.zeros(0, np.uint8),
+                                           np.zeros(1, np.int64), S, -600, -150, False, True)
+        assert len(sc) == 0 and list(off) == [0]
 
 
 # ---- randomised differential tests -----------------------------------------------------------
