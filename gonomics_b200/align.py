@@ -152,6 +152,41 @@ class Context:
         return self._batch(1 if free_end_gaps else 0, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_open,
                            gap_extend, want_cigar, cigar_cap, out)
 
+    def affine_gap_batch_twobit(self, alpha_words, alpha_len, beta_words, beta_len, scores, gap_open, gap_extend,
+                                free_end_gaps=False, want_cigar=True, cigar_cap=None, out=None, n_pairs=None):
+        """gnx_affine_batch_twobit: the batch in dnaTwoBit form (uint64 words, tightly packed).  alpha_len / beta_len are
+        int64 arrays (one TwoBit.Len per pair) or plain ints for a uniform batch (then n_pairs must be given)."""
+        alpha_words = np.ascontiguousarray(alpha_words, dtype=np.uint64)
+        beta_words = np.ascontiguousarray(beta_words, dtype=np.uint64)
+        scores = np.ascontiguousarray(scores, dtype=np.int64)
+        uniform = np.isscalar(alpha_len)
+        if uniform:
+            assert np.isscalar(beta_len) and n_pairs is not None
+            la = lb = None
+            ua, ub = int(alpha_len), int(beta_len)
+        else:
+            la = np.ascontiguousarray(alpha_len, dtype=np.int64)
+            lb = np.ascontiguousarray(beta_len, dtype=np.int64)
+            n_pairs, ua, ub = len(la), 0, 0
+        if out is not None:
+            out_score, out_off, out_cig = out
+        else:
+            out_score = np.zeros(n_pairs, dtype=np.int64)
+            out_off = np.zeros(n_pairs + 1, dtype=np.int64) if want_cigar else None
+            out_cig = np.zeros(max(int(cigar_cap or 16 * n_pairs + 64), 1), dtype=CIGAR_DTYPE) if want_cigar else None
+        cap = 0 if out_cig is None else len(out_cig)
+        rc = self._L.gnx_affine_batch_twobit(self._h, _addr(alpha_words), _addr(la), ua, _addr(beta_words), _addr(lb), ub,
+                                             n_pairs, _addr(scores), int(scores.shape[0]), int(gap_open), int(gap_extend),
+                                             GNX_FREE_END if free_end_gaps else GNX_GLOBAL, int(bool(want_cigar)),
+                                             _addr(out_score), _addr(out_cig), _addr(out_off), cap)
+        if rc == GNX_ECAP and out is None:
+            out_cig = np.zeros(max(int(out_off[-1]), 1), dtype=CIGAR_DTYPE)
+            rc = self._L.gnx_copy_last_cigars(self._h, _addr(out_cig), len(out_cig))
+        self._check(rc)
+        if want_cigar:
+            return out_score, out_off, out_cig[:int(out_off[-1])] if out is None else out_cig
+        return out_score, None, None
+
     def affine_gap_chunk_batch(self, alpha_cat, alpha_off, beta_cat, beta_off, scores, gap_open, gap_extend, chunk,
                                cigar_cap=None):
         """Batched AffineGapChunk (align/affineGap_highMem.go:227): DP over chunk-sized blocks."""

@@ -100,7 +100,8 @@ struct Slot {
     DevBuf alpha, beta, aoff, boff, cls, trace, trace_off, slots, counts, score, cig_off, cigars, edge, misc, partials;
     DevBuf best, endi, endj; // gsw extend step: first-maximum cell (right) and the traceback's end coordinates
     DevBuf work;             // checkpoint path: work list of the pairs that need the recompute walk (+ its counter)
-    PinBuf h_stage_a, h_stage_b, h_total, h_trace_off, h_score, h_off, h_cig, h_endi, h_endj;
+    DevBuf tb_a, tb_b, tb_meta; // 2-bit inputs: the chunk's packed words (+ word offsets / lengths of ragged chunks)
+    PinBuf h_stage_a, h_stage_b, h_total, h_trace_off, h_score, h_off, h_cig, h_endi, h_endj, h_tbmeta;
     // chunk in flight
     int64_t begin = 0, end = 0;
     bool busy = false;
@@ -147,6 +148,7 @@ struct gnx_ctx {
     int opt_force_lookup = -1; // -1 auto; 0/1 force the PRMT / shared-memory score lookup for ACGT pairs
     int opt_ckpt = 1;          // allow the checkpoint-and-recompute traceback for uniform freeEndGaps batches
     int opt_wide_cta = -1;     // -1 auto; 0/1 never / always run multi-strip pairs on the 4-warp CTA-per-pair kernel
+    int opt_tb_tma = 1;        // 2-bit inputs: 1 = fill16 kernels read the packed words (TMA), 0 = always unpack to bytes first
     int opt_long = -1;         // -1 auto; 0/1 never / always run multi-strip traceback batches on the tile-checkpoint kernel
     int opt_long_form = 0;     // cell formulation of its score-only pass (gnx_long.cuh FORM)
     int64_t opt_long_pool = 0; // its run-pool entries per chunk (0 = auto; tests shrink it to force the re-run pass)
@@ -156,6 +158,10 @@ struct gnx_ctx {
     size_t fill_events_used = 0;
     double last_fill_ms = 0;
     int64_t last_fill_launches = 0, last_cells = 0;
+    // 2-bit entry points: host-side offset arrays derived from the lengths (byte offsets a/b, word offsets a/b), kept
+    // between calls with the same uniform shape (a streaming caller's batches) so that they are built once
+    std::vector<int64_t> tb_off[4];
+    int64_t tb_key[3] = {-1, -1, -1}; // n_pairs, n, m of the cached uniform arrays
     // cigars retained after GNX_ECAP
     std::vector<gnx_cigar> retained;
     bool have_retained = false;
@@ -192,6 +198,7 @@ struct FillCfg {
     int64_t m_uniform = 0; // fill16: the batch's (uniform) query length
     int64_t n_uniform = 0; // checkpoint path: the batch's (uniform) target length
     int64_t long_pool = 0; // impl 18: run-pool entries per chunk (0 = long_pool_entries())
+    bool tb = false;       // impl 16 / 17 on 2-bit inputs: affine_fill16_kernel<TB> stages the packed words by TMA
 };
 
 struct Problem {
@@ -207,6 +214,7 @@ struct Problem {
     int64_t chunk = 1; // AffineGapChunk: bases per DP cell
     bool wide = false; // int64 plane values (the int32 range proof failed)
     int ext = 0;       // gsw extend step on the const-gap machinery (kind 2): 1 LeftDynamicAln, 2 RightDynamicAln
+    bool twobit = false;                // the caller's sequences are dnaTwoBit words (gnx_*_twobit entry points)
     bool profile = false;               // match scores come from a dense per-pair matrix (gnx_profile.cuh)
     const int64_t *extra_words = nullptr; // profile: per-pair workspace words besides the trace (the S matrix)
 };
@@ -487,50 +495,61 @@ void dispatch_fill3_t(const Problem &pb, const FillParams &fp, int64_t groups, i
     }
 }
 
-template <bool FREE, int CM>
+template <bool FREE, int CM, bool TB = false>
 void launch_fill16(const FillParams &fp, int64_t quads, int sm_count, int ctas_per_sm, cudaStream_t st)
 {
     static std::atomic<int> occ{0}; // per instantiation; contexts on different threads may race to fill it
     if (occ == 0) {
         int o = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_fill16_kernel<FREE, CM>, 32, 0) != cudaSuccess || o < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_fill16_kernel<FREE, CM, false, TB>, 32, 0) != cudaSuccess ||
+            o < 1)
             o = 8;
         occ = o;
     }
     const int grid = (int)std::min<int64_t>(quads, (int64_t)sm_count * std::min(occ.load(), ctas_per_sm));
-    affine_fill16_kernel<FREE, CM><<<grid, 32, 0, st>>>(fp);
+    affine_fill16_kernel<FREE, CM, false, TB><<<grid, 32, 0, st>>>(fp);
 }
 
 inline int64_t ckpt_quad_words(int64_t n) { return ((n + 16 - 2) / kCkK) * kCkRegs * 32; }
 
-template <int CM>
+template <int CM, bool TB>
 void launch_fill16_ckpt_t(const FillParams &fp, int64_t quads, int sm_count, int ctas_per_sm, cudaStream_t st)
 {
     static std::atomic<int> occ{0};
     if (occ == 0) {
         int o = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_fill16_kernel<true, CM, true>, 32, 0) != cudaSuccess || o < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, affine_fill16_kernel<true, CM, true, TB>, 32, 0) != cudaSuccess ||
+            o < 1)
             o = 8;
         occ = o;
     }
     const int grid = (int)std::min<int64_t>(quads, (int64_t)sm_count * std::min(occ.load(), ctas_per_sm));
-    affine_fill16_kernel<true, CM, true><<<grid, 32, 0, st>>>(fp);
+    affine_fill16_kernel<true, CM, true, TB><<<grid, 32, 0, st>>>(fp);
 }
 
-void launch_fill16_ckpt(const FillParams &fp, int64_t quads, int cm, int sm_count, int ctas_per_sm, cudaStream_t st)
+template <bool TB>
+void launch_fill16_ckpt_b(const FillParams &fp, int64_t quads, int cm, int sm_count, int ctas_per_sm, cudaStream_t st)
 {
     switch (cm) {
-    case 0: launch_fill16_ckpt_t<0>(fp, quads, sm_count, ctas_per_sm, st); break;
-    case 1: launch_fill16_ckpt_t<1>(fp, quads, sm_count, ctas_per_sm, st); break;
-    case 2: launch_fill16_ckpt_t<2>(fp, quads, sm_count, ctas_per_sm, st); break;
-    case 3: launch_fill16_ckpt_t<3>(fp, quads, sm_count, ctas_per_sm, st); break;
-    case 4: launch_fill16_ckpt_t<4>(fp, quads, sm_count, ctas_per_sm, st); break;
-    case 5: launch_fill16_ckpt_t<5>(fp, quads, sm_count, ctas_per_sm, st); break;
-    case 6: launch_fill16_ckpt_t<6>(fp, quads, sm_count, ctas_per_sm, st); break;
-    case 7: launch_fill16_ckpt_t<7>(fp, quads, sm_count, ctas_per_sm, st); break;
-    case 8: launch_fill16_ckpt_t<8>(fp, quads, sm_count, ctas_per_sm, st); break;
-    default: launch_fill16_ckpt_t<9>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 0: launch_fill16_ckpt_t<0, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 1: launch_fill16_ckpt_t<1, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 2: launch_fill16_ckpt_t<2, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 3: launch_fill16_ckpt_t<3, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 4: launch_fill16_ckpt_t<4, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 5: launch_fill16_ckpt_t<5, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 6: launch_fill16_ckpt_t<6, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 7: launch_fill16_ckpt_t<7, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 8: launch_fill16_ckpt_t<8, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    default: launch_fill16_ckpt_t<9, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
     }
+}
+
+void launch_fill16_ckpt(const FillParams &fp, int64_t quads, int cm, int sm_count, int ctas_per_sm, cudaStream_t st, bool tb)
+{
+    if (tb)
+        launch_fill16_ckpt_b<true>(fp, quads, cm, sm_count, ctas_per_sm, st);
+    else
+        launch_fill16_ckpt_b<false>(fp, quads, cm, sm_count, ctas_per_sm, st);
 }
 
 // second pass of the checkpoint path: recompute + walk (pass 0: slots and counts; pass 1: overflowing pairs)
@@ -572,20 +591,29 @@ void launch_ckpt_trace(gnx_ctx *ctx, const Problem &pb, const FillParams &fp, co
 }
 
 // freeEndGaps: the in-lane index of the last column is a template parameter (uniform batches: one value per call)
-void launch_fill16_free(const FillParams &fp, int64_t quads, int cm, int sm_count, int ctas_per_sm, cudaStream_t st)
+template <bool TB>
+void launch_fill16_free_b(const FillParams &fp, int64_t quads, int cm, int sm_count, int ctas_per_sm, cudaStream_t st)
 {
     switch (cm) {
-    case 0: launch_fill16<true, 0>(fp, quads, sm_count, ctas_per_sm, st); break;
-    case 1: launch_fill16<true, 1>(fp, quads, sm_count, ctas_per_sm, st); break;
-    case 2: launch_fill16<true, 2>(fp, quads, sm_count, ctas_per_sm, st); break;
-    case 3: launch_fill16<true, 3>(fp, quads, sm_count, ctas_per_sm, st); break;
-    case 4: launch_fill16<true, 4>(fp, quads, sm_count, ctas_per_sm, st); break;
-    case 5: launch_fill16<true, 5>(fp, quads, sm_count, ctas_per_sm, st); break;
-    case 6: launch_fill16<true, 6>(fp, quads, sm_count, ctas_per_sm, st); break;
-    case 7: launch_fill16<true, 7>(fp, quads, sm_count, ctas_per_sm, st); break;
-    case 8: launch_fill16<true, 8>(fp, quads, sm_count, ctas_per_sm, st); break;
-    default: launch_fill16<true, 9>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 0: launch_fill16<true, 0, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 1: launch_fill16<true, 1, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 2: launch_fill16<true, 2, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 3: launch_fill16<true, 3, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 4: launch_fill16<true, 4, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 5: launch_fill16<true, 5, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 6: launch_fill16<true, 6, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 7: launch_fill16<true, 7, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    case 8: launch_fill16<true, 8, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
+    default: launch_fill16<true, 9, TB>(fp, quads, sm_count, ctas_per_sm, st); break;
     }
+}
+
+void launch_fill16_free(const FillParams &fp, int64_t quads, int cm, int sm_count, int ctas_per_sm, cudaStream_t st, bool tb)
+{
+    if (tb)
+        launch_fill16_free_b<true>(fp, quads, cm, sm_count, ctas_per_sm, st);
+    else
+        launch_fill16_free_b<false>(fp, quads, cm, sm_count, ctas_per_sm, st);
 }
 
 // CTA-per-pair kernel for long pairs (affine_fill3w_kernel): persistent grid over the chunk's pairs.
@@ -772,6 +800,15 @@ int launch_long(gnx_ctx *ctx, const Problem &pb, const FillParams &fp, uint32_t 
     return f1 ? launch_long_t<false, 1>(ctx, pb, fp, q, st) : launch_long_t<false, 0>(ctx, pb, fp, q, st);
 }
 
+// 2-bit inputs of a host batch (gnx_affine_batch_twobit): dnaTwoBit words, tightly packed
+struct TbIn {
+    const uint64_t *a_words, *b_words;
+    const int64_t *a_woff, *b_woff; // n_pairs + 1 word offsets (host; computed by the entry point)
+    const int64_t *a_len, *b_len;   // the caller's length arrays
+    bool uniform;                   // every pair n x m
+    int64_t n, m, wn, wm;           // uniform: lengths and words per sequence
+};
+
 // Device buffers of one chunk, all addressed with GLOBAL pair indices (pointers are pre-biased).
 struct ChunkDev {
     const uint8_t *alpha, *beta;      // biased so that absolute offsets index them
@@ -788,6 +825,7 @@ struct ChunkDev {
     int64_t *best;                    // ext 2: biased by -begin (global pair index)
     int64_t *end_i, *end_j;           // ext: chunk-local
     int *work, *work_count;           // checkpoint path: work list (chunk-local pair indices) and its device counter
+    const uint64_t *alpha_words, *beta_words; // TB kernels: biased so that words + pair * wn / wm is the pair's sequence
     const int *smat;                  // profile batches: biased so that smat + smat_off[pair] is the pair's matrix
     const int64_t *smat_off;          // indexed by global pair id
 };
@@ -826,6 +864,8 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     const int grid = (int)std::min<int64_t>((np + warps_per_block - 1) / warps_per_block, max_grid);
     if (pb.profile) {
         // no sequence bytes on this path: invalid bases were found while the profiles were built
+    } else if (pb.twobit) {
+        cudaMemsetAsync(cd.cls + begin, 0, (size_t)np, st); // two bits per base: every base is < 4 <= dim
     } else if (pb.cfg.impl == 3 || pb.cfg.impl == 16 || pb.cfg.impl == 17 || pb.cfg.impl == 18) {
         // these kernels take any base < dim, so the per-pair pass is only needed to find WHICH pair is
         // invalid; gate it on the chunk's largest base (vectorised, HBM-bound)
@@ -870,6 +910,14 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     fp.out_score = cd.score;
     fp.one = 1;
     fp.chunk = (int)pb.chunk;
+    if (pb.cfg.tb) {
+        fp.alpha_words = cd.alpha_words;
+        fp.beta_words = cd.beta_words;
+        fp.n_uni = (int)pb.cfg.n_uniform;
+        fp.m_uni = (int)pb.cfg.m_uniform;
+        fp.wn = (int)((pb.cfg.n_uniform + 31) / 32);
+        fp.wm = (int)((pb.cfg.m_uniform + 31) / 32);
+    }
 
     // class 0 (ACGT only) with the PRMT tables when the matrix fits 16 bits, else the smem lookup
     FillEvent &fe = next_fill_event(ctx);
@@ -884,13 +932,15 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         const int64_t quads = (np + 3) / 4;
         fp.trace = cd.trace;                                   // checkpoint area
         fp.edge_stride = ckpt_quad_words(pb.cfg.n_uniform);    // words per quad
-        launch_fill16_ckpt(fp, quads, (int)((pb.cfg.m_uniform - 1) % 10), ctx->sm_count, ctx->opt_ctas_per_sm, st);
+        launch_fill16_ckpt(fp, quads, (int)((pb.cfg.m_uniform - 1) % 10), ctx->sm_count, ctx->opt_ctas_per_sm, st, pb.cfg.tb);
         ctx->launches++;
         ctx->last_fill_launches++;
     } else if (pb.cfg.impl == 16) {
         const int64_t quads = (np + 3) / 4;
         if (pb.kind == 1)
-            launch_fill16_free(fp, quads, (int)((pb.cfg.m_uniform - 1) % 10), ctx->sm_count, ctx->opt_ctas_per_sm, st);
+            launch_fill16_free(fp, quads, (int)((pb.cfg.m_uniform - 1) % 10), ctx->sm_count, ctx->opt_ctas_per_sm, st, pb.cfg.tb);
+        else if (pb.cfg.tb)
+            launch_fill16<false, -1, true>(fp, quads, ctx->sm_count, ctx->opt_ctas_per_sm, st);
         else
             launch_fill16<false, -1>(fp, quads, ctx->sm_count, ctx->opt_ctas_per_sm, st);
         ctx->launches++;
@@ -1168,6 +1218,10 @@ int make_plan(gnx_ctx *ctx, Problem &pb, const int64_t *aoff, const int64_t *bof
         pb.cfg.multi = false;
         pb.cfg.m_uniform = plan.max_m;
     }
+    // 2-bit inputs on the packed 16-bit kernels: the quad's words are staged by TMA (targets expanded in 4 x 512 B)
+    pb.cfg.tb = pb.twobit && ctx->opt_tb_tma && (pb.cfg.impl == 16 || pb.cfg.impl == 17) && plan.max_n <= kTbMaxN;
+    if (pb.cfg.impl == 16 && pb.cfg.tb)
+        pb.cfg.n_uniform = plan.max_n;
     // long pairs with traceback: tile checkpoints + recompute of the route's tiles instead of a trace matrix.  The
     // recompute costs ~(351 + kLongR) x 320 cells per strip crossed, i.e. a fraction ~610 / min(n, m) of the pair: worth
     // it from a couple of million cells per pair; a batch of less than two pairs per SM is latency-bound and stays on
@@ -1253,9 +1307,14 @@ bool is_pinned(const void *p)
 // ---------------------------------------------------------------------------------------------
 // Host-buffer batch: the pipelined path behind gnx_affine_batch / gnx_const_batch.
 // ---------------------------------------------------------------------------------------------
+// tb != nullptr: the bases arrive as dnaTwoBit words (alpha_cat / beta_cat are NULL; aoff / boff are the byte offsets
+// the entry point derived from the lengths, used for planning only).  Each chunk's words are copied to the device
+// (a quarter of the bytes), the packed 16-bit kernels read them directly (TMA), every other path unpacks them to
+// one byte per base ON THE DEVICE first (twobit_unpack_*_kernel, HBM-bound: ~1 % of a fill).
 int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const int64_t *aoff, const uint8_t *beta_cat,
                    const int64_t *boff, int64_t n_pairs, int64_t *out_score, gnx_cigar *out_cigar,
-                   int64_t *out_cigar_off, int64_t cigar_cap, int64_t *out_end_i = nullptr, int64_t *out_end_j = nullptr)
+                   int64_t *out_cigar_off, int64_t cigar_cap, int64_t *out_end_i = nullptr, int64_t *out_end_j = nullptr,
+                   const TbIn *tb = nullptr)
 {
     CU(cudaSetDevice(ctx->device));
     ctx->fill_events_used = 0;
@@ -1278,7 +1337,8 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
     CU(cudaMemsetAsync(ctx->status.p, 0, sizeof(int), ctx->slot[0].stream));
     CU(cudaStreamSynchronize(ctx->slot[0].stream));
 
-    const bool pin_a = is_pinned(alpha_cat), pin_b = is_pinned(beta_cat);
+    const bool pin_a = is_pinned(tb ? (const void *)tb->a_words : (const void *)alpha_cat);
+    const bool pin_b = is_pinned(tb ? (const void *)tb->b_words : (const void *)beta_cat);
     const bool pin_ao = is_pinned(aoff), pin_bo = is_pinned(boff);
     const bool pin_score = is_pinned(out_score);
     const bool pin_off = out_cigar_off && is_pinned(out_cigar_off);
@@ -1418,13 +1478,80 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
             }
             return GNX_OK;
         };
-        if ((rc = h2d(s.alpha.p, alpha_cat + a_lo, (size_t)(a_hi - a_lo), pin_a, s.h_stage_a)) != GNX_OK)
-            return rc;
-        if ((rc = h2d(s.beta.p, beta_cat + b_lo, (size_t)(b_hi - b_lo), pin_b, s.h_stage_b)) != GNX_OK)
-            return rc;
-        // offsets are small; always DMA from the caller's arrays when pinned, else pageable memcpy
-        CU(cudaMemcpyAsync(s.aoff.p, aoff + begin, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
-        CU(cudaMemcpyAsync(s.boff.p, boff + begin, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+        const uint64_t *d_wa = nullptr, *d_wb = nullptr;
+        if (!tb) {
+            if ((rc = h2d(s.alpha.p, alpha_cat + a_lo, (size_t)(a_hi - a_lo), pin_a, s.h_stage_a)) != GNX_OK)
+                return rc;
+            if ((rc = h2d(s.beta.p, beta_cat + b_lo, (size_t)(b_hi - b_lo), pin_b, s.h_stage_b)) != GNX_OK)
+                return rc;
+            // offsets are small; always DMA from the caller's arrays when pinned, else pageable memcpy
+            CU(cudaMemcpyAsync(s.aoff.p, aoff + begin, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+            CU(cudaMemcpyAsync(s.boff.p, boff + begin, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+        } else {
+            const int64_t wa_lo = tb->a_woff[begin], wa_n = tb->a_woff[end] - wa_lo;
+            const int64_t wb_lo = tb->b_woff[begin], wb_n = tb->b_woff[end] - wb_lo;
+            CU(s.tb_a.ensure((size_t)wa_n * 8 + 256)); // slack: the TMA of a tail quad reads a whole quad's words
+            CU(s.tb_b.ensure((size_t)wb_n * 8 + 256));
+            if ((rc = h2d(s.tb_a.p, tb->a_words + wa_lo, (size_t)wa_n * 8, pin_a, s.h_stage_a)) != GNX_OK)
+                return rc;
+            if ((rc = h2d(s.tb_b.p, tb->b_words + wb_lo, (size_t)wb_n * 8, pin_b, s.h_stage_b)) != GNX_OK)
+                return rc;
+            d_wa = s.tb_a.as<uint64_t>();
+            d_wb = s.tb_b.as<uint64_t>();
+            const bool need_bytes = !(pb.cfg.tb && !pb.want_cigar); // the packed score-only kernel reads no bytes
+            if (tb->uniform) { // byte offsets made on the device, bases unpacked without any offset array
+                const int g = (int)((np + 1 + 255) / 256);
+                iota_offsets_kernel<<<g, 256, 0, s.stream>>>(s.aoff.as<int64_t>(), begin, np + 1, tb->n);
+                iota_offsets_kernel<<<g, 256, 0, s.stream>>>(s.boff.as<int64_t>(), begin, np + 1, tb->m);
+                ctx->launches += 2;
+                if (need_bytes) {
+                    if (wa_n > 0)
+                        twobit_unpack_uniform_kernel<<<(int)((wa_n + 255) / 256), 256, 0, s.stream>>>(d_wa, wa_n, tb->wn, tb->n,
+                                                                                                   s.alpha.as<uint8_t>());
+                    if (wb_n > 0)
+                        twobit_unpack_uniform_kernel<<<(int)((wb_n + 255) / 256), 256, 0, s.stream>>>(d_wb, wb_n, tb->wm, tb->m,
+                                                                                                   s.beta.as<uint8_t>());
+                    ctx->launches += 2;
+                }
+            } else { // ragged: byte offsets, chunk-relative word offsets and lengths travel with the chunk
+                CU(cudaMemcpyAsync(s.aoff.p, aoff + begin, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+                CU(cudaMemcpyAsync(s.boff.p, boff + begin, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+                CU(s.tb_meta.ensure((size_t)(np + 1) * 8 * 4));
+                CU(s.h_tbmeta.ensure((size_t)(np + 1) * 8 * 4)); // pinned staging (the slot's previous chunk has been retired)
+                int64_t *hm = s.h_tbmeta.as<int64_t>();
+                int64_t *h_woa = hm, *h_wob = hm + (np + 1), *h_la = hm + 2 * (np + 1), *h_lb = hm + 3 * (np + 1);
+                for (int64_t k = 0; k <= np; ++k) {
+                    h_woa[k] = tb->a_woff[begin + k] - wa_lo;
+                    h_wob[k] = tb->b_woff[begin + k] - wb_lo;
+                    if (k < np) {
+                        h_la[k] = tb->a_len[begin + k];
+                        h_lb[k] = tb->b_len[begin + k];
+                    }
+                }
+                CU(cudaMemcpyAsync(s.tb_meta.p, hm, (size_t)(np + 1) * 8 * 4, cudaMemcpyHostToDevice, s.stream));
+                const int64_t *dm = s.tb_meta.as<int64_t>();
+                UnpackParams up;
+                up.tb.words = d_wa;
+                up.tb.word_off = dm;
+                up.tb.len = dm + 2 * (np + 1);
+                up.tb.n_seqs = np;
+                up.out_off = s.aoff.as<int64_t>();          // absolute byte offsets ...
+                up.out = s.alpha.as<uint8_t>() - a_lo;      // ... into a pointer biased by the chunk's first byte
+                up.total_words = wa_n;
+                up.uniform_words = 0;
+                if (wa_n > 0)
+                    twobit_unpack_kernel<<<(int)((wa_n + 255) / 256), 256, 0, s.stream>>>(up);
+                up.tb.words = d_wb;
+                up.tb.word_off = dm + (np + 1);
+                up.tb.len = dm + 3 * (np + 1);
+                up.out_off = s.boff.as<int64_t>();
+                up.out = s.beta.as<uint8_t>() - b_lo;
+                up.total_words = wb_n;
+                if (wb_n > 0)
+                    twobit_unpack_kernel<<<(int)((wb_n + 255) / 256), 256, 0, s.stream>>>(up);
+                ctx->launches += 2;
+            }
+        }
         (void)pin_ao;
         (void)pin_bo;
         (void)pin_off;
@@ -1441,6 +1568,10 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
         cd.a_hi = a_hi;
         cd.b_lo = b_lo;
         cd.b_hi = b_hi;
+        if (tb && tb->uniform) { // TB kernels address pair p's words as base + p * wn (global pair index)
+            cd.alpha_words = d_wa - begin * tb->wn;
+            cd.beta_words = d_wb - begin * tb->wm;
+        }
         if (pb.ext) {
             CU(s.best.ensure((size_t)np * 8));
             CU(s.endi.ensure((size_t)np * 8));
@@ -1755,6 +1886,67 @@ int run_profile_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *group_cat, const
     return GNX_OK;
 }
 
+// 2-bit entry point shared by the host-buffer and (below) device-resident forms: derive the offset arrays
+int twobit_offsets(gnx_ctx *ctx, const int64_t *alpha_len, int64_t alpha_ulen, const int64_t *beta_len, int64_t beta_ulen,
+                   int64_t n_pairs, TbIn &tb)
+{
+    std::vector<int64_t> &ao = ctx->tb_off[0], &bo = ctx->tb_off[1], &aw = ctx->tb_off[2], &bw = ctx->tb_off[3];
+    tb.a_len = alpha_len;
+    tb.b_len = beta_len;
+    if (!alpha_len && !beta_len) { // uniform batch: arithmetic offsets, cached between calls of the same shape
+        if (alpha_ulen < 0 || beta_ulen < 0)
+            return fail(ctx, GNX_EARG, "uniform lengths must be >= 0");
+        tb.uniform = true;
+        tb.n = alpha_ulen;
+        tb.m = beta_ulen;
+        tb.wn = (alpha_ulen + 31) / 32;
+        tb.wm = (beta_ulen + 31) / 32;
+        if (ctx->tb_key[0] != n_pairs || ctx->tb_key[1] != tb.n || ctx->tb_key[2] != tb.m) {
+            for (auto &v : ctx->tb_off)
+                v.resize((size_t)n_pairs + 1);
+            const int nt = n_pairs >= (1 << 20) ? 8 : 1;
+            auto work = [&](int t) {
+                const int64_t lo = (n_pairs + 1) * t / nt, hi = (n_pairs + 1) * (t + 1) / nt;
+                for (int64_t p = lo; p < hi; ++p) {
+                    ao[(size_t)p] = p * tb.n;
+                    bo[(size_t)p] = p * tb.m;
+                    aw[(size_t)p] = p * tb.wn;
+                    bw[(size_t)p] = p * tb.wm;
+                }
+            };
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; ++t)
+                th.emplace_back(work, t);
+            work(0);
+            for (auto &x : th)
+                x.join();
+            ctx->tb_key[0] = n_pairs;
+            ctx->tb_key[1] = tb.n;
+            ctx->tb_key[2] = tb.m;
+        }
+    } else {
+        if (!alpha_len || !beta_len)
+            return fail(ctx, GNX_EARG, "alpha_len and beta_len must both be given (or both NULL for a uniform batch)");
+        ctx->tb_key[0] = -1;
+        for (auto &v : ctx->tb_off)
+            v.resize((size_t)n_pairs + 1);
+        ao[0] = bo[0] = aw[0] = bw[0] = 0;
+        for (int64_t p = 0; p < n_pairs; ++p) {
+            if (alpha_len[p] < 0 || beta_len[p] < 0)
+                return fail(ctx, GNX_EARG, "negative sequence length");
+            ao[(size_t)p + 1] = ao[(size_t)p] + alpha_len[p];
+            bo[(size_t)p + 1] = bo[(size_t)p] + beta_len[p];
+            aw[(size_t)p + 1] = aw[(size_t)p] + (alpha_len[p] + 31) / 32;
+            bw[(size_t)p + 1] = bw[(size_t)p] + (beta_len[p] + 31) / 32;
+        }
+        tb.uniform = false;
+        tb.n = tb.m = tb.wn = tb.wm = 0;
+    }
+    tb.a_woff = aw.data();
+    tb.b_woff = bw.data();
+    return GNX_OK;
+}
+
 } // namespace
 
 // =================================================================================================
@@ -1826,10 +2018,12 @@ void gnx_destroy(gnx_ctx *ctx)
     for (int k = 0; k < kSlots; ++k) {
         Slot &s = ctx->slot[k];
         DevBuf *d[] = {&s.alpha, &s.beta, &s.aoff, &s.boff, &s.cls, &s.trace, &s.trace_off, &s.slots,
-                       &s.counts, &s.score, &s.cig_off, &s.cigars, &s.edge, &s.misc, &s.partials, &s.best, &s.endi, &s.endj, &s.work};
+                       &s.counts, &s.score, &s.cig_off, &s.cigars, &s.edge, &s.misc, &s.partials, &s.best, &s.endi, &s.endj, &s.work,
+                       &s.tb_a, &s.tb_b, &s.tb_meta};
         for (DevBuf *b : d)
             b->release();
-        PinBuf *h[] = {&s.h_stage_a, &s.h_stage_b, &s.h_total, &s.h_trace_off, &s.h_score, &s.h_off, &s.h_cig, &s.h_endi, &s.h_endj};
+        PinBuf *h[] = {&s.h_stage_a, &s.h_stage_b, &s.h_total, &s.h_trace_off, &s.h_score, &s.h_off, &s.h_cig, &s.h_endi, &s.h_endj,
+                       &s.h_tbmeta};
         for (PinBuf *b : h)
             b->release();
         if (s.stream)
@@ -1892,6 +2086,31 @@ int gnx_affine_batch(gnx_ctx *ctx, const uint8_t *alpha_cat, const int64_t *alph
         return rc;
     return run_host_batch(ctx, pb, alpha_cat, alpha_off, beta_cat, beta_off, n_pairs, out_score, out_cigar,
                           out_cigar_off, out_cigar ? cigar_cap : 0);
+}
+
+int gnx_affine_batch_twobit(gnx_ctx *ctx, const uint64_t *alpha_words, const int64_t *alpha_len, int64_t alpha_uniform_len,
+                            const uint64_t *beta_words, const int64_t *beta_len, int64_t beta_uniform_len, int64_t n_pairs,
+                            const int64_t *scores, int dim, int64_t gap_open, int64_t gap_extend, int mode, int want_cigar,
+                            int64_t *out_score, gnx_cigar *out_cigar, int64_t *out_cigar_off, int64_t cigar_cap)
+{
+    if (!ctx)
+        return GNX_EARG;
+    if (n_pairs < 0 || !out_score || (mode != GNX_GLOBAL && mode != GNX_FREE_END) || (n_pairs > 0 && (!alpha_words || !beta_words)))
+        return fail(ctx, GNX_EARG, "bad argument to gnx_affine_batch_twobit");
+    if (want_cigar && !out_cigar_off)
+        return fail(ctx, GNX_EARG, "out_cigar_off is required when want_cigar != 0");
+    Problem pb;
+    int rc = fill_problem(ctx, pb, mode == GNX_FREE_END ? 1 : 0, want_cigar, scores, dim, gap_open, gap_extend);
+    if (rc != GNX_OK)
+        return rc;
+    pb.twobit = true;
+    TbIn tb;
+    tb.a_words = alpha_words;
+    tb.b_words = beta_words;
+    if ((rc = twobit_offsets(ctx, alpha_len, alpha_uniform_len, beta_len, beta_uniform_len, n_pairs, tb)) != GNX_OK)
+        return rc;
+    return run_host_batch(ctx, pb, nullptr, ctx->tb_off[0].data(), nullptr, ctx->tb_off[1].data(), n_pairs, out_score, out_cigar,
+                          out_cigar_off, out_cigar ? cigar_cap : 0, nullptr, nullptr, &tb);
 }
 
 int gnx_const_batch(gnx_ctx *ctx, const uint8_t *alpha_cat, const int64_t *alpha_off, const uint8_t *beta_cat,
@@ -2169,6 +2388,8 @@ int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
         ctx->opt_ckpt = value ? 1 : 0;
     } else if (k == "wide_cta") {
         ctx->opt_wide_cta = (int)value;
+    } else if (k == "tb_tma") {
+        ctx->opt_tb_tma = value ? 1 : 0;
     } else if (k == "long_ckpt") {
         ctx->opt_long = (int)value;
     } else if (k == "long_form") {

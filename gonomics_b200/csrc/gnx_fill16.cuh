@@ -37,16 +37,52 @@ __device__ __forceinline__ unsigned uaddmax_16x2(unsigned a, unsigned b, unsigne
 constexpr int kCkK = 32;   // steps between checkpoints
 constexpr int kCkRegs = 23; // 32-bit words per lane per checkpoint
 
-template <bool FREE, int CM = -1, bool CKPT = false>
+// ---- 1-D TMA (cp.async.bulk) staging of 2-bit packed sequences: TB kernels ----------------------------------
+// The async proxy writes the packed words of a quad's four targets and four queries into shared memory and
+// signals an mbarrier with the byte count (SASS: UBLKCP + SYNCS); nothing but one elected lane touches the copy.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+constexpr int kTbMaxN = 512;                 // TB kernels unpack the quad's targets into 4 x 512 bytes of shared memory
+constexpr int kTbMaxWn = kTbMaxN / 32, kTbMaxWm = 5; // words per target / query (m <= 160)
+// base `pos` of a dnaTwoBit sequence stored as uint64 words (dna/dnaTwoBit/dnaTwoBit.go:59-65 GetBase: first base
+// in bits 63:62), read through a little-endian 32-bit view of the words
+__device__ __forceinline__ int tb_base(const uint32_t *w32, int pos)
+{
+    const uint32_t v = w32[((pos >> 5) << 1) | (((pos >> 4) & 1) ^ 1)];
+    return (int)((v >> (30 - 2 * (pos & 15))) & 3u);
+}
+
+// TB: the batch's bases arrive as dnaTwoBit words (P.alpha_words / P.beta_words, uniform lengths P.n_uni x P.m_uni,
+// sequence p at word p * wn resp. p * wm): the quad's words are staged by TMA one quad ahead, the targets expanded to
+// one byte per base in shared memory (the per-step base fetch is then an LDS), the queries read straight from the
+// packed words while the score tables are built.  Bases are 0..3, so the tables have four rows.
+template <bool FREE, int CM = -1, bool CKPT = false, bool TB = false>
 __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams P)
 {
     static_assert(CM < 0 || FREE, "CM selects the free-end column");
     static_assert(!CKPT || (FREE && CM >= 0), "checkpoints are taken on the freeEndGaps path only");
     constexpr int C = 10, LPP = 16;
+    constexpr int ROWS = TB ? 4 : kDimP;
     constexpr unsigned FULL = 0xffffffffu;
-    __shared__ int s_tabA[C * kDimP * 32];   // [c][a][thread], pair A: s sign-extended (a 16-bit LDS costs two
+    __shared__ int s_tabA[C * ROWS * 32];    // [c][a][thread], pair A: s sign-extended (a 16-bit LDS costs two
                                              // shared-memory wavefronts: ncu counted 30 per step instead of 20)
-    __shared__ int s_tabB[C * kDimP * 32];   // [c][a][thread], pair B: s * 65536
+    __shared__ int s_tabB[C * ROWS * 32];    // [c][a][thread], pair B: s * 65536
+    __shared__ __align__(16) uint64_t s_pk[TB ? 4 * (kTbMaxWn + kTbMaxWm) : 1]; // TMA landing zone: targets, then queries
+    __shared__ __align__(16) uint8_t s_tg[TB ? 4 * kTbMaxN : 16];               // the quad's targets, one byte per base
+    __shared__ __align__(8) uint64_t s_bar;
     const int tid = threadIdx.x;
     const int lane = tid % LPP, half = tid / LPP;
     const int one = P.one;
@@ -54,17 +90,66 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
     const int oe_i = (O + E) * 65537;          // integer addend: +O+E in both halves
     const unsigned e_w = wrap16x2(E);          // per-half wrapping addend for VIADDMNMX.U16x2
     const int64_t n_quads = (P.pair_end - P.pair_begin + 3) / 4;
+    // TB: one quad's packed words = 32 * wn bytes of targets + 32 * wm bytes of queries (always multiples of 16, and
+    // 16-byte aligned because chunks start at a quad boundary of a 256-byte aligned buffer)
+    const unsigned tb_bytes_t = TB ? 32u * (unsigned)P.wn : 0u, tb_bytes_q = TB ? 32u * (unsigned)P.wm : 0u;
+    auto tb_issue = [&](int64_t quad) { // lane 0: stage quad's words (its first pair is pair_begin + 4 * quad)
+        const int64_t p0 = P.pair_begin + quad * 4;
+        mbar_expect_tx(&s_bar, tb_bytes_t + tb_bytes_q);
+        bulk_g2s(s_pk, P.alpha_words + p0 * P.wn, tb_bytes_t, &s_bar);
+        bulk_g2s(s_pk + 4 * kTbMaxWn, P.beta_words + p0 * P.wm, tb_bytes_q, &s_bar);
+    };
+    unsigned tb_phase = 0;
+    if (TB) {
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        if (tid == 0 && (int64_t)blockIdx.x < n_quads)
+            tb_issue(blockIdx.x);
+    }
 
     for (int64_t quad = blockIdx.x; quad < n_quads; quad += gridDim.x) {
         const int64_t pA0 = P.pair_begin + quad * 4 + half * 2, pB0 = pA0 + 1;
         const int64_t pA = min(pA0, P.pair_end - 1), pB = min(pB0, P.pair_end - 1); // tail: recompute a valid pair
-        const int64_t a0A = P.alpha_off[pA], b0A = P.beta_off[pA];
-        const int n = (int)(P.alpha_off[pA + 1] - a0A);
-        const int m = (int)(P.beta_off[pA + 1] - b0A); // uniform batch: same n, m for every pair
-        const uint8_t *__restrict__ alA = P.alpha + a0A;
-        const uint8_t *__restrict__ alB = P.alpha + P.alpha_off[pB];
-        const uint8_t *__restrict__ beA = P.beta + b0A;
-        const uint8_t *__restrict__ beB = P.beta + P.beta_off[pB];
+        int n, m;
+        const uint8_t *__restrict__ alA, *__restrict__ alB, *__restrict__ beA = nullptr, *__restrict__ beB = nullptr;
+        const uint32_t *qwA = nullptr, *qwB = nullptr; // TB: 32-bit views of the two queries' packed words
+        if (TB) {
+            n = P.n_uni;
+            m = P.m_uni;
+            mbar_wait(&s_bar, tb_phase); // the quad's words have landed
+            tb_phase ^= 1;
+            const int kA = (int)(pA - (P.pair_begin + quad * 4)), kB = (int)(pB - (P.pair_begin + quad * 4));
+            // expand the four targets: 16 bases (one 32-bit half word) -> 16 bytes per iteration
+            const uint32_t *pk32 = reinterpret_cast<const uint32_t *>(s_pk);
+            const int hw_per = 2 * P.wn;
+            for (int h = tid; h < 4 * hw_per; h += 32) {
+                const int k = h / hw_per, hh = h - k * hw_per;
+                const uint32_t v = pk32[(k * P.wn + (hh >> 1)) * 2 + ((hh & 1) ^ 1)];
+                uint32_t x[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t r = (v >> (24 - 8 * q)) & 0xffu; // four bases, first in bits 7:6
+                    x[q] = (r >> 6) | (((r >> 4) & 3u) << 8) | (((r >> 2) & 3u) << 16) | ((r & 3u) << 24);
+                }
+                if (16 * hh < kTbMaxN)
+                    *reinterpret_cast<uint4 *>(s_tg + k * kTbMaxN + 16 * hh) = make_uint4(x[0], x[1], x[2], x[3]);
+            }
+            alA = s_tg + kA * kTbMaxN;
+            alB = s_tg + kB * kTbMaxN;
+            qwA = pk32 + (4 * kTbMaxWn + kA * P.wm) * 2;
+            qwB = pk32 + (4 * kTbMaxWn + kB * P.wm) * 2;
+        } else {
+            const int64_t a0A = P.alpha_off[pA], b0A = P.beta_off[pA];
+            n = (int)(P.alpha_off[pA + 1] - a0A);
+            m = (int)(P.beta_off[pA + 1] - b0A); // uniform batch: same n, m for every pair
+            alA = P.alpha + a0A;
+            alB = P.alpha + P.alpha_off[pB];
+            beA = P.beta + b0A;
+            beB = P.beta + P.beta_off[pB];
+        }
         const int T = n + LPP - 1;
         const int jbase = lane * C;
         unsigned aD[C];
@@ -73,16 +158,20 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
         for (int c = 0; c < C; ++c) {
             const int j = jbase + c + 1;
             const bool real = j <= m;
-            const int qA = real ? (int)beA[j - 1] : 0, qB = real ? (int)beB[j - 1] : 0;
+            int qA = 0, qB = 0;
+            if (real) {
+                qA = TB ? tb_base(qwA, j - 1) : (int)beA[j - 1];
+                qB = TB ? tb_base(qwB, j - 1) : (int)beB[j - 1];
+            }
 #pragma unroll
-            for (int a = 0; a < kDimP; ++a) {
+            for (int a = 0; a < ROWS; ++a) {
                 int vA = 0, vB = 0;
                 if (real && a < P.dim) { // padding columns score 0 against everything
                     vA = P.scores[a * P.dim + qA];
                     vB = P.scores[a * P.dim + qB];
                 }
-                s_tabA[(c * kDimP + a) * 32 + tid] = vA;
-                s_tabB[(c * kDimP + a) * 32 + tid] = vB * 65536;
+                s_tabA[(c * ROWS + a) * 32 + tid] = vA;
+                s_tabB[(c * ROWS + a) * 32 + tid] = vB * 65536;
             }
             const bool last = FREE && (j == m);
             aD[c] = last ? 0u : e_w;
@@ -113,12 +202,19 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
         };
         if (lane == 0)
             boundary(1);
+        __syncwarp(); // tables and (TB) expanded targets are complete; the landing zone is free again
+        if (TB) {
+            const int64_t next = quad + gridDim.x;
+            if (tid == 0 && next < n_quads) { // prefetch the next quad's words behind this quad's fill
+                fence_proxy_async();          // our generic-proxy reads of s_pk precede the async-proxy writes
+                tb_issue(next);
+            }
+        }
         int aA_next = 0, aB_next = 0;
         if (lane == 0) {
             aA_next = alA[0];
             aB_next = alB[0];
         }
-        __syncwarp();
 
         auto step = [&](int t, auto check_tag) {
             constexpr bool CHECK = decltype(check_tag)::value;
@@ -149,8 +245,8 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
                 unsigned It = inI, hp = hpL;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    const int sA = rowA[c * kDimP * 32];
-                    const int sB = rowB[c * kDimP * 32]; // s * 65536
+                    const int sA = rowA[c * ROWS * 32];
+                    const int sB = rowB[c * ROWS * 32]; // s * 65536
                     const unsigned MH = hp + (unsigned)sA + (unsigned)sB; // one IADD3
                     if (CKPT && c == CM) { // max(M, I) of the free-end column (meaningful in its lane only)
                         const unsigned mx = __vmaxu2(MH, It);

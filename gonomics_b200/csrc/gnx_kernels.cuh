@@ -49,6 +49,10 @@ struct FillParams {
     int64_t *out_best;            // const_fill3_kernel<EXT 2>: (row << 32 | column) of the first maximal cell, per global pair
     const int *smat;              // LOOKUP == 3: dense per-pair cell scores S[i][j] (gnx_profile.cuh), unscaled
     const int64_t *smat_off;      // LOOKUP == 3: first cell of pair p's matrix inside smat, indexed by global pair id
+    // 2-bit inputs (affine_fill16_kernel<TB>): dnaTwoBit words of a UNIFORM batch, sequence p at word p * wn / p * wm
+    // (indexed by global pair id: the pointers are biased by the chunk's first pair), lengths n_uni x m_uni
+    const uint64_t *alpha_words, *beta_words;
+    int wn, wm, n_uni, m_uni;
 };
 
 __device__ __forceinline__ int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); } // max(a+b, c)

@@ -195,6 +195,50 @@ __global__ void __launch_bounds__(256) twobit_unpack_kernel(const UnpackParams P
     }
 }
 
+// Uniform batches (every sequence `len` bases = `wps` words, tightly packed): GetBase of every position without
+// any offset array -- sequence s = word / wps writes its bytes at out + s * len.  One thread per word.
+__global__ void __launch_bounds__(256) twobit_unpack_uniform_kernel(const uint64_t *words, int64_t total_words, int64_t wps,
+                                                                    int64_t len, uint8_t *out)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= total_words)
+        return;
+    const int64_t s = w / wps, k = w - s * wps;
+    const uint64_t word = words[w];
+    uint8_t *dst = out + s * len + 32 * k;
+    const int cnt = (int)(len - 32 * k < 32 ? len - 32 * k : 32);
+    unsigned x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const unsigned r = (unsigned)(word >> (56 - 8 * j)) & 0xffu; // four bases, first in bits 7:6
+        x[j] = (r >> 6) | (((r >> 4) & 3u) << 8) | (((r >> 2) & 3u) << 16) | ((r & 3u) << 24);
+    }
+    if (cnt == 32 && ((uintptr_t)dst & 15) == 0) {
+        reinterpret_cast<uint4 *>(dst)[0] = make_uint4(x[0], x[1], x[2], x[3]);
+        reinterpret_cast<uint4 *>(dst)[1] = make_uint4(x[4], x[5], x[6], x[7]);
+    } else if (cnt == 32 && ((uintptr_t)dst & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            reinterpret_cast<unsigned *>(dst)[j] = x[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (4 * j + b < cnt)
+                    dst[4 * j + b] = (uint8_t)(x[j] >> (8 * b));
+    }
+}
+
+// off[k] = (first + k) * stride for k = 0 .. count-1: the byte offsets of a uniform batch, made on the device
+// instead of shipped over PCIe.
+__global__ void __launch_bounds__(256) iota_offsets_kernel(int64_t *off, int64_t first, int64_t count, int64_t stride)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count)
+        off[k] = (first + k) * stride;
+}
+
 // GetBase for a list of (sequence, position) queries.  A position beyond the sequence's last word is Go's
 // index-out-of-range panic (status kEIndex, first offending query).
 constexpr int kEOffset = 9, kEIndex = 10;

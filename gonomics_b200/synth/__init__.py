@@ -27,7 +27,19 @@ def _load():
         _lib.gnx_synth_pairs.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                          C.c_void_p, C.c_int]
         _lib.gnx_synth_pairs.restype = C.c_int
+        _lib.gnx_pack_uniform.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int]
+        _lib.gnx_pack_uniform.restype = C.c_int
     return _lib
+
+
+def pack_uniform(bases: np.ndarray, n_seqs: int, length: int, out=None, n_threads: int = 0) -> np.ndarray:
+    """dnaTwoBit.NewTwoBit of n_seqs sequences of `length` bases (0..3), tightly packed uint64 words (host utility for
+    benchmarks / tests: the synthetic batch in the reference's packed form)."""
+    wps = (length + 31) // 32
+    words = np.empty(n_seqs * wps, dtype=np.uint64) if out is None else out
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    _load().gnx_pack_uniform(bases.ctypes.data, n_seqs, length, words.ctypes.data, n_threads or min(os.cpu_count() or 1, 64))
+    return words
 
 
 def synth_pairs(seed: int, n_pairs: int, n_len: int, m_len: int, first_pair: int = 0, n_threads: int = 0,

@@ -122,3 +122,52 @@ int gnx_synth_pairs(uint64_t seed, int64_t first_pair, int64_t n_pairs, int64_t 
             pthread_join(tid[t], NULL);
     return 0;
 }
+
+/* dnaTwoBit.NewTwoBit (dna/dnaTwoBit/dnaTwoBit.go:68-78) of n_seqs sequences of `len` bases each (bases 0..3), tightly
+ * packed: the workload generator's way of handing the benchmark its inputs in the reference's packed form.  Host-side
+ * test/benchmark utility, multi-threaded over sequences. */
+typedef struct {
+    const uint8_t *bases;
+    uint64_t *words;
+    int64_t lo, hi, len, wps;
+} pack_job_t;
+
+static void *pack_worker(void *arg)
+{
+    pack_job_t *j = (pack_job_t *)arg;
+    for (int64_t s = j->lo; s < j->hi; s++) {
+        const uint8_t *b = j->bases + s * j->len;
+        uint64_t *w = j->words + s * j->wps;
+        for (int64_t k = 0; k < j->wps; k++) {
+            uint64_t v = 0;
+            int64_t cnt = j->len - 32 * k < 32 ? j->len - 32 * k : 32;
+            for (int64_t i = 0; i < cnt; i++)
+                v = (v << 2) | (uint64_t)(b[32 * k + i] & 3);
+            w[k] = v << (2 * (32 - cnt)); /* the last word is left-aligned (dnaTwoBit.go:39-41) */
+        }
+    }
+    return 0;
+}
+
+int gnx_pack_uniform(const uint8_t *bases, int64_t n_seqs, int64_t len, uint64_t *words, int n_threads)
+{
+    if (n_threads < 1)
+        n_threads = 1;
+    if (n_threads > 256)
+        n_threads = 256;
+    pthread_t th[256];
+    pack_job_t jobs[256];
+    const int64_t wps = (len + 31) / 32;
+    for (int t = 0; t < n_threads; t++) {
+        jobs[t].bases = bases;
+        jobs[t].words = words;
+        jobs[t].len = len;
+        jobs[t].wps = wps;
+        jobs[t].lo = n_seqs * t / n_threads;
+        jobs[t].hi = n_seqs * (t + 1) / n_threads;
+        pthread_create(&th[t], 0, pack_worker, &jobs[t]);
+    }
+    for (int t = 0; t < n_threads; t++)
+        pthread_join(th[t], 0);
+    return 0;
+}

@@ -95,6 +95,25 @@ int gnx_affine_batch(gnx_ctx *ctx, const uint8_t *alpha_cat, const int64_t *alph
                      int want_cigar, int64_t *out_score, gnx_cigar *out_cigar, int64_t *out_cigar_off,
                      int64_t cigar_cap);
 
+/* ---- affine gap on dnaTwoBit inputs ---------------------------------------------------------- *
+ * Same computation as gnx_affine_batch with the sequences in the reference's own packed form,
+ * dnaTwoBit.TwoBit{Seq []uint64; Len int} (dna/dnaTwoBit/dnaTwoBit.go:14-17,28-42: 32 bases per word,
+ * first base in bits 63:62, the last word left-aligned) -- what cmd/gsw keeps its genome and reads in.
+ * alpha_words is the concatenation of the TwoBit.Seq slices of all alphas, TIGHTLY packed: sequence p
+ * occupies ceil(Len_p / 32) words right after sequence p-1; alpha_len[p] = its TwoBit.Len.  For a batch
+ * whose alphas all have the same length pass alpha_len = NULL and that length in alpha_uniform_len (then
+ * beta_len must be NULL too and the betas uniform): no per-pair metadata crosses PCIe at all.
+ * A quarter of the bytes of gnx_affine_batch travel to the device; there the packed 16-bit kernels consume
+ * the words directly (staged into shared memory by 1-D TMA, cp.async.bulk + mbarrier) and every other
+ * kernel reads a device-side expansion.  Two bits cannot hold dna.N: callers with N / lowercase bases use
+ * the byte entry point (NewTwoBit itself mis-packs them, dnaTwoBit.go:33-37).  Results and error codes
+ * are those of gnx_affine_batch on the unpacked sequences. */
+int gnx_affine_batch_twobit(gnx_ctx *ctx, const uint64_t *alpha_words, const int64_t *alpha_len,
+                            int64_t alpha_uniform_len, const uint64_t *beta_words, const int64_t *beta_len,
+                            int64_t beta_uniform_len, int64_t n_pairs, const int64_t *scores, int dim,
+                            int64_t gap_open, int64_t gap_extend, int mode, int want_cigar, int64_t *out_score,
+                            gnx_cigar *out_cigar, int64_t *out_cigar_off, int64_t cigar_cap);
+
 /* ---- constant gap ---------------------------------------------------------------------------- *
  * Replaces align.ConstGap_highMem (align/constGap_highMem.go:11-67) and, for 1 <= len <= 10000,
  * align.ConstGap / ConstGap_customizeCheckersize (align/constGap.go:13-124). */

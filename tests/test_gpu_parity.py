@@ -234,6 +234,68 @@ def test_multi_gpu_abi_matches_single_device(ctx, shards):
         assert len(sc) == 0 and list(off) == [0]
 
 
+# ---- dnaTwoBit inputs (gnx_affine_batch_twobit) -------------------------------------------------------
+def _pack_ragged(seqs):
+    """Tightly packed NewTwoBit words of every sequence (oracle packer = dnaTwoBit.NewTwoBit) + lengths."""
+    words = [orc.new_twobit(s)[0][:(len(s) + 31) // 32] for s in seqs]
+    cat = np.concatenate(words + [np.zeros(0, dtype=np.uint64)]).astype(np.uint64)
+    return cat, np.array([len(s) for s in seqs], dtype=np.int64)
+
+
+@pytest.mark.parametrize("tma", [1, 0])
+@pytest.mark.parametrize("n,m", [(500, 150), (300, 141), (333, 142), (512, 160), (64, 33), (290, 145), (31, 150), (700, 150)])
+def test_twobit_uniform_batches(n, m, tma):
+    """Uniform 2-bit batches: the packed 16-bit kernels read the dnaTwoBit words staged by TMA (tma = 1) or a device
+    expansion (tma = 0; also n > 512); score-only and checkpoint-path traceback, free-end and global, pair counts
+    that leave a partial quad, several chunks -- all equal to the oracle on the unpacked bases."""
+    from gonomics_b200.synth import pack_uniform
+    c = align.Context(0)
+    try:
+        c.set_option("tb_tma", tma)
+        c.set_option("chunk_pairs", 1000)
+        S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX
+        for P in (2503, 5):
+            a, ao, b, bo = synth_pairs(300 + n + m, P, n, m)
+            wa, wb = pack_uniform(a, P, n), pack_uniform(b, P, m)
+            for mode in (1, 0):
+                osc, ooff, ocig = orc.batch(a, ao, b, bo, S, -600, -150, mode, True, 8)
+                sc, off, cig = c.affine_gap_batch_twobit(wa, n, wb, m, S, -600, -150, mode == 1, True, n_pairs=P)
+                sc0, _, _ = c.affine_gap_batch_twobit(wa, n, wb, m, S, -600, -150, mode == 1, False, n_pairs=P)
+                assert np.array_equal(sc, osc) and np.array_equal(sc0, osc), (n, m, P, mode)
+                assert np.array_equal(off, ooff) and np.array_equal(cig["run_length"], ocig["run_length"]) \
+                    and np.array_equal(cig["op"], ocig["op"]), (n, m, P, mode)
+    finally:
+        c.close()
+
+
+def test_twobit_ragged_and_long(ctx):
+    """Ragged 2-bit batches (per-pair lengths; empty sequences; multi-strip pairs) go through the device expansion and
+    the ordinary kernels."""
+    rng = np.random.default_rng(321)
+    al, be = [], []
+    for k in range(400):
+        n, m = int(rng.integers(0, 300)), int(rng.integers(0, 200))
+        a, b = random_pair(rng, n, m, identity=0.9)
+        al.append(a)
+        be.append(b)
+    for n, m in [(3000, 1000), (700, 2000), (33, 0), (0, 65)]:
+        a, b = random_pair(rng, n, m, identity=0.9)
+        al.append(a)
+        be.append(b)
+    wa, la = _pack_ragged(al)
+    wb, lb = _pack_ragged(be)
+    ac, ao = concat(al)
+    bc, bo = concat(be)
+    S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX
+    for mode in (0, 1):
+        osc, ooff, ocig = orc.batch(ac, ao, bc, bo, S, -600, -150, mode, True, 8)
+        sc, off, cig = ctx.affine_gap_batch_twobit(wa, la, wb, lb, S, -600, -150, mode == 1, True)
+        assert np.array_equal(sc, osc) and np.array_equal(off, ooff)
+        assert np.array_equal(cig["run_length"], ocig["run_length"]) and np.array_equal(cig["op"], ocig["op"])
+        sc0, _, _ = ctx.affine_gap_batch_twobit(wa, la, wb, lb, S, -600, -150, mode == 1, False)
+        assert np.array_equal(sc0, osc)
+
+
 # ---- randomised differential tests -----------------------------------------------------------
 PENALTIES = [(-400, -30), (-600, -150), (-300, -40), (-200, -50)]
 
