@@ -5,10 +5,12 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one pass of the hot path over one batch of synthetic pairs resident in HBM.
-Workload (BASELINE.json configs[1], "C2"): P = 10^7 pairs per GPU, target 500 x query 150,
-AffineGapLocal semantics (free end gaps), HumanChimpTwo matrix, O=-600, E=-150, score only.
-The same line also carries configs[2] ("C3": the same pairs with full traceback + CIGAR) under
-"traceback".  GCUPS counts each DP cell once: sum(n*m) / seconds / 1e9.
+Headline workload (BASELINE.json configs[2], "C3"): 10^7 pairs IN TOTAL, target 500 x query 150, AffineGapLocal
+semantics (free end gaps), HumanChimpTwo matrix, O=-600, E=-150, full traceback + CIGAR, batch-sharded over the N
+GPUs (strong scaling; `--scaling weak` keeps 10^7 pairs per GPU), inputs as dnaTwoBit words, and -- for N > 1 --
+the NCCL gather of every shard's scores AND cigars inside the timed step.  The same line carries configs[1]
+("C2": score only) under "score_only", configs[3] ("C4": 12,500 pairs of 10 kb x 10 kb per GPU) and the other
+shapes under "other_workloads".  GCUPS counts each DP cell once: sum(n*m) / seconds / 1e9.
 """
 from __future__ import annotations
 
@@ -33,6 +35,8 @@ SEED = 20260102
 # traceback adds 0.75 B per cell (three 2-bit source-plane codes)
 BYTES_PER_PAIR_SCORE = (N_LEN + 3) // 4 + (M_LEN + 3) // 4 + 16 + 8
 BYTES_PER_CELL_TRACE = 0.75
+WORKLOAD = ("C3 (BASELINE.json configs[2]): 10^7 pairs, target 500 x query 150, semi-global affine gap (AffineGapLocal), "
+            "full traceback + CIGAR, batch-sharded over the GPUs")
 
 
 def ncu_traffic(kernel: str, pairs_per_launch: float):
@@ -98,11 +102,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_gcups(n_pairs: int, want_cigar: bool, threads: int):
+def cpu_reference_gcups(n_pairs: int, want_cigar: bool, threads: int, first_pair: int = 0):
     """The oracle (C restatement of the Go path) on the host cores: the reported CPU baseline."""
     import oracle as orc
     from gonomics_b200.synth import synth_pairs
-    a, ao, b, bo = synth_pairs(SEED, n_pairs, N_LEN, M_LEN)
+    a, ao, b, bo = synth_pairs(SEED, n_pairs, N_LEN, M_LEN, first_pair=first_pair)
     t0 = time.perf_counter()
     orc.batch(a, ao, b, bo, orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, GAP_OPEN, GAP_EXTEND, 1, want_cigar, threads)
     dt = time.perf_counter() - t0
@@ -284,19 +288,18 @@ def run_reference(args):
     sample = max(2000, 4000 * threads)  # ~3 s of host work per step
     vals = []
     for i in range(args.warmup + args.steps):
-        g, dt = cpu_reference_gcups(sample, False, threads)
+        g, dt = cpu_reference_gcups(sample, True, threads, first_pair=i * sample)
         if i >= args.warmup:
             vals.append((g, dt))
     gcups = sample * N_LEN * M_LEN * len(vals) / sum(d for _, d in vals) / 1e9
     line = {
         "impl": "reference", "metric": "GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(d for _, d in vals) / len(vals),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": "C2: target 500 x query 150 semi-global affine (AffineGapLocal), score only",
-                   "matrix": "HumanChimpTwo", "gap_open": GAP_OPEN, "gap_extend": GAP_EXTEND},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "matrix": "HumanChimpTwo", "gap_open": GAP_OPEN, "gap_extend": GAP_EXTEND},
         "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": threads, "kind": "port",
-                         "sample": f"{sample} pairs of the C2 batch per step (C restatement of the Go path; "
-                                   "Go toolchain absent)"},
+                         "sample": f"{sample} pairs of the C3 batch per step, traceback + cigar (C restatement of the Go "
+                                   "path: affineGap_highMem incl. its per-call trace allocation; Go toolchain absent)"},
         "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -315,13 +318,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=10_000_000, help="pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=10_000_000, help="pairs per step: in total (strong) or per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--impl", default="gnx", choices=["gnx", "reference"])
-    ap.add_argument("--no-traceback", action="store_true", help="skip the C3 (traceback) block")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the C1 / C4-sample / const-gap block")
-    ap.add_argument("--quick", action="store_true", help="profiling runs: no e2e/cpu legs, warm-up not clamped")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C1 / C4 / const-gap / 2-bit / gsw blocks")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: headline only, warm-up not clamped")
+    ap.add_argument("--c4-pairs", type=int, default=12_500, help="10 kb x 10 kb pairs per GPU in the C4 block")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON result: everything libraries print there (e.g. "NCCL version ..."
     # under torchrun) is sent to stderr by pointing fd 1 at fd 2 for the duration of the run.
@@ -333,15 +337,17 @@ def main():
         run_reference(args)
         return
     if args.quick:
-        args.no_e2e = args.no_cpu = True
+        args.no_e2e = args.no_cpu = args.no_extra = True
     else:
         args.warmup = max(args.warmup, 3)
 
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
-    from gonomics_b200 import align
+    from gonomics_b200 import align, shard
     from gonomics_b200._lib import CIGAR_DTYPE, load
-    from gonomics_b200.synth import synth_pairs
+    from gonomics_b200.synth import pack_uniform, synth_pairs
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -353,146 +359,197 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    P = args.pairs
+    # ---- this rank's shard: contiguous pair range [lo, hi) of the global batch ------------------------
+    if args.scaling == "strong":
+        lo, hi = args.pairs * rank // world, args.pairs * (rank + 1) // world
+        total_pairs = args.pairs
+    else:
+        lo, hi = args.pairs * rank, args.pairs * (rank + 1)
+        total_pairs = args.pairs * world
+    P = hi - lo
     S = align.HumanChimpTwoScoreMatrix
     L = load()
     ctx = align.Context(local)
-    cells = P * N_LEN * M_LEN
+    cells = P * N_LEN * M_LEN            # this rank
+    cells_all = total_pairs * N_LEN * M_LEN
+    WN, WM = (N_LEN + 31) // 32, (M_LEN + 31) // 32
 
-    # ---- synthetic inputs: this rank's shard of the global batch, in pinned host memory ----------
+    pinned_ptrs = []
+
+    def pinned_array(count, dtype):
+        """Page-locked host array (gnx_host_alloc): DMA'd without a staging copy."""
+        dt = np.dtype(dtype)
+        ptr = L.gnx_host_alloc(max(count * dt.itemsize, 1))
+        if not ptr:
+            raise MemoryError("gnx_host_alloc failed")
+        pinned_ptrs.append(ptr)
+        raw = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(max(count * dt.itemsize, 1),))
+        return raw[:count * dt.itemsize].view(dt)
+
+    # ---- synthetic inputs (SURVEY 8d recipe) in pinned host memory: bytes and dnaTwoBit words -----------
     na, nb = P * N_LEN, P * M_LEN
-    import ctypes as C
-    pa, pb_ = L.gnx_host_alloc(na), L.gnx_host_alloc(nb)
-    h_alpha = np.ctypeslib.as_array(C.cast(pa, C.POINTER(C.c_uint8)), shape=(na,))
-    h_beta = np.ctypeslib.as_array(C.cast(pb_, C.POINTER(C.c_uint8)), shape=(nb,))
+    h_alpha, h_beta = pinned_array(na, np.uint8), pinned_array(nb, np.uint8)
     t0 = time.perf_counter()
-    _, ao, _, bo = synth_pairs(SEED, P, N_LEN, M_LEN, first_pair=rank * P, alpha_out=h_alpha, beta_out=h_beta)
-    ao -= ao[0]
-    bo -= bo[0]
+    _, ao, _, bo = synth_pairs(SEED, P, N_LEN, M_LEN, first_pair=lo, alpha_out=h_alpha, beta_out=h_beta)
+    h_wa, h_wb = pinned_array(P * WN, np.uint64), pinned_array(P * WM, np.uint64)
+    pack_uniform(h_alpha, P, N_LEN, out=h_wa)
+    pack_uniform(h_beta, P, M_LEN, out=h_wb)
     gen_s = time.perf_counter() - t0
-    d_alpha = torch.from_numpy(h_alpha).to(dev)
-    d_beta = torch.from_numpy(h_beta).to(dev)
+    d_alpha, d_beta = torch.from_numpy(h_alpha).to(dev), torch.from_numpy(h_beta).to(dev)
     d_ao, d_bo = torch.from_numpy(ao).to(dev), torch.from_numpy(bo).to(dev)
+    pad = torch.zeros(64, dtype=torch.int64, device=dev)  # the TMA of a tail quad reads a whole quad's words
+    d_wa = torch.cat([torch.from_numpy(h_wa.view(np.int64)).to(dev), pad])
+    d_wb = torch.cat([torch.from_numpy(h_wb.view(np.int64)).to(dev), pad])
     d_score = torch.zeros(P, dtype=torch.int64, device=dev)
     d_status = torch.zeros(1, dtype=torch.int32, device=dev)
     cig_cap = P * 12
     d_cig = torch.zeros(cig_cap * 16, dtype=torch.uint8, device=dev)
     d_off = torch.zeros(P + 1, dtype=torch.int64, device=dev)
-    gathered = torch.zeros(world * P, dtype=torch.int64, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream().cuda_stream
+    gather_bytes = [0]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def device_step(want_cigar: bool):
-        ctx.batch_device(1, d_alpha.data_ptr(), d_ao.data_ptr(), d_beta.data_ptr(), d_bo.data_ptr(), ao, bo, P, S,
-                         GAP_OPEN, GAP_EXTEND, want_cigar, d_score.data_ptr(), d_cig.data_ptr() if want_cigar else 0,
-                         d_off.data_ptr() if want_cigar else 0, cig_cap, d_status.data_ptr(), stream)
-        if world > 1:  # the path's only exchange: gather the per-shard scores (north_star)
-            dist.all_gather_into_tensor(gathered, d_score)
+    def device_step(want_cigar: bool, twobit: bool, gather: bool = True):
+        if twobit:
+            ctx.batch_device_twobit(1, d_wa.data_ptr(), N_LEN, d_wb.data_ptr(), M_LEN, P, S, GAP_OPEN, GAP_EXTEND, want_cigar,
+                                    d_score.data_ptr(), d_cig.data_ptr() if want_cigar else 0,
+                                    d_off.data_ptr() if want_cigar else 0, cig_cap, d_status.data_ptr(), stream)
+        else:
+            ctx.batch_device(1, d_alpha.data_ptr(), d_ao.data_ptr(), d_beta.data_ptr(), d_bo.data_ptr(), ao, bo, P, S,
+                             GAP_OPEN, GAP_EXTEND, want_cigar, d_score.data_ptr(), d_cig.data_ptr() if want_cigar else 0,
+                             d_off.data_ptr() if want_cigar else 0, cig_cap, d_status.data_ptr(), stream)
+        if world > 1 and gather:  # the path's only exchange (north_star): every shard's scores -- and cigars -- to every rank
+            res = shard.gather_device(d_score, d_off if want_cigar else None, d_cig if want_cigar else None, 16)
+            gather_bytes[0] = res[4]
 
-    def timed_device(want_cigar: bool):
-        for _ in range(args.warmup):
-            device_step(want_cigar)
+    def timed_device(want_cigar: bool, twobit: bool, steps=None, warmup=None):
+        steps, warmup = steps or args.steps, args.warmup if warmup is None else warmup
+        for _ in range(warmup):
+            device_step(want_cigar, twobit)
         barrier()
         launches0 = ctx.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        fill_ms = 0.0
-        fill_launches = 0
         sampler = ClockSampler(local)
         sampler.start()
         e0.record()
-        for _ in range(args.steps):
-            device_step(want_cigar)
+        for _ in range(steps):
+            device_step(want_cigar, twobit)
         e1.record()
         barrier()
         clocks = sampler.stop()
         ms = e0.elapsed_time(e1)
-        # fill-kernel device time of the LAST step (CUDA events recorded by the library on this stream)
-        f_ms, f_n, _ = ctx.last_fill_stats()
-        fill_ms, fill_launches = f_ms, f_n
+        f_ms, f_n, _ = ctx.last_fill_stats()  # fill-kernel device time of the LAST step (library CUDA events on this stream)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         assert int(d_status.item()) == 0, "device status != 0"
-        return ms, ctx.launch_count - launches0, fill_ms, fill_launches, clocks
+        return ms / steps, (ctx.launch_count - launches0) // steps, f_ms, f_n, clocks
+
+    def gather_only_ms(want_cigar: bool):
+        """Device time of the NCCL gather alone (same tensors as the timed step)."""
+        if world == 1:
+            return None
+        for _ in range(2):
+            shard.gather_device(d_score, d_off if want_cigar else None, d_cig if want_cigar else None, 16)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            shard.gather_device(d_score, d_off if want_cigar else None, d_cig if want_cigar else None, 16)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     peak, peak_src = hbm_peak()
+    n_chunks = -(-P // (1 << 18))  # chunk_pairs default: launches of the dominant kernel pair per step
 
-    # ---- C2: score only (headline value) ---------------------------------------------------------
-    ms, launches, fill_ms, fill_n, clocks = timed_device(False)
-    gcups = world * cells * args.steps / (ms * 1e-3) / 1e9
-    alg_bytes = P * BYTES_PER_PAIR_SCORE  # per step, all fill launches of the step together
-    achieved = alg_bytes / (fill_ms * 1e-3) / 1e9 if fill_ms > 0 else None
+    def ncu_measured(kernel):
+        """DRAM bytes and warp instructions per 262,144-pair launch from the ncu capture of THIS build
+        (profiles/ncu_traffic.json, regenerated by tools/ncu_traffic.py in the round's ncu step)."""
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                m = json.load(f)[kernel]
+            m.setdefault("units_per_launch", 262144)
+            return m
+        except Exception:
+            return None
+
+    # ---- C3 (headline): traceback + CIGAR, dnaTwoBit inputs resident in HBM ---------------------------
+    ms3, launches3, fill3, filln3, clocks3 = timed_device(True, True)
+    g3 = cells_all / (ms3 * 1e-3) / 1e9
+    alg3 = cells * BYTES_PER_CELL_TRACE + P * BYTES_PER_PAIR_SCORE  # this rank, per step
+    ach3 = alg3 / (fill3 * 1e-3) / 1e9 if fill3 > 0 else None
+    meas3 = ncu_measured("ckpt_path")
     line = {
-        "metric": "GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u16x2", "data": "synthetic",
-        "config": {"workload": "C2 (BASELINE.json configs[1]): %d pairs/GPU, target 500 x query 150, semi-global "
-                               "affine gap (AffineGapLocal), score only" % P,
-                   "matrix": "HumanChimpTwo", "gap_open": GAP_OPEN, "gap_extend": GAP_EXTEND,
-                   "pairs_per_gpu": P, "cells_per_step_per_gpu": cells,
-                   "l2": "inputs (%.1f GB/GPU) exceed the 126 MB L2; no flush needed" % ((na + nb) / 1e9),
-                   "sharding": "independent pair shards per rank; all_gather of scores only (N>1)",
-                   "synth_seconds": round(gen_s, 1)},
-        "gpu_launches": launches,
-        "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None,
-                     "traffic": ncu_traffic("affine_fill16_kernel", P / max(fill_n, 1)),
-                     "algorithmic_bytes_per_launch": alg_bytes / max(fill_n, 1),
-                     "peak_source": peak_src, "kernel": "affine_fill16_kernel<FREE=1> (packed 16-bit, 4 pairs/warp)",
-                     "fill_ms_per_step": fill_ms, "fill_launches_per_step": fill_n,
-                     "algorithmic_bytes_per_step": alg_bytes,
-                     "note": "score-only fill moves 187 B per 75,000-cell pair: HBM cannot bind it; the binding "
-                             "roof is integer issue (see issue_roofline and DESIGN.md)"},
+        "metric": "GCUPS", "value": g3, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "u16x2 (score pass) + int32 (path recompute)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "matrix": "HumanChimpTwo", "gap_open": GAP_OPEN, "gap_extend": GAP_EXTEND,
+                   "pairs_total": total_pairs, "pairs_per_gpu": P, "cells_per_step_per_gpu": cells,
+                   "inputs": "dnaTwoBit words resident in HBM (gnx_batch_device_twobit): packed 16-bit kernels stage them by "
+                             "TMA, the path recompute reads a device-side expansion",
+                   "l2": "inputs (%.1f GB/GPU packed) exceed the 126 MB L2; no flush needed" % ((P * (WN + WM) * 8) / 1e9),
+                   "sharding": "contiguous pair shards per rank; NCCL all_gather of scores, cigar counts and cigar records "
+                               "inside the timed step (N>1)", "synth_seconds": round(gen_s, 1)},
+        "gpu_launches": launches3,
+        "clocks": clocks3,
+        "roofline": {"bound": "hbm", "achieved": ach3, "peak": peak, "unit": "GB/s", "frac": (ach3 / peak) if ach3 else None,
+                     "traffic": (meas3["dram_bytes"] * (P / n_chunks) / meas3["units_per_launch"]) if meas3 else None,
+                     "algorithmic_bytes_per_launch": alg3 / n_chunks, "peak_source": peak_src,
+                     "kernel": "affine_fill16_kernel<FREE,CM,CKPT,TB> + ckpt_classify_kernel + affine_ckpt_trace_kernel "
+                               "(checkpoint-and-recompute: one launch of each per 262,144-pair chunk, traceback walk included)",
+                     "fill_ms_per_step": fill3, "fill_launches_per_step": filln3, "algorithmic_bytes_per_step": alg3,
+                     "note": "achieved = ALGORITHMIC bytes (0.75 B/cell of trace codes + 187 B/pair) / device time of the DP "
+                             "kernels; the path keeps checkpoints instead of a trace matrix, so measured DRAM traffic is "
+                             "below the algorithmic figure and the binding roof is integer issue (DESIGN.md section 6)"},
     }
-    if fill_ms > 0 and clocks.get("sm_mhz"):
+    if world > 1:
+        gms = gather_only_ms(True)
+        line["gather"] = {"collective": "NCCL all_gather_into_tensor x5 (sizes, scores, counts, cigars)",
+                          "bytes_received_per_rank": gather_bytes[0], "ms": gms,
+                          "GBps_per_rank": gather_bytes[0] / (gms * 1e-3) / 1e9 if gms else None}
+
+    # ---- the same step with byte-per-base inputs, and C2 (score only) both ways -----------------------
+    ms3b, _, fill3b, _, _ = timed_device(True, False, steps=3)
+    line["traceback_byte_inputs"] = {"value": cells_all / (ms3b * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": ms3b,
+                                     "fill_ms_per_step": fill3b,
+                                     "note": "C3 with []dna.Base bytes resident in HBM (gnx_batch_device)"}
+    ms2, launches2, fill2, filln2, clocks2 = timed_device(False, True)
+    ms2b, _, fill2b, _, _ = timed_device(False, False, steps=3)
+    alg2 = P * BYTES_PER_PAIR_SCORE
+    meas2 = ncu_measured("affine_fill16_kernel")
+    so = {"workload": "C2 (configs[1]): same pairs, score only", "value": cells_all / (ms2 * 1e-3) / 1e9, "unit": "GCUPS",
+          "ms_per_step": ms2, "gpu_launches": launches2, "clocks": clocks2,
+          "byte_inputs": {"value": cells_all / (ms2b * 1e-3) / 1e9, "ms_per_step": ms2b, "fill_ms_per_step": fill2b},
+          "roofline": {"bound": "hbm", "achieved": alg2 / (fill2 * 1e-3) / 1e9 if fill2 > 0 else None, "peak": peak,
+                       "unit": "GB/s", "frac": alg2 / (fill2 * 1e-3) / 1e9 / peak if fill2 > 0 else None,
+                       "traffic": (meas2["dram_bytes"] * (P / n_chunks) / meas2["units_per_launch"]) if meas2 else None,
+                       "kernel": "affine_fill16_kernel<FREE,CM,TB> (packed 16-bit, 4 pairs/warp, 2-bit inputs by TMA)",
+                       "fill_ms_per_step": fill2, "fill_launches_per_step": filln2, "algorithmic_bytes_per_step": alg2,
+                       "note": "score-only moves 187 B per 75,000-cell pair: HBM cannot bind it (see issue_roofline)"}}
+    if fill2 > 0 and clocks2.get("sm_mhz") and meas2 and meas2.get("inst_executed"):
         sm = torch.cuda.get_device_properties(local).multi_processor_count
-        slots = sm * 4 * clocks["sm_mhz"] * 1e6  # warp-instruction issue slots per second
-        # 32 lanes x 2 packed pairs = 64 cells per warp-instruction slot in the packed kernel
-        avail = slots / (cells / 64 / (fill_ms * 1e-3))
-        # instructions the kernel executes per 64 cells: smsp__inst_executed.sum of the ncu capture in
-        # profiles/r01i_ckpt_path.md (3.0786e9 for a 262,144-pair chunk of 75,000-cell pairs)
-        inst64 = 3.0786e9 / (262144 * 75000 / 64)
-        line["issue_roofline"] = {"bound": "issue", "cells_per_s_fill": cells / (fill_ms * 1e-3),
-                                  "issue_slots_per_s": slots, "issue_slots_per_64_cells": avail,
-                                  "inst_per_64_cells": inst64, "frac": inst64 / avail,
-                                  "steady_loop_inst_per_64_cells": 8.6,
-                                  "note": "the binding roof of this integer max-plus kernel: warp-instruction issue "
-                                          "slots available per 64 DP cells (one packed warp-cell) at the measured fill "
-                                          "rate vs the instructions the kernel executes for them (ncu); frac = issue "
-                                          "utilisation.  The steady loop itself needs 8.6 (7 per packed cell + per-step "
-                                          "overhead), see DESIGN.md"}
+        slots = sm * 4 * clocks2["sm_mhz"] * 1e6  # warp-instruction issue slots per second
+        avail = slots / (cells / 64 / (fill2 * 1e-3))  # 32 lanes x 2 packed pairs = 64 cells per warp-instruction slot
+        inst64 = meas2["inst_executed"] / (meas2["units_per_launch"] * N_LEN * M_LEN / 64)
+        so["issue_roofline"] = {"bound": "issue", "issue_slots_per_64_cells": avail, "inst_per_64_cells": inst64,
+                                "frac": inst64 / avail,
+                                "note": "warp-instruction issue slots available per 64 DP cells at the measured fill rate vs "
+                                        "the instructions the kernel executes for them (smsp__inst_executed of this build's "
+                                        "ncu capture, profiles/ncu_traffic.json); frac = issue utilisation"}
+    line["score_only"] = so
 
-    # ---- C3: traceback + CIGAR on the same pairs -------------------------------------------------
-    if not args.no_traceback:
-        ms3, launches3, fill3, filln3, clocks3 = timed_device(True)
-        g3 = world * cells * args.steps / (ms3 * 1e-3) / 1e9
-        alg3 = cells * BYTES_PER_CELL_TRACE + P * BYTES_PER_PAIR_SCORE
-        n_chunks3 = -(-P // (1 << 18))  # chunk_pairs default
-        ckpt_path = filln3 >= 2 * n_chunks3  # fill16+checkpoints and the recompute kernel: two fill launches per chunk
-        ach3 = alg3 / (fill3 * 1e-3) / 1e9 if fill3 > 0 else None
-        line["traceback"] = {
-            "workload": "C3 (configs[2]): same pairs, full traceback + CIGAR", "value": g3, "unit": "GCUPS",
-            "ms_per_step": ms3 / args.steps, "gpu_launches": launches3, "clocks": clocks3,
-            "roofline": {"bound": "hbm", "achieved": ach3, "peak": peak, "unit": "GB/s",
-                         "frac": (ach3 / peak) if ach3 else None,
-                         "traffic": ncu_traffic("ckpt_path" if ckpt_path else "affine_fill3_kernel_trace",
-                                                P / max(n_chunks3, 1)),
-                         "algorithmic_bytes_per_launch": alg3 / max(n_chunks3, 1), "peak_source": peak_src,
-                         "kernel": ("affine_fill16_kernel<FREE,CM,CKPT> + affine_ckpt_trace_kernel (checkpoint-and-"
-                                    "recompute: two launches per chunk, traceback walk included)") if ckpt_path
-                         else "affine_fill3_kernel<C=10,LPP=16,MODE=2,FREE=1>", "fill_ms_per_step": fill3,
-                         "fill_launches_per_step": filln3, "algorithmic_bytes_per_step": alg3}}
-
-    # ---- other BASELINE shapes (device-resident, fewer steps): C1, a C4-shaped sample, constant gap ----
-    if not args.quick and not args.no_extra:
-        def run_shape(kind, n_len, m_len, pairs, want_cigar, cap_per_pair, steps=3, ctx=ctx):
-            a, sao, b, sbo = synth_pairs(SEED + 7, pairs, n_len, m_len, first_pair=rank * pairs)
+    # ---- other BASELINE shapes: C1, C4 (full per-GPU share, device-resident AND through the host API), const gap --
+    if not args.no_extra:
+        def run_shape(kind, n_len, m_len, pairs, want_cigar, cap_per_pair, steps=3, ctx=ctx, seed=SEED + 7):
+            a, sao, b, sbo = synth_pairs(seed, pairs, n_len, m_len, first_pair=rank * pairs)
             ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
             tao, tbo = torch.from_numpy(sao).to(dev), torch.from_numpy(sbo).to(dev)
             sc = torch.zeros(pairs, dtype=torch.int64, device=dev)
@@ -513,102 +570,141 @@ def main():
             e1.record()
             barrier()
             ms_ = e0.elapsed_time(e1)
+            f_ms, _, _ = ctx.last_fill_stats()
             if world > 1:
                 t = torch.tensor([ms_], dtype=torch.float64, device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 ms_ = float(t.item())
             assert int(d_status.item()) == 0
-            return world * pairs * n_len * m_len * steps / (ms_ * 1e-3) / 1e9, ms_ / steps
+            return world * pairs * n_len * m_len * steps / (ms_ * 1e-3) / 1e9, ms_ / steps, f_ms, (a, sao, b, sbo, sc, off, cg)
 
-        g1, ms1 = run_shape(0, 1000, 150, 100_000, True, 16)
-        # C4: a 10 kb x 10 kb pair owns 82 MB of traceback matrix and the one-warp-per-pair kernel needs pairs in
-        # flight to fill the SMs, so this block gets its own context sized for the 180 GB part (75 % of what is free)
-        free_b, _ = torch.cuda.mem_get_info(dev)
-        ws4 = int(free_b * 0.75)
-        pairs4 = max(256, min(1776, ws4 // 82_300_000) // 4 * 4)
-        ctx4 = align.Context(local, ws4)
-        try:
-            g4, ms4 = run_shape(0, 10_000, 10_000, pairs4, True, 4096, steps=2, ctx=ctx4)
-        finally:
-            ctx4.close()
+        g1, ms1, _, _ = run_shape(0, 1000, 150, 100_000, True, 16)
+        gc, msc, _, _ = run_shape(2, N_LEN, M_LEN, 1_000_000, True, 400)
+        # C4 (configs[3]): 100k pairs of 10 kb x 10 kb over 8 GPUs = 12,500 per GPU, global affine + CIGAR
+        p4 = args.c4_pairs
+        g4, ms4, f4, keep = run_shape(0, 10_000, 10_000, p4, True, 600, steps=2, seed=20260104)
+        a4, ao4, b4, bo4, sc4, off4, cg4 = keep
+        cells4 = p4 * 10_000 * 10_000
+        alg4 = cells4 * BYTES_PER_CELL_TRACE
+        meas4 = ncu_measured("affine_long_kernel")
+        c4 = {"value": g4, "unit": "GCUPS", "pairs_per_gpu": p4, "ms_per_step": ms4,
+              "roofline": {"bound": "hbm", "achieved": alg4 / (f4 * 1e-3) / 1e9 if f4 > 0 else None, "peak": peak, "unit": "GB/s",
+                           "frac": alg4 / (f4 * 1e-3) / 1e9 / peak if f4 > 0 else None,
+                           "traffic": (meas4["dram_bytes"] * p4 / meas4["units_per_launch"]) if meas4 else None,
+                           "algorithmic_bytes_per_launch": alg4, "kernel": "affine_long_kernel<FREE=0> (one launch per step)",
+                           "fill_ms_per_step": f4, "peak_source": peak_src},
+              "note": "AffineGap (global) + CIGAR, device-resident; tile checkpoints + recompute of the route's tiles in "
+                      "per-warp scratch (gnx_long.cuh), no trace matrix"}
+        # through the host-buffer API (pageable numpy inputs and outputs: what a Go caller holds), H2D + D2H inside
+        t0 = time.perf_counter()
+        hsc, hoff, hcig = ctx.affine_gap_batch(a4, ao4, b4, bo4, S, GAP_OPEN, GAP_EXTEND, False, True, cigar_cap=p4 * 600)
+        dt4 = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        hsc, hoff, hcig = ctx.affine_gap_batch(a4, ao4, b4, bo4, S, GAP_OPEN, GAP_EXTEND, False, True, cigar_cap=p4 * 600)
+        dt4 = min(dt4, time.perf_counter() - t0)
+        if world > 1:
+            t = torch.tensor([dt4], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt4 = float(t.item())
+        c4["e2e"] = {"value": world * cells4 / dt4 / 1e9, "unit": "GCUPS", "seconds": dt4,
+                     "h2d_bytes_per_step": int(len(a4) + len(b4) + 16 * (p4 + 1)),
+                     "d2h_bytes_per_step": int(8 * p4 + 8 * (p4 + 1) + 16 * int(hoff[-1])),
+                     "api": "gnx_affine_batch, pageable host buffers"}
+        # parity: host API == device API everywhere; size-independent properties on every pair; oracle on a few
+        ok4 = bool(np.array_equal(hsc, sc4.cpu().numpy()) and np.array_equal(hoff, off4.cpu().numpy()))
+        rl, op = hcig["run_length"], hcig["op"]
+        ok4 &= bool(np.all(np.add.reduceat(np.where(op != 1, rl, 0), hoff[:-1]) == 10_000)
+                    and np.all(np.add.reduceat(np.where(op != 2, rl, 0), hoff[:-1]) == 10_000))
+        if rank == 0 and not args.no_cpu:
+            import oracle as orc
+            k4 = min(p4, 2 * (os.cpu_count() or 1))
+            osc, ooff, ocig = orc.batch(a4[:ao4[k4]], ao4[:k4 + 1], b4[:bo4[k4]], bo4[:k4 + 1], orc.HUMAN_CHIMP_TWO_SCORE_MATRIX,
+                                        GAP_OPEN, GAP_EXTEND, 0, True, os.cpu_count() or 1)
+            t4 = int(ooff[-1])
+            ok4 &= bool(np.array_equal(hsc[:k4], osc) and np.array_equal(hoff[:k4 + 1], ooff)
+                        and np.array_equal(rl[:t4], ocig["run_length"]) and np.array_equal(op[:t4], ocig["op"]))
+            c4["parity_pairs_vs_oracle"] = k4
+        c4["parity_spot_check"] = ok4
+        del a4, b4, sc4, off4, cg4, keep, hsc, hoff, hcig
         torch.cuda.empty_cache()
-        gc, msc = run_shape(2, N_LEN, M_LEN, 1_000_000, True, 400)
         line["other_workloads"] = {
             "c1_global_1000x150_traceback": {"value": g1, "unit": "GCUPS", "pairs_per_gpu": 100_000, "ms_per_step": ms1,
                                              "note": "AffineGap (global) + CIGAR, configs[0] shape x100"},
-            "c4_global_10kx10k_traceback": {"value": g4, "unit": "GCUPS", "pairs_per_gpu": pairs4, "ms_per_step": ms4,
-                                            "workspace_gb": round(ws4 / 1e9, 1),
-                                            "note": "AffineGap (global) + CIGAR, one warp per pair through 32 strips "
-                                                    "(one workspace-sized chunk of configs[3]: 82 MB of traceback "
-                                                    "matrix per pair, dedicated context with 75 % of free HBM)"},
+            "c4_global_10kx10k_traceback": c4,
             "const_gap_500x150_traceback": {"value": gc, "unit": "GCUPS", "pairs_per_gpu": 1_000_000,
                                             "ms_per_step": msc, "note": "ConstGap_highMem + CIGAR, g=-430"}}
-
-    # ---- 2-bit packing (HBM-bound) and the perfect-match seed step ----------------------
-    if not args.quick and not args.no_extra:
+        # 2-bit packing (HBM-bound) and the perfect-match seed / extend steps
         line["other_workloads"].update(twobit_block(ctx, L, dev, stream, rank, world, barrier, args))
 
-    # ---- e2e: the public host-buffer API, pinned host inputs, H2D + D2H inside the timed region --
+    # ---- e2e: the public host-buffer API with H2D + D2H inside the timed region ------------------------
+    # Headline e2e = what the cgo shim of INTEGRATION.md does: PAGEABLE []dna.Base bytes in, pageable results out.
+    # The other variants show what the same call delivers with page-locked buffers (gnx_host_alloc) and with the
+    # batch in dnaTwoBit form (a quarter of the H2D bytes).
     if not args.no_e2e:
-        pinned = []
+        e2e_steps = max(2, min(args.steps, 3))
+        p_score, p_off, p_cig = pinned_array(P, np.int64), pinned_array(P + 1, np.int64), pinned_array(cig_cap, CIGAR_DTYPE)
+        g_alpha, g_beta = np.array(h_alpha), np.array(h_beta)          # pageable copies ("Go slices")
+        g_wa, g_wb = np.array(h_wa), np.array(h_wb)
+        g_score, g_off, g_cig = np.zeros(P, np.int64), np.zeros(P + 1, np.int64), np.zeros(cig_cap, CIGAR_DTYPE)
 
-        def pinned_array(count, dtype):
-            """Caller-owned result buffer in page-locked memory (gnx_host_alloc): results are DMA'd straight into it."""
-            dt = np.dtype(dtype)
-            ptr = L.gnx_host_alloc(max(count * dt.itemsize, 1))
-            if not ptr:
-                raise MemoryError("gnx_host_alloc failed")
-            pinned.append(ptr)
-            raw = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(max(count * dt.itemsize, 1),))
-            return raw[:count * dt.itemsize].view(dt)
+        def e2e(want_cigar: bool, twobit: bool, pinned: bool):
+            out = (p_score, p_off if want_cigar else None, p_cig if want_cigar else None) if pinned else \
+                  (g_score, g_off if want_cigar else None, g_cig if want_cigar else None)
 
-        def e2e(want_cigar: bool):
-            out_score = pinned_array(P, np.int64)
-            out_off = pinned_array(P + 1, np.int64) if want_cigar else None
-            out_cig = pinned_array(cig_cap, CIGAR_DTYPE) if want_cigar else None
-            out = (out_score, out_off, out_cig)
-            for _ in range(2):
-                ctx.affine_gap_batch(h_alpha, ao, h_beta, bo, S, GAP_OPEN, GAP_EXTEND, True, want_cigar, out=out)
+            def call():
+                if twobit:
+                    wa, wb = (h_wa, h_wb) if pinned else (g_wa, g_wb)
+                    ctx.affine_gap_batch_twobit(wa, N_LEN, wb, M_LEN, S, GAP_OPEN, GAP_EXTEND, True, want_cigar, out=out, n_pairs=P)
+                else:
+                    al, be = (h_alpha, h_beta) if pinned else (g_alpha, g_beta)
+                    ctx.affine_gap_batch(al, ao, be, bo, S, GAP_OPEN, GAP_EXTEND, True, want_cigar, out=out)
+            call()
             barrier()
             t0 = time.perf_counter()
-            for _ in range(args.steps):
-                ctx.affine_gap_batch(h_alpha, ao, h_beta, bo, S, GAP_OPEN, GAP_EXTEND, True, want_cigar, out=out)
+            for _ in range(e2e_steps):
+                call()
             torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
+            dt = (time.perf_counter() - t0) / e2e_steps
             if world > 1:
                 t = torch.tensor([dt], dtype=torch.float64, device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dt = float(t.item())
-            h2d = na + nb + 2 * (P + 1) * 8
-            d2h = P * 8 + ((P + 1) * 8 + int(out_off[-1]) * 16 if want_cigar else 0)
-            return world * cells * args.steps / dt / 1e9, h2d, d2h, (out_score if not want_cigar else out)
-        v, h2d, d2h, sc_host = e2e(False)
-        line["e2e"] = {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "api": "gnx_affine_batch (host buffers, inputs and results pinned), score only"}
-        assert np.array_equal(sc_host, d_score.cpu().numpy()), "host-API scores differ from device-API scores"
-        if not args.no_traceback:
-            v3, h2d3, d2h3, out3 = e2e(True)
-            line["traceback"]["e2e"] = {"value": v3, "unit": "GCUPS", "h2d_bytes_per_step": h2d3,
-                                        "d2h_bytes_per_step": d2h3}
-            if rank == 0 and world == 1 and not args.no_cpu:
-                # SURVEY 8d: the first pairs of the timed batch diffed against the oracle, score AND cigar
-                import oracle as orc
-                k = min(P, 20000)
-                osc, ooff, ocig = orc.batch(h_alpha[:k * N_LEN], ao[:k + 1], h_beta[:k * M_LEN], bo[:k + 1],
-                                            orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, GAP_OPEN, GAP_EXTEND, 1, True,
-                                            os.cpu_count() or 1)
-                gsc, goff, gcig = out3
-                t = int(ooff[-1])
-                line["traceback"]["parity_spot_check"] = bool(
-                    np.array_equal(gsc[:k], osc) and np.array_equal(goff[:k + 1], ooff)
-                    and np.array_equal(gcig["run_length"][:t], ocig["run_length"])
-                    and np.array_equal(gcig["op"][:t], ocig["op"]))
-            out3 = None
-        sc_host = None
-        for ptr in pinned:
-            L.gnx_host_free(ptr)
+            h2d = (P * (WN + WM) * 8) if twobit else (na + nb + 2 * (P + 1) * 8)
+            d2h = P * 8 + ((P + 1) * 8 + int(out[1][-1]) * 16 if want_cigar else 0)
+            return {"value": cells_all / dt / 1e9, "unit": "GCUPS", "ms_per_step": dt * 1e3, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h)}, out
 
-    # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores ----------------------
+        head, out3 = e2e(True, False, False)
+        head["api"] = "gnx_affine_batch: pageable []dna.Base bytes in, pageable scores + cigars out (the cgo shim's call)"
+        assert np.array_equal(out3[0], d_score.cpu().numpy()), "host-API scores differ from device-API scores"
+        if rank == 0 and not args.no_cpu:
+            # the first pairs of the timed batch diffed against the oracle, score AND cigar
+            import oracle as orc
+            k = min(P, 20000)
+            osc, ooff, ocig = orc.batch(h_alpha[:k * N_LEN], ao[:k + 1], h_beta[:k * M_LEN], bo[:k + 1],
+                                        orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, GAP_OPEN, GAP_EXTEND, 1, True, os.cpu_count() or 1)
+            t = int(ooff[-1])
+            line["parity_spot_check"] = bool(
+                np.array_equal(out3[0][:k], osc) and np.array_equal(out3[1][:k + 1], ooff)
+                and np.array_equal(out3[2]["run_length"][:t], ocig["run_length"]) and np.array_equal(out3[2]["op"][:t], ocig["op"]))
+        ref_cig = (out3[1].copy(), out3[2][:int(out3[1][-1])].copy())
+        variants = {}
+        for name, tb_, pin_ in (("pinned_bytes", False, True), ("pageable_twobit", True, False), ("pinned_twobit", True, True)):
+            variants[name], o = e2e(True, tb_, pin_)
+            tot = int(o[1][-1])
+            assert np.array_equal(o[1], ref_cig[0]) and np.array_equal(o[2]["run_length"][:tot], ref_cig[1]["run_length"]) \
+                and np.array_equal(o[2]["op"][:tot], ref_cig[1]["op"]), f"e2e variant {name} differs"
+        head["variants"] = variants
+        line["e2e"] = head
+        so_e2e = {}
+        for name, tb_, pin_ in (("pageable_bytes", False, False), ("pinned_bytes", False, True),
+                                ("pageable_twobit", True, False), ("pinned_twobit", True, True)):
+            so_e2e[name], o = e2e(False, tb_, pin_)
+            assert np.array_equal(o[0], d_score.cpu().numpy()), f"score-only e2e variant {name} differs"
+        line["score_only"]["e2e"] = so_e2e
+        del g_alpha, g_beta, g_wa, g_wb, g_score, g_off, g_cig
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores, same workload (C3) --------
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         sample = max(2000, 12000 * threads)  # ~10 s of host work
@@ -616,18 +712,12 @@ def main():
         line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": threads, "kind": "port",
                                 "sample": f"first {sample} pairs of the batch, traceback + cigar, {dt:.1f} s "
                                           "(C restatement of the Go path; Go toolchain absent)"}
-        # spot-check: the GPU scores of that prefix equal the oracle's
-        import oracle as orc
-        k = min(sample, 20000)
-        osc, _, _ = orc.batch(h_alpha[:k * N_LEN], ao[:k + 1], h_beta[:k * M_LEN], bo[:k + 1],
-                              orc.HUMAN_CHIMP_TWO_SCORE_MATRIX, GAP_OPEN, GAP_EXTEND, 1, False, threads)
-        line["parity_spot_check"] = bool(np.array_equal(osc, d_score[:k].cpu().numpy()))
 
     if rank == 0:
         emit(line)
     ctx.close()
-    L.gnx_host_free(pa)
-    L.gnx_host_free(pb_)
+    for ptr in pinned_ptrs:
+        L.gnx_host_free(ptr)
     if world > 1:
         dist.destroy_process_group()
 

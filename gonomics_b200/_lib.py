@@ -22,7 +22,7 @@ GNX_MATCH_RIGHT, GNX_MATCH_LEFT = 0, 1
 EXPORTS = [
     "gnx_device_count", "gnx_create", "gnx_destroy", "gnx_last_error", "gnx_version", "gnx_host_alloc",
     "gnx_host_free", "gnx_affine_batch", "gnx_affine_batch_twobit", "gnx_const_batch", "gnx_affine_chunk_batch", "gnx_copy_last_cigars",
-    "gnx_multi_affine_chunk_batch", "gnx_extend_batch", "gnx_batch_device", "gnx_launch_count", "gnx_last_fill_stats", "gnx_set_option",
+    "gnx_multi_affine_chunk_batch", "gnx_extend_batch", "gnx_batch_device", "gnx_batch_device_twobit", "gnx_launch_count", "gnx_last_fill_stats", "gnx_set_option",
     "gnx_twobit_new", "gnx_twobit_free", "gnx_twobit_info", "gnx_twobit_download", "gnx_twobit_unpack", "gnx_twobit_get_bases",
     "gnx_twobit_count_matches", "gnx_twobit_pack_device", "gnx_seed_index_new", "gnx_seed_index_free", "gnx_seed_index_info",
     "gnx_seed_index_download", "gnx_seed_batch",
@@ -80,6 +80,8 @@ def load() -> C.CDLL:
     L.gnx_const_batch.restype = ci
     L.gnx_affine_batch_twobit.argtypes = [vp, vp, i64p, i64, vp, i64p, i64, i64, i64p, ci, i64, i64, ci, ci, i64p, cgp, i64p, i64]
     L.gnx_affine_batch_twobit.restype = ci
+    L.gnx_batch_device_twobit.argtypes = [vp, ci, vp, i64, vp, i64, i64, i64p, ci, i64, i64, ci, vp, vp, vp, i64, vp, vp]
+    L.gnx_batch_device_twobit.restype = ci
     L.gnx_affine_chunk_batch.argtypes = [vp, u8p, i64p, u8p, i64p, i64, i64p, ci, i64, i64, i64, i64p, cgp, i64p, i64]
     L.gnx_affine_chunk_batch.restype = ci
     L.gnx_multi_affine_chunk_batch.argtypes = [vp, u8p, i64p, i64p, i64, i64p, i64p, i64, i64p, ci, i64, i64, i64, ci,

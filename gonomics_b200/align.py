@@ -290,6 +290,17 @@ class Context:
                                       stream or None)
         self._check(rc)
 
+    def batch_device_twobit(self, kind, d_alpha_words, alpha_len, d_beta_words, beta_len, n_pairs, scores, gap_open,
+                            gap_extend, want_cigar, d_out_score, d_out_cigar=0, d_out_cigar_off=0, cigar_cap=0, d_status=0,
+                            stream=0):
+        """gnx_batch_device_twobit: a uniform batch in dnaTwoBit form, resident on the device."""
+        scores = np.ascontiguousarray(scores, dtype=np.int64)
+        rc = self._L.gnx_batch_device_twobit(self._h, int(kind), d_alpha_words, int(alpha_len), d_beta_words, int(beta_len),
+                                             int(n_pairs), _addr(scores), int(scores.shape[0]), int(gap_open),
+                                             int(gap_extend), int(bool(want_cigar)), d_out_score, d_out_cigar or None,
+                                             d_out_cigar_off or None, int(cigar_cap), d_status or None, stream or None)
+        self._check(rc)
+
 
 _default_ctx: Optional[Context] = None
 _default_lock = threading.Lock()

@@ -1294,6 +1294,29 @@ int collect_fill_stats(gnx_ctx *ctx)
     return GNX_OK;
 }
 
+// Pageable caller memory (a Go slice, a numpy array) cannot be DMA'd directly: it is copied through a page-locked
+// stage.  One memcpy thread moves ~6 GB/s, far below PCIe 5 x16, so large copies are split over a few threads.
+void par_memcpy(void *dst, const void *src, size_t bytes)
+{
+    constexpr size_t kMin = (size_t)4 << 20;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int nt = (int)std::min<size_t>({(size_t)8, (size_t)hw, bytes / kMin});
+    if (nt <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
+    for (int t = 1; t < nt; ++t) {
+        const size_t lo = std::min(bytes, per * t), hi = std::min(bytes, per * (t + 1));
+        if (hi > lo)
+            th.emplace_back([=] { memcpy((char *)dst + lo, (const char *)src + lo, hi - lo); });
+    }
+    memcpy(dst, src, std::min(bytes, per));
+    for (auto &x : th)
+        x.join();
+}
+
 bool is_pinned(const void *p)
 {
     cudaPointerAttributes at;
@@ -1411,10 +1434,10 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
             CU(cudaStreamSynchronize(s.stream));
             if (total > 0 && !direct) {
                 if (fits) {
-                    memcpy(out_cigar + cig_total, s.h_cig.p, (size_t)total * sizeof(gnx_cigar));
+                    par_memcpy(out_cigar + cig_total, s.h_cig.p, (size_t)total * sizeof(gnx_cigar));
                 } else {
                     ctx->retained.resize((size_t)(cig_total + total));
-                    memcpy(ctx->retained.data() + cig_total, s.h_cig.p, (size_t)total * sizeof(gnx_cigar));
+                    par_memcpy(ctx->retained.data() + cig_total, s.h_cig.p, (size_t)total * sizeof(gnx_cigar));
                 }
             }
             const int64_t *ho = s.h_off.as<int64_t>();
@@ -1473,7 +1496,7 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
                 CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s.stream));
             } else {
                 CU(stage.ensure(bytes));
-                memcpy(stage.p, src, bytes);
+                par_memcpy(stage.p, src, bytes);
                 CU(cudaMemcpyAsync(dst, stage.p, bytes, cudaMemcpyHostToDevice, s.stream));
             }
             return GNX_OK;
@@ -2216,43 +2239,26 @@ int gnx_copy_last_cigars(gnx_ctx *ctx, gnx_cigar *out_cigar, int64_t cigar_cap)
     return GNX_OK;
 }
 
-int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const int64_t *d_alpha_off,
-                     const uint8_t *d_beta_cat, const int64_t *d_beta_off, const int64_t *alpha_off_host,
-                     const int64_t *beta_off_host, int64_t n_pairs, const int64_t *scores, int dim, int64_t gap_open,
-                     int64_t gap_extend, int want_cigar, int64_t *d_out_score, gnx_cigar *d_out_cigar,
-                     int64_t *d_out_cigar_off, int64_t cigar_cap, int32_t *d_status, void *cuda_stream)
+// Device-resident batches: every array already in this context's device memory, work enqueued on `st`, no host
+// synchronisation.  tbd != nullptr: a UNIFORM batch in dnaTwoBit form (d_alpha_cat / d_beta_cat / the offset arrays are
+// NULL): byte offsets are made per chunk on the device and the chunk's bases expanded only when a kernel needs bytes.
+struct TbDev {
+    const uint64_t *a_words, *b_words;
+    int64_t n, m, wn, wm;
+};
+
+static int run_device_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *d_alpha_cat, const int64_t *d_alpha_off,
+                            const uint8_t *d_beta_cat, const int64_t *d_beta_off, const int64_t *alpha_off_host,
+                            const int64_t *beta_off_host, int64_t n_pairs, int64_t *d_out_score, gnx_cigar *d_out_cigar,
+                            int64_t *d_out_cigar_off, int64_t cigar_cap, int32_t *d_status, cudaStream_t st, const TbDev *tbd)
 {
-    if (!ctx)
-        return GNX_EARG;
-    if (n_pairs < 0 || kind < 0 || kind > 2 || !d_alpha_off || !d_beta_off || !d_out_score)
-        return fail(ctx, GNX_EARG, "bad argument to gnx_batch_device");
-    if (want_cigar && (!d_out_cigar_off || !d_out_cigar))
-        return fail(ctx, GNX_EARG, "d_out_cigar and d_out_cigar_off are required when want_cigar != 0");
-    CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    Problem pb;
-    int rc = fill_problem(ctx, pb, kind, want_cigar, scores, dim, gap_open, kind == 2 ? 0 : gap_extend);
-    if (rc != GNX_OK)
-        return rc;
+    int rc;
     ctx->fill_events_used = 0;
     ctx->last_fill_launches = 0;
     ctx->last_fill_ms = 0;
     ctx->last_cells = 0;
     if (n_pairs == 0)
         return GNX_OK;
-    std::vector<int64_t> ha, hb;
-    if (!alpha_off_host) {
-        ha.resize((size_t)n_pairs + 1);
-        CU(cudaMemcpyAsync(ha.data(), d_alpha_off, (size_t)(n_pairs + 1) * 8, cudaMemcpyDeviceToHost, st));
-        alpha_off_host = ha.data();
-    }
-    if (!beta_off_host) {
-        hb.resize((size_t)n_pairs + 1);
-        CU(cudaMemcpyAsync(hb.data(), d_beta_off, (size_t)(n_pairs + 1) * 8, cudaMemcpyDeviceToHost, st));
-        beta_off_host = hb.data();
-    }
-    if (!ha.empty() || !hb.empty())
-        CU(cudaStreamSynchronize(st));
     Plan plan;
     const int64_t budget_words = (int64_t)(ctx->workspace / 4); // single slot: chunks run back to back
     rc = make_plan(ctx, pb, alpha_off_host, beta_off_host, n_pairs, budget_words, plan);
@@ -2282,6 +2288,32 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
         cd.a_hi = alpha_off_host[end];
         cd.b_lo = beta_off_host[begin];
         cd.b_hi = beta_off_host[end];
+        if (tbd) {
+            CU(s.aoff.ensure((size_t)(np + 1) * 8));
+            CU(s.boff.ensure((size_t)(np + 1) * 8));
+            const int g = (int)((np + 1 + 255) / 256);
+            iota_offsets_kernel<<<g, 256, 0, st>>>(s.aoff.as<int64_t>(), begin, np + 1, tbd->n);
+            iota_offsets_kernel<<<g, 256, 0, st>>>(s.boff.as<int64_t>(), begin, np + 1, tbd->m);
+            ctx->launches += 2;
+            cd.aoff = s.aoff.as<int64_t>() - begin;
+            cd.boff = s.boff.as<int64_t>() - begin;
+            cd.alpha_words = tbd->a_words;
+            cd.beta_words = tbd->b_words;
+            if (!(pb.cfg.tb && !pb.want_cigar)) { // some kernel of this path reads bytes: expand the chunk
+                CU(s.alpha.ensure((size_t)std::max<int64_t>(cd.a_hi - cd.a_lo, 1)));
+                CU(s.beta.ensure((size_t)std::max<int64_t>(cd.b_hi - cd.b_lo, 1)));
+                const int64_t wa = np * tbd->wn, wb = np * tbd->wm;
+                if (wa > 0)
+                    twobit_unpack_uniform_kernel<<<(int)((wa + 255) / 256), 256, 0, st>>>(tbd->a_words + begin * tbd->wn, wa, tbd->wn,
+                                                                                        tbd->n, s.alpha.as<uint8_t>());
+                if (wb > 0)
+                    twobit_unpack_uniform_kernel<<<(int)((wb + 255) / 256), 256, 0, st>>>(tbd->b_words + begin * tbd->wm, wb, tbd->wm,
+                                                                                        tbd->m, s.beta.as<uint8_t>());
+                ctx->launches += 2;
+                cd.alpha = s.alpha.as<uint8_t>() - cd.a_lo;
+                cd.beta = s.beta.as<uint8_t>() - cd.b_lo;
+            }
+        }
         if (pb.want_cigar) {
             // the pinned staging is about to be rewritten by the host: fence on the upload that last read it -- the
             // previous chunk's, or the last chunk's of an earlier call that may still be queued behind other work
@@ -2334,6 +2366,74 @@ int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const i
     CU(cudaEventRecord(ctx->ev_dev, st));
     ctx->ev_dev_set = true;
     return GNX_OK;
+}
+
+int gnx_batch_device(gnx_ctx *ctx, int kind, const uint8_t *d_alpha_cat, const int64_t *d_alpha_off,
+                     const uint8_t *d_beta_cat, const int64_t *d_beta_off, const int64_t *alpha_off_host,
+                     const int64_t *beta_off_host, int64_t n_pairs, const int64_t *scores, int dim, int64_t gap_open,
+                     int64_t gap_extend, int want_cigar, int64_t *d_out_score, gnx_cigar *d_out_cigar,
+                     int64_t *d_out_cigar_off, int64_t cigar_cap, int32_t *d_status, void *cuda_stream)
+{
+    if (!ctx)
+        return GNX_EARG;
+    if (n_pairs < 0 || kind < 0 || kind > 2 || !d_alpha_off || !d_beta_off || !d_out_score)
+        return fail(ctx, GNX_EARG, "bad argument to gnx_batch_device");
+    if (want_cigar && (!d_out_cigar_off || !d_out_cigar))
+        return fail(ctx, GNX_EARG, "d_out_cigar and d_out_cigar_off are required when want_cigar != 0");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Problem pb;
+    int rc = fill_problem(ctx, pb, kind, want_cigar, scores, dim, gap_open, kind == 2 ? 0 : gap_extend);
+    if (rc != GNX_OK)
+        return rc;
+    std::vector<int64_t> ha, hb;
+    if (n_pairs > 0 && !alpha_off_host) {
+        ha.resize((size_t)n_pairs + 1);
+        CU(cudaMemcpyAsync(ha.data(), d_alpha_off, (size_t)(n_pairs + 1) * 8, cudaMemcpyDeviceToHost, st));
+        alpha_off_host = ha.data();
+    }
+    if (n_pairs > 0 && !beta_off_host) {
+        hb.resize((size_t)n_pairs + 1);
+        CU(cudaMemcpyAsync(hb.data(), d_beta_off, (size_t)(n_pairs + 1) * 8, cudaMemcpyDeviceToHost, st));
+        beta_off_host = hb.data();
+    }
+    if (!ha.empty() || !hb.empty())
+        CU(cudaStreamSynchronize(st));
+    return run_device_batch(ctx, pb, d_alpha_cat, d_alpha_off, d_beta_cat, d_beta_off, alpha_off_host, beta_off_host, n_pairs,
+                            d_out_score, d_out_cigar, d_out_cigar_off, cigar_cap, d_status, st, nullptr);
+}
+
+int gnx_batch_device_twobit(gnx_ctx *ctx, int kind, const uint64_t *d_alpha_words, int64_t alpha_len, const uint64_t *d_beta_words,
+                            int64_t beta_len, int64_t n_pairs, const int64_t *scores, int dim, int64_t gap_open,
+                            int64_t gap_extend, int want_cigar, int64_t *d_out_score, gnx_cigar *d_out_cigar,
+                            int64_t *d_out_cigar_off, int64_t cigar_cap, int32_t *d_status, void *cuda_stream)
+{
+    if (!ctx)
+        return GNX_EARG;
+    if (n_pairs < 0 || kind < 0 || kind > 1 || !d_out_score || (n_pairs > 0 && (!d_alpha_words || !d_beta_words)))
+        return fail(ctx, GNX_EARG, "bad argument to gnx_batch_device_twobit");
+    if (want_cigar && (!d_out_cigar_off || !d_out_cigar))
+        return fail(ctx, GNX_EARG, "d_out_cigar and d_out_cigar_off are required when want_cigar != 0");
+    if (((uintptr_t)d_alpha_words & 15) || ((uintptr_t)d_beta_words & 15))
+        return fail(ctx, GNX_EARG, "device word arrays must be 16-byte aligned (cp.async.bulk source)");
+    CU(cudaSetDevice(ctx->device));
+    Problem pb;
+    int rc = fill_problem(ctx, pb, kind, want_cigar, scores, dim, gap_open, gap_extend);
+    if (rc != GNX_OK)
+        return rc;
+    pb.twobit = true;
+    TbIn tb;
+    if ((rc = twobit_offsets(ctx, nullptr, alpha_len, nullptr, beta_len, n_pairs, tb)) != GNX_OK)
+        return rc;
+    TbDev td;
+    td.a_words = d_alpha_words;
+    td.b_words = d_beta_words;
+    td.n = tb.n;
+    td.m = tb.m;
+    td.wn = tb.wn;
+    td.wm = tb.wm;
+    return run_device_batch(ctx, pb, nullptr, nullptr, nullptr, nullptr, ctx->tb_off[0].data(), ctx->tb_off[1].data(), n_pairs,
+                            d_out_score, d_out_cigar, d_out_cigar_off, cigar_cap, d_status, (cudaStream_t)cuda_stream, &td);
 }
 
 int64_t gnx_launch_count(gnx_ctx *ctx) { return ctx ? ctx->launches : 0; }

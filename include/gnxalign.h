@@ -288,6 +288,15 @@ int gnx_multi_const_batch(gnx_multi *mg, const uint8_t *alpha_cat, const int64_t
                           int64_t cigar_cap);
 int gnx_multi_copy_last_cigars(gnx_multi *mg, gnx_cigar *out_cigar, int64_t cigar_cap);
 
+/* Device-resident form of gnx_affine_batch_twobit for a UNIFORM batch: sequence p's words at
+ * d_alpha_words + p * ceil(alpha_len / 32) (16-byte aligned arrays, readable 256 bytes past their end: the TMA of
+ * a tail quad fetches a whole quad's words).  kind: 0 affine global, 1 affine free-end. */
+int gnx_batch_device_twobit(gnx_ctx *ctx, int kind, const uint64_t *d_alpha_words, int64_t alpha_len,
+                            const uint64_t *d_beta_words, int64_t beta_len, int64_t n_pairs, const int64_t *scores,
+                            int dim, int64_t gap_open, int64_t gap_extend, int want_cigar, int64_t *d_out_score,
+                            gnx_cigar *d_out_cigar, int64_t *d_out_cigar_off, int64_t cigar_cap, int32_t *d_status,
+                            void *cuda_stream);
+
 /* ---- introspection (used by bench.py / tests) ------------------------------------------------ */
 /* Kernel launches issued by this context since creation (every launch of a libgnxalign kernel). */
 int64_t gnx_launch_count(gnx_ctx *ctx);

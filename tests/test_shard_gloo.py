@@ -37,6 +37,15 @@ def _worker(rank, world, port, ret):
           and np.array_equal(g_cig["run_length"], w_cig["run_length"]) and np.array_equal(g_cig["op"], w_cig["op"]))
     g2, _, _ = shard.gather_results(sc, None, None)
     ok = ok and np.array_equal(g2, w_sc)
+    # the device-tensor form bench.py times on NCCL (here: CPU tensors over gloo)
+    t_sc, t_off = torch.from_numpy(sc), torch.from_numpy(off)
+    t_cig = torch.from_numpy(np.ascontiguousarray(cig).view(np.uint8).copy())
+    a_sc, a_cnt, a_cig, metas, moved = shard.gather_device(t_sc, t_off, t_cig, cig.dtype.itemsize)
+    d_sc, d_off, d_cig = shard.compact_gathered(a_sc, a_cnt, a_cig, metas, cig.dtype)
+    ok = ok and np.array_equal(d_sc, w_sc) and np.array_equal(d_off, w_off) and moved > 0
+    ok = ok and np.array_equal(d_cig["run_length"], w_cig["run_length"]) and np.array_equal(d_cig["op"], w_cig["op"])
+    a_sc, a_cnt, _, metas, _ = shard.gather_device(t_sc, None, None)
+    ok = ok and a_cnt is None and np.array_equal(shard.compact_gathered(a_sc, None, None, metas, cig.dtype)[0], w_sc)
     ret[rank] = (ok, bounds)
     dist.destroy_process_group()
 

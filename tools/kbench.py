@@ -25,6 +25,8 @@ ap.add_argument("--check-pairs", type=int, default=5000)
 ap.add_argument("--workspace-gb", type=float, default=0)
 ap.add_argument("--cap-per-pair", type=int, default=16)
 ap.add_argument("--score-only", action="store_true")
+ap.add_argument("--twobit", action="store_true", help="inputs as dnaTwoBit words (gnx_batch_device_twobit)")
+ap.add_argument("--iters", type=int, default=4)
 ap.add_argument("configs", nargs="*", default=["fill_impl=1", "fill_impl=2"])
 args = ap.parse_args()
 P = args.pairs
@@ -32,6 +34,11 @@ a, ao, b, bo = synth_pairs(20260102, P, args.n, args.m)
 dev = torch.device("cuda:0")
 ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
 tao, tbo = torch.from_numpy(ao).to(dev), torch.from_numpy(bo).to(dev)
+if args.twobit:
+    from gonomics_b200.synth import pack_uniform
+    pad = torch.zeros(64, dtype=torch.int64, device=dev)
+    twa = torch.cat([torch.from_numpy(pack_uniform(a, P, args.n).view(np.int64)).to(dev), pad])
+    twb = torch.cat([torch.from_numpy(pack_uniform(b, P, args.m).view(np.int64)).to(dev), pad])
 score = torch.zeros(P, dtype=torch.int64, device=dev)
 off = torch.zeros(P + 1, dtype=torch.int64, device=dev)
 cap = P * args.cap_per_pair
@@ -53,12 +60,17 @@ for cfg in args.configs:
             ctx.set_option(k_, int(v_))
     for want in ((False,) if args.score_only else (False, True)):
         best_fill, best_tot = 1e9, 1e9
-        for it in range(4):
+        for it in range(args.iters):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ctx.batch_device(args.kind, ta.data_ptr(), tao.data_ptr(), tb.data_ptr(), tbo.data_ptr(), ao, bo, P, S, -600, -150,
-                             want, score.data_ptr(), cig.data_ptr(), off.data_ptr(), cap, status.data_ptr(),
-                             torch.cuda.current_stream().cuda_stream)
+            if args.twobit:
+                ctx.batch_device_twobit(args.kind, twa.data_ptr(), args.n, twb.data_ptr(), args.m, P, S, -600, -150, want,
+                                        score.data_ptr(), cig.data_ptr(), off.data_ptr(), cap, status.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream)
+            else:
+                ctx.batch_device(args.kind, ta.data_ptr(), tao.data_ptr(), tb.data_ptr(), tbo.data_ptr(), ao, bo, P, S, -600, -150,
+                                 want, score.data_ptr(), cig.data_ptr(), off.data_ptr(), cap, status.data_ptr(),
+                                 torch.cuda.current_stream().cuda_stream)
             e1.record()
             torch.cuda.synchronize()
             fill_ms, _, _ = ctx.last_fill_stats()
