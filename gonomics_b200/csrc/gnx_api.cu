@@ -579,14 +579,16 @@ void launch_ckpt_trace(gnx_ctx *ctx, const Problem &pb, const FillParams &fp, co
     q.h00_plane = pb.h00_plane;
     q.work = work;
     q.work_count = work_count;
+    q.work_next = work_count + 1;
     const int64_t np = fp.pair_end - fp.pair_begin;
-    if (pass == 0) { // screening: indel-free routes are written directly, the rest is queued
-        cudaMemsetAsync(work_count, 0, sizeof(int), st);
+    cudaMemsetAsync(work_count, 0, 2 * sizeof(int), st); // list length and cursor
+    if (pass == 0) // screening: indel-free routes are written directly, the rest is queued
         ckpt_classify_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(fp, q);
-        ctx->launches++;
-    }
-    const int64_t units = ((np + 3) / 4) * 2;
-    const int grid = (int)std::min<int64_t>(units, (int64_t)ctx->sm_count * occ.load());
+    else           // pairs whose cigar overflowed the slot (and fits the output)
+        ckpt_overflow_list_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(counts, cig_off, np, q.slot_cap, cap, work, work_count);
+    ctx->launches++;
+    // persistent grid: every half-warp keeps taking queued pairs until the list is empty
+    const int grid = (int)std::min<int64_t>((np + 1) / 2, (int64_t)ctx->sm_count * occ.load());
     affine_ckpt_trace_kernel<<<grid, 32, 0, st>>>(fp, q);
 }
 

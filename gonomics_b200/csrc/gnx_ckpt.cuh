@@ -22,6 +22,9 @@
 // (block 0 starts from the true initial state and serves steps 0 .. 32).
 #pragma once
 #include "gnx_fill16.cuh"
+#ifdef GNX_CK_DEBUG
+#include <cstdio>
+#endif
 
 namespace gnx {
 
@@ -38,7 +41,8 @@ struct CkptParams {
     int64_t out_cap;
     int h00_plane;
     int *work;                 // pass 0: chunk-local indices of the pairs that need the recompute walk
-    int *work_count;           // device counter of `work` (ckpt_classify_kernel)
+    int *work_count;           // device counter of `work` (ckpt_classify_kernel / ckpt_overflow_list_kernel)
+    int *work_next;            // device cursor: the next entry of `work` to hand to a half-warp
 };
 
 // Screening pass between the two passes: one thread per pair.  If the pair's score equals the score of the
@@ -88,6 +92,20 @@ __global__ void __launch_bounds__(128) ckpt_classify_kernel(const FillParams P, 
     Q.counts[idx] = cnt;
 }
 
+// Work list of pass 1 (pairs whose cigar overflowed the slot and still fits the output): built on the device.
+__global__ void __launch_bounds__(128) ckpt_overflow_list_kernel(const int *counts, const int64_t *cigar_off, int64_t np, int slot_cap,
+                                                                 int64_t out_cap, int *work, int *work_count)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < np && counts[idx] > slot_cap && cigar_off[idx] + counts[idx] <= out_cap)
+        work[atomicAdd(work_count, 1)] = (int)idx;
+}
+
+// Each HALF-warp works on one queued pair and takes the next one from the work list as soon as its pair is settled
+// (Q.work_next is a device cursor): routes need anything from one block (an indel near the read's end, then the
+// ungapped-tail shortcut) to all sixteen (unrelated sequences), and with static pairing a warp cost the maximum of its
+// two pairs.  The batch is uniform (n x m), so everything but the query tables, the staged target, r* and the
+// checkpoint address is kernel-invariant.
 __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillParams P, const CkptParams Q)
 {
     constexpr int C = 10, LPP = 16, WPL = 2;
@@ -98,6 +116,7 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
     __shared__ int s_tab[C * kDimP * 32];
     __shared__ uint8_t s_tgt[2 * kTgtPitch];
     __shared__ uint32_t s_tr[(kCkK + 1) * WPL * 32];
+    __shared__ int s_pre[2 * (LPP * C + 1)]; // per half: prefix sums of the walker's diagonal (route shortcuts)
     const int tid = threadIdx.x, lane = tid % LPP, half = tid / LPP;
     const int one = P.one;
     const int O = P.gap_open, E = P.gap_extend;
@@ -107,109 +126,256 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
     const int dMn = oe_s + 2 * FD - 2 * FH, dIn = oe_s + FD - FH, dDn = e_s;
     const int dMl = 2 * FD - 2 * FH, dIl = FD - FH, dDl = 0;
     const int fh_reg = FH * one;
-    const int64_t np = P.pair_end - P.pair_begin;
-    // pass 0 takes two queued pairs per warp from the work list; pass 1 (the rare cigars longer than the slot) first
-    // screens 32 candidate units per warp, one per lane, a unit being two pairs (pl, pl + 2) of a quad
-    const int64_t n_work = Q.pass == 0 ? (int64_t)*Q.work_count : 0;
-    const int64_t n_units = Q.pass == 0 ? (n_work + 1) / 2 : ((np + 3) / 4) * 2;
-    const int G = Q.pass == 1 ? 32 : 1;
-    for (int64_t ubase = (int64_t)blockIdx.x * G; ubase < n_units; ubase += (int64_t)gridDim.x * G) {
-      unsigned todo = 1u;
-      if (Q.pass == 1) {
-          const int64_t u = ubase + tid;
-          bool need = false;
-          if (u < n_units) {
-              const int64_t p0 = (u >> 1) * 4 + (u & 1); // chunk-local index of the unit's first pair; second is p0 + 2
-              need = (p0 < np && Q.counts[p0] > Q.slot_cap) || (p0 + 2 < np && Q.counts[p0 + 2] > Q.slot_cap);
-          }
-          todo = __ballot_sync(FULL, need);
-      }
-      while (todo) {
-        const int64_t unit = ubase + (__ffs(todo) - 1);
-        todo &= todo - 1;
-        // this half-warp's pair (chunk-local index pl) and where its checkpoint words live: quad pl / 4, lanes
-        // 16 * ((pl % 4) / 2) .. + 15 of each record, 16-bit half pl % 2
-        int64_t pl;
-        if (Q.pass == 0)
-            pl = (2 * unit + half < n_work) ? (int64_t)Q.work[2 * unit + half] : -1;
-        else
-            pl = (unit >> 1) * 4 + half * 2 + (unit & 1);
-        const bool valid = pl >= 0 && pl < np;
-        const int64_t idx = valid ? pl : 0;
-        const int64_t pair = P.pair_begin + idx;
-        const int64_t quad = idx >> 2;
-        const int src_lane = (int)(((idx >> 1) & 1) * LPP) + lane; // lane of the pass-1 warp that held these columns
-        const int sel = (int)(idx & 1);
-        const int64_t a0 = P.alpha_off[pair], b0 = P.beta_off[pair];
-        const int n = (int)(P.alpha_off[pair + 1] - a0), m = (int)(P.beta_off[pair + 1] - b0); // uniform batch
-        bool want = valid && (!P.pair_class || P.pair_class[pair] <= 1);
-        if (Q.pass == 1)
-            want = want && Q.counts[idx] > Q.slot_cap && Q.cigar_off[idx] + Q.counts[idx] <= Q.out_cap;
-        if (!__any_sync(FULL, want)) {
-            if (Q.pass == 0 && valid && lane == 0 && !want)
-                Q.counts[idx] = 0;
-            continue;
-        }
-        if (Q.pass == 0 && valid && lane == 0 && !want)
-            Q.counts[idx] = 0;
-        const uint8_t *__restrict__ alpha = P.alpha + a0;
-        const uint8_t *__restrict__ beta = P.beta + b0;
-        const int T = n + LPP - 1;
-        const int jbase = lane * C;
-
-        // ---- per-lane score tables, addends, staged target: exactly affine_fill3_kernel's set-up ----
-        int aM[C], aI[C], aD[C];
+    const int n_work = *Q.work_count;
+    if (n_work == 0)
+        return;
+    // uniform batch: lengths and everything derived from them
+    const int n = (int)(P.alpha_off[P.pair_begin + 1] - P.alpha_off[P.pair_begin]);
+    const int m = (int)(P.beta_off[P.pair_begin + 1] - P.beta_off[P.pair_begin]);
+    const int T = n + LPP - 1;
+    const int jbase = lane * C;
+    int aM[C], aI[C], aD[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const int j = jbase + c + 1;
-            const int q = (j <= m) ? (int)beta[j - 1] : 0;
+    for (int c = 0; c < C; ++c) {
+        const bool last = jbase + c + 1 == m;
+        aM[c] = last ? dMl : dMn;
+        aI[c] = last ? dIl : dIn;
+        aD[c] = last ? dDl : dDn;
+    }
+    const uint8_t *tg = s_tgt + half * kTgtPitch;
+    const unsigned code00 = (unsigned)(2 - Q.h00_plane) << 4;
+
+    // ---- this half's pair ----
+    bool have = false, exhausted = false, tested = false;
+    int64_t idx = 0, pair = P.pair_begin, quad = 0;
+    int src_lane = lane, sel = 0, rs = 0, S_pair = 0;
+    // walk state, kept by lane 0 of each half-warp
+    int wi = 0, wj = 0, wk = 2, need_k = 1, cur_op = 2, run = 0, cnt = 0, total = 0;
+    bool done = true;
+    uint32_t *slot = Q.slots;
+    CigarOut *dst = nullptr;
+    auto emit = [&](int op, int len) {
+        if (Q.pass == 0) {
+            if (cnt < Q.slot_cap)
+                slot[cnt] = ((uint32_t)len << 2) | (uint32_t)op;
+        } else {
+            CigarOut o;
+            o.run_length = len;
+            o.op = (unsigned char)op;
+            dst[total - 1 - cnt] = o;
+        }
+        ++cnt;
+    };
+
+    while (true) {
+        bool all_idle = false;
+#pragma unroll 1
+        for (int rep = 0; rep < 2; ++rep) {
+            // ---- a half without a pair takes the next queued one ----
+            int w = -1;
+            if (lane == 0 && !have && !exhausted)
+                w = atomicAdd(Q.work_next, 1);
+            w = __shfl_sync(FULL, w, 0, LPP);
+            bool fresh = false;
+            if (!have && !exhausted) {
+                if (w < n_work)
+                    fresh = true;
+                else
+                    exhausted = true;
+            }
+            if (!__any_sync(FULL, have || fresh)) {
+                all_idle = true;
+                break;
+            }
+            if (__any_sync(FULL, fresh)) {
+                if (fresh) {
+                    // chunk-local index idx; its checkpoint words: quad idx / 4, lanes 16 * ((idx % 4) / 2) .. + 15 of each
+                    // record, 16-bit half idx % 2
+                    idx = Q.work[w];
+                    pair = P.pair_begin + idx;
+                    quad = idx >> 2;
+                    src_lane = (int)(((idx >> 1) & 1) * LPP) + lane;
+                    sel = (int)(idx & 1);
+                    const uint8_t *__restrict__ alpha = P.alpha + P.alpha_off[pair];
+                    const uint8_t *__restrict__ beta = P.beta + P.beta_off[pair];
+                    // per-lane score tables and the staged target: exactly affine_fill3_kernel's set-up
 #pragma unroll
-            for (int a = 0; a < kDimP; ++a) {
-                int v = 0;
-                if (a < P.dim && q < P.dim)
-                    v = P.scores[a * P.dim + q] * SC + 2 * FH;
-                s_tab[(c * kDimP + a) * 32 + tid] = v;
+                    for (int c = 0; c < C; ++c) {
+                        const int j = jbase + c + 1;
+                        const int q = (j <= m) ? (int)beta[j - 1] : 0;
+#pragma unroll
+                        for (int a = 0; a < kDimP; ++a) {
+                            int v = 0;
+                            if (a < P.dim && q < P.dim)
+                                v = P.scores[a * P.dim + q] * SC + 2 * FH;
+                            s_tab[(c * kDimP + a) * 32 + tid] = v;
+                        }
+                    }
+                    for (int i = lane; i < n; i += LPP)
+                        s_tgt[half * kTgtPitch + i] = alpha[i];
+                    rs = (int)Q.rstar[pair];
+                    S_pair = (int)P.out_score[pair];
+                    wi = rs;            // current cell
+                    wj = m;
+                    wk = 2;             // current plane (0 M, 1 I, 2 D)
+                    need_k = 1;         // the plane of the current cell is the H tag of its code
+                    cur_op = 2;         // the free-end column's D run from (n,m) down to (r*,m)
+                    run = n - rs;
+                    cnt = 0;
+                    done = false;
+                    slot = Q.slots + (size_t)idx * Q.slot_cap;
+                    if (Q.pass == 1) {
+                        total = Q.counts[idx];
+                        dst = Q.out_cigar + Q.cigar_off[idx];
+                    }
+                    have = true;
+                    tested = false;
+                }
+                __syncwarp();
             }
-            const bool last = j == m;
-            aM[c] = last ? dMl : dMn;
-            aI[c] = last ? dIl : dIn;
-            aD[c] = last ? dDl : dDn;
-        }
-        for (int i = lane; i < n; i += LPP)
-            s_tgt[half * kTgtPitch + i] = alpha[i];
-        const uint8_t *tg = s_tgt + half * kTgtPitch;
-        __syncwarp();
-
-        // ---- walk state, kept by lane 0 of each half-warp ----
-        const int rs = want ? (int)Q.rstar[pair] : 0;
-        int wi = rs, wj = m;            // current cell
-        int wk = 2;                     // current plane (0 M, 1 I, 2 D)
-        int need_k = 1;                 // the plane of the current cell is the H tag of its code
-        int cur_op = 2, run = n - rs;   // the free-end column's D run from (n,m) down to (r*,m)
-        int cnt = 0;
-        bool done = !want;
-        uint32_t *slot = Q.slots + (size_t)idx * Q.slot_cap;
-        int total = 0;
-        CigarOut *dst = nullptr;
-        if (Q.pass == 1 && want) {
-            total = Q.counts[idx];
-            dst = Q.out_cigar + Q.cigar_off[idx];
-        }
-        auto emit = [&](int op, int len) {
-            if (Q.pass == 0) {
-                if (cnt < Q.slot_cap)
-                    slot[cnt] = ((uint32_t)len << 2) | (uint32_t)op;
-            } else {
-                CigarOut o;
-                o.run_length = len;
-                o.op = (unsigned char)op;
-                dst[total - 1 - cnt] = o;
+            // ---- route shortcuts that need no trace code (pass 0) ----------------------------------------------
+            // The walker stands on cell (i,j) and has to learn its plane from the cell's H tag (need_k): either the
+            // fresh pair at (r*, m), or a walk that has just left a block through a diagonal (M) step.  Its value
+            // V = H(i,j) = max(M,I,D)(i,j) is known without any recompute: V = S - (cost of the route walked so far).
+            //  (a) ungapped tail.  If V equals U(i,j), the score of the ungapped diagonal from column 0 (free
+            //      D(i-j,0) = 0) to (i,j), then M(i,j) >= U = V forces M(i,j) = H(i,j), and by the argument of
+            //      ckpt_classify_kernel no I or D value can beat M anywhere on that diagonal: tripleMaxTrace picks M
+            //      at every cell down to column 0.  The rest of the route is M x j, D x (i - j).
+            //  (b) checkpoint-verified diagonal jump.  Pass 1 saved H(32k - l, 10l + c + 1) for every lane l and
+            //      column c at every checkpoint k; the walker's diagonal meets at most one such cell c_q per
+            //      checkpoint (11 l + c = j - i + 32k - 1).  If V = H(c_q) + (substitution scores of the d diagonal
+            //      cells above c_q), then M(i,j) >= s + H(i-1,j-1) >= ... >= sum + H(c_q) = V >= M(i,j): every
+            //      inequality is tight, so M = H at (i,j) and at each of the d - 1 cells in between, i.e. the route is
+            //      M x d (ties prefer M) and lands on c_q with its plane still to be read (need_k).  The farthest
+            //      verified cell is taken: the blocks in between are never recomputed.
+            // Reads carry few indels: a typical route is settled by one or two recomputed blocks around each indel.
+#ifndef GNX_CK_NOTAIL
+            {
+                const int ti = __shfl_sync(FULL, wi, 0, LPP), tj = __shfl_sync(FULL, wj, 0, LPP);
+                const int tcnt = __shfl_sync(FULL, cnt, 0, LPP), trun = __shfl_sync(FULL, run, 0, LPP);
+                const int tcur = __shfl_sync(FULL, cur_op, 0, LPP);
+                const int tf = __shfl_sync(FULL, (int)(!done && need_k), 0, LPP);
+                const bool initial = tcnt == 0 && tcur == 2;   // nothing walked yet: V = S at (r*, m)
+                const bool tri = Q.pass == 0 && have && !tested && tf != 0 && tj > 0 && ti > 0 && tcnt < Q.slot_cap &&
+                                 (initial || tcur == 0);
+                if (__any_sync(FULL, tri)) {
+                    auto sc = [&](int row, int col) { // substitution score of cell (row, col) from the per-lane tables
+                        const int a = tg[row - 1], l = (col - 1) / C, c = (col - 1) - l * C;
+                        return (s_tab[(c * kDimP + a) * 32 + half * LPP + l] - 2 * FH) >> kTagBits;
+                    };
+                    int acc = 0, gap = 0, ci = rs, cj = m;
+                    const int e0 = (n - rs > 0) ? 1 : 0; // slot[0] is the free-end column's D run (cost 0)
+                    const int tc = initial ? -1 : tcnt;  // index of the run in progress (an M run), -1: none
+                    const int emax = max(tc, __shfl_xor_sync(FULL, tc, 16));
+                    for (int e = 0; e <= emax; ++e) { // warp-uniform trip count: the shuffle below needs all 32 lanes
+                        uint32_t v = 0;
+                        if (lane == 0 && tri && e >= e0 && e < tc)
+                            v = slot[e];
+                        v = __shfl_sync(FULL, v, 0, LPP);
+                        if (e == tc)
+                            v = (uint32_t)trun << 2; // the M run in progress
+                        if (!tri || e < e0 || e > tc)
+                            continue;
+                        const int op = (int)(v & 3u), len = (int)(v >> 2);
+                        if (op == 0) {
+                            for (int t = lane; t < len; t += LPP)
+                                acc += sc(ci - t, cj - t);
+                            ci -= len;
+                            cj -= len;
+                        } else {
+                            gap += O + len * E; // a gap run of len cells: open once, extend len times
+                            if (op == 1)
+                                cj -= len;
+                            else
+                                ci -= len;
+                        }
+                    }
+#pragma unroll
+                    for (int o = LPP / 2; o > 0; o >>= 1)
+                        acc += __shfl_xor_sync(FULL, acc, o);
+                    const int V = S_pair - gap - acc;
+                    const bool ok = tri && ci == ti && cj == tj;
+                    // prefix sums of the walker's diagonal: pre[d] = sum of s(i - t, j - t), t < d; lane l owns t in [10l, 10l+10)
+                    const int L = ok ? min(ti, tj) : 0;
+                    int part[C], mine = 0;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int t = lane * C + c;
+                        part[c] = mine;
+                        if (t < L)
+                            mine += sc(ti - t, tj - t);
+                    }
+                    int incl = mine; // inclusive scan of the lanes' chunk sums
+#pragma unroll
+                    for (int o = 1; o < LPP; o <<= 1) {
+                        const int up = __shfl_up_sync(FULL, incl, o, LPP);
+                        if (lane >= o)
+                            incl += up;
+                    }
+                    const int base = incl - mine;
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        s_pre[half * (LPP * C + 1) + lane * C + c] = base + part[c];
+                    if (lane == LPP - 1)
+                        s_pre[half * (LPP * C + 1) + LPP * C] = incl;
+                    __syncwarp();
+                    const int *pre = s_pre + half * (LPP * C + 1);
+                    // (a) ungapped tail
+                    const bool tail = ok && ti >= tj && V == pre[tj];
+                    // (b) lane q looks at checkpoint k = q + 1
+                    int dhit = 0;
+                    if (ok && !tail) {
+                        const int k = lane + 1;
+                        const int X = tj - ti + kCkK * k - 1;
+                        if (kCkK * k < T && X >= 0) {
+                            const int l2 = X / 11, c2 = X - 11 * l2;
+                            const int col = l2 * C + c2 + 1, d = tj - col;
+                            if (c2 < C && l2 < LPP && col <= m && d >= 1 && d <= L - 1) { // the cell itself is interior (row, col >= 1)
+                                const uint32_t x = __ldg(Q.ckpt + (size_t)quad * Q.quad_words + (size_t)(k - 1) * (kCkRegs * 32) + c2 * 32 +
+                                                         (src_lane - lane + l2));
+                                const int hck = (int)((x >> (16 * sel)) & 0xffffu) - 32768;
+                                if (V - pre[d] == hck)
+                                    dhit = d;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = LPP / 2; o > 0; o >>= 1)
+                        dhit = max(dhit, __shfl_xor_sync(FULL, dhit, o)); // the farthest verified cell of this half
+                    if (lane == 0 && (tail || dhit > 0)) {
+                        const int adv = tail ? tj : dhit;
+                        if (cur_op == 0) {
+                            run += adv;
+                        } else {
+                            if (run > 0)
+                                emit(cur_op, run);
+                            cur_op = 0;
+                            run = adv;
+                        }
+                        wi -= adv;
+                        wj -= adv;
+                        if (tail) {
+                            emit(0, run);
+                            if (wi > 0)
+                                emit(2, wi);
+                            Q.counts[idx] = cnt;
+                            wi = wj = 0;
+                            done = true;
+                        }
+                    }
+                }
+                if (tri)
+                    tested = true; // one attempt per standing cell
             }
-            ++cnt;
-        };
-        const unsigned code00 = (unsigned)(2 - Q.h00_plane) << 4;
-
-        while (true) {
+#endif
+            // a pair settled by the tail shortcut frees its half at once: it is refilled in the second round
+            if (__shfl_sync(FULL, (int)done, 0, LPP) != 0)
+                have = false;
+        }
+        if (all_idle)
+            break;
+        {
             // block each half needs: the one serving the step of its current cell
             int blk = 0;
             {
@@ -217,20 +383,18 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
                 blk = (wi > 0 && wj > 0) ? max(tcell - 1, 0) / kCkK : -1; // -1: only boundary cells remain
             }
             blk = __shfl_sync(FULL, blk, 0, LPP);
-            const bool hdone = __shfl_sync(FULL, (int)done, 0, LPP) != 0;
-            if (__all_sync(FULL, hdone))
-                break;
+            const int done0 = __shfl_sync(FULL, (int)done, 0, LPP); // executed by all 32 lanes (no short-circuit around it)
+            const bool hdone = !have || done0 != 0;
             const bool recompute = !hdone && blk >= 0;
             const int s0 = blk > 0 ? blk * kCkK : 0;
             // the walk enters the block at its current cell and only moves to earlier steps: no later step is needed
             int tin = (wi - 1) + (wj - 1) / C;
             tin = __shfl_sync(FULL, tin, 0, LPP);
             const int ulast_h = recompute ? min(tin - s0, kCkK) : 0;
-#ifdef GNX_CK_NOTRIM
-            const int ulast = kCkK;
-            (void)ulast_h;
-#else
             const int ulast = max(ulast_h, __shfl_xor_sync(FULL, ulast_h, 16));
+#ifdef GNX_CK_DEBUG
+            if (lane == 0 && recompute)
+                printf("pair %d block %d at (%d,%d) need_k %d cur_op %d\n", (int)idx, blk, wi, wj, need_k, cur_op);
 #endif
             if (__any_sync(FULL, recompute)) {
                 // ---- restore the state entering step s0 ----
@@ -426,8 +590,10 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
             }
             __syncwarp();
         }
-        __syncwarp();
-      }
+        // a settled pair frees its half for the next queued one
+        if (__shfl_sync(FULL, (int)done, 0, LPP) != 0)
+            have = false;
+        tested = false; // the walker has moved
     }
 }
 
