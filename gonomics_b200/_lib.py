@@ -25,7 +25,7 @@ EXPORTS = [
     "gnx_multi_affine_chunk_batch", "gnx_extend_batch", "gnx_batch_device", "gnx_batch_device_twobit", "gnx_launch_count", "gnx_last_fill_stats", "gnx_set_option",
     "gnx_twobit_new", "gnx_twobit_free", "gnx_twobit_info", "gnx_twobit_download", "gnx_twobit_unpack", "gnx_twobit_get_bases",
     "gnx_twobit_count_matches", "gnx_twobit_pack_device", "gnx_seed_index_new", "gnx_seed_index_free", "gnx_seed_index_info",
-    "gnx_seed_index_download", "gnx_seed_batch",
+    "gnx_seed_index_download", "gnx_seed_batch", "gnx_gsw_batch",
     "gnx_multi_create", "gnx_multi_destroy", "gnx_multi_device_count", "gnx_multi_last_error", "gnx_multi_context",
     "gnx_multi_shard_bounds", "gnx_multi_affine_batch", "gnx_multi_const_batch", "gnx_multi_copy_last_cigars",
 ]
@@ -40,6 +40,10 @@ CIGAR_DTYPE = np.dtype({"names": ["run_length", "op"], "formats": ["<i8", "u1"],
 # gnx_seed: genomeGraph.SeedDev without NextPart (genomeGraph/index.go:11-19)
 SEED_DTYPE = np.dtype([("target_id", "<u4"), ("target_start", "<u4"), ("query_start", "<u4"), ("length", "<u4"),
                        ("pos_strand", "<u4"), ("total_length", "<u4")])
+
+# gnx_giraf: the part of giraf.Giraf the aligner computes (include/gnxalign.h)
+GIRAF_DTYPE = np.dtype([("q_start", "<i4"), ("q_end", "<i4"), ("pos_strand", "<i4"), ("t_start", "<i4"), ("t_end", "<i4"),
+                        ("node", "<i4"), ("aln_score", "<i8"), ("flag", "<i4"), ("n_cigar", "<i4"), ("cigar_off", "<i8")])
 
 _lib = None
 
@@ -126,6 +130,8 @@ def load() -> C.CDLL:
     L.gnx_seed_index_download.restype = ci
     L.gnx_seed_batch.argtypes = [vp, vp, u8p, i64p, i64, vp, i64p, i64]
     L.gnx_seed_batch.restype = ci
+    L.gnx_gsw_batch.argtypes = [vp, vp, u8p, i64p, i64, i64p, ci, ci, vp, cgp, i64, vp]
+    L.gnx_gsw_batch.restype = ci
     L.gnx_multi_create.argtypes = [vp, ci, C.c_size_t]
     L.gnx_multi_create.restype = vp
     L.gnx_multi_destroy.argtypes = [vp]

@@ -2516,3 +2516,4 @@ int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
 
 #include "gnx_twobit_api.inl"
 #include "gnx_multi.inl"
+#include "gnx_gsw.inl"

@@ -19,6 +19,9 @@ struct gnx_seed_index {
     DevBuf key, loc, bucket;
     int64_t n = 0;
     int seed_len = 0, seed_step = 0, bucket_bits = 0, bucket_shift = 0;
+    // host copy of the nodes' bases: gnx_gsw_batch cuts its extension windows out of it (inputs are never retained)
+    std::vector<uint8_t> h_genome;
+    std::vector<int64_t> h_off;
     gnx::SeedIndexView view() const
     {
         return gnx::SeedIndexView{key.as<uint64_t>(), loc.as<uint64_t>(), n, bucket.as<int64_t>(), bucket_bits, bucket_shift};
@@ -346,6 +349,11 @@ int gnx_seed_index_new(gnx_ctx *ctx, const uint8_t *genome_cat, const int64_t *n
     ix->seed_len = seed_len;
     ix->seed_step = seed_step;
     ix->genome = new gnx_twobit();
+    ix->h_off.assign(node_off, node_off + n_nodes + 1);
+    for (auto &v : ix->h_off)
+        v -= node_off[0];
+    if (n_nodes > 0)
+        ix->h_genome.assign(genome_cat + node_off[0], genome_cat + node_off[n_nodes]);
     DevBuf d_bytes, d_off, d_cand, d_key, d_loc, d_valid, d_dst, d_tmp, d_key2, d_loc2;
     int rc = GNX_OK;
     do {

@@ -123,6 +123,30 @@ class SeedIndex:
             return seeds[:int(soff[-1])], soff
 
 
+def gsw_batch(index: "SeedIndex", reads_cat: np.ndarray, read_off: np.ndarray, scores, paired: bool = False,
+              cigar_cap: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """genomeGraph.GraphSmithWatermanToGiraf (WrapPairGiraf when paired) for every read of a block: gnx_gsw_batch.
+    Returns (records[GIRAF_DTYPE], cigars[CIGAR_DTYPE]); record r's cigar is cigars[cigar_off : cigar_off + n_cigar]
+    (n_cigar = -1: nil), ops are the bytes 'M','I','D','S'."""
+    from ._lib import CIGAR_DTYPE, GIRAF_DTYPE
+    cat = np.ascontiguousarray(reads_cat, dtype=np.uint8)
+    off = np.ascontiguousarray(read_off, dtype=np.int64)
+    S = np.ascontiguousarray(scores, dtype=np.int64)
+    n = len(off) - 1
+    recs = np.zeros(max(n, 1), dtype=GIRAF_DTYPE)
+    cap = int(cigar_cap or 4 * n + 64)
+    need = C.c_int64(0)
+    while True:
+        cig = np.zeros(max(cap, 1), dtype=CIGAR_DTYPE)
+        rc = index._L.gnx_gsw_batch(index.ctx._h, index._h, cat.ctypes.data, off.ctypes.data, n, S.ctypes.data, int(S.shape[0]),
+                                    int(bool(paired)), recs.ctypes.data, cig.ctypes.data, cap, C.byref(need))
+        if rc == GNX_ECAP and need.value > cap:
+            cap = int(need.value)
+            continue
+        index.ctx._check(rc)
+        return recs[:n], cig[:int(need.value)]
+
+
 def heapSortSeeds(a: List[SeedDev]) -> None:
     """genomeGraph.heapSortSeeds (search.go:339-373): in-place min-heap sort, i.e. descending TotalLength with
     the reference's (unstable) order among equal lengths."""

@@ -234,6 +234,33 @@ int gnx_seed_index_download(gnx_ctx *ctx, const gnx_seed_index *ix, uint64_t *ou
 int gnx_seed_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8_t *reads_cat, const int64_t *read_off,
                    int64_t n_reads, gnx_seed *out_seeds, int64_t *out_seed_off, int64_t seed_cap);
 
+/* ---- the per-read driver of cmd/gsw ---------------------------------------------- *
+ * gnx_gsw_batch   genomeGraph.GraphSmithWatermanToGiraf (genomeGraph/toGiraf.go:17-72) for every read of a block
+ *                 against a genome graph WITHOUT edges (the gnx_seed_index's nodes): seeds (seedMapMemPool), their
+ *                 ordering (heapSortSeeds / SortSeedLen), the seedCouldBeBetter early exit (genomeGraph/index.go:
+ *                 102-121), LeftAlignTraversal / RightAlignTraversal's linear-gap DPs (gap -600) on the windows of
+ *                 getLeftTargetBases / getRightBases, score / position / path bookkeeping and the cigar assembly
+ *                 (cigar.Append, Concat, AppendSoftClips; routes in the reference's traceback order).  The seed and
+ *                 extend steps of the whole block run as batched GPU calls, the reference's sequential loop is
+ *                 replayed per read over their results.  paired != 0: reads 2k / 2k+1 are the Fwd / Rev mates of
+ *                 WrapPairGiraf (:117-137) and the flags get setGirafFlags' pair bits.
+ * A gnx_giraf is the part of giraf.Giraf the aligner computes (QName / Seq / Qual / MapQ = 255 / Notes are the
+ * caller's); cigar ops are the bytes 'M','I','D','S'; n_cigar = -1 is Go's nil Cigar (no seed scored above 0).
+ * GNX_ECAP: cigar_cap too small, *out_n_cigar holds the number of elements the block needs (records are filled). */
+typedef struct {
+    int32_t q_start, q_end; /* giraf.QStart, QEnd */
+    int32_t pos_strand;     /* giraf.PosStrand */
+    int32_t t_start, t_end; /* giraf.Path.TStart, TEnd */
+    int32_t node;           /* giraf.Path.Nodes = [node]; -1: empty path */
+    int64_t aln_score;      /* giraf.AlnScore */
+    int32_t flag;           /* giraf.Flag (getGirafFlags, + setGirafFlags when paired) */
+    int32_t n_cigar;        /* len(giraf.Cigar); -1: nil */
+    int64_t cigar_off;      /* first element in out_cigar */
+} gnx_giraf;
+int gnx_gsw_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8_t *reads_cat, const int64_t *read_off,
+                  int64_t n_reads, const int64_t *scores, int dim, int paired, gnx_giraf *out, gnx_cigar *out_cigar,
+                  int64_t cigar_cap, int64_t *out_n_cigar);
+
 /* After a GNX_ECAP return: copy the retained cigars of the last batch call (total = the last
  * entry of that call's out_cigar_off). */
 int gnx_copy_last_cigars(gnx_ctx *ctx, gnx_cigar *out_cigar, int64_t cigar_cap);
