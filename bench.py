@@ -278,6 +278,109 @@ def twobit_block(ctx, L, dev, stream, rank, world, barrier, args):
     return out
 
 
+
+def gsw_block(ctx, L, dev, rank, world, args):
+    """BASELINE configs[4] shape ("C5"): paired-end 2 x 150 bp reads through the whole gsw per-read driver
+    (gnx_gsw_batch: seeds -> candidate ordering -> left/right extension DPs -> replay of GraphSmithWatermanToGiraf /
+    WrapPairGiraf) against a synthetic >= 1 Gb linear reference, host buffers in and out, blocks of 2^20 reads."""
+    import torch
+    import torch.distributed as dist
+    from gonomics_b200 import align as _al
+    from gonomics_b200 import genomegraph
+    rng = np.random.default_rng(SEED + 55)  # the same genome on every rank
+    g_len = args.gsw_genome
+    t0 = time.perf_counter()
+    genome = rng.integers(0, 4, size=g_len, dtype=np.uint8)
+    ix = genomegraph.SeedIndex([genome], 32, 32, ctx)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    pairs_total = args.gsw_pairs
+    lo, hi = pairs_total * rank // world, pairs_total * (rank + 1) // world
+    n_pairs = hi - lo
+    r_len, blk_pairs = 150, 1 << 19
+    rng = np.random.default_rng(SEED + 56 + rank)
+
+    def make_block(np_):
+        """np_ fragments of 300-500 bases; mates from the two ends on opposite strands; 1 % substitutions, a short
+        indel in 10 % of the reads; 2 % of the reads unrelated."""
+        start = rng.integers(0, g_len - 600, size=np_)
+        frag = rng.integers(300, 500, size=np_)
+        ar = np.arange(r_len)
+        fwd = genome[start[:, None] + ar[None, :]]
+        rev = genome[(start + frag - r_len)[:, None] + ar[None, :]]
+        rev = (3 - rev)[:, ::-1]
+        reads = np.empty((2 * np_, r_len), dtype=np.uint8)
+        reads[0::2], reads[1::2] = fwd, rev
+        mut = rng.random(reads.shape) < 0.01
+        reads[mut] = (reads[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) % 4
+        ind = np.nonzero(rng.random(2 * np_) < 0.10)[0]
+        pos = rng.integers(40, r_len - 40, size=len(ind))
+        for r, p in zip(ind[::2], pos[::2]):      # deletion of one base (shift left, random base at the end)
+            reads[r, p:-1] = reads[r, p + 1:]
+        for r, p in zip(ind[1::2], pos[1::2]):    # insertion of one base
+            reads[r, p + 1:] = reads[r, p:-1].copy()
+            reads[r, p] = (reads[r, p] + 1) % 4
+        junk = np.nonzero(rng.random(2 * np_) < 0.02)[0]
+        reads[junk] = rng.integers(0, 4, size=(len(junk), r_len), dtype=np.uint8)
+        return np.ascontiguousarray(reads.reshape(-1))
+
+    S = _al.HumanChimpTwoScoreMatrix
+    blocks = []
+    left = n_pairs
+    while left > 0:
+        b = min(left, blk_pairs)
+        blocks.append((make_block(b), b))
+        left -= b
+    off_full = np.arange(2 * blk_pairs + 1, dtype=np.int64) * r_len
+    genomegraph.gsw_batch(ix, blocks[0][0][:2 * 4096 * r_len], off_full[:2 * 4096 + 1], S, paired=True)  # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    mapped = proper = n_cig = 0
+    first = None
+    for cat, b in blocks:
+        recs, cig = genomegraph.gsw_batch(ix, cat, off_full[:2 * b + 1], S, paired=True, cigar_cap=8 * b)
+        mapped += int((recs["aln_score"] >= 1200).sum())
+        proper += int((recs["flag"][1::2] & 1).sum())
+        n_cig += len(cig)
+        if first is None:
+            first = (recs, cig)
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    out = {"value": pairs_total / dt / 1e6, "unit": "Mpairs/s (2 x 150 bp)", "seconds": dt, "pairs_total": pairs_total,
+           "pairs_per_gpu": n_pairs, "reference_bases": g_len, "index_entries": ix.n_entries, "index_build_s": build_s,
+           "mapped_fraction": mapped / max(2 * n_pairs, 1), "proper_pair_fraction": proper / max(n_pairs, 1),
+           "h2d_bytes_per_step": int(2 * n_pairs * r_len), "d2h_bytes_per_step": int(2 * n_pairs * 48 + 16 * n_cig),
+           "api": "gnx_gsw_batch (host buffers; seeds + extensions on the GPU, ordering / replay on the host threads)",
+           "note": "BASELINE configs[4] shape on a synthetic linear reference (the config's 3 Gb / 100 M pairs scaled to "
+                   "what one default bench run holds); reads sharded over the ranks"}
+    if rank == 0 and not args.no_cpu:
+        from oracle import gsw as ogsw
+        k = 400
+        if True:
+            gg = ogsw.LinearGenome([genome], 32, 32)  # the oracle's own seed map of the whole reference (~13 s per Gb)
+            recs, cig = first
+            cat = blocks[0][0]
+            t0 = time.perf_counter()
+            ok = True
+            for p in range(k // 2):
+                wf, wr = ogsw.wrap_pair_giraf(gg, cat[(2 * p) * r_len:(2 * p + 1) * r_len], cat[(2 * p + 1) * r_len:(2 * p + 2) * r_len], S)
+                for r, w in ((2 * p, wf), (2 * p + 1, wr)):
+                    g = recs[r]
+                    ok &= (int(g["aln_score"]), int(g["t_start"]), int(g["t_end"]), int(g["flag"]), bool(g["pos_strand"])) == \
+                          (w.AlnScore, w.TStart, w.TEnd, w.Flag, w.PosStrand)
+            out["cpu_baseline"] = {"value": (k // 2) / (time.perf_counter() - t0) / 1e6, "unit": "Mpairs/s", "cores": 1, "kind": "port",
+                                   "sample": f"first {k // 2} pairs, one thread (oracle/gsw.py: the sequential restatement of the "
+                                             "reference loop over the C restatements of seedMapMemPool / Left/RightDynamicAln)"}
+            out["parity_spot_check"] = bool(ok)
+    ix.close()
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The Go toolchain is not in
     this image, so this is the C restatement (oracle/), all host threads, bounded sample per step."""
@@ -326,6 +429,8 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the C1 / C4 / const-gap / 2-bit / gsw blocks")
     ap.add_argument("--quick", action="store_true", help="profiling runs: headline only, warm-up not clamped")
     ap.add_argument("--c4-pairs", type=int, default=12_500, help="10 kb x 10 kb pairs per GPU in the C4 block")
+    ap.add_argument("--gsw-pairs", type=int, default=10_000_000, help="read pairs (in total) of the gsw / C5 block")
+    ap.add_argument("--gsw-genome", type=int, default=1 << 30, help="bases of the synthetic reference of the gsw block")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON result: everything libraries print there (e.g. "NCCL version ..."
     # under torchrun) is sent to stderr by pointing fd 1 at fd 2 for the duration of the run.
@@ -635,6 +740,8 @@ def main():
                                             "ms_per_step": msc, "note": "ConstGap_highMem + CIGAR, g=-430"}}
         # 2-bit packing (HBM-bound) and the perfect-match seed / extend steps
         line["other_workloads"].update(twobit_block(ctx, L, dev, stream, rank, world, barrier, args))
+        # SURVEY 8f-3 / configs[4]: the whole per-read gsw driver on paired reads against a >= 1 Gb reference
+        line["other_workloads"]["c5_gsw_paired_2x150"] = gsw_block(ctx, L, dev, rank, world, args)
 
     # ---- e2e: the public host-buffer API with H2D + D2H inside the timed region ------------------------
     # Headline e2e = what the cgo shim of INTEGRATION.md does: PAGEABLE []dna.Base bytes in, pageable results out.

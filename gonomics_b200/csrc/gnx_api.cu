@@ -18,8 +18,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -162,6 +165,7 @@ struct gnx_ctx {
     // between calls with the same uniform shape (a streaming caller's batches) so that they are built once
     std::vector<int64_t> tb_off[4];
     int64_t tb_key[3] = {-1, -1, -1}; // n_pairs, n, m of the cached uniform arrays
+    PinBuf gsw_pin[12]; // gnx_gsw_batch: page-locked scratch kept between calls (gnx_gsw.inl)
     // cigars retained after GNX_ECAP
     std::vector<gnx_cigar> retained;
     bool have_retained = false;
@@ -2065,6 +2069,8 @@ void gnx_destroy(gnx_ctx *ctx)
     ctx->status.release();
     ctx->dr_misc.release();
     ctx->long_scratch.release();
+    for (PinBuf &b : ctx->gsw_pin)
+        b.release();
     if (ctx->ev_long)
         cudaEventDestroy(ctx->ev_long);
     if (ctx->ev_dev)

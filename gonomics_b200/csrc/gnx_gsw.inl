@@ -19,10 +19,6 @@
 // edge-less nodes, empty traversal paths).
 namespace {
 
-struct GswSeed {
-    uint32_t tid, tstart, qstart, len, pos, total;
-};
-
 inline bool gsw_could_be_better(int64_t seedLen, int64_t best, int64_t perfect, int64_t qlen)
 { // index.go:102-121 with the constants GraphSmithWatermanToGiraf passes (toGiraf.go:38)
     const int64_t maxMatch = 100, minMatch = 90, lsm = -196, lsmc = -296;
@@ -36,13 +32,13 @@ inline bool gsw_could_be_better(int64_t seedLen, int64_t best, int64_t perfect, 
     return false;
 }
 
-void gsw_heap_sort(std::vector<GswSeed> &a)
+void gsw_heap_sort(gnx_seed *a, int64_t n)
 { // heapSortSeeds (search.go:339-373): min-heap on TotalLength => descending order, the reference's tie order
-    auto heapify = [&](size_t size, size_t i) {
+    auto heapify = [&](int64_t size, int64_t i) {
         for (;;) {
-            const size_t l = 2 * i + 1, r = 2 * i + 2;
-            size_t m = (l < size && a[l].total < a[i].total) ? l : i;
-            if (r < size && a[r].total < a[m].total)
+            const int64_t l = 2 * i + 1, r = 2 * i + 2;
+            int64_t m = (l < size && a[l].total_length < a[i].total_length) ? l : i;
+            if (r < size && a[r].total_length < a[m].total_length)
                 m = r;
             if (m == i)
                 return;
@@ -50,12 +46,12 @@ void gsw_heap_sort(std::vector<GswSeed> &a)
             i = m;
         }
     };
-    if (a.size() < 2)
+    if (n < 2)
         return;
-    for (size_t i = a.size() / 2; i-- > 0;)
-        heapify(a.size(), i);
-    size_t size = a.size();
-    for (size_t i = a.size() - 1; i >= 1; --i) {
+    for (int64_t i = n / 2 - 1; i >= 0; --i)
+        heapify(n, i);
+    int64_t size = n;
+    for (int64_t i = n - 1; i >= 1; --i) {
         std::swap(a[0], a[i]);
         --size;
         heapify(size, 0);
@@ -90,6 +86,20 @@ template <typename F> void gsw_parallel(int64_t n, F &&fn)
 
 } // namespace
 
+namespace {
+
+// page-locked scratch of the driver, kept in the context between calls (ctx->gsw_pin[...])
+enum { GP_SEEDS, GP_SOFF, GP_A, GP_B, GP_AO, GP_BO, GP_SC, GP_EI, GP_EJ, GP_CO, GP_CG, GP_N };
+
+struct GswExt { // results of the extension DPs, indexed by extension id
+    std::vector<int64_t> l_score, l_i, l_j, r_score, r_i, r_j;
+    std::vector<int64_t> l_coff, r_coff; // per id: first cigar element, count
+    std::vector<int32_t> l_cnt, r_cnt;
+    std::vector<gnx_cigar> l_cig, r_cig;
+};
+
+} // namespace
+
 extern "C" int gnx_gsw_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8_t *reads_cat, const int64_t *read_off, int64_t n_reads,
                              const int64_t *scores, int dim, int paired, gnx_giraf *out, gnx_cigar *out_cigar, int64_t cigar_cap,
                              int64_t *out_n_cigar)
@@ -107,32 +117,47 @@ extern "C" int gnx_gsw_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8
     const std::vector<int64_t> &GO = ix->h_off;
     const int64_t gap_pen = -600; // the extension penalty LeftAlignTraversal / RightAlignTraversal pass (search.go:177,212)
     int rc;
+    const bool timing = getenv("GNX_GSW_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t_prev = now();
+    auto lap = [&](const char *what) {
+        if (timing) {
+            const auto t = now();
+            fprintf(stderr, "[gnx_gsw_batch] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+            t_prev = t;
+        }
+    };
+    PinBuf *pin = ctx->gsw_pin;
+    CU(cudaSetDevice(ctx->device));
 
-    // ---- phase 1: seeds of every read ----
-    std::vector<gnx_seed> seeds((size_t)std::max<int64_t>(8 * n_reads, 64));
-    std::vector<int64_t> soff((size_t)n_reads + 1);
-    rc = gnx_seed_batch(ctx, ix, reads_cat, read_off, n_reads, seeds.data(), soff.data(), (int64_t)seeds.size());
+    // ---- phase 1: seeds of every read (GPU), straight into page-locked memory ----
+    CU(pin[GP_SOFF].ensure((size_t)(n_reads + 1) * 8));
+    int64_t *soff = pin[GP_SOFF].as<int64_t>();
+    CU(pin[GP_SEEDS].ensure((size_t)std::max<int64_t>(4 * n_reads, 64) * sizeof(gnx_seed)));
+    rc = gnx_seed_batch(ctx, ix, reads_cat, read_off, n_reads, pin[GP_SEEDS].as<gnx_seed>(), soff,
+                        (int64_t)(pin[GP_SEEDS].cap / sizeof(gnx_seed)));
     if (rc == GNX_ECAP) {
-        seeds.resize((size_t)soff[(size_t)n_reads]);
-        rc = gnx_seed_batch(ctx, ix, reads_cat, read_off, n_reads, seeds.data(), soff.data(), (int64_t)seeds.size());
+        CU(pin[GP_SEEDS].ensure((size_t)soff[n_reads] * sizeof(gnx_seed)));
+        rc = gnx_seed_batch(ctx, ix, reads_cat, read_off, n_reads, pin[GP_SEEDS].as<gnx_seed>(), soff,
+                            (int64_t)(pin[GP_SEEDS].cap / sizeof(gnx_seed)));
     }
     if (rc != GNX_OK)
         return rc;
+    gnx_seed *seeds = pin[GP_SEEDS].as<gnx_seed>();
+    const int64_t n_seeds = soff[n_reads];
+    lap("seeds (GPU)");
 
-    // ---- phase 2: order the seeds, count the extension pairs each read can need ----
+    // ---- phase 2: order every read's seeds in place, perfect scores, reverse complements ----
     const int64_t total_bases = read_off[n_reads] - read_off[0];
-    std::vector<uint8_t> rc_cat((size_t)total_bases); // dna.ReverseComplement of every read (fastq.FastqBig.SeqRc)
-    std::vector<std::vector<GswSeed>> hits((size_t)n_reads);
-    std::vector<int64_t> perfect((size_t)n_reads), n_cand((size_t)n_reads), ext_first((size_t)n_reads + 1, 0);
-    std::vector<int64_t> la_len((size_t)n_reads + 1, 0), lb_len((size_t)n_reads + 1, 0), ra_len((size_t)n_reads + 1, 0),
-        rb_len((size_t)n_reads + 1, 0);
+    std::unique_ptr<uint8_t[]> rc_cat(new uint8_t[(size_t)std::max<int64_t>(total_bases, 1)]); // fastq.FastqBig.SeqRc
+    std::unique_ptr<int64_t[]> perfect(new int64_t[(size_t)n_reads]);
     static const uint8_t comp[13] = {3, 2, 1, 0, 4, 8, 7, 6, 5, 9, 10, 11, 12}; // dna/modify.go:72 complementArray
     std::atomic<bool> bad_base{false};
     gsw_parallel(n_reads, [&](int64_t lo, int64_t hi, int) {
         for (int64_t r = lo; r < hi; ++r) {
             const uint8_t *rd = reads_cat + read_off[r];
             const int64_t L = read_off[r + 1] - read_off[r];
-            uint8_t *rcp = rc_cat.data() + (read_off[r] - read_off[0]);
+            uint8_t *rcp = rc_cat.get() + (read_off[r] - read_off[0]);
             int64_t pf = 0;
             for (int64_t i = 0; i < L; ++i) {
                 const uint8_t b = rd[i];
@@ -144,121 +169,194 @@ extern "C" int gnx_gsw_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8
                 rcp[L - 1 - i] = comp[b];
             }
             perfect[(size_t)r] = pf;
-            std::vector<GswSeed> &h = hits[(size_t)r];
-            h.resize((size_t)(soff[(size_t)r + 1] - soff[(size_t)r]));
-            for (size_t k = 0; k < h.size(); ++k) {
-                const gnx_seed &s = seeds[(size_t)soff[(size_t)r] + k];
-                h[k] = GswSeed{s.target_id, s.target_start, s.query_start, s.length, s.pos_strand, s.total_length};
-            }
-            if (h.size() > 100) // SortSeedLen: sort.Slice, order among equal lengths unspecified -- stable here
-                std::stable_sort(h.begin(), h.end(), [](const GswSeed &a, const GswSeed &b) { return a.total > b.total; });
+            gnx_seed *h = seeds + soff[r];
+            const int64_t ns = soff[r + 1] - soff[r];
+            if (ns > 100) // SortSeedLen: sort.Slice, order among equal lengths unspecified -- stable here
+                std::stable_sort(h, h + ns, [](const gnx_seed &a, const gnx_seed &b) { return a.total_length > b.total_length; });
             else
-                gsw_heap_sort(h);
-            const int64_t ext = pf / 600 + L; // sk.extension (toGiraf.go:32)
-            int64_t nc = 0, ne = 0, la = 0, lb = 0, ra = 0, rb = 0;
-            for (const GswSeed &s : h) {
-                if (!gsw_could_be_better(s.total, 0, pf, L))
-                    break;
-                ++nc;
-                if ((int64_t)s.total == L)
-                    continue; // the seed spans the read: no extension (toGiraf.go:45-49)
-                ++ne;
-                const int64_t e = ext - s.total, node_len = GO[s.tid + 1] - GO[s.tid];
-                const int64_t ref_end = s.tstart, start = (int64_t)s.tstart + s.len;
-                la += std::max<int64_t>(0, std::min(ref_end, e));
-                lb += s.qstart;
-                ra += std::max<int64_t>(0, std::min(node_len - start, e));
-                rb += L - (s.qstart + s.len);
-            }
-            n_cand[(size_t)r] = nc;
-            ext_first[(size_t)r + 1] = ne;
-            la_len[(size_t)r + 1] = la;
-            lb_len[(size_t)r + 1] = lb;
-            ra_len[(size_t)r + 1] = ra;
-            rb_len[(size_t)r + 1] = rb;
+                gsw_heap_sort(h, ns);
         }
     });
     if (bad_base)
         return fail(ctx, GNX_EBASE, "a read holds a base >= dim (Go: index out of range in scoreMatrix[b][b])");
-    for (int64_t r = 0; r < n_reads; ++r) {
-        ext_first[(size_t)r + 1] += ext_first[(size_t)r];
-        la_len[(size_t)r + 1] += la_len[(size_t)r];
-        lb_len[(size_t)r + 1] += lb_len[(size_t)r];
-        ra_len[(size_t)r + 1] += ra_len[(size_t)r];
-        rb_len[(size_t)r + 1] += rb_len[(size_t)r];
-    }
-    const int64_t n_ext = ext_first[(size_t)n_reads];
+    lap("order seeds");
 
-    // ---- the extension pairs: target windows (getLeftTargetBases / getRightBases, search.go:133-145) and read flanks ----
-    std::vector<uint8_t> la_cat((size_t)la_len[(size_t)n_reads]), lb_cat((size_t)lb_len[(size_t)n_reads]),
-        ra_cat((size_t)ra_len[(size_t)n_reads]), rb_cat((size_t)rb_len[(size_t)n_reads]);
-    std::vector<int64_t> la_off((size_t)n_ext + 1, 0), lb_off((size_t)n_ext + 1, 0), ra_off((size_t)n_ext + 1, 0), rb_off((size_t)n_ext + 1, 0);
-    gsw_parallel(n_reads, [&](int64_t lo, int64_t hi, int) {
-        for (int64_t r = lo; r < hi; ++r) {
-            const int64_t L = read_off[r + 1] - read_off[r];
-            const uint8_t *rd = reads_cat + read_off[r], *rcp = rc_cat.data() + (read_off[r] - read_off[0]);
-            const int64_t ext = perfect[(size_t)r] / 600 + L;
-            int64_t x = ext_first[(size_t)r], la = la_len[(size_t)r], lb = lb_len[(size_t)r], ra = ra_len[(size_t)r], rb = rb_len[(size_t)r];
-            const std::vector<GswSeed> &h = hits[(size_t)r];
-            for (int64_t k = 0; k < n_cand[(size_t)r]; ++k) {
-                const GswSeed &s = h[(size_t)k];
-                if ((int64_t)s.total == L)
-                    continue;
-                const uint8_t *cur = s.pos ? rd : rcp;
-                const int64_t e = ext - s.total, node_len = GO[s.tid + 1] - GO[s.tid];
-                const uint8_t *node = G.data() + GO[s.tid];
-                const int64_t ref_end = s.tstart, start = (int64_t)s.tstart + s.len;
-                const int64_t wl = std::max<int64_t>(0, std::min(ref_end, e)), wr = std::max<int64_t>(0, std::min(node_len - start, e));
-                const int64_t ql = s.qstart, qr = L - (s.qstart + s.len);
-                memcpy(la_cat.data() + la, node + ref_end - wl, (size_t)wl);
-                memcpy(lb_cat.data() + lb, cur, (size_t)ql);
-                memcpy(ra_cat.data() + ra, node + start, (size_t)wr);
-                memcpy(rb_cat.data() + rb, cur + s.qstart + s.len, (size_t)qr);
-                la += wl;
-                lb += ql;
-                ra += wr;
-                rb += qr;
-                la_off[(size_t)x + 1] = la;
-                lb_off[(size_t)x + 1] = lb;
-                ra_off[(size_t)x + 1] = ra;
-                rb_off[(size_t)x + 1] = rb;
-                ++x;
+    // ---- the extension DPs, in two rounds so that seeds the sequential loop can never reach are (mostly) not aligned:
+    // round 1 extends every read's first (longest) seed; its score is the best score the loop holds when it looks at
+    // the second seed, and the predicate only gets stricter from there, so round 2 extends seeds 1.. up to the first
+    // one seedCouldBeBetter rejects at THAT score -- still a superset of what the replay below can ask for.
+    std::unique_ptr<int32_t[]> ext_id(new int32_t[(size_t)std::max<int64_t>(n_seeds, 1)]); // per seed: extension id or -1
+    GswExt X;
+    int64_t n_ext_total = 0;
+    auto seed_score_of = [&](const gnx_seed &s, const uint8_t *cur) {
+        int64_t v = 0; // scoreSeedSeq (align.go:81-87)
+        for (uint32_t i = s.query_start; i < s.query_start + s.length; ++i)
+            v += scores[cur[i] * dim + cur[i]];
+        return v;
+    };
+    // first[r] .. last[r]: the seed range (relative to the read) this round extends
+    auto run_round = [&](const std::vector<int32_t> &first, const std::vector<int32_t> &last) -> int {
+        std::vector<int64_t> cnt((size_t)n_reads + 1, 0), la((size_t)n_reads + 1, 0), lb((size_t)n_reads + 1, 0), ra((size_t)n_reads + 1, 0),
+            rb((size_t)n_reads + 1, 0);
+        gsw_parallel(n_reads, [&](int64_t lo, int64_t hi, int) {
+            for (int64_t r = lo; r < hi; ++r) {
+                const int64_t L = read_off[r + 1] - read_off[r], ext = perfect[(size_t)r] / 600 + L; // sk.extension (toGiraf.go:32)
+                int64_t ne = 0, a1 = 0, b1 = 0, a2 = 0, b2 = 0;
+                for (int32_t k = first[(size_t)r]; k < last[(size_t)r]; ++k) {
+                    const gnx_seed &s = seeds[soff[r] + k];
+                    if ((int64_t)s.total_length == L)
+                        continue; // the seed spans the read: no extension (toGiraf.go:45-49)
+                    ++ne;
+                    const int64_t e = ext - s.total_length, node_len = GO[s.target_id + 1] - GO[s.target_id];
+                    const int64_t ref_end = s.target_start, start = (int64_t)s.target_start + s.length;
+                    a1 += std::max<int64_t>(0, std::min(ref_end, e));
+                    b1 += s.query_start;
+                    a2 += std::max<int64_t>(0, std::min(node_len - start, e));
+                    b2 += L - (s.query_start + s.length);
+                }
+                cnt[(size_t)r + 1] = ne;
+                la[(size_t)r + 1] = a1;
+                lb[(size_t)r + 1] = b1;
+                ra[(size_t)r + 1] = a2;
+                rb[(size_t)r + 1] = b2;
+            }
+        });
+        for (int64_t r = 0; r < n_reads; ++r) {
+            cnt[(size_t)r + 1] += cnt[(size_t)r];
+            la[(size_t)r + 1] += la[(size_t)r];
+            lb[(size_t)r + 1] += lb[(size_t)r];
+            ra[(size_t)r + 1] += ra[(size_t)r];
+            rb[(size_t)r + 1] += rb[(size_t)r];
+        }
+        const int64_t ne = cnt[(size_t)n_reads];
+        if (ne == 0)
+            return GNX_OK;
+        const int64_t base = n_ext_total;
+        for (auto *v : {&X.l_score, &X.l_i, &X.l_j, &X.r_score, &X.r_i, &X.r_j, &X.l_coff, &X.r_coff})
+            v->resize((size_t)(base + ne));
+        X.l_cnt.resize((size_t)(base + ne));
+        X.r_cnt.resize((size_t)(base + ne));
+        for (int side = 0; side < 2; ++side) { // 0 left (getLeftTargetBases), 1 right (getRightBases), search.go:133-145
+            const std::vector<int64_t> &alen = side ? ra : la, &blen = side ? rb : lb;
+            CU(pin[GP_A].ensure((size_t)alen[(size_t)n_reads] + 16));
+            CU(pin[GP_B].ensure((size_t)blen[(size_t)n_reads] + 16));
+            CU(pin[GP_AO].ensure((size_t)(ne + 1) * 8));
+            CU(pin[GP_BO].ensure((size_t)(ne + 1) * 8));
+            uint8_t *A = pin[GP_A].as<uint8_t>(), *B = pin[GP_B].as<uint8_t>();
+            int64_t *AO = pin[GP_AO].as<int64_t>(), *BO = pin[GP_BO].as<int64_t>();
+            AO[0] = BO[0] = 0;
+            gsw_parallel(n_reads, [&](int64_t lo, int64_t hi, int) {
+                for (int64_t r = lo; r < hi; ++r) {
+                    const int64_t L = read_off[r + 1] - read_off[r], ext = perfect[(size_t)r] / 600 + L;
+                    const uint8_t *rd = reads_cat + read_off[r], *rcp = rc_cat.get() + (read_off[r] - read_off[0]);
+                    int64_t x = cnt[(size_t)r], ap = alen[(size_t)r], bp = blen[(size_t)r];
+                    for (int32_t k = first[(size_t)r]; k < last[(size_t)r]; ++k) {
+                        const gnx_seed &s = seeds[soff[r] + k];
+                        if ((int64_t)s.total_length == L)
+                            continue;
+                        const uint8_t *cur = s.pos_strand ? rd : rcp;
+                        const int64_t e = ext - s.total_length, node_len = GO[s.target_id + 1] - GO[s.target_id];
+                        const uint8_t *node = G.data() + GO[s.target_id];
+                        const int64_t ref_end = s.target_start, start = (int64_t)s.target_start + s.length;
+                        if (side == 0) {
+                            const int64_t w = std::max<int64_t>(0, std::min(ref_end, e)), q = s.query_start;
+                            memcpy(A + ap, node + ref_end - w, (size_t)w);
+                            memcpy(B + bp, cur, (size_t)q);
+                            ap += w;
+                            bp += q;
+                            ext_id[(size_t)(soff[r] + k)] = (int32_t)(base + x);
+                        } else {
+                            const int64_t w = std::max<int64_t>(0, std::min(node_len - start, e)), q = L - (s.query_start + s.length);
+                            memcpy(A + ap, node + start, (size_t)w);
+                            memcpy(B + bp, cur + s.query_start + s.length, (size_t)q);
+                            ap += w;
+                            bp += q;
+                        }
+                        AO[x + 1] = ap;
+                        BO[x + 1] = bp;
+                        ++x;
+                    }
+                }
+            });
+            CU(pin[GP_SC].ensure((size_t)ne * 8));
+            CU(pin[GP_EI].ensure((size_t)ne * 8));
+            CU(pin[GP_EJ].ensure((size_t)ne * 8));
+            CU(pin[GP_CO].ensure((size_t)(ne + 1) * 8));
+            CU(pin[GP_CG].ensure((size_t)std::max<int64_t>(4 * ne, 64) * sizeof(gnx_cigar)));
+            int64_t *co = pin[GP_CO].as<int64_t>();
+            int e = gnx_extend_batch(ctx, side ? GNX_EXT_RIGHT : GNX_EXT_LEFT, A, AO, B, BO, ne, scores, dim, gap_pen, 1,
+                                     pin[GP_SC].as<int64_t>(), pin[GP_EI].as<int64_t>(), pin[GP_EJ].as<int64_t>(),
+                                     pin[GP_CG].as<gnx_cigar>(), co, (int64_t)(pin[GP_CG].cap / sizeof(gnx_cigar)));
+            if (e == GNX_ECAP) {
+                CU(pin[GP_CG].ensure((size_t)co[ne] * sizeof(gnx_cigar)));
+                e = gnx_copy_last_cigars(ctx, pin[GP_CG].as<gnx_cigar>(), co[ne]);
+            }
+            if (e != GNX_OK)
+                return e;
+            std::vector<int64_t> &sc = side ? X.r_score : X.l_score, &ei = side ? X.r_i : X.l_i, &ej = side ? X.r_j : X.l_j,
+                                 &cf = side ? X.r_coff : X.l_coff;
+            std::vector<int32_t> &cn = side ? X.r_cnt : X.l_cnt;
+            std::vector<gnx_cigar> &cg = side ? X.r_cig : X.l_cig;
+            const int64_t cbase = (int64_t)cg.size();
+            cg.resize((size_t)(cbase + co[ne]));
+            memcpy(cg.data() + cbase, pin[GP_CG].p, (size_t)co[ne] * sizeof(gnx_cigar));
+            memcpy(sc.data() + base, pin[GP_SC].p, (size_t)ne * 8);
+            memcpy(ei.data() + base, pin[GP_EI].p, (size_t)ne * 8);
+            memcpy(ej.data() + base, pin[GP_EJ].p, (size_t)ne * 8);
+            for (int64_t x = 0; x < ne; ++x) {
+                cf[(size_t)(base + x)] = cbase + co[x];
+                cn[(size_t)(base + x)] = (int32_t)(co[x + 1] - co[x]);
             }
         }
-    });
-
-    // ---- phase 2b: every left and right DP in two batched calls ----
-    std::vector<int64_t> l_score((size_t)n_ext), l_i((size_t)n_ext), l_j((size_t)n_ext), l_coff((size_t)n_ext + 1, 0);
-    std::vector<int64_t> r_score((size_t)n_ext), r_i((size_t)n_ext), r_j((size_t)n_ext), r_coff((size_t)n_ext + 1, 0);
-    std::vector<gnx_cigar> l_cig, r_cig;
-    auto extend = [&](int side, std::vector<uint8_t> &a, std::vector<int64_t> &ao, std::vector<uint8_t> &b, std::vector<int64_t> &bo,
-                      std::vector<int64_t> &sc, std::vector<int64_t> &ei, std::vector<int64_t> &ej, std::vector<int64_t> &co,
-                      std::vector<gnx_cigar> &cg) -> int {
-        if (n_ext == 0)
-            return GNX_OK;
-        cg.resize((size_t)std::max<int64_t>(6 * n_ext, 64));
-        uint8_t dummy = 0;
-        int e = gnx_extend_batch(ctx, side, a.empty() ? &dummy : a.data(), ao.data(), b.empty() ? &dummy : b.data(), bo.data(), n_ext,
-                                 scores, dim, gap_pen, 1, sc.data(), ei.data(), ej.data(), cg.data(), co.data(), (int64_t)cg.size());
-        if (e == GNX_ECAP) {
-            cg.resize((size_t)co[(size_t)n_ext]);
-            e = gnx_copy_last_cigars(ctx, cg.data(), (int64_t)cg.size());
-        }
-        return e;
+        n_ext_total += ne;
+        return GNX_OK;
     };
-    if ((rc = extend(GNX_EXT_LEFT, la_cat, la_off, lb_cat, lb_off, l_score, l_i, l_j, l_coff, l_cig)) != GNX_OK)
+    std::vector<int32_t> first((size_t)n_reads), last((size_t)n_reads);
+    for (int64_t r = 0; r < n_reads; ++r) {
+        first[(size_t)r] = 0;
+        last[(size_t)r] = soff[r + 1] > soff[r] ? 1 : 0; // pred(seed 0, best 0) holds for every seed
+    }
+    for (int64_t k = 0; k < n_seeds; ++k)
+        ext_id[(size_t)k] = -1;
+    if ((rc = run_round(first, last)) != GNX_OK)
         return rc;
-    if ((rc = extend(GNX_EXT_RIGHT, ra_cat, ra_off, rb_cat, rb_off, r_score, r_i, r_j, r_coff, r_cig)) != GNX_OK)
+    lap("round 1 (first seeds)");
+    const int64_t n_ext1 = n_ext_total;
+    gsw_parallel(n_reads, [&](int64_t lo, int64_t hi, int) {
+        for (int64_t r = lo; r < hi; ++r) {
+            const int64_t ns = soff[r + 1] - soff[r], L = read_off[r + 1] - read_off[r];
+            first[(size_t)r] = last[(size_t)r] = 1;
+            if (ns < 2)
+                continue;
+            const gnx_seed &s0 = seeds[soff[r]];
+            const uint8_t *cur = s0.pos_strand ? reads_cat + read_off[r] : rc_cat.get() + (read_off[r] - read_off[0]);
+            int64_t sc0 = seed_score_of(s0, cur);
+            const int32_t id = ext_id[(size_t)soff[r]];
+            if (id >= 0)
+                sc0 += X.l_score[(size_t)id] + X.r_score[(size_t)id];
+            const int64_t best1 = std::max<int64_t>(sc0, 0); // currBest.AlnScore after the first seed
+            int32_t k = 1;
+            while (k < ns && gsw_could_be_better(seeds[soff[r] + k].total_length, best1, perfect[(size_t)r], L))
+                ++k;
+            last[(size_t)r] = k;
+        }
+    });
+    if ((rc = run_round(first, last)) != GNX_OK)
         return rc;
+    lap("round 2 (remaining seeds)");
+    if (timing)
+        fprintf(stderr, "[gnx_gsw_batch] reads %lld seeds %lld extension pairs %lld + %lld\n", (long long)n_reads, (long long)n_seeds,
+                (long long)n_ext1, (long long)(n_ext_total - n_ext1));
 
     // ---- phase 3: replay of the reference's per-read loop over the precomputed DPs ----
     std::vector<GswCigar> cig_out((size_t)n_reads);
     std::vector<uint8_t> has_cig((size_t)n_reads, 0);
+    std::atomic<bool> missing{false};
     gsw_parallel(n_reads, [&](int64_t lo, int64_t hi, int) {
         GswCigar left, right, cig;
         for (int64_t r = lo; r < hi; ++r) {
             const int64_t L = read_off[r + 1] - read_off[r];
-            const uint8_t *rd = reads_cat + read_off[r], *rcp = rc_cat.data() + (read_off[r] - read_off[0]);
+            const uint8_t *rd = reads_cat + read_off[r], *rcp = rc_cat.get() + (read_off[r] - read_off[0]);
             const int64_t pf = perfect[(size_t)r];
             gnx_giraf g;
             memset(&g, 0, sizeof g);
@@ -266,51 +364,52 @@ extern "C" int gnx_gsw_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8
             g.node = -1;
             left.clear();   // sk.leftAlignment / rightAlignment / queryEnd live across the seeds of ONE read
             right.clear();
-            int64_t query_end = 0, x = ext_first[(size_t)r];
-            const std::vector<GswSeed> &h = hits[(size_t)r];
-            for (size_t k = 0; k < h.size(); ++k) {
-                const GswSeed &s = h[k];
-                if (!gsw_could_be_better(s.total, g.aln_score, pf, L))
-                    break; // k < n_cand always holds here: the predicate at best >= 0 implies the predicate at 0
-                const uint8_t *cur = s.pos ? rd : rcp;
-                int64_t seed_score = 0; // scoreSeedSeq (align.go:81-87)
-                for (uint32_t i = s.qstart; i < s.qstart + s.len; ++i)
-                    seed_score += scores[cur[i] * dim + cur[i]];
+            int64_t query_end = 0;
+            const int64_t ns = soff[r + 1] - soff[r];
+            for (int64_t k = 0; k < ns; ++k) {
+                const gnx_seed &s = seeds[soff[r] + k];
+                if (!gsw_could_be_better(s.total_length, g.aln_score, pf, L))
+                    break;
+                const uint8_t *cur = s.pos_strand ? rd : rcp;
+                const int64_t seed_score = seed_score_of(s, cur);
                 int64_t tstart, tend, qstart, score;
-                if ((int64_t)s.total == L) {
-                    tstart = s.tstart;
-                    tend = (int64_t)s.tstart + s.len;
-                    qstart = s.qstart;
+                if ((int64_t)s.total_length == L) {
+                    tstart = s.target_start;
+                    tend = (int64_t)s.target_start + s.length;
+                    qstart = s.query_start;
                     score = seed_score;
                 } else {
-                    const int64_t e = pf / 600 + L - s.total, node_len = GO[s.tid + 1] - GO[s.tid];
-                    const int64_t ref_end = s.tstart, start = (int64_t)s.tstart + s.len;
+                    const int32_t x = ext_id[(size_t)(soff[r] + k)];
+                    if (x < 0) { // cannot happen: the rounds extend a superset of what this loop reaches
+                        missing = true;
+                        break;
+                    }
+                    const int64_t e = pf / 600 + L - s.total_length;
+                    const int64_t ref_end = s.target_start, start = (int64_t)s.target_start + s.length;
                     const int64_t wl = std::max<int64_t>(0, std::min(ref_end, e));
-                    (void)node_len;
                     left.clear();
-                    for (int64_t c = l_coff[(size_t)x]; c < l_coff[(size_t)x + 1]; ++c)
-                        left.emplace_back(l_cig[(size_t)c].run_length, l_cig[(size_t)c].op);
+                    for (int64_t c = X.l_coff[(size_t)x]; c < X.l_coff[(size_t)x] + X.l_cnt[(size_t)x]; ++c)
+                        left.emplace_back(X.l_cig[(size_t)c].run_length, X.l_cig[(size_t)c].op);
                     right.clear();
-                    for (int64_t c = r_coff[(size_t)x]; c < r_coff[(size_t)x + 1]; ++c)
-                        right.emplace_back(r_cig[(size_t)c].run_length, r_cig[(size_t)c].op);
-                    tstart = ref_end - wl + l_i[(size_t)x]; // refEnd - len(s.Seq) - len(seq) + targetStart (search.go:178)
-                    qstart = l_j[(size_t)x];
-                    tend = r_i[(size_t)x] + start;          // targetEnd + start (:214)
-                    query_end = r_j[(size_t)x];
-                    score = l_score[(size_t)x] + seed_score + r_score[(size_t)x];
-                    ++x;
+                    for (int64_t c = X.r_coff[(size_t)x]; c < X.r_coff[(size_t)x] + X.r_cnt[(size_t)x]; ++c)
+                        right.emplace_back(X.r_cig[(size_t)c].run_length, X.r_cig[(size_t)c].op);
+                    tstart = ref_end - wl + X.l_i[(size_t)x]; // refEnd - len(s.Seq) - len(seq) + targetStart (search.go:178)
+                    qstart = X.l_j[(size_t)x];
+                    tend = X.r_i[(size_t)x] + start;          // targetEnd + start (:214)
+                    query_end = X.r_j[(size_t)x];
+                    score = X.l_score[(size_t)x] + seed_score + X.r_score[(size_t)x];
                 }
                 if (score > g.aln_score) { // toGiraf.go:56-64
                     g.q_start = (int32_t)qstart;
-                    g.q_end = (int32_t)((int64_t)s.qstart + qstart + query_end + s.total - 1);
-                    g.pos_strand = s.pos ? 1 : 0;
+                    g.q_end = (int32_t)((int64_t)s.query_start + qstart + query_end + s.total_length - 1);
+                    g.pos_strand = s.pos_strand ? 1 : 0;
                     g.t_start = (int32_t)tstart;
                     g.t_end = (int32_t)tend;
-                    g.node = (int32_t)s.tid;
+                    g.node = (int32_t)s.target_id;
                     g.aln_score = score;
                     // cigar.Concat(cigar.Append(left, {TotalLength, 'M'}), right)
                     cig = left;
-                    gsw_append(cig, s.total, 'M');
+                    gsw_append(cig, s.total_length, 'M');
                     if (!right.empty()) {
                         gsw_append(cig, right[0].first, right[0].second);
                         cig.insert(cig.end(), right.begin() + 1, right.end());
@@ -339,6 +438,9 @@ extern "C" int gnx_gsw_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8
             out[r] = g;
         }
     });
+    if (missing)
+        return fail(ctx, GNX_ECUDA, "gnx_gsw_batch: internal error (a replayed seed has no extension result)");
+    lap("replay");
     if (paired) { // setGirafFlags (toGiraf.go:126-137): as written there, the forward mate gets 8 + 16 + 16
         for (int64_t p = 0; p + 1 < n_reads; p += 2) {
             gnx_giraf &f = out[p], &v = out[p + 1];
@@ -379,5 +481,6 @@ extern "C" int gnx_gsw_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8
             }
         }
     });
+    lap("pack results");
     return GNX_OK;
 }
