@@ -12,7 +12,7 @@ func GoAffineGapLocalEngine(scores [][]int64, gapOpen int64, gapExtend int64) (i
 	i := make(chan TargetQueryPair, 1000)
 	o := make(chan TargetQueryPair, 1000)
 	go func() {
-		const maxBatch = 1 << 16
+		const maxBatch = 1 << 18 // one kernel chunk of the library (gnx_set_option "chunk_pairs")
 		batch := make([]TargetQueryPair, 0, maxBatch)
 		for first := range i {
 			batch = append(batch[:0], first)

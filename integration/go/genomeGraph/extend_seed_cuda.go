@@ -24,6 +24,7 @@ import (
 	"github.com/vertgenlab/gonomics/cigar"
 	"github.com/vertgenlab/gonomics/dna"
 	"github.com/vertgenlab/gonomics/fastq"
+	"github.com/vertgenlab/gonomics/giraf"
 )
 
 func gnxCheck(ctx *C.gnx_ctx, rc C.int) {
@@ -138,4 +139,63 @@ func ExtendBatch(ctx unsafe.Pointer, left bool, alphas, betas [][]dna.Base, scor
 		routes[i] = cig[coff[i]:coff[i+1]:coff[i+1]]
 	}
 	return score[:n], routes, endI[:n], endJ[:n]
+}
+
+// GswBatch is the whole per-read driver for a block of reads (gnx_gsw_batch): GraphSmithWatermanToGiraf
+// (toGiraf.go:17-72) for every read -- WrapPairGiraf (:117-137) when paired, reads 2k / 2k+1 being the mates -- with
+// the seed and extension steps of the block batched on the GPU and the reference's per-read loop replayed over their
+// results inside the library.  The caller fills in what the aligner does not compute (QName, Seq, Qual, Notes) exactly
+// as GraphSmithWatermanToGiraf does; RoutineFqPairToGiraf (routines.go) becomes "collect a block of pairs from the
+// channel, call GswBatch, send the pairs on".
+func (ix *GpuSeedIndex) GswBatch(reads []fastq.FastqBig, scores [][]int64, paired bool) []giraf.Giraf {
+	n := len(reads)
+	if n == 0 {
+		return nil
+	}
+	seqs := make([][]dna.Base, n)
+	for i := range reads {
+		seqs[i] = reads[i].Seq
+	}
+	cat, off := concatBases(seqs)
+	dim := len(scores)
+	flat := make([]int64, dim*dim)
+	for i := range scores {
+		copy(flat[i*dim:], scores[i])
+	}
+	recs := make([]C.gnx_giraf, n)
+	cig := make([]cigar.Cigar, 4*n+64) // cigar.Cigar{RunLength int; Op byte} == gnx_cigar (16 B)
+	var need C.int64_t
+	pairedFlag := C.int(0)
+	if paired {
+		pairedFlag = 1
+	}
+	call := func() C.int {
+		return C.gnx_gsw_batch(ix.ctx, ix.h, (*C.uint8_t)(unsafe.Pointer(&cat[0])), (*C.int64_t)(unsafe.Pointer(&off[0])), C.int64_t(n),
+			(*C.int64_t)(unsafe.Pointer(&flat[0])), C.int(dim), pairedFlag, &recs[0], (*C.gnx_cigar)(unsafe.Pointer(&cig[0])),
+			C.int64_t(len(cig)), &need)
+	}
+	rc := call()
+	if rc == C.GNX_ECAP && int(need) > len(cig) {
+		cig = make([]cigar.Cigar, need)
+		rc = call()
+	}
+	gnxCheck(ix.ctx, rc)
+	out := make([]giraf.Giraf, n)
+	for r := range reads {
+		g := &recs[r]
+		out[r] = giraf.Giraf{QName: reads[r].Name, QStart: int(g.q_start), QEnd: int(g.q_end), PosStrand: g.pos_strand != 0,
+			Path: giraf.Path{TStart: int(g.t_start), TEnd: int(g.t_end)}, AlnScore: int(g.aln_score), MapQ: 255, Flag: uint8(g.flag),
+			Seq: reads[r].Seq, Qual: reads[r].Qual, Notes: []giraf.Note{{Tag: []byte{'X', 'O'}, Type: 'Z', Value: "~"}}}
+		if g.node >= 0 {
+			out[r].Path.Nodes = []uint32{uint32(g.node)}
+		}
+		if g.n_cigar >= 0 {
+			out[r].Cigar = cig[g.cigar_off : g.cigar_off+C.int64_t(g.n_cigar) : g.cigar_off+C.int64_t(g.n_cigar)]
+		}
+		if !out[r].PosStrand { // toGiraf.go:65-70
+			out[r].Seq = reads[r].SeqRc
+			fastq.ReverseQualUint8Record(out[r].Qual)
+		}
+	}
+	return out
 }
