@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("GNX_LIB") or os.path.join(_HERE, "libgnxalign.so")  #
 
 GNX_OK, GNX_EBASE, GNX_ECAP, GNX_ECHUNK, GNX_EEMPTY, GNX_ECUDA, GNX_EARG, GNX_ERANGE, GNX_EDIVZERO, GNX_EOFFSET, GNX_EINDEX = range(11)
 GNX_GLOBAL, GNX_FREE_END = 0, 1
-GNX_EXT_LEFT, GNX_EXT_RIGHT = 1, 2
+GNX_EXT_LEFT, GNX_EXT_RIGHT, GNX_EXT_LEFT_LOCAL, GNX_EXT_RIGHT_LOCAL = 1, 2, 3, 4
 GNX_MATCH_RIGHT, GNX_MATCH_LEFT = 0, 1
 
 # every symbol include/gnxalign.h declares (tests check that the library exports all of them)

@@ -218,6 +218,7 @@ struct Problem {
     int64_t chunk = 1; // AffineGapChunk: bases per DP cell
     bool wide = false; // int64 plane values (the int32 range proof failed)
     int ext = 0;       // gsw extend step on the const-gap machinery (kind 2): 1 LeftDynamicAln, 2 RightDynamicAln
+    bool ext_local = false; // ... in their older LeftLocal / RightLocal form ('=' / 'X' ops, route in alignment order)
     bool twobit = false;                // the caller's sequences are dnaTwoBit words (gnx_*_twobit entry points)
     bool profile = false;               // match scores come from a dense per-pair matrix (gnx_profile.cuh)
     const int64_t *extra_words = nullptr; // profile: per-pair workspace words besides the trace (the S matrix)
@@ -842,6 +843,7 @@ void launch_traceback_ext(const Problem &pb, const ChunkDev &cd, const TracePara
     memset(&ep, 0, sizeof ep);
     ep.t = tp;
     ep.side = pb.ext;
+    ep.local = pb.ext_local ? 1 : 0;
     ep.alpha = cd.alpha;
     ep.beta = cd.beta;
     ep.dim = pb.dim;
@@ -1085,7 +1087,8 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
                                                                (CigarOut *)cigars, cap, status);
     else
         expand_kernel<<<(int)((np + 127) / 128), 128, 0, st>>>(cd.slots, slot_cap_of(pb), cd.counts, cig_off, np,
-                                                              (CigarOut *)cigars, cap, status, pb.ext);
+                                                              (CigarOut *)cigars, cap, status,
+                                                              pb.ext ? (pb.ext_local ? 2 : 1) : 0);
     ctx->launches++;
     TraceParams tp;
     memset(&tp, 0, sizeof tp);
@@ -2193,8 +2196,11 @@ int gnx_extend_batch(gnx_ctx *ctx, int side, const uint8_t *alpha_cat, const int
 {
     if (!ctx)
         return GNX_EARG;
-    if (n_pairs < 0 || !alpha_off || !beta_off || !out_score || (side != GNX_EXT_LEFT && side != GNX_EXT_RIGHT))
+    if (n_pairs < 0 || !alpha_off || !beta_off || !out_score || side < GNX_EXT_LEFT || side > GNX_EXT_RIGHT_LOCAL)
         return fail(ctx, GNX_EARG, "bad argument to gnx_extend_batch");
+    const bool local = side >= GNX_EXT_LEFT_LOCAL;
+    if (local)
+        side -= 2;
     if (want_cigar && !out_cigar_off)
         return fail(ctx, GNX_EARG, "out_cigar_off is required when want_cigar != 0");
     if (dim > kDimP)
@@ -2206,6 +2212,7 @@ int gnx_extend_batch(gnx_ctx *ctx, int side, const uint8_t *alpha_cat, const int
     if (rc != GNX_OK)
         return rc;
     pb.ext = side;
+    pb.ext_local = local;
     return run_host_batch(ctx, pb, alpha_cat, alpha_off, beta_cat, beta_off, n_pairs, out_score, out_cigar,
                           out_cigar_off, out_cigar ? cigar_cap : 0, out_end_i, out_end_j);
 }

@@ -1099,6 +1099,9 @@ struct ExtTraceParams {
     const int64_t *score;     // per global pair (left: the starting value)
     const int64_t *best;      // per global pair (right: row << 32 | column)
     int64_t *end_i, *end_j;   // per pair in chunk
+    int local;                // LeftLocal / RightLocal (genomeGraph/localAlignment.go:95-196): the same DPs with
+                              // cigar.TripleMaxTraceExtended -- a diagonal step is '=' when the substitution score is
+                              // positive (a > prev) and 'X' otherwise -- and the route reversed into alignment order
 };
 
 __global__ void traceback_ext_kernel(const ExtTraceParams E)
@@ -1132,8 +1135,13 @@ __global__ void traceback_ext_kernel(const ExtTraceParams E)
         } else {
             CigarOut o;
             o.run_length = run;
-            o.op = (unsigned char)(op == 0 ? 'M' : (op == 1 ? 'I' : 'D'));
-            dst[cnt] = o; // traceback order is the final order
+            if (E.local) {
+                o.op = (unsigned char)(op == 0 ? '=' : (op == 1 ? 'I' : (op == 2 ? 'D' : 'X')));
+                dst[P.counts[idx] - 1 - cnt] = o; // cigar.ReverseCigar
+            } else {
+                o.op = (unsigned char)(op == 0 ? 'M' : (op == 1 ? 'I' : 'D'));
+                dst[cnt] = o; // traceback order is the final order
+            }
         }
         ++cnt;
     };
@@ -1172,16 +1180,20 @@ __global__ void traceback_ext_kernel(const ExtTraceParams E)
         } else {
             k = (i == 0) ? 1 : 2;
         }
-        if (k == cur_op) {
+        int sub = 0;
+        if (k == 0 && (E.side == 1 || E.local))
+            sub = E.scores[(int)al[i - 1] * E.dim + (int)be[j - 1]];
+        const int kop = (E.local && k == 0 && sub <= 0) ? 3 : k; // run-length op: 3 = 'X' (TripleMaxTraceExtended: a <= prev)
+        if (kop == cur_op) {
             ++run;
         } else {
             if (cur_op >= 0)
                 emit(cur_op, run);
-            cur_op = k;
+            cur_op = kop;
             run = 1;
         }
         if (E.side == 1)
-            v -= (k == 0) ? (long long)E.scores[(int)al[i - 1] * E.dim + (int)be[j - 1]] : (long long)E.gap;
+            v -= (k == 0) ? (long long)sub : (long long)E.gap;
         i -= (k != 1);
         if (k != 2) {
             --j;
@@ -1226,7 +1238,10 @@ __global__ void expand_kernel(const uint32_t *slots, int slot_cap, const int *co
         CigarOut o;
         o.run_length = (long long)(v >> 2);
         o.op = (unsigned char)(v & 3u);
-        if (ext) {
+        if (ext == 2) { // LeftLocal / RightLocal: extended ops, alignment order
+            o.op = (unsigned char)(o.op == 0 ? '=' : (o.op == 1 ? 'I' : (o.op == 2 ? 'D' : 'X')));
+            out[off + cnt - 1 - k] = o;
+        } else if (ext) {
             o.op = (unsigned char)(o.op == 0 ? 'M' : (o.op == 1 ? 'I' : 'D'));
             out[off + k] = o;
         } else {

@@ -52,6 +52,20 @@ def RightDynamicAln(alpha, beta, scores, matrix=None, gapPen: int = -600, dynami
     return extend_pairs(GNX_EXT_RIGHT, [alpha], [beta], scores, gapPen, ctx)[0]
 
 
+def LeftLocal(alpha, beta, scores, gapPen: int = -600, m=None, trace=None, ctx=None):
+    """genomeGraph.LeftLocal (genomeGraph/localAlignment.go:95-140): (score, route, minI, maxI, minJ, maxJ); ops '=','X','I','D'."""
+    from ._lib import GNX_EXT_LEFT_LOCAL
+    sc, route, i, j = extend_pairs(GNX_EXT_LEFT_LOCAL, [alpha], [beta], scores, gapPen, ctx)[0]
+    return sc, route, i, len(alpha), j, len(beta)
+
+
+def RightLocal(alpha, beta, scores, gapPen: int = -600, m=None, trace=None, ctx=None):
+    """genomeGraph.RightLocal (genomeGraph/localAlignment.go:142-196): (score, route, 0, maxI, 0, maxJ)."""
+    from ._lib import GNX_EXT_RIGHT_LOCAL
+    sc, route, i, j = extend_pairs(GNX_EXT_RIGHT_LOCAL, [alpha], [beta], scores, gapPen, ctx)[0]
+    return sc, route, 0, i, 0, j
+
+
 # ---- the perfect-match seed step (SURVEY.md 8f-2) ---------------------------------------------------
 class SeedDev(NamedTuple):
     """genomeGraph.SeedDev (genomeGraph/index.go:11-19); NextPart is always nil for edge-less nodes."""

@@ -165,7 +165,13 @@ int gnx_multi_affine_chunk_batch(gnx_ctx *ctx, const uint8_t *group_cat, const i
  * Op = 'M', 'I' or 'D' (cigar/cigar.go:15-18), in TRACEBACK order -- the reference does not reverse the
  * route inside these functions.  With want_cigar = 0 only scores (and, for the right side, the end cell;
  * -1 for the left side) are produced.  dim <= 5. */
-enum { GNX_EXT_LEFT = 1, GNX_EXT_RIGHT = 2 };
+/*   GNX_EXT_LEFT_LOCAL / GNX_EXT_RIGHT_LOCAL: genomeGraph.LeftLocal / RightLocal (genomeGraph/localAlignment.go:95-196),
+ *                  the older forms of the same two DPs: cigar.TripleMaxTraceExtended (cigar/tools.go:69-81) writes a
+ *                  diagonal step as '=' when the substitution score is positive and 'X' otherwise, and the route is
+ *                  reversed into alignment order (cigar.ReverseCigar).  Scores and end cells are those of the
+ *                  LEFT / RIGHT forms: LeftLocal returns (score, route, minI = out_end_i, len(alpha), minJ =
+ *                  out_end_j, len(beta)), RightLocal (score, route, 0, maxI = out_end_i, 0, maxJ = out_end_j). */
+enum { GNX_EXT_LEFT = 1, GNX_EXT_RIGHT = 2, GNX_EXT_LEFT_LOCAL = 3, GNX_EXT_RIGHT_LOCAL = 4 };
 int gnx_extend_batch(gnx_ctx *ctx, int side, const uint8_t *alpha_cat, const int64_t *alpha_off,
                      const uint8_t *beta_cat, const int64_t *beta_off, int64_t n_pairs, const int64_t *scores,
                      int dim, int64_t gap_pen, int want_cigar, int64_t *out_score, int64_t *out_end_i,

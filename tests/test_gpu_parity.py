@@ -890,3 +890,33 @@ def test_extend_ties_n_and_long(ctx):
     with pytest.raises(_lib.GnxError) as ei:  # a base outside the matrix: Go panics
         _check_extend(ctx, [np.array([0, 1, 7], np.uint8)], [np.array([0, 1], np.uint8)], S, -600)
     assert ei.value.code == _lib.GNX_EBASE
+
+
+def test_left_right_local_older_forms(ctx):
+    """genomeGraph.LeftLocal / RightLocal (localAlignment.go:95-196) as modes of gnx_extend_batch: '=' / 'X' ops and the
+    route in alignment order, against the plain-Python restatement (oracle/local.py)."""
+    from oracle import local as oloc
+    from gonomics_b200 import genomegraph
+    from gonomics_b200._lib import GNX_EXT_LEFT_LOCAL, GNX_EXT_RIGHT_LOCAL
+    rng = np.random.default_rng(4321)
+    S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX
+    al, be = [], []
+    for t in range(160):
+        n, m = int(rng.integers(0, 60)), int(rng.integers(0, 50))
+        a, b = random_pair(rng, n, m, identity=float(rng.choice([0.6, 0.9, 1.0])))
+        if t % 7 == 0:
+            unit = rng.integers(0, 4, size=2, dtype=np.uint8)
+            a, b = np.resize(unit, n).astype(np.uint8), np.resize(unit[::-1], m).astype(np.uint8)
+        if t % 9 == 0 and n:
+            a[int(rng.integers(0, n))] = 4
+        al.append(a)
+        be.append(b)
+    for side, fn in ((GNX_EXT_LEFT_LOCAL, oloc.left_local), (GNX_EXT_RIGHT_LOCAL, oloc.right_local)):
+        got = genomegraph.extend_pairs(side, al, be, S, -600, ctx)
+        for p, (a, b) in enumerate(zip(al, be)):
+            sc, route, min_i, max_i, min_j, max_j = fn(a, b, S, -600)
+            end = (min_i, min_j) if side == GNX_EXT_LEFT_LOCAL else (max_i, max_j)
+            assert (got[p][0], [tuple(x) for x in got[p][1]], got[p][2], got[p][3]) == (sc, route, end[0], end[1]), (side, p, len(a), len(b))
+    a, b = al[3], be[3]
+    assert genomegraph.LeftLocal(a, b, S, -600, ctx=ctx)[0] == oloc.left_local(a, b, S, -600)[0]
+    assert genomegraph.RightLocal(a, b, S, -600, ctx=ctx)[3] == oloc.right_local(a, b, S, -600)[3]
