@@ -22,7 +22,7 @@ GNX_MATCH_RIGHT, GNX_MATCH_LEFT = 0, 1
 EXPORTS = [
     "gnx_device_count", "gnx_create", "gnx_destroy", "gnx_last_error", "gnx_version", "gnx_host_alloc",
     "gnx_host_free", "gnx_affine_batch", "gnx_affine_batch_twobit", "gnx_const_batch", "gnx_affine_chunk_batch", "gnx_copy_last_cigars",
-    "gnx_multi_affine_chunk_batch", "gnx_extend_batch", "gnx_batch_device", "gnx_batch_device_twobit", "gnx_launch_count", "gnx_last_fill_stats", "gnx_set_option",
+    "gnx_multi_affine_chunk_batch", "gnx_extend_batch", "gnx_batch_device", "gnx_batch_device_twobit", "gnx_launch_count", "gnx_last_fill_stats", "gnx_last_kernel_path", "gnx_set_option",
     "gnx_twobit_new", "gnx_twobit_free", "gnx_twobit_info", "gnx_twobit_download", "gnx_twobit_unpack", "gnx_twobit_get_bases",
     "gnx_twobit_count_matches", "gnx_twobit_pack_device", "gnx_seed_index_new", "gnx_seed_index_free", "gnx_seed_index_info",
     "gnx_seed_index_download", "gnx_seed_batch", "gnx_gsw_batch",
@@ -132,6 +132,8 @@ def load() -> C.CDLL:
     L.gnx_seed_batch.restype = ci
     L.gnx_gsw_batch.argtypes = [vp, vp, u8p, i64p, i64, i64p, ci, ci, vp, cgp, i64, vp]
     L.gnx_gsw_batch.restype = ci
+    L.gnx_last_kernel_path.argtypes = [vp, vp, vp]
+    L.gnx_last_kernel_path.restype = ci
     L.gnx_multi_create.argtypes = [vp, ci, C.c_size_t]
     L.gnx_multi_create.restype = vp
     L.gnx_multi_destroy.argtypes = [vp]

@@ -97,6 +97,12 @@ class Context:
     def launch_count(self) -> int:
         return int(self._L.gnx_launch_count(self._h))
 
+    def last_kernel_path(self) -> Tuple[int, int]:
+        """(impl, flags) of the last batch call: see gnx_last_kernel_path in include/gnxalign.h."""
+        impl, flags = C.c_int(0), C.c_int(0)
+        self._check(self._L.gnx_last_kernel_path(self._h, C.byref(impl), C.byref(flags)))
+        return impl.value, flags.value
+
     def last_fill_stats(self) -> Tuple[float, int, int]:
         ms, n, cells = C.c_double(0), C.c_int64(0), C.c_int64(0)
         self._check(self._L.gnx_last_fill_stats(self._h, C.byref(ms), C.byref(n), C.byref(cells)))

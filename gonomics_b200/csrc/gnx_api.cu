@@ -103,6 +103,9 @@ struct Slot {
     DevBuf alpha, beta, aoff, boff, cls, trace, trace_off, slots, counts, score, cig_off, cigars, edge, misc, partials;
     DevBuf best, endi, endj; // gsw extend step: first-maximum cell (right) and the traceback's end coordinates
     DevBuf work;             // checkpoint path: work list of the pairs that need the recompute walk (+ its counter)
+    DevBuf rag;                 // ragged batches: quad_pairs | quad_ck_off | pair_slot (RagTables)
+    PinBuf h_rag;
+    bool ev_rag_set = false;    // device-resident path: ev_total marks the last upload out of h_rag
     DevBuf tb_a, tb_b, tb_meta; // 2-bit inputs: the chunk's packed words (+ word offsets / lengths of ragged chunks)
     PinBuf h_stage_a, h_stage_b, h_total, h_trace_off, h_score, h_off, h_cig, h_endi, h_endj, h_tbmeta;
     // chunk in flight
@@ -151,6 +154,7 @@ struct gnx_ctx {
     int opt_force_lookup = -1; // -1 auto; 0/1 force the PRMT / shared-memory score lookup for ACGT pairs
     int opt_ckpt = 1;          // allow the checkpoint-and-recompute traceback for uniform freeEndGaps batches
     int opt_wide_cta = -1;     // -1 auto; 0/1 never / always run multi-strip pairs on the 4-warp CTA-per-pair kernel
+    int opt_rag = 1;           // ragged batches may use the packed 16-bit kernels (quads binned on the host)
     int opt_tb_tma = 1;        // 2-bit inputs: 1 = fill16 kernels read the packed words (TMA), 0 = always unpack to bytes first
     int opt_long = -1;         // -1 auto; 0/1 never / always run multi-strip traceback batches on the tile-checkpoint kernel
     int opt_long_form = 0;     // cell formulation of its score-only pass (gnx_long.cuh FORM)
@@ -161,6 +165,7 @@ struct gnx_ctx {
     size_t fill_events_used = 0;
     double last_fill_ms = 0;
     int64_t last_fill_launches = 0, last_cells = 0;
+    int last_impl = 0, last_flags = 0; // kernel family the last batch call planned (gnx_last_kernel_path)
     // 2-bit entry points: host-side offset arrays derived from the lengths (byte offsets a/b, word offsets a/b), kept
     // between calls with the same uniform shape (a streaming caller's batches) so that they are built once
     std::vector<int64_t> tb_off[4];
@@ -202,6 +207,7 @@ struct FillCfg {
     int64_t m_uniform = 0; // fill16: the batch's (uniform) query length
     int64_t n_uniform = 0; // checkpoint path: the batch's (uniform) target length
     int64_t long_pool = 0; // impl 18: run-pool entries per chunk (0 = long_pool_entries())
+    bool rag = false;      // impl 16 / 17 on a ragged batch: quads come from RagTables
     bool tb = false;       // impl 16 / 17 on 2-bit inputs: affine_fill16_kernel<TB> stages the packed words by TMA
 };
 
@@ -339,9 +345,13 @@ bool fill16_ok(const gnx_ctx *ctx, const Problem &pb, int64_t min_n, int64_t max
     // checkpoint-and-recompute traceback (gnx_ckpt.cuh): freeEndGaps only, target staged in shared memory, and
     // worth it only when the target is well longer than the query (the path then skips most of the rows)
     if (for_ckpt && (!pb.want_cigar || !ctx->opt_ckpt || pb.kind != 1 || pb.chunk > 1 || pb.profile || pb.ext || max_n > kRing ||
-                     max_n < 2 * max_m))
+                     min_n < 2 * max_m))
         return false;
-    if (min_n != max_n || min_m != max_m || max_n < 1 || max_m < 1 || max_m > 160) // uniform batch only
+    if (min_n < 1 || min_m < 1 || max_m > 160) // every pair non-empty, queries within the 16 x 10 columns of a half-warp
+        return false;
+    // uniform batches address their quads arithmetically; ragged ones go through quads the host bins by
+    // (last-column index, target length) -- see RagTables
+    if ((min_n != max_n || min_m != max_m) && (!ctx->opt_rag || pb.chunk > 1 || pb.profile || pb.ext))
         return false;
     const int64_t O = pb.gap_open, E = pb.gap_extend;
     if (O > 0 || E > 0)
@@ -560,7 +570,7 @@ void launch_fill16_ckpt(const FillParams &fp, int64_t quads, int cm, int sm_coun
 // second pass of the checkpoint path: recompute + walk (pass 0: slots and counts; pass 1: overflowing pairs)
 void launch_ckpt_trace(gnx_ctx *ctx, const Problem &pb, const FillParams &fp, const uint32_t *ckpt, const int64_t *rstar,
                        uint32_t *slots, int *counts, int pass, const int64_t *cig_off, gnx_cigar *cigars, int64_t cap,
-                       int *work, int *work_count, cudaStream_t st)
+                       int *work, int *work_count, cudaStream_t st, const int *pair_slot = nullptr, const int64_t *quad_ck_off = nullptr)
 {
     static std::atomic<int> occ{0};
     if (occ == 0) {
@@ -585,6 +595,8 @@ void launch_ckpt_trace(gnx_ctx *ctx, const Problem &pb, const FillParams &fp, co
     q.work = work;
     q.work_count = work_count;
     q.work_next = work_count + 1;
+    q.pair_slot = pair_slot;
+    q.quad_ck_off = quad_ck_off;
     const int64_t np = fp.pair_end - fp.pair_begin;
     cudaMemsetAsync(work_count, 0, 2 * sizeof(int), st); // list length and cursor
     if (pass == 0) // screening: indel-free routes are written directly, the rest is queued
@@ -833,9 +845,90 @@ struct ChunkDev {
     int64_t *end_i, *end_j;           // ext: chunk-local
     int *work, *work_count;           // checkpoint path: work list (chunk-local pair indices) and its device counter
     const uint64_t *alpha_words, *beta_words; // TB kernels: biased so that words + pair * wn / wm is the pair's sequence
+    // ragged batches on the packed 16-bit kernels (RagTables): device copies + the quad range of every last-column group
+    const int *quad_pairs, *pair_slot;
+    const int64_t *quad_ck_off;
+    int64_t cm_first[12];
     const int *smat;                  // profile batches: biased so that smat + smat_off[pair] is the pair's matrix
     const int64_t *smat_off;          // indexed by global pair id
 };
+
+// Ragged batches on the packed 16-bit kernels.  A quad's four pairs advance in lock step, so they must share the
+// target length n (the step count) and -- with free end gaps -- the in-lane index (m - 1) % 10 of the last query column
+// (a template parameter of the kernels); query lengths are otherwise free.  The host bins a chunk's pairs by
+// (that index, n) with a counting sort and cuts every bin into quads; the last quad of a bin may have empty slots.
+struct RagTables {
+    std::vector<int> quad_pairs, pair_slot, count;
+    std::vector<int64_t> quad_ck_off;
+    int64_t cm_first[12];
+    int64_t n_quads = 0, ck_words = 0;
+};
+
+void build_rag_tables(const Problem &pb, const int64_t *aoff, const int64_t *boff, int64_t begin, int64_t np, int64_t max_n,
+                      RagTables &R)
+{
+    const bool free_end = pb.kind == 1;
+    const int64_t stride = max_n + 1, groups = free_end ? 10 : 1;
+    R.count.assign((size_t)(groups * stride + 1), 0);
+    auto key_of = [&](int64_t k) {
+        const int64_t n = aoff[begin + k + 1] - aoff[begin + k], m = boff[begin + k + 1] - boff[begin + k];
+        return (free_end ? (m - 1) % 10 : 0) * stride + n;
+    };
+    for (int64_t k = 0; k < np; ++k)
+        R.count[(size_t)key_of(k) + 1]++;
+    // quads per key, first quad of every key
+    std::vector<int64_t> first_quad((size_t)(groups * stride + 1), 0);
+    int64_t nq = 0;
+    for (int64_t key = 0; key < groups * stride; ++key) {
+        if (key % stride == 0)
+            R.cm_first[key / stride] = nq;
+        first_quad[(size_t)key] = nq;
+        nq += (R.count[(size_t)key + 1] + 3) / 4;
+    }
+    for (int64_t g = groups; g < 12; ++g)
+        R.cm_first[g] = nq;
+    R.n_quads = nq;
+    R.quad_pairs.assign((size_t)nq * 4, -1);
+    R.pair_slot.resize((size_t)np);
+    R.quad_ck_off.resize((size_t)nq + 1);
+    std::vector<int> fill((size_t)(groups * stride), 0); // pairs placed so far per key
+    for (int64_t k = 0; k < np; ++k) {
+        const int64_t key = key_of(k);
+        const int64_t slot = first_quad[(size_t)key] * 4 + fill[(size_t)key]++;
+        R.quad_pairs[(size_t)slot] = (int)k;
+        R.pair_slot[(size_t)k] = (int)slot;
+    }
+    int64_t words = 0;
+    for (int64_t key = 0; key < groups * stride; ++key) {
+        const int64_t n = key % stride, q0 = first_quad[(size_t)key], q1 = q0 + (R.count[(size_t)key + 1] + 3) / 4;
+        const int64_t w = pb.cfg.impl == 17 ? ((n + 16 - 2) / kCkK) * kCkRegs * 32 : 0;
+        for (int64_t q = q0; q < q1; ++q) {
+            R.quad_ck_off[(size_t)q] = words;
+            words += w;
+        }
+    }
+    R.quad_ck_off[(size_t)nq] = words;
+    R.ck_words = words;
+}
+
+// Upload a chunk's RagTables into the slot's device buffer and point the chunk at them.
+int upload_rag_tables(gnx_ctx *ctx, Slot &s, const RagTables &R, int64_t np, ChunkDev &cd, cudaStream_t st)
+{
+    const size_t b_qp = (size_t)R.n_quads * 4 * sizeof(int), b_off = ((size_t)R.n_quads + 1) * 8, b_ps = (size_t)np * sizeof(int);
+    const size_t o_off = (b_qp + 15) & ~(size_t)15, o_ps = (o_off + b_off + 15) & ~(size_t)15, total = o_ps + b_ps;
+    CU(s.rag.ensure(total + 16));
+    CU(s.h_rag.ensure(total + 16));
+    uint8_t *h = s.h_rag.as<uint8_t>();
+    memcpy(h, R.quad_pairs.data(), b_qp);
+    memcpy(h + o_off, R.quad_ck_off.data(), b_off);
+    memcpy(h + o_ps, R.pair_slot.data(), b_ps);
+    CU(cudaMemcpyAsync(s.rag.p, h, total, cudaMemcpyHostToDevice, st));
+    cd.quad_pairs = s.rag.as<int>();
+    cd.quad_ck_off = reinterpret_cast<const int64_t *>(s.rag.as<uint8_t>() + o_off);
+    cd.pair_slot = reinterpret_cast<const int *>(s.rag.as<uint8_t>() + o_ps);
+    memcpy(cd.cm_first, R.cm_first, sizeof cd.cm_first);
+    return GNX_OK;
+}
 
 void launch_traceback_ext(const Problem &pb, const ChunkDev &cd, const TraceParams &tp, int64_t np, cudaStream_t st)
 {
@@ -931,7 +1024,29 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     FillEvent &fe = next_fill_event(ctx);
     cudaEventRecord(fe.a, st);
     const int lookup0 = pb.chunk > 1 ? 2 : ((ctx->opt_force_lookup == 1 || !pb.prmt_ok) ? 1 : 0);
-    if (pb.cfg.impl == 18) { // long pairs: score, checkpoints, recompute and walk in one persistent launch
+    if (pb.cfg.rag) {
+        fp.quad_pairs = cd.quad_pairs;
+        fp.quad_ck_off = cd.quad_ck_off;
+    }
+    if (pb.cfg.rag && (pb.cfg.impl == 16 || pb.cfg.impl == 17)) {
+        // one launch per last-column group (free end gaps: the index is a template parameter), each over its own quads
+        fp.trace = cd.trace;
+        const int groups = pb.kind == 1 ? 10 : 1;
+        for (int g = 0; g < groups; ++g) {
+            fp.quad_first = cd.cm_first[g];
+            fp.n_quads = cd.cm_first[g + 1] - cd.cm_first[g];
+            if (fp.n_quads <= 0)
+                continue;
+            if (pb.cfg.impl == 17)
+                launch_fill16_ckpt(fp, fp.n_quads, g, ctx->sm_count, ctx->opt_ctas_per_sm, st, false);
+            else if (pb.kind == 1)
+                launch_fill16_free(fp, fp.n_quads, g, ctx->sm_count, ctx->opt_ctas_per_sm, st, false);
+            else
+                launch_fill16<false, -1>(fp, fp.n_quads, ctx->sm_count, ctx->opt_ctas_per_sm, st);
+            ctx->launches++;
+            ctx->last_fill_launches++;
+        }
+    } else if (pb.cfg.impl == 18) { // long pairs: score, checkpoints, recompute and walk in one persistent launch
         const int rc = launch_long(ctx, pb, fp, cd.slots, cd.counts, 0, nullptr, nullptr, 0, st);
         if (rc != GNX_OK)
             return rc;
@@ -1032,7 +1147,8 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
         tp.pass = 0;
         tp.pair_class = pb.profile ? nullptr : cd.cls;
         if (pb.cfg.impl == 17) {
-            launch_ckpt_trace(ctx, pb, fp, cd.trace, cd.best, cd.slots, cd.counts, 0, nullptr, nullptr, 0, cd.work, cd.work_count, st);
+            launch_ckpt_trace(ctx, pb, fp, cd.trace, cd.best, cd.slots, cd.counts, 0, nullptr, nullptr, 0, cd.work, cd.work_count, st,
+                              pb.cfg.rag ? cd.pair_slot : nullptr, pb.cfg.rag ? cd.quad_ck_off : nullptr);
             cudaEventRecord(fe.b, st);
             ctx->last_fill_launches++;
         } else if (pb.ext)
@@ -1137,7 +1253,8 @@ int enqueue_chunk_expand(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, in
                 return rc;
             ctx->launches--; // counted below
         } else
-            launch_ckpt_trace(ctx, pb, fp, cd.trace, cd.best, cd.slots, cd.counts, 1, cig_off, cigars, cap, cd.work, cd.work_count, st);
+            launch_ckpt_trace(ctx, pb, fp, cd.trace, cd.best, cd.slots, cd.counts, 1, cig_off, cigars, cap, cd.work, cd.work_count, st,
+                              pb.cfg.rag ? cd.pair_slot : nullptr, pb.cfg.rag ? cd.quad_ck_off : nullptr);
     } else if (pb.ext)
         launch_traceback_ext(pb, cd, tp, np, st);
     else if (tp.kind == 2 && tp.layout == 3)
@@ -1228,7 +1345,8 @@ int make_plan(gnx_ctx *ctx, Problem &pb, const int64_t *aoff, const int64_t *bof
         pb.cfg.m_uniform = plan.max_m;
     }
     // 2-bit inputs on the packed 16-bit kernels: the quad's words are staged by TMA (targets expanded in 4 x 512 B)
-    pb.cfg.tb = pb.twobit && ctx->opt_tb_tma && (pb.cfg.impl == 16 || pb.cfg.impl == 17) && plan.max_n <= kTbMaxN;
+    pb.cfg.rag = (pb.cfg.impl == 16 || pb.cfg.impl == 17) && (plan.min_n != plan.max_n || plan.min_m != plan.max_m);
+    pb.cfg.tb = pb.twobit && ctx->opt_tb_tma && (pb.cfg.impl == 16 || pb.cfg.impl == 17) && plan.max_n <= kTbMaxN && !pb.cfg.rag;
     if (pb.cfg.impl == 16 && pb.cfg.tb)
         pb.cfg.n_uniform = plan.max_n;
     // long pairs with traceback: tile checkpoints + recompute of the route's tiles instead of a trace matrix.  The
@@ -1244,6 +1362,8 @@ int make_plan(gnx_ctx *ctx, Problem &pb, const int64_t *aoff, const int64_t *bof
         pb.cfg.long_pool = ctx->opt_long_pool;
     }
     plan.any_long = pb.cfg.multi && pb.cfg.impl != 18;
+    ctx->last_impl = pb.cfg.impl;
+    ctx->last_flags = (pb.cfg.rag ? 1 : 0) | (pb.cfg.tb ? 2 : 0) | (pb.wide ? 4 : 0) | (pb.cfg.multi ? 8 : 0);
     plan.bounds.push_back(0);
     if (!pb.extra_words && plan.min_n == plan.max_n && plan.min_m == plan.max_m) { // uniform batch: chunk bounds are arithmetic
         const int64_t gsz = 32 / pb.cfg.lpp; // pairs that share trace rows
@@ -1387,6 +1507,7 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
         int64_t begin, end;
         ChunkDev cd;
     };
+    RagTables rag_tab; // ragged batches on the packed 16-bit kernels: rebuilt per chunk
     std::vector<Pending> pending;
 
     auto finish = [&](const Pending &pd) -> int {
@@ -1604,6 +1725,11 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
             cd.alpha_words = d_wa - begin * tb->wn;
             cd.beta_words = d_wb - begin * tb->wm;
         }
+        if (pb.cfg.rag) { // the slot's previous chunk has been retired: its staging is free
+            build_rag_tables(pb, aoff, boff, begin, np, plan.max_n, rag_tab);
+            if ((rc = upload_rag_tables(ctx, s, rag_tab, np, cd, s.stream)) != GNX_OK)
+                return rc;
+        }
         if (pb.ext) {
             CU(s.best.ensure((size_t)np * 8));
             CU(s.endi.ensure((size_t)np * 8));
@@ -1617,7 +1743,7 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
             int64_t *to = s.h_trace_off.as<int64_t>();
             int64_t acc = compute_trace_offsets(pb, aoff, boff, begin, np, to);
             if (pb.cfg.impl == 17) { // checkpoint area: whole quads; r* per pair
-                acc = std::max(acc, ((np + 3) / 4) * ckpt_quad_words(pb.cfg.n_uniform));
+                acc = pb.cfg.rag ? std::max(acc, rag_tab.ck_words) : std::max(acc, ((np + 3) / 4) * ckpt_quad_words(pb.cfg.n_uniform));
                 CU(s.best.ensure((size_t)np * 8));
                 cd.best = s.best.as<int64_t>() - begin;
                 CU(s.work.ensure((size_t)np * 4 + 64));
@@ -2051,11 +2177,11 @@ void gnx_destroy(gnx_ctx *ctx)
         Slot &s = ctx->slot[k];
         DevBuf *d[] = {&s.alpha, &s.beta, &s.aoff, &s.boff, &s.cls, &s.trace, &s.trace_off, &s.slots,
                        &s.counts, &s.score, &s.cig_off, &s.cigars, &s.edge, &s.misc, &s.partials, &s.best, &s.endi, &s.endj, &s.work,
-                       &s.tb_a, &s.tb_b, &s.tb_meta};
+                       &s.tb_a, &s.tb_b, &s.tb_meta, &s.rag};
         for (DevBuf *b : d)
             b->release();
         PinBuf *h[] = {&s.h_stage_a, &s.h_stage_b, &s.h_total, &s.h_trace_off, &s.h_score, &s.h_off, &s.h_cig, &s.h_endi, &s.h_endj,
-                       &s.h_tbmeta};
+                       &s.h_tbmeta, &s.h_rag};
         for (PinBuf *b : h)
             b->release();
         if (s.stream)
@@ -2289,6 +2415,7 @@ static int run_device_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *d_alpha_ca
     CU(cudaMemsetAsync(ctx->dr_misc.p, 0, 16, st)); // running cigar total (two ping-pong words)
     const int64_t n_chunks = (int64_t)plan.bounds.size() - 1;
     CU(s.cls.ensure((size_t)n_pairs));
+    RagTables rag_tab;
     for (int64_t ci = 0; ci < n_chunks; ++ci) {
         const int64_t begin = plan.bounds[ci], end = plan.bounds[ci + 1], np = end - begin;
         ChunkDev cd;
@@ -2329,6 +2456,15 @@ static int run_device_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *d_alpha_ca
                 cd.beta = s.beta.as<uint8_t>() - cd.b_lo;
             }
         }
+        if (pb.cfg.rag) {
+            if (s.ev_rag_set) // the staging of the previous chunk's (or call's) tables may still be in flight
+                CU(cudaEventSynchronize(s.ev_total));
+            build_rag_tables(pb, alpha_off_host, beta_off_host, begin, np, plan.max_n, rag_tab);
+            if ((rc = upload_rag_tables(ctx, s, rag_tab, np, cd, st)) != GNX_OK)
+                return rc;
+            CU(cudaEventRecord(s.ev_total, st));
+            s.ev_rag_set = true;
+        }
         if (pb.want_cigar) {
             // the pinned staging is about to be rewritten by the host: fence on the upload that last read it -- the
             // previous chunk's, or the last chunk's of an earlier call that may still be queued behind other work
@@ -2338,7 +2474,7 @@ static int run_device_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *d_alpha_ca
             int64_t *to = s.h_trace_off.as<int64_t>();
             int64_t acc = compute_trace_offsets(pb, alpha_off_host, beta_off_host, begin, np, to);
             if (pb.cfg.impl == 17) { // checkpoint area: whole quads; r* per pair
-                acc = std::max(acc, ((np + 3) / 4) * ckpt_quad_words(pb.cfg.n_uniform));
+                acc = pb.cfg.rag ? std::max(acc, rag_tab.ck_words) : std::max(acc, ((np + 3) / 4) * ckpt_quad_words(pb.cfg.n_uniform));
                 CU(s.best.ensure((size_t)np * 8));
                 cd.best = s.best.as<int64_t>() - begin;
                 CU(s.work.ensure((size_t)np * 4 + 64));
@@ -2468,6 +2604,17 @@ int gnx_last_fill_stats(gnx_ctx *ctx, double *fill_ms, int64_t *fill_launches, i
     return GNX_OK;
 }
 
+int gnx_last_kernel_path(gnx_ctx *ctx, int *impl, int *flags)
+{
+    if (!ctx)
+        return GNX_EARG;
+    if (impl)
+        *impl = ctx->last_impl;
+    if (flags)
+        *flags = ctx->last_flags;
+    return GNX_OK;
+}
+
 int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
 {
     if (!ctx || !name)
@@ -2503,6 +2650,8 @@ int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
         ctx->opt_ckpt = value ? 1 : 0;
     } else if (k == "wide_cta") {
         ctx->opt_wide_cta = (int)value;
+    } else if (k == "ragged16") {
+        ctx->opt_rag = value ? 1 : 0;
     } else if (k == "tb_tma") {
         ctx->opt_tb_tma = value ? 1 : 0;
     } else if (k == "long_ckpt") {

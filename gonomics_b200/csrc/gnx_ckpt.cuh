@@ -43,6 +43,9 @@ struct CkptParams {
     int *work;                 // pass 0: chunk-local indices of the pairs that need the recompute walk
     int *work_count;           // device counter of `work` (ckpt_classify_kernel / ckpt_overflow_list_kernel)
     int *work_next;            // device cursor: the next entry of `work` to hand to a half-warp
+    // ragged batches: where pass 1 put each pair (quad * 4 + slot) and each quad's checkpoint words
+    const int *pair_slot;      // per pair in chunk, or nullptr (uniform batch: the pair's own index)
+    const int64_t *quad_ck_off;
 };
 
 // Screening pass between the two passes: one thread per pair.  If the pair's score equals the score of the
@@ -129,18 +132,15 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
     const int n_work = *Q.work_count;
     if (n_work == 0)
         return;
-    // uniform batch: lengths and everything derived from them
-    const int n = (int)(P.alpha_off[P.pair_begin + 1] - P.alpha_off[P.pair_begin]);
-    const int m = (int)(P.beta_off[P.pair_begin + 1] - P.beta_off[P.pair_begin]);
-    const int T = n + LPP - 1;
+    // lengths of this half's pair and everything derived from them (set when the pair is taken)
+    int n = 0, m = 0, T = 0;
     const int jbase = lane * C;
     int aM[C], aI[C], aD[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        const bool last = jbase + c + 1 == m;
-        aM[c] = last ? dMl : dMn;
-        aI[c] = last ? dIl : dIn;
-        aD[c] = last ? dDl : dDn;
+        aM[c] = dMn;
+        aI[c] = dIn;
+        aD[c] = dDn;
     }
     const uint8_t *tg = s_tgt + half * kTgtPitch;
     const unsigned code00 = (unsigned)(2 - Q.h00_plane) << 4;
@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
     // ---- this half's pair ----
     bool have = false, exhausted = false, tested = false;
     int64_t idx = 0, pair = P.pair_begin, quad = 0;
+    const uint32_t *ck_base = Q.ckpt; // the pair's quad's checkpoint words
     int src_lane = lane, sel = 0, rs = 0, S_pair = 0;
     // walk state, kept by lane 0 of each half-warp
     int wi = 0, wj = 0, wk = 2, need_k = 1, cur_op = 2, run = 0, cnt = 0, total = 0;
@@ -193,11 +194,23 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
                     // record, 16-bit half idx % 2
                     idx = Q.work[w];
                     pair = P.pair_begin + idx;
-                    quad = idx >> 2;
-                    src_lane = (int)(((idx >> 1) & 1) * LPP) + lane;
-                    sel = (int)(idx & 1);
+                    const int64_t slot_id = Q.pair_slot ? (int64_t)Q.pair_slot[idx] : idx; // where pass 1 held this pair
+                    quad = slot_id >> 2;
+                    src_lane = (int)(((slot_id >> 1) & 1) * LPP) + lane;
+                    sel = (int)(slot_id & 1);
+                    ck_base = Q.ckpt + (Q.quad_ck_off ? (size_t)Q.quad_ck_off[quad] : (size_t)quad * Q.quad_words);
                     const uint8_t *__restrict__ alpha = P.alpha + P.alpha_off[pair];
                     const uint8_t *__restrict__ beta = P.beta + P.beta_off[pair];
+                    n = (int)(P.alpha_off[pair + 1] - P.alpha_off[pair]);
+                    m = (int)(P.beta_off[pair + 1] - P.beta_off[pair]);
+                    T = n + LPP - 1;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const bool last = jbase + c + 1 == m;
+                        aM[c] = last ? dMl : dMn;
+                        aI[c] = last ? dIl : dIn;
+                        aD[c] = last ? dDl : dDn;
+                    }
                     // per-lane score tables and the staged target: exactly affine_fill3_kernel's set-up
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
@@ -332,8 +345,7 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
                             const int l2 = X / 11, c2 = X - 11 * l2;
                             const int col = l2 * C + c2 + 1, d = tj - col;
                             if (c2 < C && l2 < LPP && col <= m && d >= 1 && d <= L - 1) { // the cell itself is interior (row, col >= 1)
-                                const uint32_t x = __ldg(Q.ckpt + (size_t)quad * Q.quad_words + (size_t)(k - 1) * (kCkRegs * 32) + c2 * 32 +
-                                                         (src_lane - lane + l2));
+                                const uint32_t x = __ldg(ck_base + (size_t)(k - 1) * (kCkRegs * 32) + c2 * 32 + (src_lane - lane + l2));
                                 const int hck = (int)((x >> (16 * sel)) & 0xffffu) - 32768;
                                 if (V - pre[d] == hck)
                                     dhit = d;
@@ -401,7 +413,7 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
                 int Hc[C], Dt[C];
                 int hpL, edgeI = 0, edgeH = 0;
                 if (blk > 0 && recompute) {
-                    const uint32_t *src = Q.ckpt + (size_t)quad * Q.quad_words + (size_t)(blk - 1) * (kCkRegs * 32) + src_lane;
+                    const uint32_t *src = ck_base + (size_t)(blk - 1) * (kCkRegs * 32) + src_lane;
                     auto val = [&](uint32_t x) { return ((int)((x >> (16 * sel)) & 0xffffu) - 32768) * SC; };
 #pragma unroll
                     for (int c = 0; c < C; ++c) {

@@ -89,7 +89,12 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
     const int O = P.gap_open, E = P.gap_extend;
     const int oe_i = (O + E) * 65537;          // integer addend: +O+E in both halves
     const unsigned e_w = wrap16x2(E);          // per-half wrapping addend for VIADDMNMX.U16x2
-    const int64_t n_quads = (P.pair_end - P.pair_begin + 3) / 4;
+    // Quads: four consecutive pairs of a uniform batch, or -- RAGGED batches -- the rows quad_first .. quad_first +
+    // n_quads - 1 of P.quad_pairs: four chunk-local pair indices (-1 = empty slot) that the host binned so that the
+    // quad's pairs share the target length n and, with free end gaps, the in-lane index CM of the last query column;
+    // query lengths may differ inside a quad (columns past a pair's m are padding that scores 0).
+    const bool binned = !TB && P.quad_pairs != nullptr;
+    const int64_t n_quads = binned ? P.n_quads : (P.pair_end - P.pair_begin + 3) / 4;
     // TB: one quad's packed words = 32 * wn bytes of targets + 32 * wm bytes of queries (always multiples of 16, and
     // 16-byte aligned because chunks start at a quad boundary of a 256-byte aligned buffer)
     const unsigned tb_bytes_t = TB ? 32u * (unsigned)P.wn : 0u, tb_bytes_q = TB ? 32u * (unsigned)P.wm : 0u;
@@ -111,14 +116,26 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
     }
 
     for (int64_t quad = blockIdx.x; quad < n_quads; quad += gridDim.x) {
-        const int64_t pA0 = P.pair_begin + quad * 4 + half * 2, pB0 = pA0 + 1;
-        const int64_t pA = min(pA0, P.pair_end - 1), pB = min(pB0, P.pair_end - 1); // tail: recompute a valid pair
-        int n, m;
+        int64_t pA0, pB0, pA, pB; // the half-warp's two pairs (global indices); pX0 < 0 / >= pair_end: empty slot
+        if (binned) {
+            const int *qp = P.quad_pairs + (P.quad_first + quad) * 4;
+            const int iA = qp[half * 2], iB = qp[half * 2 + 1], i0 = qp[0]; // slot 0 always holds a pair
+            pA0 = iA >= 0 ? P.pair_begin + iA : P.pair_end;
+            pB0 = iB >= 0 ? P.pair_begin + iB : P.pair_end;
+            pA = P.pair_begin + (iA >= 0 ? iA : i0);
+            pB = P.pair_begin + (iB >= 0 ? iB : i0);
+        } else {
+            pA0 = P.pair_begin + quad * 4 + half * 2;
+            pB0 = pA0 + 1;
+            pA = min(pA0, P.pair_end - 1); // tail: recompute a valid pair
+            pB = min(pB0, P.pair_end - 1);
+        }
+        int n, m, mB;
         const uint8_t *__restrict__ alA, *__restrict__ alB, *__restrict__ beA = nullptr, *__restrict__ beB = nullptr;
         const uint32_t *qwA = nullptr, *qwB = nullptr; // TB: 32-bit views of the two queries' packed words
         if (TB) {
             n = P.n_uni;
-            m = P.m_uni;
+            m = mB = P.m_uni;
             mbar_wait(&s_bar, tb_phase); // the quad's words have landed
             tb_phase ^= 1;
             const int kA = (int)(pA - (P.pair_begin + quad * 4)), kB = (int)(pB - (P.pair_begin + quad * 4));
@@ -144,7 +161,8 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
         } else {
             const int64_t a0A = P.alpha_off[pA], b0A = P.beta_off[pA];
             n = (int)(P.alpha_off[pA + 1] - a0A);
-            m = (int)(P.beta_off[pA + 1] - b0A); // uniform batch: same n, m for every pair
+            m = (int)(P.beta_off[pA + 1] - b0A); // pair A's query length; pair B's may differ in a binned quad
+            mB = (int)(P.beta_off[pB + 1] - P.beta_off[pB]);
             alA = P.alpha + a0A;
             alB = P.alpha + P.alpha_off[pB];
             beA = P.beta + b0A;
@@ -157,25 +175,27 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int j = jbase + c + 1;
-            const bool real = j <= m;
+            const bool realA = j <= m, realB = j <= mB;
             int qA = 0, qB = 0;
-            if (real) {
+            if (realA)
                 qA = TB ? tb_base(qwA, j - 1) : (int)beA[j - 1];
+            if (realB)
                 qB = TB ? tb_base(qwB, j - 1) : (int)beB[j - 1];
-            }
 #pragma unroll
             for (int a = 0; a < ROWS; ++a) {
                 int vA = 0, vB = 0;
-                if (real && a < P.dim) { // padding columns score 0 against everything
-                    vA = P.scores[a * P.dim + qA];
-                    vB = P.scores[a * P.dim + qB];
+                if (a < P.dim) { // padding columns score 0 against everything
+                    if (realA)
+                        vA = P.scores[a * P.dim + qA];
+                    if (realB)
+                        vB = P.scores[a * P.dim + qB];
                 }
                 s_tabA[(c * ROWS + a) * 32 + tid] = vA;
                 s_tabB[(c * ROWS + a) * 32 + tid] = vB * 65536;
             }
-            const bool last = FREE && (j == m);
-            aD[c] = last ? 0u : e_w;
-            aH[c] = last ? 0 : oe_i;
+            const bool lastA = FREE && (j == m), lastB = FREE && (j == mB); // per pair: halves of the packed addends
+            aD[c] = (lastA ? 0u : (e_w & 0xffffu)) | (lastB ? 0u : (e_w & 0xffff0000u));
+            aH[c] = (lastA ? 0 : (O + E)) + (lastB ? 0 : (O + E) * 65536);
         }
         unsigned Dt[C], Hc[C];
 #pragma unroll
@@ -185,16 +205,19 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
             Hc[c] = h0;
             Dt[c] = h0 + (unsigned)aH[c];          // D(1,j) = I(0,j) + O + E   (or I(0,m) in the free last column)
         }
-        const bool lastlane = FREE && lane == (m - 1) / C;
-        const unsigned aDl = lastlane ? 0u : e_w; // addends of column CM in this lane (zero in the free-end column)
-        const int aHl = lastlane ? 0 : oe_i;
+        const bool lastlaneA = FREE && lane == (m - 1) / C, lastlaneB = FREE && lane == (mB - 1) / C;
+        // addends of column CM in this lane (zero in a pair's free-end column), per 16-bit half
+        const unsigned aDl = (lastlaneA ? 0u : (e_w & 0xffffu)) | (lastlaneB ? 0u : (e_w & 0xffff0000u));
+        const int aHl = (lastlaneA ? 0 : (O + E)) + (lastlaneB ? 0 : (O + E) * 65536);
         unsigned hpL = (jbase == 0) ? pack16(P.h00) : pack16(O + jbase * E);
         unsigned edgeI = 0, edgeH = 0;
         unsigned bI = 0, bH = 0;
         // CKPT: (value << 16 | row) of the last row that reached the free-end column's running maximum, per pair;
         // row 0 stands for the boundary D(1,m) = I(0,m)
-        unsigned bestA = (unsigned)(O + m * E + 32768) << 16, bestB = bestA;
-        uint32_t *ck = CKPT ? P.trace + (size_t)quad * P.edge_stride : nullptr; // edge_stride: words per quad
+        unsigned bestA = (unsigned)(O + m * E + 32768) << 16, bestB = (unsigned)(O + mB * E + 32768) << 16;
+        uint32_t *ck = nullptr; // checkpoint words of this quad (edge_stride: words per quad of a uniform batch)
+        if (CKPT)
+            ck = P.trace + (binned ? (size_t)P.quad_ck_off[P.quad_first + quad] : (size_t)quad * P.edge_stride);
         auto boundary = [&](int r) {
             const int d0 = FREE ? 0 : (O + r * E);
             bI = pack16(d0 + O + E);
@@ -311,21 +334,24 @@ __global__ void __launch_bounds__(32, 16) affine_fill16_kernel(const FillParams 
                 step(t, std::true_type{});
         }
 
-        const int lm = (m - 1) / C, cm = (m - 1) % C;
-        if (lane == lm) {
-            unsigned h = Hc[0];
+        { // H(n, m) of each pair sits in the lane and column that own its last query column
+            const int lmA = (m - 1) / C, cmA = (m - 1) % C, lmB = (mB - 1) / C, cmB = (mB - 1) % C;
+            unsigned hA = Hc[0], hB = Hc[0];
 #pragma unroll
-            for (int c = 1; c < C; ++c)
-                if (c == cm)
-                    h = Hc[c];
-            if (pA0 < P.pair_end)
-                P.out_score[pA0] = (int64_t)(int)(h & 0xffffu) - 32768;
-            if (pB0 < P.pair_end)
-                P.out_score[pB0] = (int64_t)(int)(h >> 16) - 32768;
-            if (CKPT) {
-                if (pA0 < P.pair_end)
+            for (int c = 1; c < C; ++c) {
+                if (c == cmA)
+                    hA = Hc[c];
+                if (c == cmB)
+                    hB = Hc[c];
+            }
+            if (lane == lmA && pA0 < P.pair_end) {
+                P.out_score[pA0] = (int64_t)(int)(hA & 0xffffu) - 32768;
+                if (CKPT)
                     P.out_best[pA0] = (int64_t)(bestA & 0xffffu);
-                if (pB0 < P.pair_end)
+            }
+            if (lane == lmB && pB0 < P.pair_end) {
+                P.out_score[pB0] = (int64_t)(int)(hB >> 16) - 32768;
+                if (CKPT)
                     P.out_best[pB0] = (int64_t)(bestB & 0xffffu);
             }
         }

@@ -53,6 +53,10 @@ struct FillParams {
     // (indexed by global pair id: the pointers are biased by the chunk's first pair), lengths n_uni x m_uni
     const uint64_t *alpha_words, *beta_words;
     int wn, wm, n_uni, m_uni;
+    // ragged batches on the packed 16-bit kernels: quads binned by (last-column index, target length) on the host
+    const int *quad_pairs;        // 4 chunk-local pair indices per quad (-1 = empty slot; slot 0 always filled)
+    const int64_t *quad_ck_off;   // CKPT: first checkpoint word of every quad
+    int64_t quad_first, n_quads;  // this launch covers quads quad_first .. quad_first + n_quads - 1
 };
 
 __device__ __forceinline__ int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); } // max(a+b, c)

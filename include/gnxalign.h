@@ -336,6 +336,11 @@ int64_t gnx_launch_count(gnx_ctx *ctx);
 /* Device time (ms, CUDA events on the launching stream) and launches of the DP fill kernels of
  * the last batch call; used for the roofline line of bench.py. */
 int gnx_last_fill_stats(gnx_ctx *ctx, double *fill_ms, int64_t *fill_launches, int64_t *cells);
+/* Kernel family the last batch call on this context planned: impl 1 first-generation kernels, 3 affine_fill3 /
+ * const_fill3 (int32), 16 affine_fill16 (packed 16-bit, score only), 17 affine_fill16 with checkpoints +
+ * affine_ckpt_trace (read-sized traceback), 18 affine_long (tile checkpoints, long pairs); flags: 1 ragged batch on
+ * host-binned quads, 2 dnaTwoBit words staged by TMA, 4 int64 fallback, 8 multi-strip pairs. */
+int gnx_last_kernel_path(gnx_ctx *ctx, int *impl, int *flags);
 /* Tuning knobs (name/value), e.g. "cols_per_lane", "block_threads", "chunk_pairs". Returns GNX_EARG
  * for an unknown name. */
 int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value);

@@ -920,3 +920,52 @@ def test_left_right_local_older_forms(ctx):
     a, b = al[3], be[3]
     assert genomegraph.LeftLocal(a, b, S, -600, ctx=ctx)[0] == oloc.left_local(a, b, S, -600)[0]
     assert genomegraph.RightLocal(a, b, S, -600, ctx=ctx)[3] == oloc.right_local(a, b, S, -600)[3]
+
+
+def _ragged_reads(rng, P, nlo, nhi, mlo, mhi):
+    al, be = [], []
+    for _ in range(P):
+        n, m = int(rng.integers(nlo, nhi + 1)), int(rng.integers(mlo, mhi + 1))
+        a, b = random_pair(rng, n, m, identity=float(rng.choice([0.75, 0.95, 1.0])))
+        al.append(a)
+        be.append(b)
+    return al, be
+
+
+def test_ragged_batches_on_the_packed_16bit_kernels():
+    """Ragged read batches (per-pair n and m) run on affine_fill16 (score only) and on the checkpoint-and-recompute
+    path (traceback): quads binned on the host by (last-column index, target length).  Checked against the oracle and
+    by the kernel path the library reports; several chunks; 2-bit ragged input; the int32 kernels as the other side."""
+    rng = np.random.default_rng(1717)
+    al, be = _ragged_reads(rng, 3001, 300, 500, 100, 150)
+    al += [al[0][:301].copy(), al[1][:300].copy()]   # bins with a single pair
+    be += [be[0][:150].copy(), be[1][:101].copy()]
+    S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX
+    c = align.Context(0)
+    try:
+        c.set_option("chunk_pairs", 1100)
+        check_batch(c, al, be, S, -600, -150, 1, want_cigar=True)
+        assert c.last_kernel_path() == (17, 1)
+        check_batch(c, al, be, S, -600, -150, 1, want_cigar=False)
+        assert c.last_kernel_path() == (16, 1)
+        # global mode, score only (the 16-bit range proof holds for short targets and cheap extensions)
+        gl, gb = _ragged_reads(rng, 800, 20, 200, 5, 160)
+        check_batch(c, gl, gb, orc.DEFAULT_SCORE_MATRIX, -400, -30, 0, want_cigar=False)
+        assert c.last_kernel_path() == (16, 1)
+        # the same batch with the ragged path switched off: the int32 kernels
+        c.set_option("ragged16", 0)
+        check_batch(c, al[:500], be[:500], S, -600, -150, 1, want_cigar=True)
+        assert c.last_kernel_path()[0] == 3
+        c.set_option("ragged16", 1)
+        # ragged 2-bit input: device expansion, then the same binned quads
+        wa, la = _pack_ragged(al)
+        wb, lb = _pack_ragged(be)
+        ac, ao = concat(al)
+        bc, bo = concat(be)
+        osc, ooff, ocig = orc.batch(ac, ao, bc, bo, S, -600, -150, 1, True, 8)
+        sc, off, cig = c.affine_gap_batch_twobit(wa, la, wb, lb, S, -600, -150, True, True)
+        assert c.last_kernel_path() == (17, 1)
+        assert np.array_equal(sc, osc) and np.array_equal(off, ooff)
+        assert np.array_equal(cig["run_length"], ocig["run_length"]) and np.array_equal(cig["op"], ocig["op"])
+    finally:
+        c.close()
