@@ -683,6 +683,58 @@ def main():
             assert int(d_status.item()) == 0
             return world * pairs * n_len * m_len * steps / (ms_ * 1e-3) / 1e9, ms_ / steps, f_ms, (a, sao, b, sbo, sc, off, cg)
 
+        # ragged read batches (target 300-500 x query 100-150, trimmed copies of the C3 pairs): the packed 16-bit kernels
+        # on host-binned quads -- what a batch of adapter-trimmed reads against variable windows looks like
+        def run_ragged(pairs, steps=3):
+            a, sao, b, sbo = synth_pairs(SEED + 9, pairs, N_LEN, M_LEN, first_pair=rank * pairs)
+            rr = np.random.default_rng(SEED + 9 + rank)
+            nl, ml = rr.integers(300, N_LEN + 1, size=pairs), rr.integers(100, M_LEN + 1, size=pairs)
+            rao, rbo = np.zeros(pairs + 1, np.int64), np.zeros(pairs + 1, np.int64)
+            np.cumsum(nl, out=rao[1:])
+            np.cumsum(ml, out=rbo[1:])
+            # keep the first nl bases of each target and the first ml of each query (vectorised gather)
+            ia = np.repeat(sao[:-1] - rao[:-1], nl) + np.arange(rao[-1])
+            ib = np.repeat(sbo[:-1] - rbo[:-1], ml) + np.arange(rbo[-1])
+            ra, rb = a[ia], b[ib]
+            ta, tb = torch.from_numpy(ra).to(dev), torch.from_numpy(rb).to(dev)
+            tao, tbo = torch.from_numpy(rao).to(dev), torch.from_numpy(rbo).to(dev)
+            sc = torch.zeros(pairs, dtype=torch.int64, device=dev)
+            off = torch.zeros(pairs + 1, dtype=torch.int64, device=dev)
+            cg = torch.zeros(pairs * 12 * 16, dtype=torch.uint8, device=dev)
+            rcells = int((nl * ml).sum())
+            res = {}
+            for want in (True, False):
+                def one():
+                    ctx.batch_device(1, ta.data_ptr(), tao.data_ptr(), tb.data_ptr(), tbo.data_ptr(), rao, rbo, pairs, S, GAP_OPEN,
+                                     GAP_EXTEND, want, sc.data_ptr(), cg.data_ptr(), off.data_ptr(), pairs * 12, d_status.data_ptr(), stream)
+                one()
+                one()
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    one()
+                e1.record()
+                barrier()
+                ms_ = e0.elapsed_time(e1) / steps
+                if world > 1:
+                    t = torch.tensor([ms_], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms_ = float(t.item())
+                assert int(d_status.item()) == 0
+                res["traceback" if want else "score_only"] = {"value": world * rcells / (ms_ * 1e-3) / 1e9, "unit": "GCUPS",
+                                                               "ms_per_step": ms_, "kernel_path": list(ctx.last_kernel_path())}
+            if rank == 0 and not args.no_cpu:
+                import oracle as orc
+                k = min(pairs, 4000)
+                osc, ooff, ocig = orc.batch(ra[:rao[k]], rao[:k + 1], rb[:rbo[k]], rbo[:k + 1], orc.HUMAN_CHIMP_TWO_SCORE_MATRIX,
+                                            GAP_OPEN, GAP_EXTEND, 1, False, os.cpu_count() or 1)
+                res["parity_spot_check"] = bool(np.array_equal(osc, sc[:k].cpu().numpy()))
+            res["pairs_per_gpu"] = pairs
+            res["note"] = ("AffineGapLocal on RAGGED pairs, target 300-500 x query 100-150 (uniformly drawn), device-resident: "
+                           "kernel_path (17, 1) / (16, 1) = the packed 16-bit kernels on host-binned quads")
+            return res
+        ragged = run_ragged(2_000_000)
         g1, ms1, _, _ = run_shape(0, 1000, 150, 100_000, True, 16)
         gc, msc, _, _ = run_shape(2, N_LEN, M_LEN, 1_000_000, True, 400)
         # C4 (configs[3]): 100k pairs of 10 kb x 10 kb over 8 GPUs = 12,500 per GPU, global affine + CIGAR
@@ -733,6 +785,7 @@ def main():
         del a4, b4, sc4, off4, cg4, keep, hsc, hoff, hcig
         torch.cuda.empty_cache()
         line["other_workloads"] = {
+            "c3_ragged_300-500x100-150": ragged,
             "c1_global_1000x150_traceback": {"value": g1, "unit": "GCUPS", "pairs_per_gpu": 100_000, "ms_per_step": ms1,
                                              "note": "AffineGap (global) + CIGAR, configs[0] shape x100"},
             "c4_global_10kx10k_traceback": c4,

@@ -132,14 +132,26 @@ inline std::pair<int64_t, std::vector<Cigar>> AffineGapLocal(const std::vector<d
 {
     return detail::one(1, target, query, scores, gapOpen, gapExtend);
 }
-// align/affineGap.go:73 (the checkerboard only bounds the reference's memory; sizes are accepted and unused)
-inline std::pair<int64_t, std::vector<Cigar>> AffineGap_customizeCheckersize(const std::vector<dna::Base> &alpha,
-                                                                             const std::vector<dna::Base> &beta,
-                                                                             const Matrix &scores, int64_t gapOpen,
-                                                                             int64_t gapExtend, int, int)
+namespace detail {
+// One checkerboard: the low-memory drivers equal the high-memory result.  Past one board the reference's stitching
+// has defects that the GPU path does not reproduce: fail instead of returning a different cigar.
+inline void require_one_board(const std::vector<dna::Base> &alpha, const std::vector<dna::Base> &beta, int ci, int cj,
+                              const char *what)
 {
     if (alpha.empty() || beta.empty())
         throw std::out_of_range("runtime error: index out of range (empty sequence)");
+    if ((int64_t)alpha.size() > ci || (int64_t)beta.size() > cj)
+        throw std::invalid_argument(std::string(what) + ": input spans more than one checkerboard; the reference's "
+                                    "multi-board stitching is not reproduced -- call the _highMem function");
+}
+} // namespace detail
+// align/affineGap.go:73
+inline std::pair<int64_t, std::vector<Cigar>> AffineGap_customizeCheckersize(const std::vector<dna::Base> &alpha,
+                                                                             const std::vector<dna::Base> &beta,
+                                                                             const Matrix &scores, int64_t gapOpen,
+                                                                             int64_t gapExtend, int checkersize_i, int checkersize_j)
+{
+    detail::require_one_board(alpha, beta, checkersize_i, checkersize_j, "AffineGap_customizeCheckersize");
     return detail::one(0, alpha, beta, scores, gapOpen, gapExtend);
 }
 // align/affineGap.go:59
@@ -158,10 +170,10 @@ inline std::pair<int64_t, std::vector<Cigar>> ConstGap_highMem(const std::vector
 // align/constGap.go:73
 inline std::pair<int64_t, std::vector<Cigar>> ConstGap_customizeCheckersize(const std::vector<dna::Base> &alpha,
                                                                             const std::vector<dna::Base> &beta,
-                                                                            const Matrix &scores, int64_t gapPen, int, int)
+                                                                            const Matrix &scores, int64_t gapPen, int checkersize_i,
+                                                                            int checkersize_j)
 {
-    if (alpha.empty() || beta.empty())
-        throw std::out_of_range("runtime error: index out of range (empty sequence)");
+    detail::require_one_board(alpha, beta, checkersize_i, checkersize_j, "ConstGap_customizeCheckersize");
     return detail::one(2, alpha, beta, scores, gapPen, 0);
 }
 // align/constGap.go:13
@@ -265,6 +277,8 @@ inline std::unique_ptr<AffineGapLocalEngine> GoAffineGapLocalEngine(const Matrix
         const std::vector<int64_t> flat = detail::flatten(scores);
         std::vector<TargetQueryPair> batch;
         TargetQueryPair p;
+        try { // an exception escaping a std::thread is std::terminate: a failing batch (e.g. a base >= dim, the reference
+              // goroutine's panic) ends the stream instead -- outputs is closed, consumers never block forever
         while (in->recv(p)) {
             batch.clear();
             batch.push_back(std::move(p));
@@ -296,7 +310,9 @@ inline std::unique_ptr<AffineGapLocalEngine> GoAffineGapLocalEngine(const Matrix
                 out->send(std::move(batch[(size_t)k]));
             }
         }
-        out->close(); // close(outputs) when inputs closes (:178)
+        } catch (const std::exception &) {
+        }
+        out->close(); // close(outputs) when inputs closes (:178) -- and when a batch fails
     });
     return e;
 }

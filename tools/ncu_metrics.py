@@ -6,7 +6,8 @@ import sys
 
 rep = sys.argv[1]
 which = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+out = open(rep).read() if rep.endswith(".csv") else \
+    subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2 + which]
 KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread",

@@ -30,7 +30,10 @@ for spec in sys.argv[2:]:
     rep = parts[0]
     units = int(parts[1]) if len(parts) > 1 and parts[1] else 262144
     pats = [re.compile(p) for p in parts[2].split(",")] if len(parts) > 2 and parts[2] else None
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):  # `ncu -i x.ncu-rep --page raw --csv` exported on the GPU box (reports are too big to bring back)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, un = rows[0], rows[1]
     ik = hdr.index("Kernel Name")
