@@ -104,8 +104,9 @@ struct Slot {
     DevBuf best, endi, endj; // gsw extend step: first-maximum cell (right) and the traceback's end coordinates
     DevBuf work;             // checkpoint path: work list of the pairs that need the recompute walk (+ its counter)
     DevBuf rag;                 // ragged batches: quad_pairs | quad_ck_off | pair_slot (RagTables)
-    PinBuf h_rag;
-    bool ev_rag_set = false;    // device-resident path: ev_total marks the last upload out of h_rag
+    PinBuf h_rag, h_rag2;       // page-locked staging of the tables (the device-resident path alternates between the two)
+    cudaEvent_t ev_rag[2] = {nullptr, nullptr};
+    bool ev_rag_set[2] = {false, false};
     DevBuf tb_a, tb_b, tb_meta; // 2-bit inputs: the chunk's packed words (+ word offsets / lengths of ragged chunks)
     PinBuf h_stage_a, h_stage_b, h_total, h_trace_off, h_score, h_off, h_cig, h_endi, h_endj, h_tbmeta;
     // chunk in flight
@@ -858,7 +859,7 @@ struct ChunkDev {
 // (a template parameter of the kernels); query lengths are otherwise free.  The host bins a chunk's pairs by
 // (that index, n) with a counting sort and cuts every bin into quads; the last quad of a bin may have empty slots.
 struct RagTables {
-    std::vector<int> quad_pairs, pair_slot, count;
+    std::vector<int> quad_pairs, pair_slot, count, keys, first_slot;
     std::vector<int64_t> quad_ck_off;
     int64_t cm_first[12];
     int64_t n_quads = 0, ck_words = 0;
@@ -868,57 +869,79 @@ void build_rag_tables(const Problem &pb, const int64_t *aoff, const int64_t *bof
                       RagTables &R)
 {
     const bool free_end = pb.kind == 1;
-    const int64_t stride = max_n + 1, groups = free_end ? 10 : 1;
-    R.count.assign((size_t)(groups * stride + 1), 0);
-    auto key_of = [&](int64_t k) {
+    const int64_t stride = max_n + 1, groups = free_end ? 10 : 1, nkeys = groups * stride;
+    // inside a group the quads run from the LONGEST targets to the shortest: the persistent grid takes quads
+    // round-robin, so the launch ends on short quads instead of waiting for a straggler (key = ... + max_n - n)
+    R.keys.resize((size_t)np);
+    R.count.assign((size_t)nkeys + 1, 0);
+    for (int64_t k = 0; k < np; ++k) {
         const int64_t n = aoff[begin + k + 1] - aoff[begin + k], m = boff[begin + k + 1] - boff[begin + k];
-        return (free_end ? (m - 1) % 10 : 0) * stride + n;
-    };
-    for (int64_t k = 0; k < np; ++k)
-        R.count[(size_t)key_of(k) + 1]++;
-    // quads per key, first quad of every key
-    std::vector<int64_t> first_quad((size_t)(groups * stride + 1), 0);
-    int64_t nq = 0;
-    for (int64_t key = 0; key < groups * stride; ++key) {
+        const int key = (int)((free_end ? (m - 1) % 10 : 0) * stride + (max_n - n));
+        R.keys[(size_t)k] = key;
+        R.count[(size_t)key + 1]++;
+    }
+    // first slot (= 4 x first quad) and checkpoint words of every key
+    R.first_slot.resize((size_t)nkeys);
+    R.quad_ck_off.clear();
+    int64_t nq = 0, words = 0;
+    for (int64_t key = 0; key < nkeys; ++key) {
         if (key % stride == 0)
             R.cm_first[key / stride] = nq;
-        first_quad[(size_t)key] = nq;
-        nq += (R.count[(size_t)key + 1] + 3) / 4;
+        R.first_slot[(size_t)key] = (int)(nq * 4);
+        const int64_t q = (R.count[(size_t)key + 1] + 3) / 4;
+        if (q > 0) {
+            const int64_t n = max_n - key % stride;
+            const int64_t w = pb.cfg.impl == 17 ? ((n + 16 - 2) / kCkK) * kCkRegs * 32 : 0;
+            for (int64_t i = 0; i < q; ++i) {
+                R.quad_ck_off.push_back(words);
+                words += w;
+            }
+            nq += q;
+        }
     }
     for (int64_t g = groups; g < 12; ++g)
         R.cm_first[g] = nq;
+    R.quad_ck_off.push_back(words);
     R.n_quads = nq;
+    R.ck_words = words;
     R.quad_pairs.assign((size_t)nq * 4, -1);
     R.pair_slot.resize((size_t)np);
-    R.quad_ck_off.resize((size_t)nq + 1);
-    std::vector<int> fill((size_t)(groups * stride), 0); // pairs placed so far per key
     for (int64_t k = 0; k < np; ++k) {
-        const int64_t key = key_of(k);
-        const int64_t slot = first_quad[(size_t)key] * 4 + fill[(size_t)key]++;
+        const int slot = R.first_slot[(size_t)R.keys[(size_t)k]]++;
         R.quad_pairs[(size_t)slot] = (int)k;
-        R.pair_slot[(size_t)k] = (int)slot;
+        R.pair_slot[(size_t)k] = slot;
     }
-    int64_t words = 0;
-    for (int64_t key = 0; key < groups * stride; ++key) {
-        const int64_t n = key % stride, q0 = first_quad[(size_t)key], q1 = q0 + (R.count[(size_t)key + 1] + 3) / 4;
-        const int64_t w = pb.cfg.impl == 17 ? ((n + 16 - 2) / kCkK) * kCkRegs * 32 : 0;
-        for (int64_t q = q0; q < q1; ++q) {
-            R.quad_ck_off[(size_t)q] = words;
-            words += w;
-        }
-    }
-    R.quad_ck_off[(size_t)nq] = words;
-    R.ck_words = words;
+}
+
+// Tables of every chunk of a plan, built up front by a few host threads (a chunk's tables take ~1 ms of scalar work
+// per 100k pairs: built one chunk at a time in front of the launches they would throttle the pipeline).
+void build_all_rag_tables(const Problem &pb, const int64_t *aoff, const int64_t *boff, const std::vector<int64_t> &bounds,
+                          int64_t max_n, std::vector<RagTables> &all)
+{
+    const int64_t nc = (int64_t)bounds.size() - 1;
+    all.resize((size_t)nc);
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)8, (int64_t)std::thread::hardware_concurrency(), nc}));
+    std::atomic<int64_t> next{0};
+    auto work = [&] {
+        for (int64_t c = next++; c < nc; c = next++)
+            build_rag_tables(pb, aoff, boff, bounds[(size_t)c], bounds[(size_t)c + 1] - bounds[(size_t)c], max_n, all[(size_t)c]);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t)
+        th.emplace_back(work);
+    work();
+    for (auto &x : th)
+        x.join();
 }
 
 // Upload a chunk's RagTables into the slot's device buffer and point the chunk at them.
-int upload_rag_tables(gnx_ctx *ctx, Slot &s, const RagTables &R, int64_t np, ChunkDev &cd, cudaStream_t st)
+int upload_rag_tables(gnx_ctx *ctx, Slot &s, PinBuf &stage, const RagTables &R, int64_t np, ChunkDev &cd, cudaStream_t st)
 {
     const size_t b_qp = (size_t)R.n_quads * 4 * sizeof(int), b_off = ((size_t)R.n_quads + 1) * 8, b_ps = (size_t)np * sizeof(int);
     const size_t o_off = (b_qp + 15) & ~(size_t)15, o_ps = (o_off + b_off + 15) & ~(size_t)15, total = o_ps + b_ps;
     CU(s.rag.ensure(total + 16));
-    CU(s.h_rag.ensure(total + 16));
-    uint8_t *h = s.h_rag.as<uint8_t>();
+    CU(stage.ensure(total + 16));
+    uint8_t *h = stage.as<uint8_t>();
     memcpy(h, R.quad_pairs.data(), b_qp);
     memcpy(h + o_off, R.quad_ck_off.data(), b_off);
     memcpy(h + o_ps, R.pair_slot.data(), b_ps);
@@ -1507,7 +1530,9 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
         int64_t begin, end;
         ChunkDev cd;
     };
-    RagTables rag_tab; // ragged batches on the packed 16-bit kernels: rebuilt per chunk
+    std::vector<RagTables> rag_all; // ragged batches on the packed 16-bit kernels: every chunk's quad tables
+    if (pb.cfg.rag)
+        build_all_rag_tables(pb, aoff, boff, plan.bounds, plan.max_n, rag_all);
     std::vector<Pending> pending;
 
     auto finish = [&](const Pending &pd) -> int {
@@ -1726,8 +1751,7 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
             cd.beta_words = d_wb - begin * tb->wm;
         }
         if (pb.cfg.rag) { // the slot's previous chunk has been retired: its staging is free
-            build_rag_tables(pb, aoff, boff, begin, np, plan.max_n, rag_tab);
-            if ((rc = upload_rag_tables(ctx, s, rag_tab, np, cd, s.stream)) != GNX_OK)
+            if ((rc = upload_rag_tables(ctx, s, s.h_rag, rag_all[(size_t)ci], np, cd, s.stream)) != GNX_OK)
                 return rc;
         }
         if (pb.ext) {
@@ -1743,7 +1767,8 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
             int64_t *to = s.h_trace_off.as<int64_t>();
             int64_t acc = compute_trace_offsets(pb, aoff, boff, begin, np, to);
             if (pb.cfg.impl == 17) { // checkpoint area: whole quads; r* per pair
-                acc = pb.cfg.rag ? std::max(acc, rag_tab.ck_words) : std::max(acc, ((np + 3) / 4) * ckpt_quad_words(pb.cfg.n_uniform));
+                acc = pb.cfg.rag ? std::max(acc, rag_all[(size_t)ci].ck_words)
+                                 : std::max(acc, ((np + 3) / 4) * ckpt_quad_words(pb.cfg.n_uniform));
                 CU(s.best.ensure((size_t)np * 8));
                 cd.best = s.best.as<int64_t>() - begin;
                 CU(s.work.ensure((size_t)np * 4 + 64));
@@ -2155,6 +2180,8 @@ gnx_ctx *gnx_create(int device, size_t workspace_bytes)
         cudaStreamCreateWithFlags(&ctx->slot[k].stream, cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&ctx->slot[k].ev_total, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->slot[k].ev_done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->slot[k].ev_rag[0], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->slot[k].ev_rag[1], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&ctx->ev_long, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_dev, cudaEventDisableTiming);
@@ -2181,7 +2208,7 @@ void gnx_destroy(gnx_ctx *ctx)
         for (DevBuf *b : d)
             b->release();
         PinBuf *h[] = {&s.h_stage_a, &s.h_stage_b, &s.h_total, &s.h_trace_off, &s.h_score, &s.h_off, &s.h_cig, &s.h_endi, &s.h_endj,
-                       &s.h_tbmeta, &s.h_rag};
+                       &s.h_tbmeta, &s.h_rag, &s.h_rag2};
         for (PinBuf *b : h)
             b->release();
         if (s.stream)
@@ -2190,6 +2217,9 @@ void gnx_destroy(gnx_ctx *ctx)
             cudaEventDestroy(s.ev_total);
         if (s.ev_done)
             cudaEventDestroy(s.ev_done);
+        for (cudaEvent_t e : s.ev_rag)
+            if (e)
+                cudaEventDestroy(e);
     }
     for (auto &fe : ctx->fill_events) {
         cudaEventDestroy(fe.a);
@@ -2415,7 +2445,9 @@ static int run_device_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *d_alpha_ca
     CU(cudaMemsetAsync(ctx->dr_misc.p, 0, 16, st)); // running cigar total (two ping-pong words)
     const int64_t n_chunks = (int64_t)plan.bounds.size() - 1;
     CU(s.cls.ensure((size_t)n_pairs));
-    RagTables rag_tab;
+    std::vector<RagTables> rag_all;
+    if (pb.cfg.rag)
+        build_all_rag_tables(pb, alpha_off_host, beta_off_host, plan.bounds, plan.max_n, rag_all);
     for (int64_t ci = 0; ci < n_chunks; ++ci) {
         const int64_t begin = plan.bounds[ci], end = plan.bounds[ci + 1], np = end - begin;
         ChunkDev cd;
@@ -2456,14 +2488,14 @@ static int run_device_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *d_alpha_ca
                 cd.beta = s.beta.as<uint8_t>() - cd.b_lo;
             }
         }
-        if (pb.cfg.rag) {
-            if (s.ev_rag_set) // the staging of the previous chunk's (or call's) tables may still be in flight
-                CU(cudaEventSynchronize(s.ev_total));
-            build_rag_tables(pb, alpha_off_host, beta_off_host, begin, np, plan.max_n, rag_tab);
-            if ((rc = upload_rag_tables(ctx, s, rag_tab, np, cd, st)) != GNX_OK)
+        if (pb.cfg.rag) { // two staging buffers: the host stays two chunks ahead of the uploads
+            const int par = (int)(ci & 1);
+            if (s.ev_rag_set[par]) // the upload that last read this staging buffer (two chunks or one call ago)
+                CU(cudaEventSynchronize(s.ev_rag[par]));
+            if ((rc = upload_rag_tables(ctx, s, par ? s.h_rag2 : s.h_rag, rag_all[(size_t)ci], np, cd, st)) != GNX_OK)
                 return rc;
-            CU(cudaEventRecord(s.ev_total, st));
-            s.ev_rag_set = true;
+            CU(cudaEventRecord(s.ev_rag[par], st));
+            s.ev_rag_set[par] = true;
         }
         if (pb.want_cigar) {
             // the pinned staging is about to be rewritten by the host: fence on the upload that last read it -- the
@@ -2474,7 +2506,8 @@ static int run_device_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *d_alpha_ca
             int64_t *to = s.h_trace_off.as<int64_t>();
             int64_t acc = compute_trace_offsets(pb, alpha_off_host, beta_off_host, begin, np, to);
             if (pb.cfg.impl == 17) { // checkpoint area: whole quads; r* per pair
-                acc = pb.cfg.rag ? std::max(acc, rag_tab.ck_words) : std::max(acc, ((np + 3) / 4) * ckpt_quad_words(pb.cfg.n_uniform));
+                acc = pb.cfg.rag ? std::max(acc, rag_all[(size_t)ci].ck_words)
+                                 : std::max(acc, ((np + 3) / 4) * ckpt_quad_words(pb.cfg.n_uniform));
                 CU(s.best.ensure((size_t)np * 8));
                 cd.best = s.best.as<int64_t>() - begin;
                 CU(s.work.ensure((size_t)np * 4 + 64));
