@@ -1452,7 +1452,12 @@ void par_memcpy(void *dst, const void *src, size_t bytes)
 {
     constexpr size_t kMin = (size_t)4 << 20;
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const int nt = (int)std::min<size_t>({(size_t)8, (size_t)hw, bytes / kMin});
+    static const int cap = [] { // GNX_MEMCPY_THREADS overrides the default of 8 staging threads
+        const char *e = getenv("GNX_MEMCPY_THREADS");
+        const int v = e ? atoi(e) : 8;
+        return v < 1 ? 1 : (v > 64 ? 64 : v);
+    }();
+    const int nt = (int)std::min<size_t>({(size_t)cap, (size_t)hw, bytes / kMin});
     if (nt <= 1) {
         memcpy(dst, src, bytes);
         return;
