@@ -103,6 +103,7 @@ struct Slot {
     DevBuf alpha, beta, aoff, boff, cls, trace, trace_off, slots, counts, score, cig_off, cigars, edge, misc, partials;
     DevBuf best, endi, endj; // gsw extend step: first-maximum cell (right) and the traceback's end coordinates
     DevBuf work;             // checkpoint path: work list of the pairs that need the recompute walk (+ its counter)
+    DevBuf qctr;             // packed 16-bit kernels: the quad cursor of their dynamic schedule (self-resetting, zeroed once)
     DevBuf rag;                 // ragged batches: quad_pairs | quad_ck_off | pair_slot (RagTables)
     PinBuf h_rag, h_rag2;       // page-locked staging of the tables (the device-resident path alternates between the two)
     cudaEvent_t ev_rag[2] = {nullptr, nullptr};
@@ -364,7 +365,8 @@ bool fill16_ok(const gnx_ctx *ctx, const Problem &pb, int64_t min_n, int64_t max
     }
     // free end gaps: H(i,j) >= O + jE (enter from D(i,0)=0);  global: H(i,j) >= 2O + (i+j)E
     const int64_t hlow = pb.kind == 1 ? O + 161 * E : 2 * O + (max_n + 161) * E;
-    const int64_t lb = hlow + (O + E) + smin - 64;
+    // two gap opens below the lowest H: the kernel forms I + O + E and D + O + E (GNX_F16_SHORT_CHAIN)
+    const int64_t lb = hlow + 2 * (O + E) + smin - 64;
     const int64_t ub = smax * std::min(max_n, max_m) + smax + 64;
     return lb >= -32768 && ub <= 32767 && -smin <= 32000 && smax <= 32000;
 }
@@ -845,6 +847,7 @@ struct ChunkDev {
     int64_t *best;                    // ext 2: biased by -begin (global pair index)
     int64_t *end_i, *end_j;           // ext: chunk-local
     int *work, *work_count;           // checkpoint path: work list (chunk-local pair indices) and its device counter
+    unsigned *quad_ctr;               // affine_fill16_kernel: quad cursor of this slot (nullptr: static round-robin)
     const uint64_t *alpha_words, *beta_words; // TB kernels: biased so that words + pair * wn / wm is the pair's sequence
     // ragged batches on the packed 16-bit kernels (RagTables): device copies + the quad range of every last-column group
     const int *quad_pairs, *pair_slot;
@@ -853,6 +856,21 @@ struct ChunkDev {
     const int *smat;                  // profile batches: biased so that smat + smat_off[pair] is the pair's matrix
     const int64_t *smat_off;          // indexed by global pair id
 };
+
+// The slot's quad cursor: allocated and zeroed once; every affine_fill16_kernel launch leaves it at zero again.
+cudaError_t slot_quad_ctr(Slot &s, ChunkDev &cd)
+{
+    if (!s.qctr.p) {
+        cudaError_t e = s.qctr.ensure(64);
+        if (e != cudaSuccess)
+            return e;
+        e = cudaMemset(s.qctr.p, 0, 64);
+        if (e != cudaSuccess)
+            return e;
+    }
+    cd.quad_ctr = s.qctr.as<unsigned>();
+    return cudaSuccess;
+}
 
 // Ragged batches on the packed 16-bit kernels.  A quad's four pairs advance in lock step, so they must share the
 // target length n (the step count) and -- with free end gaps -- the in-lane index (m - 1) % 10 of the last query column
@@ -1034,6 +1052,7 @@ int enqueue_chunk_compute(gnx_ctx *ctx, const Problem &pb, const ChunkDev &cd, i
     fp.out_score = cd.score;
     fp.one = 1;
     fp.chunk = (int)pb.chunk;
+    fp.quad_ctr = cd.quad_ctr;
     if (pb.cfg.tb) {
         fp.alpha_words = cd.alpha_words;
         fp.beta_words = cd.beta_words;
@@ -1741,6 +1760,7 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
 
         ChunkDev cd;
         memset(&cd, 0, sizeof cd);
+        CU(slot_quad_ctr(s, cd));
         cd.alpha = s.alpha.as<uint8_t>() - a_lo;
         cd.beta = s.beta.as<uint8_t>() - b_lo;
         cd.aoff = s.aoff.as<int64_t>() - begin;
@@ -2209,7 +2229,7 @@ void gnx_destroy(gnx_ctx *ctx)
         Slot &s = ctx->slot[k];
         DevBuf *d[] = {&s.alpha, &s.beta, &s.aoff, &s.boff, &s.cls, &s.trace, &s.trace_off, &s.slots,
                        &s.counts, &s.score, &s.cig_off, &s.cigars, &s.edge, &s.misc, &s.partials, &s.best, &s.endi, &s.endj, &s.work,
-                       &s.tb_a, &s.tb_b, &s.tb_meta, &s.rag};
+                       &s.tb_a, &s.tb_b, &s.tb_meta, &s.rag, &s.qctr};
         for (DevBuf *b : d)
             b->release();
         PinBuf *h[] = {&s.h_stage_a, &s.h_stage_b, &s.h_total, &s.h_trace_off, &s.h_score, &s.h_off, &s.h_cig, &s.h_endi, &s.h_endj,
@@ -2457,6 +2477,7 @@ static int run_device_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *d_alpha_ca
         const int64_t begin = plan.bounds[ci], end = plan.bounds[ci + 1], np = end - begin;
         ChunkDev cd;
         memset(&cd, 0, sizeof cd);
+        CU(slot_quad_ctr(s, cd));
         cd.alpha = d_alpha_cat;
         cd.beta = d_beta_cat;
         cd.aoff = d_alpha_off;

@@ -57,6 +57,9 @@ struct FillParams {
     const int *quad_pairs;        // 4 chunk-local pair indices per quad (-1 = empty slot; slot 0 always filled)
     const int64_t *quad_ck_off;   // CKPT: first checkpoint word of every quad
     int64_t quad_first, n_quads;  // this launch covers quads quad_first .. quad_first + n_quads - 1
+    // dynamic schedule of the packed 16-bit kernels: a cursor that is zero at launch and zero again when the grid is
+    // done (the fetch that draws n_quads + gridDim.x - 1 is the last one and resets it); nullptr = static round-robin
+    unsigned *quad_ctr;
 };
 
 __device__ __forceinline__ int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); } // max(a+b, c)
