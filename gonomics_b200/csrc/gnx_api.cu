@@ -158,6 +158,8 @@ struct gnx_ctx {
     int opt_wide_cta = -1;     // -1 auto; 0/1 never / always run multi-strip pairs on the 4-warp CTA-per-pair kernel
     int opt_rag = 1;           // ragged batches may use the packed 16-bit kernels (quads binned on the host)
     int opt_tb_tma = 1;        // 2-bit inputs: 1 = fill16 kernels read the packed words (TMA), 0 = always unpack to bytes first
+    int opt_pack_stage = 1;    // pageable byte inputs of large uniform batches are packed to 2 bits per base while staged
+    int pack_backoff = 0;      // calls left that skip the attempt (the last one met a base >= 4)
     int opt_long = -1;         // -1 auto; 0/1 never / always run multi-strip traceback batches on the tile-checkpoint kernel
     int opt_long_form = 0;     // cell formulation of its score-only pass (gnx_long.cuh FORM)
     int64_t opt_long_pool = 0; // its run-pool entries per chunk (0 = auto; tests shrink it to force the re-run pass)
@@ -824,12 +826,18 @@ int launch_long(gnx_ctx *ctx, const Problem &pb, const FillParams &fp, uint32_t 
 
 // 2-bit inputs of a host batch (gnx_affine_batch_twobit): dnaTwoBit words, tightly packed
 struct TbIn {
-    const uint64_t *a_words, *b_words;
-    const int64_t *a_woff, *b_woff; // n_pairs + 1 word offsets (host; computed by the entry point)
-    const int64_t *a_len, *b_len;   // the caller's length arrays
-    bool uniform;                   // every pair n x m
-    int64_t n, m, wn, wm;           // uniform: lengths and words per sequence
+    const uint64_t *a_words = nullptr, *b_words = nullptr;
+    const int64_t *a_woff = nullptr, *b_woff = nullptr; // n_pairs + 1 word offsets (host; computed by the entry point)
+    const int64_t *a_len = nullptr, *b_len = nullptr;   // the caller's length arrays
+    bool uniform = false;           // every pair n x m
+    int64_t n = 0, m = 0, wn = 0, wm = 0; // uniform: lengths and words per sequence
+    // from_bytes: the caller passed one byte per base in PAGEABLE memory (gnx_affine_batch).  Such input has to be
+    // copied through a page-locked stage anyway; that pass packs it to dnaTwoBit words instead (a quarter of the bytes
+    // to write, to DMA and to read on the device) and the chunk then runs exactly like a gnx_affine_batch_twobit chunk.
+    // Uniform batches only (word offsets are p * wn / p * wm, a_woff / b_woff stay NULL).
+    bool from_bytes = false;
 };
+constexpr int GNX_RETRY_BYTES = -1000; // internal: a from_bytes chunk met a base >= 4 -- redo the call on the byte path
 
 // Device buffers of one chunk, all addressed with GLOBAL pair indices (pointers are pre-biased).
 struct ChunkDev {
@@ -1493,6 +1501,91 @@ void par_memcpy(void *dst, const void *src, size_t bytes)
         x.join();
 }
 
+// dnaTwoBit.NewTwoBit of `count` sequences of `len` bases each (one byte per base, back to back) into `wlen` words per
+// sequence: 32 bases per word, the first in bits 63:62, the tail word left-aligned (dna/dnaTwoBit/dnaTwoBit.go:28-42).
+// Four bases at a time: t * 0x40100401 drops the four 2-bit fields of a little-endian 32-bit load into the product's
+// top byte.  Returns false if any base is >= 4 (such input cannot be packed: the caller falls back to bytes, where the
+// kernels report the pair).
+bool pack_range(uint64_t *dst, const uint8_t *src, int64_t count, int64_t len, int64_t wlen)
+{
+    uint64_t bad = 0;
+    const int64_t full = len / 32, tail = len - full * 32;
+    for (int64_t p = 0; p < count; ++p) {
+        const uint8_t *b = src + p * len;
+        uint64_t *w = dst + p * wlen;
+        for (int64_t k = 0; k < full; ++k, b += 32) {
+            uint64_t x[4];
+            memcpy(x, b, 32);
+            bad |= x[0] | x[1] | x[2] | x[3];
+            uint64_t v = 0;
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t lo = (uint32_t)x[q], hi = (uint32_t)(x[q] >> 32);
+                v = (v << 16) | (uint64_t)(((lo * 0x40100401u) >> 24) << 8) | (uint64_t)((hi * 0x40100401u) >> 24);
+            }
+            w[k] = v;
+        }
+        if (tail) {
+            uint64_t v = 0;
+            for (int64_t i = 0; i < tail; ++i) {
+                bad |= b[i];
+                v |= (uint64_t)(b[i] & 3u) << (62 - 2 * i);
+            }
+            w[full] = v;
+        }
+    }
+    return (bad & 0xfcfcfcfcfcfcfcfcull) == 0;
+}
+
+bool pack_stage(uint64_t *dst, const uint8_t *src, int64_t count, int64_t len, int64_t wlen)
+{
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    static const int cap = [] { // GNX_PACK_THREADS overrides the default of 16 packing threads
+        const char *e = getenv("GNX_PACK_THREADS");
+        const int v = e ? atoi(e) : 16;
+        return v < 1 ? 1 : (v > 64 ? 64 : v);
+    }();
+    const int nt = (int)std::min<int64_t>({(int64_t)cap, (int64_t)hw, std::max<int64_t>(1, count * len >> 21)});
+    if (nt <= 1)
+        return pack_range(dst, src, count, len, wlen);
+    std::vector<std::thread> th;
+    std::vector<char> ok((size_t)nt, 1);
+    for (int t = 1; t < nt; ++t) {
+        const int64_t lo = count * t / nt, hi = count * (t + 1) / nt;
+        th.emplace_back([=, &ok] { ok[(size_t)t] = pack_range(dst + lo * wlen, src + lo * len, hi - lo, len, wlen); });
+    }
+    ok[0] = pack_range(dst, src, count / nt, len, wlen);
+    for (auto &x : th)
+        x.join();
+    for (char c : ok)
+        if (!c)
+            return false;
+    return true;
+}
+
+// every offset equals p * len (p = 0 .. n_pairs): the batch is uniform and starts at byte 0
+bool offsets_uniform(const int64_t *off, int64_t n_pairs, int64_t len)
+{
+    const int nt = n_pairs >= (1 << 20) ? (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    std::vector<char> ok((size_t)nt, 1);
+    auto work = [&](int t) {
+        const int64_t lo = (n_pairs + 1) * t / nt, hi = (n_pairs + 1) * (t + 1) / nt;
+        bool good = true;
+        for (int64_t p = lo; p < hi && good; ++p)
+            good = off[p] == p * len;
+        ok[(size_t)t] = good;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t)
+        th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th)
+        x.join();
+    for (char c : ok)
+        if (!c)
+            return false;
+    return true;
+}
+
 bool is_pinned(const void *p)
 {
     cudaPointerAttributes at;
@@ -1536,8 +1629,13 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
     CU(cudaMemsetAsync(ctx->status.p, 0, sizeof(int), ctx->slot[0].stream));
     CU(cudaStreamSynchronize(ctx->slot[0].stream));
 
-    const bool pin_a = is_pinned(tb ? (const void *)tb->a_words : (const void *)alpha_cat);
-    const bool pin_b = is_pinned(tb ? (const void *)tb->b_words : (const void *)beta_cat);
+    if (tb && tb->from_bytes && !pb.cfg.tb) { // the plan did not pick the kernels that read packed words: stay on bytes
+        tb = nullptr;
+        pb.twobit = false;
+    }
+    const bool pack = tb && tb->from_bytes;
+    const bool pin_a = !pack && is_pinned(tb ? (const void *)tb->a_words : (const void *)alpha_cat);
+    const bool pin_b = !pack && is_pinned(tb ? (const void *)tb->b_words : (const void *)beta_cat);
     const bool pin_ao = is_pinned(aoff), pin_bo = is_pinned(boff);
     const bool pin_score = is_pinned(out_score);
     const bool pin_off = out_cigar_off && is_pinned(out_cigar_off);
@@ -1690,14 +1788,24 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
             CU(cudaMemcpyAsync(s.aoff.p, aoff + begin, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
             CU(cudaMemcpyAsync(s.boff.p, boff + begin, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
         } else {
-            const int64_t wa_lo = tb->a_woff[begin], wa_n = tb->a_woff[end] - wa_lo;
-            const int64_t wb_lo = tb->b_woff[begin], wb_n = tb->b_woff[end] - wb_lo;
+            const int64_t wa_lo = pack ? begin * tb->wn : tb->a_woff[begin], wa_n = (pack ? end * tb->wn : tb->a_woff[end]) - wa_lo;
+            const int64_t wb_lo = pack ? begin * tb->wm : tb->b_woff[begin], wb_n = (pack ? end * tb->wm : tb->b_woff[end]) - wb_lo;
             CU(s.tb_a.ensure((size_t)wa_n * 8 + 256)); // slack: the TMA of a tail quad reads a whole quad's words
             CU(s.tb_b.ensure((size_t)wb_n * 8 + 256));
-            if ((rc = h2d(s.tb_a.p, tb->a_words + wa_lo, (size_t)wa_n * 8, pin_a, s.h_stage_a)) != GNX_OK)
-                return rc;
-            if ((rc = h2d(s.tb_b.p, tb->b_words + wb_lo, (size_t)wb_n * 8, pin_b, s.h_stage_b)) != GNX_OK)
-                return rc;
+            if (pack) { // pageable bytes -> packed words in the page-locked stage -> device
+                CU(s.h_stage_a.ensure((size_t)wa_n * 8 + 8));
+                CU(s.h_stage_b.ensure((size_t)wb_n * 8 + 8));
+                if (!pack_stage(s.h_stage_a.as<uint64_t>(), alpha_cat + a_lo, np, tb->n, tb->wn) ||
+                    !pack_stage(s.h_stage_b.as<uint64_t>(), beta_cat + b_lo, np, tb->m, tb->wm))
+                    return GNX_RETRY_BYTES;
+                CU(cudaMemcpyAsync(s.tb_a.p, s.h_stage_a.p, (size_t)wa_n * 8, cudaMemcpyHostToDevice, s.stream));
+                CU(cudaMemcpyAsync(s.tb_b.p, s.h_stage_b.p, (size_t)wb_n * 8, cudaMemcpyHostToDevice, s.stream));
+            } else {
+                if ((rc = h2d(s.tb_a.p, tb->a_words + wa_lo, (size_t)wa_n * 8, pin_a, s.h_stage_a)) != GNX_OK)
+                    return rc;
+                if ((rc = h2d(s.tb_b.p, tb->b_words + wb_lo, (size_t)wb_n * 8, pin_b, s.h_stage_b)) != GNX_OK)
+                    return rc;
+            }
             d_wa = s.tb_a.as<uint64_t>();
             d_wb = s.tb_b.as<uint64_t>();
             const bool need_bytes = !(pb.cfg.tb && !pb.want_cigar); // the packed score-only kernel reads no bytes
@@ -2299,6 +2407,33 @@ int gnx_affine_batch(gnx_ctx *ctx, const uint8_t *alpha_cat, const int64_t *alph
     int rc = fill_problem(ctx, pb, mode == GNX_FREE_END ? 1 : 0, want_cigar, scores, dim, gap_open, gap_extend);
     if (rc != GNX_OK)
         return rc;
+    // Large uniform batches in pageable memory: pack to 2 bits per base while staging (TbIn).  A base >= 4 (N under a
+    // 5 x 5 matrix, or an invalid code) cannot be packed: the call is redone on bytes, and the next calls on this
+    // context skip the attempt for a while.
+    if (ctx->pack_backoff > 0)
+        ctx->pack_backoff--;
+    else if (ctx->opt_pack_stage && ctx->opt_tb_tma && n_pairs >= 4096 && dim >= 4 && alpha_cat && beta_cat) {
+        const int64_t n = alpha_off[1] - alpha_off[0], m = beta_off[1] - beta_off[0];
+        if (n >= 1 && n <= kTbMaxN && m >= 1 && m <= 160 && !is_pinned(alpha_cat) && !is_pinned(beta_cat) &&
+            offsets_uniform(alpha_off, n_pairs, n) && offsets_uniform(beta_off, n_pairs, m)) {
+            Problem pb2 = pb;
+            pb2.twobit = true;
+            TbIn tb;
+            tb.uniform = tb.from_bytes = true;
+            tb.n = n;
+            tb.m = m;
+            tb.wn = (n + 31) / 32;
+            tb.wm = (m + 31) / 32;
+            rc = run_host_batch(ctx, pb2, alpha_cat, alpha_off, beta_cat, beta_off, n_pairs, out_score, out_cigar, out_cigar_off,
+                                out_cigar ? cigar_cap : 0, nullptr, nullptr, &tb);
+            if (rc != GNX_RETRY_BYTES)
+                return rc;
+            cudaDeviceSynchronize(); // chunks in flight are abandoned: the byte path redoes the whole call
+            for (int k = 0; k < kSlots; ++k)
+                ctx->slot[k].busy = false;
+            ctx->pack_backoff = 16;
+        }
+    }
     return run_host_batch(ctx, pb, alpha_cat, alpha_off, beta_cat, beta_off, n_pairs, out_score, out_cigar,
                           out_cigar_off, out_cigar ? cigar_cap : 0);
 }
@@ -2711,6 +2846,9 @@ int gnx_set_option(gnx_ctx *ctx, const char *name, int64_t value)
         ctx->opt_wide_cta = (int)value;
     } else if (k == "ragged16") {
         ctx->opt_rag = value ? 1 : 0;
+    } else if (k == "pack_stage") {
+        ctx->opt_pack_stage = value ? 1 : 0;
+        ctx->pack_backoff = 0;
     } else if (k == "tb_tma") {
         ctx->opt_tb_tma = value ? 1 : 0;
     } else if (k == "long_ckpt") {

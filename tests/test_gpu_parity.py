@@ -268,6 +268,48 @@ def test_twobit_uniform_batches(n, m, tma):
         c.close()
 
 
+@pytest.mark.parametrize("n,m", [(500, 150), (333, 142), (96, 64), (31, 150), (512, 160)])
+def test_pageable_bytes_are_packed_while_staged(n, m):
+    """gnx_affine_batch on a large uniform batch in pageable memory: the staging pass packs the bytes to dnaTwoBit
+    words (pack_stage = 1, the default) and the chunk runs on the TMA-fed kernels; same scores and cigars as with the
+    byte staging (pack_stage = 0) and as the oracle.  A base >= 4 anywhere makes the call fall back to the byte path,
+    which reports the pair (GNX_EBASE); a 5 x 5 matrix (N is a legal base) never packs."""
+    c = align.Context(0)
+    try:
+        c.set_option("chunk_pairs", 3000)
+        S = orc.HUMAN_CHIMP_TWO_SCORE_MATRIX
+        P = 8195  # several chunks, a partial quad at the end
+        a, ao, b, bo = synth_pairs(900 + n + m, P, n, m)
+        for mode in (1, 0):
+            osc, ooff, ocig = orc.batch(a, ao, b, bo, S, -600, -150, mode, True, 8)
+            for pack in (1, 0):
+                c.set_option("pack_stage", pack)
+                sc, off, cig = c.affine_gap_batch(a, ao, b, bo, S, -600, -150, mode == 1, True)
+                sc0, _, _ = c.affine_gap_batch(a, ao, b, bo, S, -600, -150, mode == 1, False)
+                assert np.array_equal(sc, osc) and np.array_equal(sc0, osc), (n, m, mode, pack)
+                assert np.array_equal(off, ooff) and np.array_equal(cig["run_length"], ocig["run_length"]) \
+                    and np.array_equal(cig["op"], ocig["op"]), (n, m, mode, pack)
+        c.set_option("pack_stage", 1)
+        bad = a.copy()
+        bad[(P - 7) * n + n // 2] = 7  # in the last chunk: earlier chunks are already in flight when it is met
+        with pytest.raises(_lib.GnxError) as ei:
+            c.affine_gap_batch(bad, ao, b, bo, S, -600, -150, True, True)
+        assert ei.value.code == _lib.GNX_EBASE
+        # the context is still usable; an N (legal under the 5 x 5 matrix) sends the call to the byte path as well
+        c.set_option("pack_stage", 1)  # (clears the back-off of the failed attempt)
+        sc, _, _ = c.affine_gap_batch(a, ao, b, bo, S, -600, -150, True, False)
+        assert np.array_equal(sc, orc.batch(a, ao, b, bo, S, -600, -150, 1, False, 8)[0])
+        withn = a.copy()
+        withn[(P - 7) * n + n // 2] = 4
+        withn[5] = 4
+        scn, offn, cign = c.affine_gap_batch(withn, ao, b, bo, S, -600, -150, True, True)
+        on = orc.batch(withn, ao, b, bo, S, -600, -150, 1, True, 8)
+        assert np.array_equal(scn, on[0]) and np.array_equal(offn, on[1]) and np.array_equal(cign["op"], on[2]["op"]) \
+            and np.array_equal(cign["run_length"], on[2]["run_length"])
+    finally:
+        c.close()
+
+
 def test_twobit_ragged_and_long(ctx):
     """Ragged 2-bit batches (per-pair lengths; empty sequences; multi-strip pairs) go through the device expansion and
     the ordinary kernels."""
