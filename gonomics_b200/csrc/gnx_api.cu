@@ -383,7 +383,7 @@ inline int64_t group_trace_words(const Problem &pb, int64_t n_eff, int64_t m)
     if (c.impl == 18) // tile checkpoints live in per-warp scratch, not per pair
         return 0;
     if (c.impl == 17) // checkpoints: kCkRegs words per lane every kCkK steps; a group is half a quad
-        return ((n_eff + 16 - 2) / kCkK) * kCkRegs * 16;
+        return ck_count(n_eff) * kCkRegs * 16;
     if (pb.kind == 2 && c.impl != 3)
         return const_trace_words(n_eff, m, c.C);
     const int64_t strips = (m + (int64_t)c.lpp * c.C - 1) / ((int64_t)c.lpp * c.C);
@@ -530,7 +530,7 @@ void launch_fill16(const FillParams &fp, int64_t quads, int sm_count, int ctas_p
     affine_fill16_kernel<FREE, CM, false, TB><<<grid, 32, 0, st>>>(fp);
 }
 
-inline int64_t ckpt_quad_words(int64_t n) { return ((n + 16 - 2) / kCkK) * kCkRegs * 32; }
+inline int64_t ckpt_quad_words(int64_t n) { return ck_count(n) * kCkRegs * 32; }
 
 template <int CM, bool TB>
 void launch_fill16_ckpt_t(const FillParams &fp, int64_t quads, int sm_count, int ctas_per_sm, cudaStream_t st)
@@ -917,7 +917,7 @@ void build_rag_tables(const Problem &pb, const int64_t *aoff, const int64_t *bof
         const int64_t q = (R.count[(size_t)key + 1] + 3) / 4;
         if (q > 0) {
             const int64_t n = max_n - key % stride;
-            const int64_t w = pb.cfg.impl == 17 ? ((n + 16 - 2) / kCkK) * kCkRegs * 32 : 0;
+            const int64_t w = pb.cfg.impl == 17 ? ckpt_quad_words(n) : 0;
             for (int64_t i = 0; i < q; ++i) {
                 R.quad_ck_off.push_back(words);
                 words += w;

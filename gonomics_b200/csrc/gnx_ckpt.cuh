@@ -112,13 +112,17 @@ __global__ void __launch_bounds__(128) ckpt_overflow_list_kernel(const int *coun
 __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillParams P, const CkptParams Q)
 {
     constexpr int C = 10, LPP = 16, WPL = 2;
+    // SK rows between neighbouring lanes, as in pass 1: cell (i,j) belongs to step (i - 1) + SK * ((j - 1) / C).  A
+    // restarted block lacks the tags of D and of the incoming I for its first SK steps (pass 1 saved clean values; the
+    // neighbour's edge a lane reads was produced SK steps earlier), so block b > 0 serves steps 32b + SK .. 32b + SK + 31.
+    constexpr int SK = kCkSkew;
     constexpr int SC = kScale, FI = kFI, FD = kFD, FH = kFH;
     constexpr int NEG = kNeg32, CLR = ~(kScale - 1);
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int kTgtPitch = kRing + 64;
     __shared__ int s_tab[C * kDimP * 32];
     __shared__ uint8_t s_tgt[2 * kTgtPitch];
-    __shared__ uint32_t s_tr[(kCkK + 1) * WPL * 32];
+    __shared__ uint32_t s_tr[(kCkK + SK) * WPL * 32];
     __shared__ int s_pre[2 * (LPP * C + 1)]; // per half: prefix sums of the walker's diagonal (route shortcuts)
     const int tid = threadIdx.x, lane = tid % LPP, half = tid / LPP;
     const int one = P.one;
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
                     const uint8_t *__restrict__ beta = P.beta + P.beta_off[pair];
                     n = (int)(P.alpha_off[pair + 1] - P.alpha_off[pair]);
                     m = (int)(P.beta_off[pair + 1] - P.beta_off[pair]);
-                    T = n + LPP - 1;
+                    T = n + SK * (LPP - 1);
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         const bool last = jbase + c + 1 == m;
@@ -255,8 +259,8 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
             //      ckpt_classify_kernel no I or D value can beat M anywhere on that diagonal: tripleMaxTrace picks M
             //      at every cell down to column 0.  The rest of the route is M x j, D x (i - j).
             //  (b) checkpoint-verified diagonal jump.  Pass 1 saved H(32k - l, 10l + c + 1) for every lane l and
-            //      column c at every checkpoint k; the walker's diagonal meets at most one such cell c_q per
-            //      checkpoint (11 l + c = j - i + 32k - 1).  If V = H(c_q) + (substitution scores of the d diagonal
+            //      column c at every checkpoint k (skew 2: H(32k - 2l, ...)); the walker's diagonal meets at most one such
+            //      cell c_q per checkpoint ((10 + SK) l + c = j - i + 32k - 1).  If V = H(c_q) + (substitution scores of the d diagonal
             //      cells above c_q), then M(i,j) >= s + H(i-1,j-1) >= ... >= sum + H(c_q) = V >= M(i,j): every
             //      inequality is tight, so M = H at (i,j) and at each of the d - 1 cells in between, i.e. the route is
             //      M x d (ties prefer M) and lands on c_q with its plane still to be read (need_k).  The farthest
@@ -340,9 +344,9 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
                     int dhit = 0;
                     if (ok && !tail) {
                         const int k = lane + 1;
-                        const int X = tj - ti + kCkK * k - 1;
+                        const int X = tj - ti + kCkK * k - 1; // = (C + SK) l + c for the cell H(32k - SK l, C l + c + 1) on the walker's diagonal
                         if (kCkK * k < T && X >= 0) {
-                            const int l2 = X / 11, c2 = X - 11 * l2;
+                            const int l2 = X / (C + SK), c2 = X - (C + SK) * l2;
                             const int col = l2 * C + c2 + 1, d = tj - col;
                             if (c2 < C && l2 < LPP && col <= m && d >= 1 && d <= L - 1) { // the cell itself is interior (row, col >= 1)
                                 const uint32_t x = __ldg(ck_base + (size_t)(k - 1) * (kCkRegs * 32) + c2 * 32 + (src_lane - lane + l2));
@@ -391,8 +395,8 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
             // block each half needs: the one serving the step of its current cell
             int blk = 0;
             {
-                const int tcell = (wi - 1) + (wj - 1) / C;
-                blk = (wi > 0 && wj > 0) ? max(tcell - 1, 0) / kCkK : -1; // -1: only boundary cells remain
+                const int tcell = (wi - 1) + SK * ((wj - 1) / C);
+                blk = (wi > 0 && wj > 0) ? max(tcell - SK, 0) / kCkK : -1; // -1: only boundary cells remain
             }
             blk = __shfl_sync(FULL, blk, 0, LPP);
             const int done0 = __shfl_sync(FULL, (int)done, 0, LPP); // executed by all 32 lanes (no short-circuit around it)
@@ -400,9 +404,9 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
             const bool recompute = !hdone && blk >= 0;
             const int s0 = blk > 0 ? blk * kCkK : 0;
             // the walk enters the block at its current cell and only moves to earlier steps: no later step is needed
-            int tin = (wi - 1) + (wj - 1) / C;
+            int tin = (wi - 1) + SK * ((wj - 1) / C);
             tin = __shfl_sync(FULL, tin, 0, LPP);
-            const int ulast_h = recompute ? min(tin - s0, kCkK) : 0;
+            const int ulast_h = recompute ? min(tin - s0, kCkK + SK - 1) : 0;
             const int ulast = max(ulast_h, __shfl_xor_sync(FULL, ulast_h, 16));
 #ifdef GNX_CK_DEBUG
             if (lane == 0 && recompute)
@@ -411,7 +415,7 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
             if (__any_sync(FULL, recompute)) {
                 // ---- restore the state entering step s0 ----
                 int Hc[C], Dt[C];
-                int hpL, edgeI = 0, edgeH = 0;
+                int hpL, edgeI = 0, edgeH = 0, edgeIp = 0, edgeHp = 0;
                 if (blk > 0 && recompute) {
                     const uint32_t *src = ck_base + (size_t)(blk - 1) * (kCkRegs * 32) + src_lane;
                     auto val = [&](uint32_t x) { return ((int)((x >> (16 * sel)) & 0xffffu) - 32768) * SC; };
@@ -423,6 +427,10 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
                     hpL = val(__ldg(src + 20 * 32));
                     edgeI = val(__ldg(src + 21 * 32));
                     edgeH = val(__ldg(src + 22 * 32));
+                    if (SK == 2) {
+                        edgeIp = val(__ldg(src + 23 * 32));
+                        edgeHp = val(__ldg(src + 24 * 32));
+                    }
                 } else {
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
@@ -437,9 +445,13 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
 #pragma unroll 1
                 for (int u = 0; u <= ulast; ++u) {
                     const int t = s0 + u;
-                    const int r = t - lane + 1;
-                    int inI = __shfl_up_sync(FULL, edgeI, 1, LPP);
-                    int inH = __shfl_up_sync(FULL, edgeH, 1, LPP);
+                    const int r = t - SK * lane + 1;
+                    int inI = __shfl_up_sync(FULL, SK == 2 ? edgeIp : edgeI, 1, LPP);
+                    int inH = __shfl_up_sync(FULL, SK == 2 ? edgeHp : edgeH, 1, LPP);
+                    if (SK == 2) { // every step, active or not: the neighbour reads the edge of two steps ago
+                        edgeIp = edgeI;
+                        edgeHp = edgeH;
+                    }
                     if (lane == 0) { // freeEndGaps: D(i,0) = 0, so I's candidate from column 0 is O + E
                         inI = iD;
                         inH = 0;
@@ -479,10 +491,10 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
             // block, off the boundaries) is consumed in one go -- the codes along the way are exactly what the
             // one-cell-at-a-time walk would have read.
             {
-                const int lo = blk > 0 ? s0 + 1 : 0; // first step whose codes this block serves
+                const int lo = blk > 0 ? s0 + SK : 0; // first step whose codes this block serves
                 auto load = [&](int i, int j) -> unsigned {
                     const int l = (j - 1) / C, c = (j - 1) - l * C;
-                    const int u = (i - 1) + l - s0;
+                    const int u = (i - 1) + SK * l - s0;
                     const int q = c >= 5 ? 1 : 0, cc = c - 5 * q;
                     return (s_tr[(u * WPL + q) * 32 + half * LPP + l] >> (32 - kTagBits * (5 - cc))) & (kScale - 1);
                 };
@@ -509,7 +521,7 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
                     {
                         const int d = lane + 1, ci = bi - d, cj = bj - d;
                         bool isM = false;
-                        if (bw && bk == 0 && ci > 0 && cj > 0 && (ci - 1) + (cj - 1) / C >= lo)
+                        if (bw && bk == 0 && ci > 0 && cj > 0 && (ci - 1) + SK * ((cj - 1) / C) >= lo)
                             isM = ((load(ci, cj) >> 4) & 3u) == 2u; // H tag 2 = plane M
                         const unsigned ball = __ballot_sync(FULL, isM);
                         const unsigned mine = (ball >> (half * LPP)) & 0xffffu;
@@ -572,7 +584,7 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
                         unsigned nw = 0;
                         bool leave = false;
                         if (wi > 0 && wj > 0) {
-                            if ((wi - 1) + (wj - 1) / C < lo) { // the path leaves this block: an earlier one is needed
+                            if ((wi - 1) + SK * ((wj - 1) / C) < lo) { // the path leaves this block: an earlier one is needed
                                 need_k = (wk == 0);
                                 if (!need_k)
                                     wk = kn;

@@ -34,8 +34,20 @@ __device__ __forceinline__ unsigned uaddmax_16x2(unsigned a, unsigned b, unsigne
 // which is where the reference's traceback leaves the free-end column: walking up from (n,m) in plane D, the
 // source of D(i,m) is T(M, I, D)(i-1,m) with ties M >= I >= D (align/align.go:76-84), D(i,m) being the running
 // maximum itself, so the walk stays in D exactly until the last row that reached it.
-constexpr int kCkK = 32;   // steps between checkpoints
-constexpr int kCkRegs = 23; // 32-bit words per lane per checkpoint
+#ifndef GNX_F16_SKEW
+#define GNX_F16_SKEW 2      // rows between neighbouring lanes of the freeEndGaps kernels (see SK below)
+#endif
+constexpr int kCkK = 32;    // steps between checkpoints
+// The checkpoint path keeps skew 1: measured with skew 2 (parity-clean, 88 tests) pass 1 gains 1 % (its steady phase
+// is cut into 32-step runs by the saves) while affine_ckpt_trace_kernel loses 15 % (a route that crosses the 15 lanes
+// spans 30 steps instead of 15, i.e. one more 32-step block to recompute per pair).
+#ifndef GNX_CK_SKEW
+#define GNX_CK_SKEW 1
+#endif
+constexpr int kCkSkew = GNX_CK_SKEW;                // geometry shared by pass 1 (here) and affine_ckpt_trace_kernel
+constexpr int kCkRegs = kCkSkew == 2 ? 25 : 23;     // 32-bit words per lane per checkpoint (skew 2: + the edges of the step before)
+// checkpoints of a pair with target length n: the states entering steps 32, 64, ... < n + kCkSkew * 15
+__host__ __device__ inline int64_t ck_count(int64_t n) { return (n + kCkSkew * 15 - 1) / kCkK; }
 
 // ---- 1-D TMA (cp.async.bulk) staging of 2-bit packed sequences: TB kernels ----------------------------------
 // The async proxy writes the packed words of a quad's four targets and four queries into shared memory and
@@ -89,11 +101,8 @@ __device__ __forceinline__ int tb_base(const uint32_t *w32, int pos)
 //     with (H = I = O + jE, D(next) = H + O + E, its edges likewise) is a fixed point of such a row when the first
 //     column is free (H(r,0) = 0), so the lane still holds exactly that boundary when row 1 arrives;
 //   * past row n a lane keeps computing on a clamped target index, after H(n, CM) has been copied aside.
-// Used by the score-only freeEndGaps kernels with a compile-time last column; the checkpoints of CKPT are read by
-// affine_ckpt_trace_kernel in the SK = 1 geometry.
-#ifndef GNX_F16_SKEW
-#define GNX_F16_SKEW 2
-#endif
+// Used by the freeEndGaps kernels with a compile-time last column (score-only and CKPT; affine_ckpt_trace_kernel
+// re-runs its blocks in the same geometry, kCkSkew).
 // SHIFTED (GNX_F16_SHORT_CHAIN): the one-op chain.  With Hs = H + O + E kept instead of H (row boundary, diagonal and
 // edge included; a uniform shift of every H), a cell is
 //     Y   = max(D + O + E, Hs(r-1,j-1) + s)       VIADDMNMX      (no I in it)
@@ -112,7 +121,7 @@ template <bool FREE, int CM = -1, bool CKPT = false, bool TB = false>
 __global__ void __launch_bounds__(32, (TB && GNX_TB_JOINT) ? 10 : 16) affine_fill16_kernel(const FillParams P)
 {
     constexpr bool JT = TB && GNX_TB_JOINT;
-    constexpr int SK = (!CKPT && FREE && CM >= 0) ? GNX_F16_SKEW : 1;
+    constexpr int SK = (FREE && CM >= 0) ? (CKPT ? kCkSkew : GNX_F16_SKEW) : 1;
     constexpr bool SH = GNX_F16_SHORT_CHAIN != 0;
     static_assert(CM < 0 || FREE, "CM selects the free-end column");
     static_assert(!CKPT || (FREE && CM >= 0), "checkpoints are taken on the freeEndGaps path only");
@@ -400,8 +409,11 @@ __global__ void __launch_bounds__(32, (TB && GNX_TB_JOINT) ? 10 : 16) affine_fil
                     }
                     if (CKPT && c == CM) { // max(M, I) of the free-end column (meaningful in its lane only)
                         const unsigned mx = __vmaxu2(MH, It);
-                        bestA = max(bestA, __byte_perm((unsigned)r, mx, 0x5410)); // mxA << 16 | r: later rows win ties
-                        bestB = max(bestB, __byte_perm((unsigned)r, mx, 0x7610));
+                        // ramp steps: a virtual row holds I(0,m) and counts as row 0 (= the initial value); rows past n do not count
+                        const unsigned rb = RAMP ? (unsigned)max(r, 0) : (unsigned)r;
+                        const unsigned keep = (RAMP && r > n) ? 0u : 0xffffffffu;
+                        bestA = max(bestA, __byte_perm(rb, mx, 0x5410) & keep); // mxA << 16 | r: later rows win ties
+                        bestB = max(bestB, __byte_perm(rb, mx, 0x7610) & keep);
                     }
                     const unsigned H = umax3_16x2(MH, It, Dt[c]);
                     const unsigned Ho = (unsigned)madd((int)H, one, oe_i);
@@ -433,6 +445,10 @@ __global__ void __launch_bounds__(32, (TB && GNX_TB_JOINT) ? 10 : 16) affine_fil
             dst[20 * 32] = hpL - (unsigned)(hs * 65537);
             dst[21 * 32] = edgeI;
             dst[22 * 32] = edgeH - (unsigned)(hs * 65537);
+            if (SK == 2) {
+                dst[23 * 32] = edgeIp;
+                dst[24 * 32] = edgeHp - (unsigned)(hs * 65537);
+            }
         };
         using Steady = std::integral_constant<int, 0>;
         using Check = std::integral_constant<int, 1>;
@@ -442,12 +458,30 @@ __global__ void __launch_bounds__(32, (TB && GNX_TB_JOINT) ? 10 : 16) affine_fil
 #pragma unroll 2
             for (; t < SK * (LPP - 1); ++t)
                 step(t, Ramp{});
+            if (CKPT) {
+#pragma unroll 1
+                while (t < n - 1) { // steady phase in runs that end at the next checkpoint
+                    if ((t & (kCkK - 1)) == 0 && t > 0)
+                        save(t);
+                    const int tend = min(n - 1, (t | (kCkK - 1)) + 1);
 #pragma unroll 4
-            for (; t < n - 1; ++t)
-                step(t, Steady{});
+                    for (; t < tend; ++t)
+                        step(t, Steady{});
+                }
 #pragma unroll 2
-            for (; t < T; ++t)
-                step(t, Ramp{});
+                for (; t < T; ++t) {
+                    if ((t & (kCkK - 1)) == 0 && t > 0)
+                        save(t);
+                    step(t, Ramp{});
+                }
+            } else {
+#pragma unroll 4
+                for (; t < n - 1; ++t)
+                    step(t, Steady{});
+#pragma unroll 2
+                for (; t < T; ++t)
+                    step(t, Ramp{});
+            }
         } else {
 #pragma unroll 1
         for (; t < SK * (LPP - 1); ++t)
