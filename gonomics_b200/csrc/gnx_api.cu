@@ -174,7 +174,7 @@ struct gnx_ctx {
     // between calls with the same uniform shape (a streaming caller's batches) so that they are built once
     std::vector<int64_t> tb_off[4];
     int64_t tb_key[3] = {-1, -1, -1}; // n_pairs, n, m of the cached uniform arrays
-    PinBuf gsw_pin[12]; // gnx_gsw_batch: page-locked scratch kept between calls (gnx_gsw.inl)
+    PinBuf gsw_pin[32]; // gnx_gsw_batch: page-locked scratch kept between calls (gnx_gsw.inl)
     // cigars retained after GNX_ECAP
     std::vector<gnx_cigar> retained;
     bool have_retained = false;

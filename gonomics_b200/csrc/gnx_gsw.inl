@@ -68,10 +68,17 @@ inline void gsw_append(GswCigar &a, int64_t run, uint8_t op)
         a.emplace_back(run, op);
 }
 
-template <typename F> void gsw_parallel(int64_t n, F &&fn)
+inline int gsw_threads(int64_t n)
 {
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)hw, (int64_t)32, n / 256 + 1}));
+    return (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)hw, (int64_t)32, n / 256 + 1}));
+}
+
+// fn(lo, hi, t) on thread t of gsw_threads(n): the split depends on n only, so two passes over the same n see the
+// same ranges (run_round's counting pass leaves per-thread prefix sums that its gather pass completes)
+template <typename F> void gsw_parallel(int64_t n, F &&fn)
+{
+    const int nt = gsw_threads(n);
     if (nt == 1) {
         fn(0, n, 0);
         return;
@@ -88,14 +95,15 @@ template <typename F> void gsw_parallel(int64_t n, F &&fn)
 
 namespace {
 
-// page-locked scratch of the driver, kept in the context between calls (ctx->gsw_pin[...])
-enum { GP_SEEDS, GP_SOFF, GP_A, GP_B, GP_AO, GP_BO, GP_SC, GP_EI, GP_EJ, GP_CO, GP_CG, GP_N };
+// page-locked scratch of the driver, kept in the context between calls (ctx->gsw_pin[...]).  The extension results
+// (score, end cell, cigar offsets, cigars) stay where gnx_extend_batch wrote them: one set per (round, side).
+enum { GP_SEEDS, GP_SOFF, GP_A, GP_B, GP_AO, GP_BO, GP_RES, GP_N = GP_RES + 2 * 2 * 5 };
+enum { GR_SC, GR_EI, GR_EJ, GR_CO, GR_CG };
+inline int gp_res(int round, int side, int what) { return GP_RES + (round * 2 + side) * 5 + what; }
 
-struct GswExt { // results of the extension DPs, indexed by extension id
-    std::vector<int64_t> l_score, l_i, l_j, r_score, r_i, r_j;
-    std::vector<int64_t> l_coff, r_coff; // per id: first cigar element, count
-    std::vector<int32_t> l_cnt, r_cnt;
-    std::vector<gnx_cigar> l_cig, r_cig;
+struct GswSide { // one (round, side) result set
+    const int64_t *score = nullptr, *end_i = nullptr, *end_j = nullptr, *coff = nullptr;
+    const gnx_cigar *cig = nullptr;
 };
 
 } // namespace
@@ -186,70 +194,74 @@ extern "C" int gnx_gsw_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8
     // the second seed, and the predicate only gets stricter from there, so round 2 extends seeds 1.. up to the first
     // one seedCouldBeBetter rejects at THAT score -- still a superset of what the replay below can ask for.
     std::unique_ptr<int32_t[]> ext_id(new int32_t[(size_t)std::max<int64_t>(n_seeds, 1)]); // per seed: extension id or -1
-    GswExt X;
-    int64_t n_ext_total = 0;
+    GswSide X[2][2]; // [round][side]
+    int64_t n_ext_round[2] = {0, 0};
     auto seed_score_of = [&](const gnx_seed &s, const uint8_t *cur) {
         int64_t v = 0; // scoreSeedSeq (align.go:81-87)
         for (uint32_t i = s.query_start; i < s.query_start + s.length; ++i)
             v += scores[cur[i] * dim + cur[i]];
         return v;
     };
+    // per read: extension pairs and window / query bases of both sides, as prefix sums (thread-local after the counting
+    // pass, completed with the thread's base in the gather pass)
+    struct RoundCnt {
+        int64_t n, la, lb, ra, rb;
+    };
+    std::unique_ptr<RoundCnt[]> pre(new RoundCnt[(size_t)n_reads + 1]);
+    const int nthr = gsw_threads(n_reads);
+    std::vector<RoundCnt> tbase((size_t)nthr + 1);
     // first[r] .. last[r]: the seed range (relative to the read) this round extends
-    auto run_round = [&](const std::vector<int32_t> &first, const std::vector<int32_t> &last) -> int {
-        std::vector<int64_t> cnt((size_t)n_reads + 1, 0), la((size_t)n_reads + 1, 0), lb((size_t)n_reads + 1, 0), ra((size_t)n_reads + 1, 0),
-            rb((size_t)n_reads + 1, 0);
-        gsw_parallel(n_reads, [&](int64_t lo, int64_t hi, int) {
+    auto run_round = [&](int round, const int32_t *first, const int32_t *last) -> int {
+        gsw_parallel(n_reads, [&](int64_t lo, int64_t hi, int t) {
+            RoundCnt acc = {0, 0, 0, 0, 0};
             for (int64_t r = lo; r < hi; ++r) {
+                pre[(size_t)r] = acc; // exclusive, relative to the thread's first read
                 const int64_t L = read_off[r + 1] - read_off[r], ext = perfect[(size_t)r] / 600 + L; // sk.extension (toGiraf.go:32)
-                int64_t ne = 0, a1 = 0, b1 = 0, a2 = 0, b2 = 0;
                 for (int32_t k = first[(size_t)r]; k < last[(size_t)r]; ++k) {
                     const gnx_seed &s = seeds[soff[r] + k];
                     if ((int64_t)s.total_length == L)
                         continue; // the seed spans the read: no extension (toGiraf.go:45-49)
-                    ++ne;
+                    ++acc.n;
                     const int64_t e = ext - s.total_length, node_len = GO[s.target_id + 1] - GO[s.target_id];
                     const int64_t ref_end = s.target_start, start = (int64_t)s.target_start + s.length;
-                    a1 += std::max<int64_t>(0, std::min(ref_end, e));
-                    b1 += s.query_start;
-                    a2 += std::max<int64_t>(0, std::min(node_len - start, e));
-                    b2 += L - (s.query_start + s.length);
+                    acc.la += std::max<int64_t>(0, std::min(ref_end, e));
+                    acc.lb += s.query_start;
+                    acc.ra += std::max<int64_t>(0, std::min(node_len - start, e));
+                    acc.rb += L - (s.query_start + s.length);
                 }
-                cnt[(size_t)r + 1] = ne;
-                la[(size_t)r + 1] = a1;
-                lb[(size_t)r + 1] = b1;
-                ra[(size_t)r + 1] = a2;
-                rb[(size_t)r + 1] = b2;
             }
+            tbase[(size_t)t + 1] = acc;
         });
-        for (int64_t r = 0; r < n_reads; ++r) {
-            cnt[(size_t)r + 1] += cnt[(size_t)r];
-            la[(size_t)r + 1] += la[(size_t)r];
-            lb[(size_t)r + 1] += lb[(size_t)r];
-            ra[(size_t)r + 1] += ra[(size_t)r];
-            rb[(size_t)r + 1] += rb[(size_t)r];
+        tbase[0] = {0, 0, 0, 0, 0};
+        for (int t = 0; t < nthr; ++t) {
+            tbase[(size_t)t + 1].n += tbase[(size_t)t].n;
+            tbase[(size_t)t + 1].la += tbase[(size_t)t].la;
+            tbase[(size_t)t + 1].lb += tbase[(size_t)t].lb;
+            tbase[(size_t)t + 1].ra += tbase[(size_t)t].ra;
+            tbase[(size_t)t + 1].rb += tbase[(size_t)t].rb;
         }
-        const int64_t ne = cnt[(size_t)n_reads];
+        const RoundCnt tot = tbase[(size_t)nthr];
+        const int64_t ne = tot.n;
+        n_ext_round[round] = ne;
+        lap("  count");
         if (ne == 0)
             return GNX_OK;
-        const int64_t base = n_ext_total;
-        for (auto *v : {&X.l_score, &X.l_i, &X.l_j, &X.r_score, &X.r_i, &X.r_j, &X.l_coff, &X.r_coff})
-            v->resize((size_t)(base + ne));
-        X.l_cnt.resize((size_t)(base + ne));
-        X.r_cnt.resize((size_t)(base + ne));
+        const int64_t base = round ? n_ext_round[0] : 0;
         for (int side = 0; side < 2; ++side) { // 0 left (getLeftTargetBases), 1 right (getRightBases), search.go:133-145
-            const std::vector<int64_t> &alen = side ? ra : la, &blen = side ? rb : lb;
-            CU(pin[GP_A].ensure((size_t)alen[(size_t)n_reads] + 16));
-            CU(pin[GP_B].ensure((size_t)blen[(size_t)n_reads] + 16));
+            CU(pin[GP_A].ensure((size_t)(side ? tot.ra : tot.la) + 16));
+            CU(pin[GP_B].ensure((size_t)(side ? tot.rb : tot.lb) + 16));
             CU(pin[GP_AO].ensure((size_t)(ne + 1) * 8));
             CU(pin[GP_BO].ensure((size_t)(ne + 1) * 8));
             uint8_t *A = pin[GP_A].as<uint8_t>(), *B = pin[GP_B].as<uint8_t>();
             int64_t *AO = pin[GP_AO].as<int64_t>(), *BO = pin[GP_BO].as<int64_t>();
             AO[0] = BO[0] = 0;
-            gsw_parallel(n_reads, [&](int64_t lo, int64_t hi, int) {
+            gsw_parallel(n_reads, [&](int64_t lo, int64_t hi, int t) {
+                const RoundCnt tb = tbase[(size_t)t];
                 for (int64_t r = lo; r < hi; ++r) {
                     const int64_t L = read_off[r + 1] - read_off[r], ext = perfect[(size_t)r] / 600 + L;
                     const uint8_t *rd = reads_cat + read_off[r], *rcp = rc_cat.get() + (read_off[r] - read_off[0]);
-                    int64_t x = cnt[(size_t)r], ap = alen[(size_t)r], bp = blen[(size_t)r];
+                    const RoundCnt &pr = pre[(size_t)r];
+                    int64_t x = tb.n + pr.n, ap = side ? tb.ra + pr.ra : tb.la + pr.la, bp = side ? tb.rb + pr.rb : tb.lb + pr.lb;
                     for (int32_t k = first[(size_t)r]; k < last[(size_t)r]; ++k) {
                         const gnx_seed &s = seeds[soff[r] + k];
                         if ((int64_t)s.total_length == L)
@@ -278,50 +290,51 @@ extern "C" int gnx_gsw_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8
                     }
                 }
             });
-            CU(pin[GP_SC].ensure((size_t)ne * 8));
-            CU(pin[GP_EI].ensure((size_t)ne * 8));
-            CU(pin[GP_EJ].ensure((size_t)ne * 8));
-            CU(pin[GP_CO].ensure((size_t)(ne + 1) * 8));
-            CU(pin[GP_CG].ensure((size_t)std::max<int64_t>(4 * ne, 64) * sizeof(gnx_cigar)));
-            int64_t *co = pin[GP_CO].as<int64_t>();
+            lap("  gather windows");
+            PinBuf &p_sc = pin[gp_res(round, side, GR_SC)], &p_ei = pin[gp_res(round, side, GR_EI)], &p_ej = pin[gp_res(round, side, GR_EJ)],
+                   &p_co = pin[gp_res(round, side, GR_CO)], &p_cg = pin[gp_res(round, side, GR_CG)];
+            CU(p_sc.ensure((size_t)ne * 8));
+            CU(p_ei.ensure((size_t)ne * 8));
+            CU(p_ej.ensure((size_t)ne * 8));
+            CU(p_co.ensure((size_t)(ne + 1) * 8));
+            CU(p_cg.ensure((size_t)std::max<int64_t>(4 * ne, 64) * sizeof(gnx_cigar)));
+            int64_t *co = p_co.as<int64_t>();
             int e = gnx_extend_batch(ctx, side ? GNX_EXT_RIGHT : GNX_EXT_LEFT, A, AO, B, BO, ne, scores, dim, gap_pen, 1,
-                                     pin[GP_SC].as<int64_t>(), pin[GP_EI].as<int64_t>(), pin[GP_EJ].as<int64_t>(),
-                                     pin[GP_CG].as<gnx_cigar>(), co, (int64_t)(pin[GP_CG].cap / sizeof(gnx_cigar)));
+                                     p_sc.as<int64_t>(), p_ei.as<int64_t>(), p_ej.as<int64_t>(), p_cg.as<gnx_cigar>(), co,
+                                     (int64_t)(p_cg.cap / sizeof(gnx_cigar)));
             if (e == GNX_ECAP) {
-                CU(pin[GP_CG].ensure((size_t)co[ne] * sizeof(gnx_cigar)));
-                e = gnx_copy_last_cigars(ctx, pin[GP_CG].as<gnx_cigar>(), co[ne]);
+                CU(p_cg.ensure((size_t)co[ne] * sizeof(gnx_cigar)));
+                e = gnx_copy_last_cigars(ctx, p_cg.as<gnx_cigar>(), co[ne]);
             }
             if (e != GNX_OK)
                 return e;
-            std::vector<int64_t> &sc = side ? X.r_score : X.l_score, &ei = side ? X.r_i : X.l_i, &ej = side ? X.r_j : X.l_j,
-                                 &cf = side ? X.r_coff : X.l_coff;
-            std::vector<int32_t> &cn = side ? X.r_cnt : X.l_cnt;
-            std::vector<gnx_cigar> &cg = side ? X.r_cig : X.l_cig;
-            const int64_t cbase = (int64_t)cg.size();
-            cg.resize((size_t)(cbase + co[ne]));
-            memcpy(cg.data() + cbase, pin[GP_CG].p, (size_t)co[ne] * sizeof(gnx_cigar));
-            memcpy(sc.data() + base, pin[GP_SC].p, (size_t)ne * 8);
-            memcpy(ei.data() + base, pin[GP_EI].p, (size_t)ne * 8);
-            memcpy(ej.data() + base, pin[GP_EJ].p, (size_t)ne * 8);
-            for (int64_t x = 0; x < ne; ++x) {
-                cf[(size_t)(base + x)] = cbase + co[x];
-                cn[(size_t)(base + x)] = (int32_t)(co[x + 1] - co[x]);
-            }
+            X[round][side].score = p_sc.as<int64_t>();
+            X[round][side].end_i = p_ei.as<int64_t>();
+            X[round][side].end_j = p_ej.as<int64_t>();
+            X[round][side].coff = co;
+            X[round][side].cig = p_cg.as<gnx_cigar>();
+            lap("  gnx_extend_batch");
         }
-        n_ext_total += ne;
         return GNX_OK;
     };
-    std::vector<int32_t> first((size_t)n_reads), last((size_t)n_reads);
-    for (int64_t r = 0; r < n_reads; ++r) {
-        first[(size_t)r] = 0;
-        last[(size_t)r] = soff[r + 1] > soff[r] ? 1 : 0; // pred(seed 0, best 0) holds for every seed
-    }
-    for (int64_t k = 0; k < n_seeds; ++k)
-        ext_id[(size_t)k] = -1;
-    if ((rc = run_round(first, last)) != GNX_OK)
+    std::unique_ptr<int32_t[]> first(new int32_t[(size_t)n_reads]), last(new int32_t[(size_t)n_reads]);
+    gsw_parallel(n_reads, [&](int64_t lo, int64_t hi, int) {
+        for (int64_t r = lo; r < hi; ++r) {
+            first[(size_t)r] = 0;
+            last[(size_t)r] = soff[r + 1] > soff[r] ? 1 : 0; // pred(seed 0, best 0) holds for every seed
+        }
+    });
+    memset(ext_id.get(), 0xff, (size_t)std::max<int64_t>(n_seeds, 1) * sizeof(int32_t)); // -1
+    if ((rc = run_round(0, first.get(), last.get())) != GNX_OK)
         return rc;
     lap("round 1 (first seeds)");
-    const int64_t n_ext1 = n_ext_total;
+    const int64_t n_ext1 = n_ext_round[0];
+    // extension x of either round: its result set and index there
+    auto ext_of = [&](int32_t x, int side, int64_t &local) -> const GswSide & {
+        const int round = x >= n_ext1 ? 1 : 0;
+        local = x - (round ? n_ext1 : 0);
+        return X[round][side];
+    };
     gsw_parallel(n_reads, [&](int64_t lo, int64_t hi, int) {
         for (int64_t r = lo; r < hi; ++r) {
             const int64_t ns = soff[r + 1] - soff[r], L = read_off[r + 1] - read_off[r];
@@ -333,7 +346,7 @@ extern "C" int gnx_gsw_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8
             int64_t sc0 = seed_score_of(s0, cur);
             const int32_t id = ext_id[(size_t)soff[r]];
             if (id >= 0)
-                sc0 += X.l_score[(size_t)id] + X.r_score[(size_t)id];
+                sc0 += X[0][0].score[(size_t)id] + X[0][1].score[(size_t)id];
             const int64_t best1 = std::max<int64_t>(sc0, 0); // currBest.AlnScore after the first seed
             int32_t k = 1;
             while (k < ns && gsw_could_be_better(seeds[soff[r] + k].total_length, best1, perfect[(size_t)r], L))
@@ -341,9 +354,10 @@ extern "C" int gnx_gsw_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8
             last[(size_t)r] = k;
         }
     });
-    if ((rc = run_round(first, last)) != GNX_OK)
+    if ((rc = run_round(1, first.get(), last.get())) != GNX_OK)
         return rc;
     lap("round 2 (remaining seeds)");
+    const int64_t n_ext_total = n_ext_round[0] + n_ext_round[1];
     if (timing)
         fprintf(stderr, "[gnx_gsw_batch] reads %lld seeds %lld extension pairs %lld + %lld\n", (long long)n_reads, (long long)n_seeds,
                 (long long)n_ext1, (long long)(n_ext_total - n_ext1));
@@ -387,17 +401,19 @@ extern "C" int gnx_gsw_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8
                     const int64_t e = pf / 600 + L - s.total_length;
                     const int64_t ref_end = s.target_start, start = (int64_t)s.target_start + s.length;
                     const int64_t wl = std::max<int64_t>(0, std::min(ref_end, e));
+                    int64_t xl = 0;
+                    const GswSide &Lx = ext_of(x, 0, xl), &Rx = ext_of(x, 1, xl);
                     left.clear();
-                    for (int64_t c = X.l_coff[(size_t)x]; c < X.l_coff[(size_t)x] + X.l_cnt[(size_t)x]; ++c)
-                        left.emplace_back(X.l_cig[(size_t)c].run_length, X.l_cig[(size_t)c].op);
+                    for (int64_t c = Lx.coff[xl]; c < Lx.coff[xl + 1]; ++c)
+                        left.emplace_back(Lx.cig[c].run_length, Lx.cig[c].op);
                     right.clear();
-                    for (int64_t c = X.r_coff[(size_t)x]; c < X.r_coff[(size_t)x] + X.r_cnt[(size_t)x]; ++c)
-                        right.emplace_back(X.r_cig[(size_t)c].run_length, X.r_cig[(size_t)c].op);
-                    tstart = ref_end - wl + X.l_i[(size_t)x]; // refEnd - len(s.Seq) - len(seq) + targetStart (search.go:178)
-                    qstart = X.l_j[(size_t)x];
-                    tend = X.r_i[(size_t)x] + start;          // targetEnd + start (:214)
-                    query_end = X.r_j[(size_t)x];
-                    score = X.l_score[(size_t)x] + seed_score + X.r_score[(size_t)x];
+                    for (int64_t c = Rx.coff[xl]; c < Rx.coff[xl + 1]; ++c)
+                        right.emplace_back(Rx.cig[c].run_length, Rx.cig[c].op);
+                    tstart = ref_end - wl + Lx.end_i[xl]; // refEnd - len(s.Seq) - len(seq) + targetStart (search.go:178)
+                    qstart = Lx.end_j[xl];
+                    tend = Rx.end_i[xl] + start;          // targetEnd + start (:214)
+                    query_end = Rx.end_j[xl];
+                    score = Lx.score[xl] + seed_score + Rx.score[xl];
                 }
                 if (score > g.aln_score) { // toGiraf.go:56-64
                     g.q_start = (int32_t)qstart;
