@@ -24,7 +24,7 @@ EXPORTS = [
     "gnx_host_free", "gnx_affine_batch", "gnx_affine_batch_twobit", "gnx_const_batch", "gnx_affine_chunk_batch", "gnx_copy_last_cigars",
     "gnx_multi_affine_chunk_batch", "gnx_extend_batch", "gnx_batch_device", "gnx_batch_device_twobit", "gnx_launch_count", "gnx_last_fill_stats", "gnx_last_kernel_path", "gnx_set_option",
     "gnx_twobit_new", "gnx_twobit_free", "gnx_twobit_info", "gnx_twobit_download", "gnx_twobit_unpack", "gnx_twobit_get_bases",
-    "gnx_twobit_count_matches", "gnx_twobit_pack_device", "gnx_seed_index_new", "gnx_seed_index_free", "gnx_seed_index_info",
+    "gnx_twobit_count_matches", "gnx_twobit_pack_device", "gnx_pack_twobit_host", "gnx_seed_index_new", "gnx_seed_index_free", "gnx_seed_index_info",
     "gnx_seed_index_download", "gnx_seed_batch", "gnx_gsw_batch",
     "gnx_multi_create", "gnx_multi_destroy", "gnx_multi_device_count", "gnx_multi_last_error", "gnx_multi_context",
     "gnx_multi_shard_bounds", "gnx_multi_affine_batch", "gnx_multi_const_batch", "gnx_multi_copy_last_cigars",
@@ -120,6 +120,8 @@ def load() -> C.CDLL:
     L.gnx_twobit_count_matches.restype = ci
     L.gnx_twobit_pack_device.argtypes = [vp, u8p, i64, ci, vp, vp]
     L.gnx_twobit_pack_device.restype = ci
+    L.gnx_pack_twobit_host.argtypes = [u8p, i64, i64, vp]
+    L.gnx_pack_twobit_host.restype = ci
     L.gnx_seed_index_new.argtypes = [vp, u8p, i64p, i64, ci, ci, C.POINTER(vp)]
     L.gnx_seed_index_new.restype = ci
     L.gnx_seed_index_free.argtypes = [vp]

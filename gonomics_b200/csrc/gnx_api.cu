@@ -2438,6 +2438,15 @@ int gnx_affine_batch(gnx_ctx *ctx, const uint8_t *alpha_cat, const int64_t *alph
                           out_cigar_off, out_cigar ? cigar_cap : 0);
 }
 
+int gnx_pack_twobit_host(const uint8_t *bases, int64_t count, int64_t len, uint64_t *words)
+{
+    if (count < 0 || len < 0 || (count > 0 && len > 0 && (!bases || !words)))
+        return GNX_EARG;
+    if (count == 0 || len == 0)
+        return GNX_OK;
+    return pack_stage(words, bases, count, len, (len + 31) / 32) ? GNX_OK : GNX_EBASE;
+}
+
 int gnx_affine_batch_twobit(gnx_ctx *ctx, const uint64_t *alpha_words, const int64_t *alpha_len, int64_t alpha_uniform_len,
                             const uint64_t *beta_words, const int64_t *beta_len, int64_t beta_uniform_len, int64_t n_pairs,
                             const int64_t *scores, int dim, int64_t gap_open, int64_t gap_extend, int mode, int want_cigar,

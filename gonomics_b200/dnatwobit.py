@@ -112,6 +112,21 @@ class TwoBit:
         return self._host()[1]
 
 
+def pack_uniform_host(bases, count: int, length: int) -> np.ndarray:
+    """dnaTwoBit.NewTwoBit of `count` sequences of `length` bases each (back to back in `bases`) on the host threads of
+    the library (gnx_pack_twobit_host; no GPU involved): (length + 31) // 32 uint64 words per sequence -- the input
+    format of affine_gap_batch_twobit.  Raises GnxError(GNX_EBASE) when a base is >= 4."""
+    seq = np.ascontiguousarray(bases, dtype=np.uint8)
+    if seq.size < count * length:
+        raise ValueError("bases is shorter than count * length")
+    words = np.empty(count * ((length + 31) // 32), dtype=np.uint64)
+    L = _lib.load()
+    rc = L.gnx_pack_twobit_host(seq.ctypes.data_as(L.gnx_pack_twobit_host.argtypes[0]), count, length, words.ctypes.data)
+    if rc != _lib.GNX_OK:
+        raise _lib.GnxError(rc, "gnx_pack_twobit_host: a base is >= 4" if rc == _lib.GNX_EBASE else "gnx_pack_twobit_host failed")
+    return words
+
+
 def NewTwoBit(inSeq, ctx: Optional[Context] = None) -> TwoBit:
     """dnaTwoBit.NewTwoBit (dnaTwoBit.go:68)."""
     return TwoBit(TwoBitSet.from_seqs([np.asarray(inSeq, dtype=np.uint8)], 0, ctx))

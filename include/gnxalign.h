@@ -212,6 +212,12 @@ int gnx_twobit_count_matches(gnx_ctx *ctx, int dir, const gnx_twobit *one, const
                              const int64_t *q_start_two, int64_t n_q, int64_t *out_matches);
 int gnx_twobit_pack_device(gnx_ctx *ctx, const uint8_t *d_seq, int64_t n_bases, int lead, uint64_t *d_words,
                            void *cuda_stream);
+/* dnaTwoBit.NewTwoBit on the HOST (no GPU involved; this is the packer gnx_affine_batch runs while it stages pageable
+ * bytes, exposed so that a caller can prepare gnx_affine_batch_twobit input with the same threads): `count`
+ * sequences of `len` bases each, back to back in `bases`, into (len + 31) / 32 words per sequence, first base in
+ * bits 63:62, tail left-aligned (dna/dnaTwoBit/dnaTwoBit.go:28-42).  GNX_EBASE if a base is >= 4 (the reference
+ * would OR its high bits into the neighbouring bases; words are then unspecified). */
+int gnx_pack_twobit_host(const uint8_t *bases, int64_t count, int64_t len, uint64_t *words);
 
 /* ---- perfect-match seeds of cmd/gsw --------------------------------------------- *
  * gnx_seed_index_new  genomeGraph.IndexGenomeIntoMap(genome, seedLen, seedStep) (genomeGraph/index.go:21-44)

@@ -84,6 +84,23 @@ func PackTwoBit(seqs []dnaTwoBit.TwoBit) ([]uint64, []int64) {
 	return words, lens
 }
 
+// PackBasesUniform is dnaTwoBit.NewTwoBit of count sequences of length n held back to back as dna.Base bytes, done by
+// the library's host threads (gnx_pack_twobit_host: the packer gnx_affine_batch itself runs while it stages a large
+// uniform batch, so callers of AffineGapBatchCat get it implicitly).  Panics like scores[a][b] for a base >= 4.
+func PackBasesUniform(cat []dna.Base, count int, n int) []uint64 {
+	words := make([]uint64, count*((n+31)/32))
+	if count == 0 || n == 0 {
+		return words
+	}
+	rc := C.gnx_pack_twobit_host((*C.uint8_t)(unsafe.Pointer(&cat[0])), C.int64_t(count), C.int64_t(n), (*C.uint64_t)(unsafe.Pointer(&words[0])))
+	if rc == C.GNX_EBASE {
+		panic("runtime error: index out of range")
+	} else if rc != C.GNX_OK {
+		log.Panicf("gnxalign: gnx_pack_twobit_host failed (%d)", int(rc))
+	}
+	return words
+}
+
 // ---- the profile DP and the progressive multiple alignment (cmd/faChunkAlign) -----------------------------------
 // multipleAffineGap / multipleAffineGapChunk (align/affineGap_highMem.go:274-353) keep their signatures; nearestGroups /
 // nearestGroupsChunk (align/multiAlign.go:27-57) evaluate ALL group pairs of a round in one GPU call

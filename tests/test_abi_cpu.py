@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 from gonomics_b200 import _lib, build
@@ -59,3 +60,27 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".c", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "gnx_oracle" not in txt, f
+
+
+def test_host_packer_matches_the_oracle():
+    """gnx_pack_twobit_host (the packer gnx_affine_batch runs while it stages pageable bytes; pure host code, no GPU):
+    word for word dnaTwoBit.NewTwoBit of every sequence (the oracle's packer, itself pinned to the reference's
+    known answers in test_twobit_oracle.py), for lengths around the word and 4-base boundaries, many sequences
+    (several threads) and the GNX_EBASE report for a base >= 4."""
+    import oracle as orc
+    from gonomics_b200 import _lib, dnatwobit
+    rng = np.random.default_rng(11)
+    for length, count in ((1, 5), (3, 7), (4, 3), (31, 9), (32, 9), (33, 9), (64, 4), (150, 1000), (500, 333), (97, 70000)):
+        seqs = rng.integers(0, 4, size=(count, length), dtype=np.uint8)
+        words = dnatwobit.pack_uniform_host(seqs.reshape(-1), count, length)
+        wl = (length + 31) // 32
+        assert words.shape == (count * wl,)
+        for p in list(range(min(count, 40))) + [count - 1, count // 2]:
+            want = orc.new_twobit(seqs[p])[0][:wl]
+            assert np.array_equal(words[p * wl:(p + 1) * wl], want), (length, count, p)
+    bad = rng.integers(0, 4, size=(50000, 40), dtype=np.uint8)
+    bad[49990, 39] = 4
+    with pytest.raises(_lib.GnxError) as ei:
+        dnatwobit.pack_uniform_host(bad.reshape(-1), 50000, 40)
+    assert ei.value.code == _lib.GNX_EBASE
+    assert dnatwobit.pack_uniform_host(np.zeros(0, dtype=np.uint8), 0, 10).size == 0
