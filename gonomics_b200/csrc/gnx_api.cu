@@ -1808,7 +1808,8 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
             }
             d_wa = s.tb_a.as<uint64_t>();
             d_wb = s.tb_b.as<uint64_t>();
-            const bool need_bytes = !(pb.cfg.tb && !pb.want_cigar); // the packed score-only kernel reads no bytes
+            // the packed 16-bit kernels read the words; so do the screening and recompute kernels of the checkpoint path
+            const bool need_bytes = !(pb.cfg.tb && (!pb.want_cigar || pb.cfg.impl == 17));
             if (tb->uniform) { // byte offsets made on the device, bases unpacked without any offset array
                 const int g = (int)((np + 1 + 255) / 256);
                 iota_offsets_kernel<<<g, 256, 0, s.stream>>>(s.aoff.as<int64_t>(), begin, np + 1, tb->n);
@@ -2643,7 +2644,7 @@ static int run_device_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *d_alpha_ca
             cd.boff = s.boff.as<int64_t>() - begin;
             cd.alpha_words = tbd->a_words;
             cd.beta_words = tbd->b_words;
-            if (!(pb.cfg.tb && !pb.want_cigar)) { // some kernel of this path reads bytes: expand the chunk
+            if (!(pb.cfg.tb && (!pb.want_cigar || pb.cfg.impl == 17))) { // some kernel of this path reads bytes: expand the chunk
                 CU(s.alpha.ensure((size_t)std::max<int64_t>(cd.a_hi - cd.a_lo, 1)));
                 CU(s.beta.ensure((size_t)std::max<int64_t>(cd.b_hi - cd.b_lo, 1)));
                 const int64_t wa = np * tbd->wn, wb = np * tbd->wm;

@@ -69,16 +69,25 @@ __global__ void __launch_bounds__(128) ckpt_classify_kernel(const FillParams P, 
         Q.counts[idx] = 0;
         return;
     }
-    const int64_t a0 = P.alpha_off[pair], b0 = P.beta_off[pair];
-    const int n = (int)(P.alpha_off[pair + 1] - a0), m = (int)(P.beta_off[pair + 1] - b0);
+    // 2-bit batches (P.alpha_words set): the bases are read from the dnaTwoBit words, there is no byte copy on the device
+    const bool tbm = P.alpha_words != nullptr;
+    const int64_t a0 = tbm ? 0 : P.alpha_off[pair], b0 = tbm ? 0 : P.beta_off[pair];
+    const int n = tbm ? P.n_uni : (int)(P.alpha_off[pair + 1] - a0), m = tbm ? P.m_uni : (int)(P.beta_off[pair + 1] - b0);
     const int rs = (int)Q.rstar[pair];
     bool shortcut = false;
     if (rs >= m && m >= 1) {
-        const uint8_t *__restrict__ al = P.alpha + a0 + (rs - m);
-        const uint8_t *__restrict__ be = P.beta + b0;
         long long sum = 0;
-        for (int k = 0; k < m; ++k)
-            sum += P.scores[(int)al[k] * P.dim + (int)be[k]];
+        if (tbm) {
+            const uint32_t *wa = reinterpret_cast<const uint32_t *>(P.alpha_words + pair * P.wn);
+            const uint32_t *wb = reinterpret_cast<const uint32_t *>(P.beta_words + pair * P.wm);
+            for (int k = 0; k < m; ++k)
+                sum += P.scores[tb_base(wa, rs - m + k) * P.dim + tb_base(wb, k)];
+        } else {
+            const uint8_t *__restrict__ al = P.alpha + a0 + (rs - m);
+            const uint8_t *__restrict__ be = P.beta + b0;
+            for (int k = 0; k < m; ++k)
+                sum += P.scores[(int)al[k] * P.dim + (int)be[k]];
+        }
         shortcut = sum == P.out_score[pair];
     }
     if (!shortcut) {
@@ -109,7 +118,10 @@ __global__ void __launch_bounds__(128) ckpt_overflow_list_kernel(const int *coun
 // ungapped-tail shortcut) to all sixteen (unrelated sequences), and with static pairing a warp cost the maximum of its
 // two pairs.  The batch is uniform (n x m), so everything but the query tables, the staged target, r* and the
 // checkpoint address is kernel-invariant.
-__global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillParams P, const CkptParams Q)
+#ifndef GNX_CK_MINB
+#define GNX_CK_MINB 12
+#endif
+__global__ void __launch_bounds__(32, GNX_CK_MINB) affine_ckpt_trace_kernel(const FillParams P, const CkptParams Q)
 {
     constexpr int C = 10, LPP = 16, WPL = 2;
     // SK rows between neighbouring lanes, as in pass 1: cell (i,j) belongs to step (i - 1) + SK * ((j - 1) / C).  A
@@ -203,10 +215,13 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
                     src_lane = (int)(((slot_id >> 1) & 1) * LPP) + lane;
                     sel = (int)(slot_id & 1);
                     ck_base = Q.ckpt + (Q.quad_ck_off ? (size_t)Q.quad_ck_off[quad] : (size_t)quad * Q.quad_words);
-                    const uint8_t *__restrict__ alpha = P.alpha + P.alpha_off[pair];
-                    const uint8_t *__restrict__ beta = P.beta + P.beta_off[pair];
-                    n = (int)(P.alpha_off[pair + 1] - P.alpha_off[pair]);
-                    m = (int)(P.beta_off[pair + 1] - P.beta_off[pair]);
+                    const bool tbm = P.alpha_words != nullptr; // 2-bit batch: bases come from the dnaTwoBit words
+                    const uint8_t *__restrict__ alpha = tbm ? nullptr : P.alpha + P.alpha_off[pair];
+                    const uint8_t *__restrict__ beta = tbm ? nullptr : P.beta + P.beta_off[pair];
+                    const uint32_t *wa = tbm ? reinterpret_cast<const uint32_t *>(P.alpha_words + pair * P.wn) : nullptr;
+                    const uint32_t *wb = tbm ? reinterpret_cast<const uint32_t *>(P.beta_words + pair * P.wm) : nullptr;
+                    n = tbm ? P.n_uni : (int)(P.alpha_off[pair + 1] - P.alpha_off[pair]);
+                    m = tbm ? P.m_uni : (int)(P.beta_off[pair + 1] - P.beta_off[pair]);
                     T = n + SK * (LPP - 1);
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
@@ -219,7 +234,7 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         const int j = jbase + c + 1;
-                        const int q = (j <= m) ? (int)beta[j - 1] : 0;
+                        const int q = (j <= m) ? (tbm ? tb_base(wb, j - 1) : (int)beta[j - 1]) : 0;
 #pragma unroll
                         for (int a = 0; a < kDimP; ++a) {
                             int v = 0;
@@ -228,8 +243,18 @@ __global__ void __launch_bounds__(32, 12) affine_ckpt_trace_kernel(const FillPar
                             s_tab[(c * kDimP + a) * 32 + tid] = v;
                         }
                     }
-                    for (int i = lane; i < n; i += LPP)
-                        s_tgt[half * kTgtPitch + i] = alpha[i];
+                    if (tbm) { // 16 bases (one 32-bit half word) per lane and iteration
+                        for (int h = lane; 16 * h < n; h += LPP) {
+                            const uint32_t v = wa[((h >> 1) << 1) | ((h & 1) ^ 1)];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (16 * h + i < n)
+                                    s_tgt[half * kTgtPitch + 16 * h + i] = (uint8_t)((v >> (30 - 2 * i)) & 3u);
+                        }
+                    } else {
+                        for (int i = lane; i < n; i += LPP)
+                            s_tgt[half * kTgtPitch + i] = alpha[i];
+                    }
                     rs = (int)Q.rstar[pair];
                     S_pair = (int)P.out_score[pair];
                     wi = rs;            // current cell
