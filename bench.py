@@ -864,7 +864,7 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dt = float(t.item())
             h2d = (P * (WN + WM) * 8) if twobit else (na + nb + 2 * (P + 1) * 8)  # the host buffers handed to the call
-            packed = twobit or (pack and not pinned)
+            packed = twobit or pack
             pcie = (P * (WN + WM) * 8) if packed else (na + nb + 2 * (P + 1) * 8)  # what crosses PCIe
             d2h = P * 8 + ((P + 1) * 8 + int(out[1][-1]) * 16 if want_cigar else 0)
             return {"value": cells_all / dt / 1e9, "unit": "GCUPS", "ms_per_step": dt * 1e3, "h2d_bytes_per_step": int(h2d),

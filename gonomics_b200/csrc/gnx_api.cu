@@ -831,9 +831,9 @@ struct TbIn {
     const int64_t *a_len = nullptr, *b_len = nullptr;   // the caller's length arrays
     bool uniform = false;           // every pair n x m
     int64_t n = 0, m = 0, wn = 0, wm = 0; // uniform: lengths and words per sequence
-    // from_bytes: the caller passed one byte per base in PAGEABLE memory (gnx_affine_batch).  Such input has to be
-    // copied through a page-locked stage anyway; that pass packs it to dnaTwoBit words instead (a quarter of the bytes
-    // to write, to DMA and to read on the device) and the chunk then runs exactly like a gnx_affine_batch_twobit chunk.
+    // from_bytes: the caller passed one byte per base (gnx_affine_batch).  Pageable input has to be copied through a
+    // page-locked stage anyway; that pass packs it to dnaTwoBit words instead (a quarter of the bytes to write, to DMA
+    // and to read on the device) and the chunk then runs exactly like a gnx_affine_batch_twobit chunk.
     // Uniform batches only (word offsets are p * wn / p * wm, a_woff / b_woff stay NULL).
     bool from_bytes = false;
 };
@@ -2415,8 +2415,10 @@ int gnx_affine_batch(gnx_ctx *ctx, const uint8_t *alpha_cat, const int64_t *alph
         ctx->pack_backoff--;
     else if (ctx->opt_pack_stage && ctx->opt_tb_tma && n_pairs >= 4096 && dim >= 4 && alpha_cat && beta_cat) {
         const int64_t n = alpha_off[1] - alpha_off[0], m = beta_off[1] - beta_off[0];
-        if (n >= 1 && n <= kTbMaxN && m >= 1 && m <= 160 && !is_pinned(alpha_cat) && !is_pinned(beta_cat) &&
-            offsets_uniform(alpha_off, n_pairs, n) && offsets_uniform(beta_off, n_pairs, m)) {
+        // (page-locked input is packed too: its DMA needs no staging pass, but a quarter of the PCIe bytes is worth the
+        // host threads -- score-only batches are PCIe-bound otherwise)
+        if (n >= 1 && n <= kTbMaxN && m >= 1 && m <= 160 && offsets_uniform(alpha_off, n_pairs, n) &&
+            offsets_uniform(beta_off, n_pairs, m)) {
             Problem pb2 = pb;
             pb2.twobit = true;
             TbIn tb;

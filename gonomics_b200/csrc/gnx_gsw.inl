@@ -363,12 +363,17 @@ extern "C" int gnx_gsw_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8
                 (long long)n_ext1, (long long)(n_ext_total - n_ext1));
 
     // ---- phase 3: replay of the reference's per-read loop over the precomputed DPs ----
-    std::vector<GswCigar> cig_out((size_t)n_reads);
-    std::vector<uint8_t> has_cig((size_t)n_reads, 0);
+    // every thread appends the cigars of its (contiguous) reads to its own arena; out[r].cigar_off is arena-relative
+    // until the arenas are laid end to end in the caller's buffer below
+    std::vector<std::vector<gnx_cigar>> arena((size_t)nthr);
     std::atomic<bool> missing{false};
-    gsw_parallel(n_reads, [&](int64_t lo, int64_t hi, int) {
-        GswCigar left, right, cig;
+    gsw_parallel(n_reads, [&](int64_t lo, int64_t hi, int t) {
+        GswCigar left, right, cig, best_cig;
+        std::vector<gnx_cigar> &mine = arena[(size_t)t];
+        mine.reserve((size_t)(hi - lo) * 3);
         for (int64_t r = lo; r < hi; ++r) {
+            bool has_cig = false;
+            best_cig.clear();
             const int64_t L = read_off[r + 1] - read_off[r];
             const uint8_t *rd = reads_cat + read_off[r], *rcp = rc_cat.get() + (read_off[r] - read_off[0]);
             const int64_t pf = perfect[(size_t)r];
@@ -435,7 +440,7 @@ extern "C" int gnx_gsw_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8
                     for (const auto &c : cig)
                         if (c.second == 'M' || c.second == 'I' || c.second == 'S' || c.second == '=' || c.second == 'X')
                             qlen += c.first;
-                    GswCigar &dst = cig_out[(size_t)r];
+                    GswCigar &dst = best_cig;
                     if (qstart == 0 && qlen >= L) {
                         dst = cig;
                     } else {
@@ -447,10 +452,18 @@ extern "C" int gnx_gsw_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8
                             dst.emplace_back(L - qstart - qlen, 'S');
                         }
                     }
-                    has_cig[(size_t)r] = 1;
+                    has_cig = true;
                 }
             }
             g.flag = (g.pos_strand ? 4 : 0) + (g.aln_score < 1200 ? 2 : 0); // getGirafFlags (:187-196)
+            g.cigar_off = (int64_t)mine.size();
+            g.n_cigar = has_cig ? (int32_t)best_cig.size() : -1; // -1: Cigar == nil (no seed beat score 0)
+            for (const auto &c : best_cig) {
+                gnx_cigar o = gnx_cigar();
+                o.run_length = c.first;
+                o.op = c.second;
+                mine.push_back(o);
+            }
             out[r] = g;
         }
     });
@@ -458,45 +471,42 @@ extern "C" int gnx_gsw_batch(gnx_ctx *ctx, const gnx_seed_index *ix, const uint8
         return fail(ctx, GNX_ECUDA, "gnx_gsw_batch: internal error (a replayed seed has no extension result)");
     lap("replay");
     if (paired) { // setGirafFlags (toGiraf.go:126-137): as written there, the forward mate gets 8 + 16 + 16
-        for (int64_t p = 0; p + 1 < n_reads; p += 2) {
-            gnx_giraf &f = out[p], &v = out[p + 1];
-            f.flag += 8 + 16 + 16;
-            const int64_t d = (int64_t)f.t_start - v.t_start;
-            bool proper = false;
-            if ((d < 0 ? -d : d) < 10000) {
-                if (f.t_start < v.t_start && f.pos_strand && !v.pos_strand)
-                    proper = true;
-                if (f.t_start > v.t_start && !f.pos_strand && v.pos_strand)
-                    proper = true;
+        gsw_parallel(n_reads / 2, [&](int64_t lo, int64_t hi, int) {
+            for (int64_t q = lo; q < hi; ++q) {
+                gnx_giraf &f = out[2 * q], &v = out[2 * q + 1];
+                f.flag += 8 + 16 + 16;
+                const int64_t d = (int64_t)f.t_start - v.t_start;
+                bool proper = false;
+                if ((d < 0 ? -d : d) < 10000) {
+                    if (f.t_start < v.t_start && f.pos_strand && !v.pos_strand)
+                        proper = true;
+                    if (f.t_start > v.t_start && !f.pos_strand && v.pos_strand)
+                        proper = true;
+                }
+                if (proper) {
+                    f.flag += 1;
+                    v.flag += 1;
+                }
+                f.flag &= 0xff; // Flag is a uint8
+                v.flag &= 0xff;
             }
-            if (proper) {
-                f.flag += 1;
-                v.flag += 1;
-            }
-            f.flag &= 0xff; // Flag is a uint8
-            v.flag &= 0xff;
-        }
+        });
     }
-    int64_t total = 0;
-    for (int64_t r = 0; r < n_reads; ++r) {
-        out[r].cigar_off = total;
-        out[r].n_cigar = has_cig[(size_t)r] ? (int32_t)cig_out[(size_t)r].size() : -1; // -1: Cigar == nil (no seed beat score 0)
-        total += (int64_t)cig_out[(size_t)r].size();
-    }
+    std::vector<int64_t> abase((size_t)nthr + 1, 0);
+    for (int t = 0; t < nthr; ++t)
+        abase[(size_t)t + 1] = abase[(size_t)t] + (int64_t)arena[(size_t)t].size();
+    const int64_t total = abase[(size_t)nthr];
     if (out_n_cigar)
         *out_n_cigar = total;
-    if (total > cigar_cap || (total > 0 && !out_cigar))
-        return fail(ctx, GNX_ECAP, "cigar_cap too small for the block's cigars (out_n_cigar holds the size needed)");
-    gsw_parallel(n_reads, [&](int64_t lo, int64_t hi, int) {
-        for (int64_t r = lo; r < hi; ++r) {
-            gnx_cigar *dst = out_cigar + out[r].cigar_off;
-            for (const auto &c : cig_out[(size_t)r]) {
-                dst->run_length = c.first;
-                dst->op = c.second;
-                ++dst;
-            }
-        }
+    const bool fits = total <= cigar_cap && (total == 0 || out_cigar);
+    gsw_parallel(n_reads, [&](int64_t lo, int64_t hi, int t) { // same split as the replay: thread t owns arena t
+        for (int64_t r = lo; r < hi; ++r)
+            out[r].cigar_off += abase[(size_t)t];
+        if (fits && !arena[(size_t)t].empty())
+            memcpy(out_cigar + abase[(size_t)t], arena[(size_t)t].data(), arena[(size_t)t].size() * sizeof(gnx_cigar));
     });
+    if (!fits)
+        return fail(ctx, GNX_ECAP, "cigar_cap too small for the block's cigars (out_n_cigar holds the size needed)");
     lap("pack results");
     return GNX_OK;
 }

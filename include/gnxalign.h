@@ -348,7 +348,7 @@ int gnx_last_fill_stats(gnx_ctx *ctx, double *fill_ms, int64_t *fill_launches, i
  * host-binned quads, 2 dnaTwoBit words staged by TMA, 4 int64 fallback, 8 multi-strip pairs. */
 int gnx_last_kernel_path(gnx_ctx *ctx, int *impl, int *flags);
 /* Tuning knobs (name/value), e.g. "cols_per_lane", "block_threads", "chunk_pairs"; "pack_stage" (default 1):
- * gnx_affine_batch packs large uniform batches held in PAGEABLE memory to dnaTwoBit words while it stages them
+ * gnx_affine_batch packs large uniform batches to dnaTwoBit words on the host threads while it stages them
  * (a quarter of the PCIe bytes; falls back to bytes when a base >= 4 is met); "tb_tma" (default 1): 2-bit input is
  * read by the packed 16-bit kernels through TMA instead of being expanded first.  Returns GNX_EARG for an unknown
  * name. */
