@@ -464,6 +464,10 @@ def main():
     ap.add_argument("--gsw-pairs", type=int, default=10_000_000, help="read pairs (in total) of the gsw / C5 block")
     ap.add_argument("--gsw-genome", type=int, default=1 << 30, help="bases of the synthetic reference of the gsw block")
     args = ap.parse_args()
+    # one rank per GPU shares the box's cores: cap the library's host threads (staging, packing, gsw host phases)
+    lws = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    if lws > 1 and "GNX_HOST_THREADS" not in os.environ:
+        os.environ["GNX_HOST_THREADS"] = str(max(2, (os.cpu_count() or 1) // lws))
     # stdout carries exactly ONE line, the JSON result: everything libraries print there (e.g. "NCCL version ..."
     # under torchrun) is sent to stderr by pointing fd 1 at fd 2 for the duration of the run.
     global _RESULT_FD

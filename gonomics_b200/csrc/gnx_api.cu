@@ -1473,12 +1473,24 @@ int collect_fill_stats(gnx_ctx *ctx)
     return GNX_OK;
 }
 
+// Host threads this process may use for staging, packing and the gsw driver's host phases: the hardware concurrency,
+// or GNX_HOST_THREADS when several processes share the box (one rank per GPU).
+unsigned host_threads()
+{
+    static const unsigned n = [] {
+        const char *e = getenv("GNX_HOST_THREADS");
+        const int v = e ? atoi(e) : 0;
+        return v >= 1 ? (unsigned)v : std::max(1u, std::thread::hardware_concurrency());
+    }();
+    return n;
+}
+
 // Pageable caller memory (a Go slice, a numpy array) cannot be DMA'd directly: it is copied through a page-locked
 // stage.  One memcpy thread moves ~6 GB/s, far below PCIe 5 x16, so large copies are split over a few threads.
 void par_memcpy(void *dst, const void *src, size_t bytes)
 {
     constexpr size_t kMin = (size_t)4 << 20;
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned hw = host_threads();
     static const int cap = [] { // GNX_MEMCPY_THREADS overrides the default of 8 staging threads
         const char *e = getenv("GNX_MEMCPY_THREADS");
         const int v = e ? atoi(e) : 8;
@@ -1538,7 +1550,7 @@ bool pack_range(uint64_t *dst, const uint8_t *src, int64_t count, int64_t len, i
 
 bool pack_stage(uint64_t *dst, const uint8_t *src, int64_t count, int64_t len, int64_t wlen)
 {
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned hw = host_threads();
     static const int cap = [] { // GNX_PACK_THREADS overrides the default of 16 packing threads
         const char *e = getenv("GNX_PACK_THREADS");
         const int v = e ? atoi(e) : 16;
@@ -1899,7 +1911,8 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
         if (pb.want_cigar) {
             CU(s.h_trace_off.ensure((size_t)(np + 1) * 8));
             int64_t *to = s.h_trace_off.as<int64_t>();
-            int64_t acc = compute_trace_offsets(pb, aoff, boff, begin, np, to);
+            const bool need_to = pb.cfg.impl != 17; // the checkpoint path addresses its area by quad
+            int64_t acc = need_to ? compute_trace_offsets(pb, aoff, boff, begin, np, to) : 0;
             if (pb.cfg.impl == 17) { // checkpoint area: whole quads; r* per pair
                 acc = pb.cfg.rag ? std::max(acc, rag_all[(size_t)ci].ck_words)
                                  : std::max(acc, ((np + 3) / 4) * ckpt_quad_words(pb.cfg.n_uniform));
@@ -1911,7 +1924,8 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
             }
             CU(s.trace.ensure((size_t)std::max<int64_t>(acc, 1) * 4));
             CU(s.trace_off.ensure((size_t)(np + 1) * 8));
-            CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+            if (need_to)
+                CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, s.stream));
             CU(s.slots.ensure(slots_bytes(pb, np)));
             CU(s.counts.ensure((size_t)np * 4));
             CU(s.cig_off.ensure((size_t)(np + 1) * 8));
@@ -2677,7 +2691,9 @@ static int run_device_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *d_alpha_ca
                 CU(cudaEventSynchronize(s.ev_done));
             CU(s.h_trace_off.ensure((size_t)(np + 1) * 8));
             int64_t *to = s.h_trace_off.as<int64_t>();
-            int64_t acc = compute_trace_offsets(pb, alpha_off_host, beta_off_host, begin, np, to);
+            // the checkpoint path addresses its area by quad: no per-pair trace offsets to compute or upload
+            const bool need_to = pb.cfg.impl != 17;
+            int64_t acc = need_to ? compute_trace_offsets(pb, alpha_off_host, beta_off_host, begin, np, to) : 0;
             if (pb.cfg.impl == 17) { // checkpoint area: whole quads; r* per pair
                 acc = pb.cfg.rag ? std::max(acc, rag_all[(size_t)ci].ck_words)
                                  : std::max(acc, ((np + 3) / 4) * ckpt_quad_words(pb.cfg.n_uniform));
@@ -2689,7 +2705,8 @@ static int run_device_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *d_alpha_ca
             }
             CU(s.trace.ensure((size_t)std::max<int64_t>(acc, 1) * 4));
             CU(s.trace_off.ensure((size_t)(np + 1) * 8));
-            CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, st));
+            if (need_to)
+                CU(cudaMemcpyAsync(s.trace_off.p, to, (size_t)(np + 1) * 8, cudaMemcpyHostToDevice, st));
             CU(cudaEventRecord(s.ev_done, st));
             s.ev_done_set = true;
             CU(s.slots.ensure(slots_bytes(pb, np)));

@@ -70,7 +70,7 @@ inline void gsw_append(GswCigar &a, int64_t run, uint8_t op)
 
 inline int gsw_threads(int64_t n)
 {
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned hw = host_threads();
     return (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)hw, (int64_t)32, n / 256 + 1}));
 }
 

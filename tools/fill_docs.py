@@ -4,7 +4,7 @@
 Every number in those two files that comes from a bench run sits between an HTML-comment pair
 `<!--KEY-->value<!--/-->`; this script rewrites the values (idempotent, so it is re-run after each new bench).
 
-    python tools/fill_docs.py [--one profiles/r02j_bench_1gpu.json] [--multi 'profiles/r02k_bench_*gpu.json']
+    python tools/fill_docs.py [--one profiles/r02q_bench_1gpu.json] [--multi 'profiles/r02q_bench_[248]gpu.json']
 """
 from __future__ import annotations
 
@@ -30,6 +30,8 @@ def values(d):
         "C3DEV": f0(d["value"]), "C3BYTES": f0(d["traceback_byte_inputs"]["value"]), "C3E2E": f0(e["value"]),
         "C3PIN": f0(e["variants"]["pinned_bytes"]["value"]), "C3PTB": f0(e["variants"]["pageable_twobit"]["value"]),
         "C3NTB": f0(e["variants"]["pinned_twobit"]["value"]), "C3FRAC": f"{d['roofline']['frac']:.3f}",
+        "C3UNP": f0(e["variants"]["pageable_bytes_staged_unpacked"]["value"]),
+        "C2UNP": f0(so["e2e"]["pageable_bytes_staged_unpacked"]["value"]),
         "C2DEV": f0(so["value"]), "C2BYTES": f0(so["byte_inputs"]["value"]),
         "C2E2E": f0(so["e2e"]["pageable_bytes"]["value"]), "C2PIN": f0(so["e2e"]["pinned_bytes"]["value"]),
         "C2PTB": f0(so["e2e"]["pageable_twobit"]["value"]), "C2NTB": f0(so["e2e"]["pinned_twobit"]["value"]),
@@ -71,8 +73,8 @@ def scaling_table(lines):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--one", default=os.path.join(ROOT, "profiles/r02j_bench_1gpu.json"))
-    ap.add_argument("--multi", default=os.path.join(ROOT, "profiles/r02k_bench_*gpu.json"))
+    ap.add_argument("--one", default=os.path.join(ROOT, "profiles/r02q_bench_1gpu.json"))
+    ap.add_argument("--multi", default=os.path.join(ROOT, "profiles/r02q_bench_[248]gpu.json"))
     a = ap.parse_args()
     one = json.load(open(a.one))
     v = values(one)
