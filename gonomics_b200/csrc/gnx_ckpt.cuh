@@ -135,7 +135,11 @@ __global__ void __launch_bounds__(32, GNX_CK_MINB) affine_ckpt_trace_kernel(cons
     __shared__ int s_tab[C * kDimP * 32];
     __shared__ uint8_t s_tgt[2 * kTgtPitch];
     __shared__ uint32_t s_tr[(kCkK + SK) * WPL * 32];
-    __shared__ int s_pre[2 * (LPP * C + 1)]; // per half: prefix sums of the walker's diagonal (route shortcuts)
+    // per half: prefix sums of the walker's diagonal (route shortcuts).  They live in the trace-code area: the shortcut
+    // tests of an iteration are over before its recompute writes the codes, and 18.1 KB per CTA instead of 19.3 lets a
+    // twelfth warp onto the SM.
+    static_assert(sizeof(int) * 2 * (LPP * C + 1) <= sizeof(s_tr), "s_pre must fit in s_tr");
+    int *const s_pre = reinterpret_cast<int *>(s_tr);
     const int tid = threadIdx.x, lane = tid % LPP, half = tid / LPP;
     const int one = P.one;
     const int O = P.gap_open, E = P.gap_extend;
