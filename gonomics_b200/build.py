@@ -8,8 +8,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgnxalign.so")
-SOURCES = ["gnx_api.cu"]
-DEPS = ["gnx_api.cu", "gnx_kernels.cuh", "gnx_fill3.cuh", "gnx_fill16.cuh", "gnx_ckpt.cuh", "gnx_long.cuh", "gnx_profile.cuh", "gnx_twobit.cuh", "gnx_twobit_api.inl", "gnx_multi.inl", "gnx_gsw.inl", os.path.join("..", "..", "include", "gnxalign.h")]
+SOURCES = ["gnx_api.cu", "gnx_pack_host.cpp"]
+DEPS = ["gnx_api.cu", "gnx_pack_host.cpp", "gnx_kernels.cuh", "gnx_fill3.cuh", "gnx_fill16.cuh", "gnx_ckpt.cuh", "gnx_long.cuh", "gnx_profile.cuh", "gnx_twobit.cuh", "gnx_twobit_api.inl", "gnx_multi.inl", "gnx_gsw.inl", os.path.join("..", "..", "include", "gnxalign.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math", "-Xcompiler", "-fPIC,-O2,-Wall,-pthread", "-shared", "-cudart", "shared"]
 

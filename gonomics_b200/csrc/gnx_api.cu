@@ -27,6 +27,8 @@
 #include <thread>
 #include <vector>
 
+extern "C" bool gnx_pack_range_host(uint64_t *dst, const uint8_t *src, int64_t count, int64_t len, int64_t wlen); // gnx_pack_host.cpp
+
 namespace {
 
 using namespace gnx;
@@ -1514,38 +1516,11 @@ void par_memcpy(void *dst, const void *src, size_t bytes)
 }
 
 // dnaTwoBit.NewTwoBit of `count` sequences of `len` bases each (one byte per base, back to back) into `wlen` words per
-// sequence: 32 bases per word, the first in bits 63:62, the tail word left-aligned (dna/dnaTwoBit/dnaTwoBit.go:28-42).
-// Four bases at a time: t * 0x40100401 drops the four 2-bit fields of a little-endian 32-bit load into the product's
-// top byte.  Returns false if any base is >= 4 (such input cannot be packed: the caller falls back to bytes, where the
-// kernels report the pair).
-bool pack_range(uint64_t *dst, const uint8_t *src, int64_t count, int64_t len, int64_t wlen)
+// sequence: gnx_pack_host.cpp (scalar / AVX2).  Returns false if any base is >= 4 (such input cannot be packed: the
+// caller falls back to bytes, where the kernels report the pair).
+inline bool pack_range(uint64_t *dst, const uint8_t *src, int64_t count, int64_t len, int64_t wlen)
 {
-    uint64_t bad = 0;
-    const int64_t full = len / 32, tail = len - full * 32;
-    for (int64_t p = 0; p < count; ++p) {
-        const uint8_t *b = src + p * len;
-        uint64_t *w = dst + p * wlen;
-        for (int64_t k = 0; k < full; ++k, b += 32) {
-            uint64_t x[4];
-            memcpy(x, b, 32);
-            bad |= x[0] | x[1] | x[2] | x[3];
-            uint64_t v = 0;
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t lo = (uint32_t)x[q], hi = (uint32_t)(x[q] >> 32);
-                v = (v << 16) | (uint64_t)(((lo * 0x40100401u) >> 24) << 8) | (uint64_t)((hi * 0x40100401u) >> 24);
-            }
-            w[k] = v;
-        }
-        if (tail) {
-            uint64_t v = 0;
-            for (int64_t i = 0; i < tail; ++i) {
-                bad |= b[i];
-                v |= (uint64_t)(b[i] & 3u) << (62 - 2 * i);
-            }
-            w[full] = v;
-        }
-    }
-    return (bad & 0xfcfcfcfcfcfcfcfcull) == 0;
+    return gnx_pack_range_host(dst, src, count, len, wlen);
 }
 
 bool pack_stage(uint64_t *dst, const uint8_t *src, int64_t count, int64_t len, int64_t wlen)

@@ -84,3 +84,24 @@ def test_host_packer_matches_the_oracle():
         dnatwobit.pack_uniform_host(bad.reshape(-1), 50000, 40)
     assert ei.value.code == _lib.GNX_EBASE
     assert dnatwobit.pack_uniform_host(np.zeros(0, dtype=np.uint8), 0, 10).size == 0
+
+
+def test_host_packer_simd_equals_scalar(lib):
+    """The run-time-selected (AVX2 where the CPU has it) and the scalar form of the host packer give the same words
+    and the same verdict on invalid bases."""
+    rng = np.random.default_rng(12)
+    for fn in (lib.gnx_pack_range_host, lib.gnx_pack_range_host_scalar):
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64]
+        fn.restype = ctypes.c_bool
+    for length, count in ((500, 2000), (150, 3001), (64, 10), (33, 77), (7, 100)):
+        seqs = rng.integers(0, 4, size=count * length, dtype=np.uint8)
+        wl = (length + 31) // 32
+        a, b = np.zeros(count * wl, np.uint64), np.zeros(count * wl, np.uint64)
+        assert lib.gnx_pack_range_host(a.ctypes.data, seqs.ctypes.data, count, length, wl)
+        assert lib.gnx_pack_range_host_scalar(b.ctypes.data, seqs.ctypes.data, count, length, wl)
+        assert np.array_equal(a, b), (length, count)
+        for pos in (0, length // 2, count * length - 1):
+            bad = seqs.copy()
+            bad[pos] = 4 + (pos % 3) * 60
+            assert not lib.gnx_pack_range_host(a.ctypes.data, bad.ctypes.data, count, length, wl)
+            assert not lib.gnx_pack_range_host_scalar(b.ctypes.data, bad.ctypes.data, count, length, wl)

@@ -14,6 +14,9 @@ g_len = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 26
 rng = np.random.default_rng(5)
 genome = rng.integers(0, 4, size=g_len, dtype=np.uint8)
 ctx = align.Context(0)
+for kv in os.environ.get("GSW_OPTS", "").split(","):  # e.g. GSW_OPTS=chunk_pairs=1048576
+    if "=" in kv:
+        ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 ix = genomegraph.SeedIndex([genome], 32, 32, ctx)
 start = rng.integers(0, g_len - 600, size=pairs)
 frag = rng.integers(300, 500, size=pairs)
