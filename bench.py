@@ -837,7 +837,7 @@ def main():
     # The other variants show what the same call delivers with page-locked buffers (gnx_host_alloc) and with the
     # batch in dnaTwoBit form (a quarter of the H2D bytes).
     if not args.no_e2e:
-        e2e_steps = max(2, min(args.steps, 3))
+        e2e_steps = max(2, min(args.steps, 5))
         p_score, p_off, p_cig = pinned_array(P, np.int64), pinned_array(P + 1, np.int64), pinned_array(cig_cap, CIGAR_DTYPE)
         g_alpha, g_beta = np.array(h_alpha), np.array(h_beta)          # pageable copies ("Go slices")
         g_wa, g_wb = np.array(h_wa), np.array(h_wb)
