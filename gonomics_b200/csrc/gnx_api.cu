@@ -1542,9 +1542,9 @@ void par_memcpy(void *dst, const void *src, size_t bytes)
 {
     constexpr size_t kMin = (size_t)4 << 20;
     const unsigned hw = host_threads();
-    static const int cap = [] { // GNX_MEMCPY_THREADS overrides the default of 8 staging threads
+    static const int cap = [] { // GNX_MEMCPY_THREADS overrides the default of 16 staging threads
         const char *e = getenv("GNX_MEMCPY_THREADS");
-        const int v = e ? atoi(e) : 8;
+        const int v = e ? atoi(e) : 16;
         return v < 1 ? 1 : (v > 64 ? 64 : v);
     }();
     const int nt = (int)std::min<size_t>({(size_t)cap, (size_t)hw, bytes / kMin});
@@ -1754,8 +1754,21 @@ int run_host_batch(gnx_ctx *ctx, Problem &pb, const uint8_t *alpha_cat, const in
                 }
             }
             const int64_t *ho = s.h_off.as<int64_t>();
-            for (int64_t k = 0; k < np; ++k)
-                out_cigar_off[pd.begin + k] = cig_total + ho[k];
+            {   // chunk-relative offsets -> the caller's absolute ones (a few threads: 10^7 pairs per call add up)
+                const int nt = np >= (1 << 16) ? (int)std::min(4u, host_threads()) : 1;
+                const int64_t base_off = cig_total;
+                int64_t *dst_off = out_cigar_off + pd.begin;
+                auto work = [=](int t) {
+                    for (int64_t k = np * t / nt, e = np * (t + 1) / nt; k < e; ++k)
+                        dst_off[k] = base_off + ho[k];
+                };
+                std::vector<std::thread> th;
+                for (int t = 1; t < nt; ++t)
+                    th.emplace_back(work, t);
+                work(0);
+                for (auto &x : th)
+                    x.join();
+            }
             cig_total += total;
             out_cigar_off[pd.end] = cig_total;
         } else {
