@@ -388,6 +388,7 @@ __global__ void __launch_bounds__(32, GNX_CK_MINB) affine_ckpt_trace_kernel(cons
 #pragma unroll
                     for (int o = LPP / 2; o > 0; o >>= 1)
                         dhit = max(dhit, __shfl_xor_sync(FULL, dhit, o)); // the farthest verified cell of this half
+                    __syncwarp(); // s_pre shares its storage with s_tr: its reads are over before this iteration's recompute writes codes
                     if (lane == 0 && (tail || dhit > 0)) {
                         const int adv = tail ? tj : dhit;
                         if (cur_op == 0) {
