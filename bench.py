@@ -635,7 +635,7 @@ def main():
         "config": {"workload": WORKLOAD, "matrix": "HumanChimpTwo", "gap_open": GAP_OPEN, "gap_extend": GAP_EXTEND,
                    "pairs_total": total_pairs, "pairs_per_gpu": P, "cells_per_step_per_gpu": cells,
                    "inputs": "dnaTwoBit words resident in HBM (gnx_batch_device_twobit): packed 16-bit kernels stage them by "
-                             "TMA, the path recompute reads a device-side expansion",
+                             "TMA, the screening and recompute kernels read the words as well",
                    "l2": "inputs (%.1f GB/GPU packed) exceed the 126 MB L2; no flush needed" % ((P * (WN + WM) * 8) / 1e9),
                    "sharding": "contiguous pair shards per rank; NCCL all_gather of scores, cigar counts and cigar records "
                                "inside the timed step (N>1)", "synth_seconds": round(gen_s, 1)},
