@@ -1526,6 +1526,8 @@ int collect_fill_stats(gnx_ctx *ctx)
 
 // Host threads this process may use for staging, packing and the gsw driver's host phases: the hardware concurrency,
 // or GNX_HOST_THREADS when several processes share the box (one rank per GPU).
+thread_local unsigned tl_host_thread_share = 0; // gnx_multi_*: a shard's thread takes 1 / shards of the process's threads
+
 unsigned host_threads()
 {
     static const unsigned n = [] {
@@ -1533,7 +1535,7 @@ unsigned host_threads()
         const int v = e ? atoi(e) : 0;
         return v >= 1 ? (unsigned)v : std::max(1u, std::thread::hardware_concurrency());
     }();
-    return n;
+    return tl_host_thread_share ? std::max(1u, std::min(n, tl_host_thread_share)) : n;
 }
 
 // Pageable caller memory (a Go slice, a numpy array) cannot be DMA'd directly: it is copied through a page-locked

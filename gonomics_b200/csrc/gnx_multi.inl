@@ -59,10 +59,13 @@ int multi_run(gnx_multi *mg, int kind, const uint8_t *alpha_cat, const int64_t *
     std::vector<int> rc((size_t)world, GNX_OK);
     std::vector<int64_t> total((size_t)world, 0);
     std::vector<std::vector<int64_t>> soff((size_t)world), loff((size_t)world); // rebased offsets, shard cigar offsets
+    const unsigned all_threads = host_threads();
     auto shard = [&](int r) {
         const int64_t lo = cut[(size_t)r], hi = cut[(size_t)r + 1], np = hi - lo;
         if (np == 0)
             return;
+        // the shards stage and pack concurrently: each takes its share of the process's host threads
+        tl_host_thread_share = std::max(2u, all_threads / (unsigned)world);
         // offsets rebased to the shard (the single-device entry points take absolute offsets into the arrays they
         // are given; rebasing lets the bases be passed as a sub-range without a copy)
         std::vector<int64_t> &so = soff[(size_t)r];
@@ -114,6 +117,7 @@ int multi_run(gnx_multi *mg, int kind, const uint8_t *alpha_cat, const int64_t *
         for (int r = 1; r < world; ++r)
             th.emplace_back(shard, r);
         shard(0);
+        tl_host_thread_share = 0; // shard 0 ran on the caller's thread: give it its full share back
         for (auto &t : th)
             t.join();
     }
