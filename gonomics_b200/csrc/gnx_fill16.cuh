@@ -8,12 +8,15 @@
 //   * maxes are the unsigned 16x2 forms, and
 //   * the plain adds (M = H_diag + s, H + O + E) stay ordinary 32-bit integer adds on the FMA pipe:
 //     X = uB*65536 + uA, so X + (dB*65536 + dA) = (uB+dB)*65536 + (uA+dA) exactly as long as each half
-//     stays inside [0, 65535] -- which the host proves before dispatching this kernel (analyse16()).
+//     stays inside [0, 65535] -- which the host proves before dispatching this kernel (fill16_ok()).
 // Score-only needs no -inf at all: row 0 is I(0,j), column 0 is D(i,0) and every other state is a max
 // that contains a finite candidate (DESIGN.md "Arithmetic width"), so there is no sentinel to keep
 // away from the range limits.  Padding columns (j > m) get zero substitution scores, which keeps their
 // (unused) values within one gap-open of real cells.
-// Requires: uniform batch (all pairs n x m), m <= 160, dim <= 5, O <= 0, score only.
+// Requires: m <= 160, dim <= 5, O <= 0, the range proof of fill16_ok(); pairs in quads that share the target length
+// (a uniform batch, or the host-binned quads of a ragged one); score only, or -- CKPT -- score + checkpoints + r*.
+// Template parameters: FREE (freeEndGaps), CM (compile-time last-column index), CKPT, TB (dnaTwoBit words by TMA and
+// the joint score table); SK / quad cursor: see below.
 #pragma once
 #include "gnx_fill3.cuh"
 
